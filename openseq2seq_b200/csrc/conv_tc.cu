@@ -1,0 +1,530 @@
+// 1-D convolution as an implicit GEMM on the sm_100a tensor cores (tcgen05 + TMEM + TMA).
+//
+// Reference op being replaced: tf.layers.conv1d(use_bias=False, padding="SAME") as called from
+// open_seq2seq/parts/cnns/conv_blocks.py:195-206 (main conv) and :79-85 (1x1 residual conv), plus
+// the two gradients TF autodiff derives from it (dgrad, wgrad).
+//
+// Activations are NWC bf16 [B, T, C] (C contiguous). No im2col buffer is ever materialised: for a
+// filter tap k the A-operand tile is simply the activation slab shifted by k*dilation rows, which a
+// 3-D TMA box fetches directly (rows outside [0, T) are zero-filled by the TMA unit, which is
+// exactly SAME padding).
+//
+//  * tapgemm_kmajor  (forward and dgrad):  D[t, n] = sum_k sum_c A[b, t + off0 + k*step, c] * Wk[n, c]
+//      A tile  : 128 rows(t) x 64 c, K-major, SWIZZLE_128B        (TMA 3-D box {64,128,1})
+//      B tile  : BN rows(n)  x 64 c, K-major, SWIZZLE_128B        (TMA 2-D box {64,BN})
+//      forward : Wk = W^T[k] stored [K][C_out][C_in];   off0 = -pad_left, step = +dilation
+//      dgrad   : Wk = W[k]   stored [K][C_in][C_out];   off0 = +pad_left, step = -dilation
+//  * tapgemm_mnmajor (wgrad): dW[k][ci, co] += sum_{b,t} X[b, t + k*dil - pad_left, ci] * dY[b, t, co]
+//      both operands are MN-major (the reduction index t is the smem row), so X and dY are used in
+//      their natural NWC layout with no transposed copies.
+//
+// Warp roles (192 threads, persistent CTAs, 1 CTA / SM):
+//   warp 0 : TMA producer (one elected lane)        warp 1 : tcgen05.mma issuer (one elected lane)
+//   warps 2-5 : epilogue, TMEM -> registers -> global; the accumulator is double buffered in TMEM so
+//   the epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace os2s {
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;       // bf16 elements per 128-byte swizzle row
+constexpr int kABytes = kTileM * kChunkK * 2;
+constexpr int kNumThreads = 192;
+constexpr int kSmemBudget = 220 * 1024;
+
+enum OutMode : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ACC = 2 };
+
+struct KMajorParams {
+  int B, T_out, n_mtiles, n_ntiles, N_total;
+  int K_taps, c_chunks;
+  int t_off0, t_step;
+  void* out;
+  long long out_row_stride;    // elements
+  long long out_batch_stride;  // elements
+  int out_mode;
+};
+
+template <int BN>
+__host__ __device__ constexpr int num_stages() {
+  int s = kSmemBudget / (kABytes + BN * kChunkK * 2);
+  return s > 8 ? 8 : s;
+}
+
+template <int BN>
+__host__ __device__ constexpr uint32_t tmem_cols() {
+  return (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+}
+
+struct PipeState {
+  uint32_t stage = 0, phase = 0;
+  template <int S>
+  __device__ __forceinline__ void advance() {
+    if (++stage == S) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+// Layout of the dynamic shared memory (1024-byte aligned for SWIZZLE_128B):
+//   [A stages][B stages][full bars][empty bars][tmem_full x2][tmem_empty x2][tmem ptr]
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const KMajorParams p) {
+  constexpr int S = num_stages<BN>();
+  constexpr int kBBytes = BN * kChunkK * 2;
+  constexpr uint32_t kTmemCols = tmem_cols<BN>();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + S * kBBytes);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int tiles_per_n = p.B * p.n_mtiles;
+  const int n_tiles = tiles_per_n * p.n_ntiles;
+  const int n_iters = p.K_taps * p.c_chunks;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      PipeState ps;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int nt = tile / tiles_per_n;
+        const int rem = tile - nt * tiles_per_n;
+        const int b = rem / p.n_mtiles;
+        const int t0 = (rem - b * p.n_mtiles) * kTileM;
+        const int n0 = nt * BN;
+        for (int k = 0; k < p.K_taps; ++k) {
+          const int trow = t0 + p.t_off0 + k * p.t_step;
+          const int brow = k * p.N_total + n0;
+          for (int c = 0; c < p.c_chunks; ++c) {
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            mbar_expect_tx(&full_bar[ps.stage], kABytes + kBBytes);
+            tma_load_3d(smem_a + ps.stage * kABytes, &map_a, &full_bar[ps.stage], c * kChunkK, trow, b);
+            tma_load_2d(smem_b + ps.stage * kBBytes, &map_b, &full_bar[ps.stage], c * kChunkK, brow);
+            ps.advance<S>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(kTileM, BN, 0, 0);
+      PipeState ps;
+      uint32_t ti = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int it = 0; it < n_iters; ++it) {
+          mbar_wait(&full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + ps.stage * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + ps.stage * kBBytes);
+#pragma unroll
+          for (int kk = 0; kk < kChunkK / 16; ++kk) {
+            const uint64_t da = make_sdesc(a_addr + kk * 32, 0, 1024);
+            const uint64_t db = make_sdesc(b_addr + kk * 32, 0, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[ps.stage]);
+          if (it == n_iters - 1) umma_commit(&tfull_bar[as]);
+          ps.advance<S>();
+        }
+      }
+    }
+  } else {
+    // Epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32).
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int nt = tile / tiles_per_n;
+      const int rem = tile - nt * tiles_per_n;
+      const int b = rem / p.n_mtiles;
+      const int t = (rem - b * p.n_mtiles) * kTileM + row;
+      const int n0 = nt * BN;
+      const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      const bool valid = t < p.T_out;
+      const long long off = (long long)b * p.out_batch_stride + (long long)t * p.out_row_stride + n0;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+          if (p.out_mode == OUT_BF16) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + ch * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 v;
+              v.x = pack_bf16(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
+              v.y = pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
+              v.z = pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
+              v.w = pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
+              dst[q] = v;
+            }
+          } else {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + ch * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
+                                     __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+              if (p.out_mode == OUT_F32_ACC) {
+                const float4 o = dst[q];
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              }
+              dst[q] = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------ wgrad
+struct MNMajorParams {
+  int B, T, t_chunks;          // t_chunks = ceil(T / 64)
+  int K_taps, dil, pad_left;
+  int m_tiles, n_tiles;        // C_in / 128, C_out / BN
+  int splits, b_per_split;
+  float* dw;                   // [K][C_in][C_out] fp32, accumulated with red.add
+  int C_in, C_out;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                const MNMajorParams p) {
+  constexpr int S = num_stages<BN>();
+  constexpr int kBBytes = BN * kChunkK * 2;
+  constexpr int kBoxBytes = 64 * 64 * 2;  // one {64 c, 64 t} box
+  constexpr uint32_t kTmemCols = tmem_cols<BN>();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + S * kBBytes);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int units_per_split = p.K_taps * p.m_tiles * p.n_tiles;
+  const int n_units = units_per_split * p.splits;
+
+  // unit -> (split, tap, m tile, n tile); taps fastest so concurrent CTAs share X / dY in L2.
+  auto decode = [&](int unit, int& s, int& k, int& mi, int& ni) {
+    s = unit / units_per_split;
+    int r = unit - s * units_per_split;
+    const int mn = r / p.K_taps;
+    k = r - mn * p.K_taps;
+    mi = mn / p.n_tiles;
+    ni = mn - mi * p.n_tiles;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      PipeState ps;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        int s, k, mi, ni;
+        decode(unit, s, k, mi, ni);
+        const int tsh = k * p.dil - p.pad_left;
+        const int b_lo = s * p.b_per_split;
+        const int b_hi = min(p.B, b_lo + p.b_per_split);
+        for (int b = b_lo; b < b_hi; ++b) {
+          for (int tc = 0; tc < p.t_chunks; ++tc) {
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            mbar_expect_tx(&full_bar[ps.stage], kABytes + kBBytes);
+            uint8_t* sa = smem_a + ps.stage * kABytes;
+            uint8_t* sb = smem_b + ps.stage * kBBytes;
+#pragma unroll
+            for (int h = 0; h < kTileM / 64; ++h)
+              tma_load_3d(sa + h * kBoxBytes, &map_x, &full_bar[ps.stage], mi * kTileM + h * 64,
+                          tc * 64 + tsh, b);
+#pragma unroll
+            for (int h = 0; h < BN / 64; ++h)
+              tma_load_3d(sb + h * kBoxBytes, &map_dy, &full_bar[ps.stage], ni * BN + h * 64, tc * 64, b);
+            ps.advance<S>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(kTileM, BN, 1, 1);
+      PipeState ps;
+      uint32_t ti = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++ti) {
+        int s, k, mi, ni;
+        decode(unit, s, k, mi, ni);
+        const int b_lo = s * p.b_per_split;
+        const int b_hi = min(p.B, b_lo + p.b_per_split);
+        const int n_iters = (b_hi - b_lo) * p.t_chunks;
+        const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int it = 0; it < n_iters; ++it) {
+          mbar_wait(&full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + ps.stage * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + ps.stage * kBBytes);
+#pragma unroll
+          for (int kk = 0; kk < 64 / 16; ++kk) {
+            // 16 reduction rows = 2 KB further into every 64-wide box
+            const uint64_t da = make_sdesc(a_addr + kk * 2048, kBoxBytes, 1024);
+            const uint64_t db = make_sdesc(b_addr + kk * 2048, kBoxBytes, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[ps.stage]);
+          if (it == n_iters - 1) umma_commit(&tfull_bar[as]);
+          ps.advance<S>();
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint32_t ti = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++ti) {
+      int s, k, mi, ni;
+      decode(unit, s, k, mi, ni);
+      const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      float* dst = p.dw + ((long long)k * p.C_in + mi * kTileM + row) * p.C_out + ni * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        tmem_ld_wait();
+        if (p.splits == 1) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            reinterpret_cast<float4*>(dst + ch * 32)[q] =
+                make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
+                            __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + ch * 32 + q * 4),
+                         "f"(__uint_as_float(r[q * 4 + 0])), "f"(__uint_as_float(r[q * 4 + 1])),
+                         "f"(__uint_as_float(r[q * 4 + 2])), "f"(__uint_as_float(r[q * 4 + 3]))
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------ launchers
+template <int BN>
+static size_t smem_bytes() {
+  return (size_t)num_stages<BN>() * (kABytes + BN * kChunkK * 2) + (2 * num_stages<BN>() + 4) * 8 + 16 + 1024;
+}
+
+template <int BN>
+static int launch_kmajor(const CUtensorMap* ma, const CUtensorMap* mb, const KMajorParams& p,
+                         cudaStream_t st) {
+  static bool attr_done = false;
+  const size_t smem = smem_bytes<BN>();
+  if (!attr_done) {
+    OS2S_CUDA(cudaFuncSetAttribute(tapgemm_kmajor<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int tiles = p.B * p.n_mtiles * p.n_ntiles;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  tapgemm_kmajor<BN><<<grid, kNumThreads, smem, st>>>(*ma, *mb, p);
+  return check_launch("tapgemm_kmajor");
+}
+
+template <int BN>
+static int launch_mnmajor(const CUtensorMap* mx, const CUtensorMap* mdy, const MNMajorParams& p,
+                          cudaStream_t st) {
+  static bool attr_done = false;
+  const size_t smem = smem_bytes<BN>();
+  if (!attr_done) {
+    OS2S_CUDA(cudaFuncSetAttribute(tapgemm_mnmajor<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int units = p.K_taps * p.m_tiles * p.n_tiles * p.splits;
+  const int grid = units < device_sm_count() ? units : device_sm_count();
+  tapgemm_mnmajor<BN><<<grid, kNumThreads, smem, st>>>(*mx, *mdy, p);
+  return check_launch("tapgemm_mnmajor");
+}
+
+// Largest supported N tile dividing n (K-major B operand: any multiple of 16 up to 256).
+static int pick_bn_kmajor(int n) {
+  const int cands[] = {256, 192, 128, 224, 160, 96, 64};
+  for (int c : cands)
+    if (n % c == 0) return c;
+  return 0;
+}
+// wgrad N tile must be a multiple of 64 (one TMA box per 64 channels).
+static int pick_bn_mnmajor(int n) {
+  const int cands[] = {256, 192, 128, 64};
+  for (int c : cands)
+    if (n % c == 0) return c;
+  return 0;
+}
+
+// Shared driver for forward / dgrad.
+//   act    : [B, T, C_red] bf16   (conv input for forward, dY for dgrad)
+//   wmat   : [K][N_total][C_red] bf16 (C_red contiguous)
+//   out    : [B, T, N_total]  (bf16, or fp32 with optional accumulate)
+int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
+                int K, int t_off0, int t_step, int out_mode, cudaStream_t st) {
+  if (C_red % 64 != 0) return fail(ERR_UNSUPPORTED, "conv_tc: reduction channels must be a multiple of 64");
+  const int BN = pick_bn_kmajor(N_total);
+  if (BN == 0) return fail(ERR_UNSUPPORTED, "conv_tc: output channels must be a multiple of 64");
+  if (B <= 0 || T <= 0 || K <= 0) return fail(ERR_INVALID, "conv_tc: bad shape");
+  uint64_t adims[3] = {(uint64_t)C_red, (uint64_t)T, (uint64_t)B};
+  uint64_t astr[2] = {(uint64_t)C_red * 2, (uint64_t)T * C_red * 2};
+  uint32_t abox[3] = {64, 128, 1};
+  const CUtensorMap* ma = get_tmap_bf16(act, 3, adims, astr, abox);
+  uint64_t bdims[2] = {(uint64_t)C_red, (uint64_t)K * N_total};
+  uint64_t bstr[1] = {(uint64_t)C_red * 2};
+  uint32_t bbox[2] = {64, (uint32_t)BN};
+  const CUtensorMap* mb = get_tmap_bf16(wmat, 2, bdims, bstr, bbox);
+  if (!ma || !mb) return ERR_CUDA;
+  KMajorParams p;
+  p.B = B;
+  p.T_out = T;
+  p.n_mtiles = (T + kTileM - 1) / kTileM;
+  p.n_ntiles = N_total / BN;
+  p.N_total = N_total;
+  p.K_taps = K;
+  p.c_chunks = C_red / 64;
+  p.t_off0 = t_off0;
+  p.t_step = t_step;
+  p.out = out;
+  p.out_row_stride = N_total;
+  p.out_batch_stride = (long long)T * N_total;
+  p.out_mode = out_mode;
+  switch (BN) {
+    case 256: return launch_kmajor<256>(ma, mb, p, st);
+    case 224: return launch_kmajor<224>(ma, mb, p, st);
+    case 192: return launch_kmajor<192>(ma, mb, p, st);
+    case 160: return launch_kmajor<160>(ma, mb, p, st);
+    case 128: return launch_kmajor<128>(ma, mb, p, st);
+    case 96: return launch_kmajor<96>(ma, mb, p, st);
+    case 64: return launch_kmajor<64>(ma, mb, p, st);
+  }
+  return fail(ERR_UNSUPPORTED, "conv_tc: no tile for N");
+}
+
+// wgrad: dw[K][C_in][C_out] (fp32) += X^T * dY per tap. dw must be zeroed by the caller when
+// splits > 1 (the kernel reduces with red.global.add); with splits == 1 it is overwritten.
+int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out, int K,
+               int dil, int pad_left, int* splits_used, cudaStream_t st) {
+  if (C_in % 128 != 0) return fail(ERR_UNSUPPORTED, "conv_wgrad: C_in must be a multiple of 128");
+  const int BN = pick_bn_mnmajor(C_out);
+  if (BN == 0) return fail(ERR_UNSUPPORTED, "conv_wgrad: C_out must be a multiple of 64");
+  uint64_t xd[3] = {(uint64_t)C_in, (uint64_t)T, (uint64_t)B};
+  uint64_t xs[2] = {(uint64_t)C_in * 2, (uint64_t)T * C_in * 2};
+  uint32_t box[3] = {64, 64, 1};
+  const CUtensorMap* mx = get_tmap_bf16(x, 3, xd, xs, box);
+  uint64_t yd[3] = {(uint64_t)C_out, (uint64_t)T, (uint64_t)B};
+  uint64_t ys[2] = {(uint64_t)C_out * 2, (uint64_t)T * C_out * 2};
+  const CUtensorMap* mdy = get_tmap_bf16(dy, 3, yd, ys, box);
+  if (!mx || !mdy) return ERR_CUDA;
+  MNMajorParams p;
+  p.B = B;
+  p.T = T;
+  p.t_chunks = (T + 63) / 64;
+  p.K_taps = K;
+  p.dil = dil;
+  p.pad_left = pad_left;
+  p.m_tiles = C_in / kTileM;
+  p.n_tiles = C_out / BN;
+  p.dw = dw;
+  p.C_in = C_in;
+  p.C_out = C_out;
+  // Split the (b, t) reduction so that there are at least ~2 waves of work units.
+  const int base_units = K * p.m_tiles * p.n_tiles;
+  const int sms = device_sm_count();
+  int splits = 1;
+  while (splits < B && base_units * splits < 2 * sms) splits *= 2;
+  if (splits > B) splits = B;
+  p.b_per_split = (B + splits - 1) / splits;
+  p.splits = (B + p.b_per_split - 1) / p.b_per_split;
+  if (splits_used) *splits_used = p.splits;
+  if (p.splits > 1) {
+    OS2S_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * C_in * C_out * sizeof(float), st));
+  }
+  switch (BN) {
+    case 256: return launch_mnmajor<256>(mx, mdy, p, st);
+    case 192: return launch_mnmajor<192>(mx, mdy, p, st);
+    case 128: return launch_mnmajor<128>(mx, mdy, p, st);
+    case 64: return launch_mnmajor<64>(mx, mdy, p, st);
+  }
+  return fail(ERR_UNSUPPORTED, "conv_wgrad: no tile for N");
+}
+
+}  // namespace os2s

@@ -1,0 +1,138 @@
+"""ORACLE (test infrastructure only -- never imported by the product path).
+
+CPU restatement, in NumPy, of the reference's librosa-backend log-mel featurizer used by Jasper:
+
+  open_seq2seq/data/speech2text/speech_utils.py:216-222  normalize_signal
+  open_seq2seq/data/speech2text/speech_utils.py:271-272  preemphasis
+  open_seq2seq/data/speech2text/speech_utils.py:322-441  get_speech_features_librosa (logfbank branch :396-406,
+                                                         per-feature normalisation :411-417)
+  open_seq2seq/data/speech2text/speech2text.py:167-183   precomputed mel basis
+  open_seq2seq/data/speech2text/speech2text.py:251-257,313-317  zero padding of the batch / pad_to
+
+The arithmetic itself lives in librosa==0.6.3 (pinned in the reference's requirements.txt:8), which
+is NOT under /root/reference and is not installed here.  Its published algorithm is restated:
+  librosa.core.stft(y, n_fft, hop, win_length, center=True, window=np.hanning):
+      window = np.hanning(win_length) (symmetric), zero-padded centrally to n_fft; y reflect-padded
+      by n_fft//2 on both sides; frames = 1 + len(y)//hop; complex64 output.
+  librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax): Slaney mel scale (htk=False), triangular
+      filters on np.linspace(0, sr/2, 1+n_fft//2), Slaney area normalisation 2/(f[i+2]-f[i]).
+Parity status: the reference has no golden vectors for this backend ("parity unpinned" by its own
+tests); the restatement is triangulated against torchaudio's independent
+Slaney filterbank and torch.stft in tests/test_oracle_featurizer.py.
+"""
+import math
+
+import numpy as np
+
+
+def normalize_signal(signal, gain=None):
+    """speech_utils.py:216-222."""
+    if gain is None:
+        gain = 1.0 / (np.max(np.abs(signal)) + 1e-5)
+    return signal * gain
+
+
+def preemphasis(signal, coeff=0.97):
+    """speech_utils.py:271-272."""
+    return np.append(signal[0], signal[1:] - coeff * signal[:-1])
+
+
+def _hz_to_mel_slaney(f):
+    f = np.asarray(f, dtype=np.float64)
+    f_sp = 200.0 / 3
+    mels = f / f_sp
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        log_t = min_log_mel + np.log(np.maximum(f, 1e-300) / min_log_hz) / logstep
+    return np.where(f >= min_log_hz, log_t, mels)
+
+
+def _mel_to_hz_slaney(m):
+    m = np.asarray(m, dtype=np.float64)
+    f_sp = 200.0 / 3
+    freqs = f_sp * m
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), freqs)
+
+
+def mel_filterbank(sr=16000, n_fft=512, n_mels=64, fmin=0.0, fmax=None):
+    """librosa.filters.mel (0.6.3) restated: [n_mels, 1 + n_fft//2] float64."""
+    if fmax is None:
+        fmax = sr / 2.0
+    n_bins = 1 + n_fft // 2
+    fftfreqs = np.linspace(0.0, sr / 2.0, n_bins)
+    mel_pts = np.linspace(_hz_to_mel_slaney(fmin), _hz_to_mel_slaney(fmax), n_mels + 2)
+    mel_f = _mel_to_hz_slaney(mel_pts)
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fftfreqs[None, :]
+    weights = np.zeros((n_mels, n_bins))
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        weights[i] = np.maximum(0, np.minimum(lower, upper))
+    enorm = 2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels])
+    weights *= enorm[:, None]
+    return weights
+
+
+def stft_power(signal, n_fft=512, hop=160, win_length=320):
+    """|librosa.core.stft(...)|**2 -> [1 + n_fft//2, frames] (float32, from complex64)."""
+    window = np.hanning(win_length)
+    lpad = (n_fft - win_length) // 2
+    fft_window = np.zeros(n_fft)
+    fft_window[lpad:lpad + win_length] = window
+    y = np.pad(np.asarray(signal), n_fft // 2, mode="reflect")
+    n_frames = 1 + (len(y) - n_fft) // hop
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(n_frames)[:, None]
+    frames = y[idx] * fft_window[None, :]
+    spec = np.fft.rfft(frames, n=n_fft, axis=1).astype(np.complex64)  # librosa dtype
+    return (np.abs(spec) ** 2.0).T
+
+
+def num_fft_for(window_size=20e-3, sample_freq=16000):
+    """speech_utils.py:358 / speech2text.py:170-175."""
+    return 2 ** math.ceil(math.log2(window_size * sample_freq))
+
+
+def logfbank_features(signal_int16, sample_freq=16000, num_features=64, window_size=20e-3,
+                      window_stride=10e-3, dither=0.0, norm_per_feature=True, mel_basis=None,
+                      rng=None):
+    """get_speech_features_librosa(features_type='logfbank') without augmentation.
+
+    Returns (features [frames, num_features] float64, duration seconds)."""
+    signal = normalize_signal(np.asarray(signal_int16).astype(np.float32))
+    duration = len(signal) * 1.0 / sample_freq
+    n_win = int(sample_freq * window_size)
+    n_hop = int(sample_freq * window_stride)
+    n_fft = num_fft_for(window_size, sample_freq)
+    if dither > 0:
+        rng = rng or np.random
+        signal = signal + dither * rng.randn(*signal.shape)
+    signal = preemphasis(signal, coeff=0.97)
+    S = stft_power(signal, n_fft=n_fft, hop=n_hop, win_length=n_win)
+    if mel_basis is None:
+        mel_basis = mel_filterbank(sample_freq, n_fft, n_mels=num_features, fmin=0,
+                                   fmax=int(sample_freq / 2))
+    features = np.log(np.dot(mel_basis, S) + 1e-20).T
+    axis = 0 if norm_per_feature else None
+    mean = np.mean(features, axis=axis)
+    std = np.std(features, axis=axis)
+    features = (features - mean) / std
+    return features, duration
+
+
+def batch_features(signals_int16, pad_to=16, **kw):
+    """padded_batch + pad_to of speech2text.py:251-257,313-317: ([B,T,F] float64, lengths int32)."""
+    feats = [logfbank_features(s, **kw)[0] for s in signals_int16]
+    lens = np.array([f.shape[0] for f in feats], dtype=np.int32)
+    T = int(lens.max())
+    if pad_to > 0 and T % pad_to != 0:
+        T += pad_to - T % pad_to
+    out = np.zeros((len(feats), T, feats[0].shape[1]))
+    for i, f in enumerate(feats):
+        out[i, :f.shape[0]] = f
+    return out, lens

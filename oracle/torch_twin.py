@@ -1,0 +1,191 @@
+"""ORACLE (test infrastructure only -- never imported by the product path).
+
+PyTorch-CPU fp32 "fast twin" of the NumPy oracle: the same graph as oracle/encoder.py +
+oracle/ctc.py + oracle/optimizer.py, expressed with torch CPU ops so that (a) autograd supplies the
+backward pass the reference gets from TF autodiff, and (b) it is fast enough to be timed as the
+CPU baseline in bench.py (`cpu_baseline.kind = "port"`; TF1 cannot be installed offline).
+
+Follows the same reference lines as the NumPy oracle:
+  open_seq2seq/encoders/tdnn_encoder.py:87-265, open_seq2seq/parts/cnns/conv_blocks.py:61-232,
+  open_seq2seq/decoders/fc_decoders.py:105-158, open_seq2seq/losses/ctc_loss.py:44-89,
+  open_seq2seq/optimizers/{optimizers.py:289-378,novograd.py:93-126,mp_wrapper.py:44-122}.
+It is validated against the NumPy restatement in tests/test_oracle_encoder.py.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .encoder import same_padding
+
+
+def conv1d_same(x, w, stride=1, dilation=1):
+    """x [B,T,Cin], w [K,Cin,Cout] (TF layout) -> [B,T_out,Cout]."""
+    B, T, C = x.shape
+    K = w.shape[0]
+    _, pl, pr = same_padding(T, K, stride, dilation)
+    xin = F.pad(x.transpose(1, 2), (pl, pr))
+    y = F.conv1d(xin, w.permute(2, 1, 0), stride=stride, dilation=dilation)
+    return y.transpose(1, 2)
+
+
+def batch_norm_train(x, gamma, beta, eps=1e-3):
+    mean = x.mean(dim=(0, 1))
+    var = x.var(dim=(0, 1), unbiased=False)
+    return (x - mean) * torch.rsqrt(var + eps) * gamma + beta, mean, var
+
+
+def sequence_mask(lengths, maxlen, dtype):
+    return (torch.arange(maxlen)[None, :] < lengths[:, None]).to(dtype)[:, :, None]
+
+
+def tdnn_encode(x, src_len, layers, params, training=True, bn_eps=1e-3, use_conv_mask=True,
+                dropout_masks=None, collect=None, stats=None):
+    """Same contract as oracle.encoder.tdnn_encode, on torch tensors (autograd-capable)."""
+    src_len = src_len.clone()
+    max_len = x.shape[1]
+    mask = sequence_mask(src_len, max_len, x.dtype) if use_conv_mask else None
+    feats = x
+    res_agg = []
+    for bi, layer in enumerate(layers):
+        K = layer["kernel_size"][0]
+        stride = layer["stride"][0]
+        dil = layer["dilation"][0]
+        residual = layer.get("residual", False)
+        dense = layer.get("residual_dense", False)
+        if use_conv_mask:
+            feats = feats * mask
+        layer_res = None
+        if residual:
+            layer_res = feats
+            if dense:
+                res_agg.append(layer_res)
+                layer_res = list(res_agg)
+            else:
+                layer_res = [layer_res]
+        for ri in range(layer["repeat"]):
+            name = "conv%d%d" % (bi + 1, ri + 1)
+            src_len = (src_len + stride - 1) // stride
+            max_len = (max_len + stride - 1) // stride
+            if ri > 0 and use_conv_mask:
+                feats = feats * mask
+            if use_conv_mask and stride > 1:
+                mask = sequence_mask(src_len, max_len, x.dtype)
+            conv = conv1d_same(feats, params[name + "/kernel"], stride, dil)
+            if collect is not None:
+                collect[name + "/conv"] = conv
+            bn, mean, var = batch_norm_train(conv, params[name + "/bn/gamma"], params[name + "/bn/beta"], bn_eps)
+            if stats is not None:
+                stats[name + "/bn"] = (mean.detach(), var.detach(), conv.shape[0] * conv.shape[1])
+            if residual and ri == layer["repeat"] - 1:
+                for j, res in enumerate(layer_res):
+                    rname = (name + "/res_%d" % j) if dense else (name + "/res")
+                    bname = (name + "/res_bn_%d" % j) if dense else (name + "/res_bn")
+                    rc = conv1d_same(res, params[rname + "/kernel"], 1, 1)
+                    rb, mean, var = batch_norm_train(rc, params[bname + "/gamma"], params[bname + "/beta"], bn_eps)
+                    if stats is not None:
+                        stats[bname] = (mean.detach(), var.detach(), rc.shape[0] * rc.shape[1])
+                    bn = bn + rb
+            out = torch.relu(bn)
+            if training and dropout_masks is not None and name in dropout_masks:
+                m, keep = dropout_masks[name]
+                out = out * m / keep
+            feats = out
+            if collect is not None:
+                collect[name + "/out"] = feats
+    return feats, src_len
+
+
+def fc_decode(enc_out, kernel, bias):
+    B, T, H = enc_out.shape
+    logits = enc_out.reshape(B * T, H) @ kernel + bias
+    return logits.reshape(B, T, -1).transpose(0, 1)  # [T,B,V]
+
+
+def ctc_loss_mean(logits_tbv, labels, label_lens, input_lens):
+    """CTCLoss._compute_loss: mean over batch of per-utterance NLL, blank = V-1,
+    ignore_longer_outputs_than_inputs (zero_infinity) and NaN masking."""
+    V = logits_tbv.shape[2]
+    lp = F.log_softmax(logits_tbv.float(), dim=2)
+    per = F.ctc_loss(lp, labels, input_lens, label_lens, blank=V - 1, reduction="none", zero_infinity=True)
+    per = torch.where(torch.isnan(per), torch.zeros_like(per), per)
+    return per.mean()
+
+
+def xavier_init(shape, uniform, gen):
+    """tf.contrib.layers.xavier_initializer: n = (fan_in + fan_out)/2."""
+    if len(shape) == 3:
+        fan_in, fan_out = shape[0] * shape[1], shape[0] * shape[2]
+    else:
+        fan_in, fan_out = shape
+    n = (fan_in + fan_out) / 2.0
+    if uniform:
+        lim = math.sqrt(3.0 / n)
+        return (torch.rand(shape, generator=gen) * 2 - 1) * lim
+    std = math.sqrt(1.3 / n)
+    t = torch.empty(shape)
+    torch.nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2 * std, b=2 * std, generator=gen)
+    return t
+
+
+def init_params(layers, num_features, vocab, seed=0):
+    """Parameter dict with the reference's variable names."""
+    gen = torch.Generator().manual_seed(seed)
+    p = {}
+    c_in = num_features
+    block_inputs = []
+    for bi, layer in enumerate(layers):
+        K = layer["kernel_size"][0]
+        c_out = layer["num_channels"]
+        residual = layer.get("residual", False)
+        dense = layer.get("residual_dense", False)
+        if residual:
+            if dense:
+                block_inputs.append(c_in)
+                res_ch = list(block_inputs)
+            else:
+                res_ch = [c_in]
+        for ri in range(layer["repeat"]):
+            name = "conv%d%d" % (bi + 1, ri + 1)
+            p[name + "/kernel"] = xavier_init((K, c_in, c_out), False, gen)
+            p[name + "/bn/gamma"] = torch.ones(c_out)
+            p[name + "/bn/beta"] = torch.zeros(c_out)
+            if residual and ri == layer["repeat"] - 1:
+                for j, rc in enumerate(res_ch):
+                    rname = (name + "/res_%d" % j) if dense else (name + "/res")
+                    bname = (name + "/res_bn_%d" % j) if dense else (name + "/res_bn")
+                    p[rname + "/kernel"] = xavier_init((1, rc, c_out), False, gen)
+                    p[bname + "/gamma"] = torch.ones(c_out)
+                    p[bname + "/beta"] = torch.zeros(c_out)
+            c_in = c_out
+    p["fc/kernel"] = xavier_init((c_in, vocab), True, gen)
+    p["fc/bias"] = torch.zeros(vocab)
+    return p
+
+
+def forward_loss(params, layers, feats, feat_len, labels, label_lens, training=True, dropout_masks=None,
+                 collect=None):
+    enc, out_len = tdnn_encode(feats, feat_len, layers, params, training=training,
+                               dropout_masks=dropout_masks, collect=collect)
+    logits = fc_decode(enc, params["fc/kernel"], params["fc/bias"])
+    loss = ctc_loss_mean(logits, labels, label_lens, out_len)
+    return loss, logits, out_len
+
+
+def larc_novograd_step(params, grads, momentum, lr, beta1=0.95, beta2=0.98, epsilon=1e-8,
+                       weight_decay=0.001, larc_eta=0.001, min_update=1e-7, larc_eps=1e-7):
+    """optimizers.py:333-377 (clip mode) then novograd.py:93-126 (reference-as-written EMA)."""
+    with torch.no_grad():
+        for name, w in params.items():
+            g = grads[name]
+            v_norm = w.norm()
+            g_norm = g.norm()
+            r = torch.clamp(larc_eta * v_norm / (lr * (g_norm + larc_eps)), min=min_update, max=1.0)
+            g = g * r
+            g2 = (g * g).sum()
+            g = g / torch.sqrt(g2 + epsilon)
+            g = g + weight_decay * w
+            m = momentum.get(name)
+            m = g if m is None else beta1 * m + g
+            momentum[name] = m
+            w -= lr * m
