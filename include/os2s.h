@@ -17,6 +17,7 @@
 #ifndef OS2S_H_
 #define OS2S_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -62,6 +63,110 @@ int os2s_conv1d_wgrad(const void* x, const void* dy, float* dw, int B, int T, in
  * be NULL.  Replaces the fp32->fp16 assign of mp_wrapper.py:104-109 when used standalone. */
 int os2s_weight_cast_transpose(const float* w_master, void* w_bf16, void* wt_bf16, int K, int C_in,
                                int C_out, void* stream);
+
+/* ---- K3/K4: batch norm (training) + residual sum + ReLU + dropout + sequence mask ------------
+ * reference: tf.layers.batch_normalization(training=True) conv_blocks.py:208-227 / :91-101,
+ * residual sum :154, activation :166, tf.nn.dropout tdnn_encoder.py:255, mask :185-186,204-205. */
+
+/* stats[0..C) += sum_rows y ; stats[C..2C) += sum_rows y^2   (y bf16 [M,C]; stats pre-zeroed) */
+int os2s_bn_stats(const void* y, float* stats, int M, int C, void* stream);
+
+/* out = rowmask(dropout(act(sum_j gamma_j*(y_j-mean_j)*invstd_j + beta_j))), bf16 [B,T,C].
+ * The *_host arrays hold n_branch device pointers (branch 0 = main conv, 1.. = residual convs).
+ * mean_invstd[j] ([2][C]) is written for backward; moving[j] ([2][C] moving_mean, moving_variance,
+ * may be NULL) is updated in place.  lens (int32 [B], may be NULL) gives valid rows per utterance;
+ * rows t >= lens[b] are written as zeros.  keep = dropout keep probability (1 disables dropout);
+ * apply_relu: 0 = identity, 1 = relu, with relu_clip > 0 -> min(relu(x), relu_clip). */
+int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* const* stats_host,
+                      const float* const* gamma_host, const float* const* beta_host,
+                      float* const* mean_invstd_host, float* const* moving_host, void* out,
+                      const int* lens, int B, int T, int C, float eps, float momentum, float keep,
+                      uint64_t seed, int apply_relu, float relu_clip, void* stream);
+
+/* Backward of the above.  dA: gradient wrt `out` (bf16, or fp32 when dA_is_f32), a: the forward
+ * output (its zeros encode relu / dropout / mask).  Writes dy[j] (bf16 [M,C]) for every branch and
+ * dgamma[j], dbeta[j] (fp32 [C]).  red: fp32 scratch [(1+n_branch)*C], zeroed by this call. */
+int os2s_bn_bwd(int n_branch, const void* const* y_host, const float* const* mean_invstd_host,
+                const float* const* gamma_host, float* const* dgamma_host, float* const* dbeta_host,
+                void* const* dy_host, const void* dA, int dA_is_f32, const void* a, float* red, int M,
+                int C, float keep, int apply_relu, void* stream);
+
+/* ---- K5: tf.layers.dense of FullyConnectedTimeDecoder (fc_decoders.py:135-140) --------------
+ * logits fp32 [M,V] = x bf16 [M,H] * w fp32 [H,V] + bias;  V <= 32. */
+int os2s_fc_fwd(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V,
+                void* stream);
+/* dx bf16 [M,H] (may be NULL), dw fp32 [H,V], db fp32 [V] (dw/db overwritten; may be NULL). */
+int os2s_fc_bwd(const void* x, const float* dlogits, const float* w, void* dx, float* dw, float* db,
+                int M, int H, int V, void* stream);
+
+/* ---- K6: tf.nn.ctc_loss(ignore_longer_outputs_than_inputs=True) + mask_nans (ctc_loss.py:77-89)
+ * logits fp32, element (b,t,v) at logits[b*stride_b + t*stride_t + v]; blank = V-1.
+ * labels int32 [B,L_max], label_lens/input_lens int32 [B].
+ * loss[b] = -log p(l|x) (0 for skipped/NaN utterances); grad [B,T,V] fp32 contiguous =
+ * d(mean_b loss)/dlogits * (*loss_scale_dev) (loss_scale_dev may be NULL = 1).
+ * workspace: os2s_ctc_workspace_bytes(B,T,L_max) bytes of device memory. */
+size_t os2s_ctc_workspace_bytes(int B, int T, int L_max);
+int os2s_ctc_loss_fwd_bwd(const float* logits, const int* labels, const int* label_lens,
+                          const int* input_lens, float* grad, float* loss, void* workspace,
+                          size_t workspace_bytes, const float* loss_scale_dev, int B, int T, int V,
+                          int L_max, long long stride_b, long long stride_t, void* stream);
+
+/* ---- K7: tf.nn.ctc_greedy_decoder(merge_repeated) (fc_decoders.py:247-250) --------------------
+ * tokens int32 [B,T] (first out_lens[b] entries valid), neg_sum_logits fp32 [B] (may be NULL). */
+int os2s_ctc_greedy(const float* logits, const int* input_lens, int* tokens, int* out_lens,
+                    float* neg_sum_logits, int B, int T, int V, long long stride_b,
+                    long long stride_t, int merge_repeated, void* stream);
+
+/* ---- K8: optimizer chain (mp_wrapper.py, optimizers.py LARC, automatic_loss_scaler.py,
+ *          novograd.py, lr_policies.py poly_decay) as three launches ---------------------------- */
+typedef struct os2s_opt_hparams {
+  int algo;              /* 0 = NovoGrad, 1 = Momentum SGD */
+  float beta1, beta2, epsilon, weight_decay, momentum;
+  int grad_averaging;
+  int ema_persist;       /* 0 = reference as written (v_t = |g_t|^2), 1 = corrected NovoGrad EMA */
+  float larc_eta;        /* <= 0 disables LARC */
+  float larc_eps, larc_min_update;
+  int larc_mode;         /* 0 = clip, 1 = scale */
+  float lr0, min_lr, power;
+  long long decay_steps, begin_decay_at, warmup_steps;
+  int use_loss_scaler;   /* Backoff scaler on/off */
+  float scale_min, scale_max, step_factor;
+  long long step_window;
+  int world_size;        /* gradients are SUMS over this many ranks */
+} os2s_opt_hparams;
+
+/* Tensor table (all device memory, owned by the caller):
+ *   w,g,m,wb : arrays [n_tensors] of device pointers (fp32 master, fp32 gradient of loss*scale,
+ *              fp32 momentum, bf16 working copy or 0)
+ *   sizes    : int64 [n_tensors];  chunk_tensor int32 / chunk_offset int64 [n_chunks] with chunks of
+ *              os2s_opt_chunk_elems() elements
+ *   norms fp32 [2*n_tensors] and nonfinite int32 [1] zeroed once at creation; coef, ema fp32 [n_tensors]
+ *   fstate fp32 [8]: [0] loss scale, [1] lr of the last step, [2] global grad norm
+ *   istate int64 [8]: [0] scaler iteration, [1] last overflow iteration (init -1), [2] global_step,
+ *                     [3] last step skipped?, [4] skipped-step count */
+int os2s_opt_chunk_elems(void);
+int os2s_opt_step(void* const* w, void* const* g, void* const* m, void* const* wb,
+                  const long long* sizes, const int* chunk_tensor, const long long* chunk_offset,
+                  int n_tensors, int n_chunks, const os2s_opt_hparams* hp, float* norms,
+                  int* nonfinite, float* fstate, long long* istate, float* coef, float* ema,
+                  void* stream);
+
+/* wt[k][c][r] = w[k][r][c] for n tensors in one launch (bf16). src/dst: device arrays of device
+ * pointers; K,R,C: host int arrays. tile_start: device int64 [n+1] prefix of K*ceil(R/32)*ceil(C/32);
+ * Rdev/Cdev device copies of R/C. */
+int os2s_multi_transpose(void* const* src, void* const* dst, const int* Rdev, const int* Cdev,
+                         const long long* tile_start, int n_tensors, long long total_tiles,
+                         void* stream);
+
+/* ---- K1: Speech2TextDataLayer featurizer (speech_utils.py:322-441, librosa backend, logfbank) -
+ * wave int16 (all utterances concatenated), offsets int64 [B], n_samples int32 [B];
+ * mel fp32 [F][n_fft/2+1], window fp32 [win]; out [B,T_pad,F] bf16 and/or fp32 (either may be
+ * NULL), out_lens int32 [B] = frames per utterance. absmax_ws: uint32 [B], raw_ws: fp32 [B*T_pad*F]. */
+int os2s_logmel_forward(const int16_t* wave, const long long* offsets, const int* n_samples, int B,
+                        const float* mel, const float* window, int n_fft, int win, int hop, int F,
+                        int T_pad, int max_samples, float dither, uint64_t seed, float preemph,
+                        void* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,4 +35,131 @@ int os2s_weight_cast_transpose(const float* w_master, void* w_bf16, void* wt_bf1
   return weight_cast_transpose(w_master, w_bf16, wt_bf16, K, C_in, C_out, (cudaStream_t)stream);
 }
 
+
+int os2s_bn_stats(const void* y, float* stats, int M, int C, void* stream) {
+  if (!y || !stats) return fail(ERR_INVALID, "os2s_bn_stats: null pointer");
+  return bn_stats(y, stats, M, C, (cudaStream_t)stream);
+}
+
+int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* const* stats_host,
+                      const float* const* gamma_host, const float* const* beta_host,
+                      float* const* mean_invstd_host, float* const* moving_host, void* out,
+                      const int* lens, int B, int T, int C, float eps, float momentum, float keep,
+                      uint64_t seed, int apply_relu, float relu_clip, void* stream) {
+  if (n_branch < 1 || n_branch > kMaxBranches) return fail(ERR_INVALID, "os2s_bn_apply_fwd: 1..12 branches");
+  if (!y_host || !stats_host || !gamma_host || !beta_host || !mean_invstd_host || !out)
+    return fail(ERR_INVALID, "os2s_bn_apply_fwd: null pointer");
+  if (!(keep > 0.f && keep <= 1.f)) return fail(ERR_INVALID, "os2s_bn_apply_fwd: keep must be in (0,1]");
+  BnFwdParams p;
+  for (int j = 0; j < n_branch; ++j) {
+    p.br[j].y = (const __nv_bfloat16*)y_host[j];
+    p.br[j].stats = stats_host[j];
+    p.br[j].gamma = gamma_host[j];
+    p.br[j].beta = beta_host[j];
+    p.br[j].mean_invstd = mean_invstd_host[j];
+    p.br[j].moving = moving_host ? moving_host[j] : nullptr;
+  }
+  p.n_branch = n_branch;
+  p.out = (__nv_bfloat16*)out;
+  p.lens = lens;
+  p.B = B; p.T = T; p.C = C;
+  p.eps = eps; p.momentum = momentum; p.keep = keep; p.seed = seed;
+  p.relu_clip = relu_clip; p.apply_relu = apply_relu;
+  return bn_apply_fwd(p, (cudaStream_t)stream);
+}
+
+int os2s_bn_bwd(int n_branch, const void* const* y_host, const float* const* mean_invstd_host,
+                const float* const* gamma_host, float* const* dgamma_host, float* const* dbeta_host,
+                void* const* dy_host, const void* dA, int dA_is_f32, const void* a, float* red, int M,
+                int C, float keep, int apply_relu, void* stream) {
+  if (n_branch < 1 || n_branch > kMaxBranches) return fail(ERR_INVALID, "os2s_bn_bwd: 1..12 branches");
+  if (!y_host || !mean_invstd_host || !gamma_host || !dgamma_host || !dbeta_host || !dy_host || !dA || !red)
+    return fail(ERR_INVALID, "os2s_bn_bwd: null pointer");
+  if (apply_relu && !a) return fail(ERR_INVALID, "os2s_bn_bwd: forward output required for relu backward");
+  BnBwdParams p;
+  for (int j = 0; j < n_branch; ++j) {
+    p.br[j].y = (const __nv_bfloat16*)y_host[j];
+    p.br[j].mean_invstd = mean_invstd_host[j];
+    p.br[j].gamma = gamma_host[j];
+    p.br[j].dgamma = dgamma_host[j];
+    p.br[j].dbeta = dbeta_host[j];
+    p.br[j].dy = (__nv_bfloat16*)dy_host[j];
+  }
+  p.n_branch = n_branch;
+  p.dA = dA; p.dA_is_f32 = dA_is_f32; p.a = (const __nv_bfloat16*)a;
+  p.red = red; p.M = M; p.C = C; p.keep = keep; p.apply_relu = apply_relu;
+  OS2S_CUDA(cudaMemsetAsync(red, 0, (size_t)(1 + n_branch) * C * sizeof(float), (cudaStream_t)stream));
+  return bn_bwd(p, (cudaStream_t)stream);
+}
+
+int os2s_fc_fwd(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V,
+                void* stream) {
+  if (!x || !w || !logits) return fail(ERR_INVALID, "os2s_fc_fwd: null pointer");
+  return fc_fwd(x, w, bias, logits, M, H, V, (cudaStream_t)stream);
+}
+
+int os2s_fc_bwd(const void* x, const float* dlogits, const float* w, void* dx, float* dw, float* db,
+                int M, int H, int V, void* stream) {
+  if (!x || !dlogits || !w) return fail(ERR_INVALID, "os2s_fc_bwd: null pointer");
+  if ((dw == nullptr) != (db == nullptr)) return fail(ERR_INVALID, "os2s_fc_bwd: dw and db go together");
+  return fc_bwd(x, dlogits, w, dx, dw, db, M, H, V, (cudaStream_t)stream);
+}
+
+size_t os2s_ctc_workspace_bytes(int B, int T, int L_max) { return ctc_workspace_bytes(B, T, L_max); }
+
+int os2s_ctc_loss_fwd_bwd(const float* logits, const int* labels, const int* label_lens,
+                          const int* input_lens, float* grad, float* loss, void* workspace,
+                          size_t workspace_bytes, const float* loss_scale_dev, int B, int T, int V,
+                          int L_max, long long stride_b, long long stride_t, void* stream) {
+  if (!logits || !labels || !label_lens || !input_lens || !grad || !loss || !workspace)
+    return fail(ERR_INVALID, "os2s_ctc_loss_fwd_bwd: null pointer");
+  if (B <= 0 || T <= 0 || V < 2 || L_max < 0) return fail(ERR_INVALID, "os2s_ctc_loss_fwd_bwd: bad shape");
+  return ctc_loss_fwd_bwd(logits, labels, label_lens, input_lens, grad, loss, (float*)workspace, workspace_bytes,
+                          loss_scale_dev, B, T, V, L_max, stride_b, stride_t, (cudaStream_t)stream);
+}
+
+int os2s_ctc_greedy(const float* logits, const int* input_lens, int* tokens, int* out_lens,
+                    float* neg_sum_logits, int B, int T, int V, long long stride_b,
+                    long long stride_t, int merge_repeated, void* stream) {
+  if (!logits || !input_lens || !tokens || !out_lens) return fail(ERR_INVALID, "os2s_ctc_greedy: null pointer");
+  return ctc_greedy(logits, input_lens, tokens, out_lens, neg_sum_logits, B, T, V, stride_b, stride_t,
+                    merge_repeated, (cudaStream_t)stream);
+}
+
+int os2s_opt_chunk_elems(void) { return opt_chunk_elems(); }
+
+int os2s_opt_step(void* const* w, void* const* g, void* const* m, void* const* wb,
+                  const long long* sizes, const int* chunk_tensor, const long long* chunk_offset,
+                  int n_tensors, int n_chunks, const os2s_opt_hparams* hp, float* norms,
+                  int* nonfinite, float* fstate, long long* istate, float* coef, float* ema,
+                  void* stream) {
+  if (!w || !g || !m || !wb || !sizes || !chunk_tensor || !chunk_offset || !hp || !norms || !nonfinite ||
+      !fstate || !istate || !coef || !ema)
+    return fail(ERR_INVALID, "os2s_opt_step: null pointer");
+  if (hp->world_size < 1) return fail(ERR_INVALID, "os2s_opt_step: world_size < 1");
+  OptTable tab{w, g, m, wb, sizes, chunk_tensor, chunk_offset, n_tensors, n_chunks};
+  return opt_step(tab, *hp, norms, nonfinite, fstate, istate, coef, ema, (cudaStream_t)stream);
+}
+
+int os2s_multi_transpose(void* const* src, void* const* dst, const int* Rdev, const int* Cdev,
+                         const long long* tile_start, int n_tensors, long long total_tiles,
+                         void* stream) {
+  if (!src || !dst || !Rdev || !Cdev || !tile_start) return fail(ERR_INVALID, "os2s_multi_transpose: null pointer");
+  TransposeTable tab{src, dst, Rdev, Cdev, tile_start, n_tensors};
+  return multi_transpose(tab, total_tiles, (cudaStream_t)stream);
+}
+
+int os2s_logmel_forward(const int16_t* wave, const long long* offsets, const int* n_samples, int B,
+                        const float* mel, const float* window, int n_fft, int win, int hop, int F,
+                        int T_pad, int max_samples, float dither, uint64_t seed, float preemph,
+                        void* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
+                        void* stream) {
+  if (!wave || !offsets || !n_samples || !mel || !window || !absmax_ws || !raw_ws)
+    return fail(ERR_INVALID, "os2s_logmel_forward: null pointer");
+  if (!out_bf16 && !out_f32) return fail(ERR_INVALID, "os2s_logmel_forward: no output buffer");
+  return logmel_forward(wave, offsets, n_samples, B, mel, window, n_fft, win, hop, F, T_pad, max_samples, dither,
+                        seed, preemph, (unsigned int*)absmax_ws, raw_ws, out_bf16, out_f32, out_lens,
+                        (cudaStream_t)stream);
+}
+
 }  // extern "C"

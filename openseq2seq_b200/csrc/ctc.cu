@@ -1,0 +1,437 @@
+// FullyConnectedCTCDecoder projection, CTC loss forward/backward and greedy CTC decoding.
+//
+// Reference ops being replaced:
+//   tf.layers.dense            open_seq2seq/decoders/fc_decoders.py:135-140   (K5)
+//   tf.nn.ctc_loss             open_seq2seq/losses/ctc_loss.py:77-89           (K6, a CPU kernel in TF1)
+//   tf.nn.ctc_greedy_decoder   open_seq2seq/decoders/fc_decoders.py:247-250   (K7)
+// Logits are kept batch-major [B, T, V] fp32 in HBM (the time-major [T,B,V] view the reference
+// exposes is a stride permutation, never a copy); all kernels take explicit (t, b) strides.
+#include "common.h"
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+namespace os2s {
+
+constexpr float kNegBig = -1e30f;
+
+__device__ __forceinline__ float log_add(float a, float b) {
+  const float m = fmaxf(a, b);
+  const float d = -fabsf(a - b);
+  return m + log1pf(__expf(d));
+}
+
+// ------------------------------------------------------------------ FC forward (small-N GEMM)
+// logits[m, v] = sum_h x[m, h] * w[h, v] + bias[v];  x bf16 [M, H], w fp32 [H, V] staged in smem.
+// One warp computes two rows at a time; lane l owns h = l, l+32, ...; V <= 32.
+constexpr int kFcThreads = 256;
+template <int VMAX>
+__global__ void __launch_bounds__(kFcThreads)
+fc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+              float* __restrict__ logits, int M, int H, int V) {
+  extern __shared__ float wsh[];  // [H][V]
+  for (int i = threadIdx.x; i < H * V; i += kFcThreads) wsh[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * kFcThreads + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * kFcThreads) >> 5;
+  for (int m0 = warp_global * 2; m0 < M; m0 += n_warps * 2) {
+    const bool two = (m0 + 1) < M;
+    float acc0[VMAX], acc1[VMAX];
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) acc0[v] = acc1[v] = 0.f;
+    const __nv_bfloat16* x0 = x + (size_t)m0 * H;
+    const __nv_bfloat16* x1 = x + (size_t)(two ? m0 + 1 : m0) * H;
+    for (int h = lane; h < H; h += 32) {
+      const float a0 = __bfloat162float(x0[h]);
+      const float a1 = __bfloat162float(x1[h]);
+      const float* wr = &wsh[h * V];
+#pragma unroll
+      for (int v = 0; v < VMAX; ++v) {
+        if (v < V) {
+          const float wv = wr[v];
+          acc0[v] += a0 * wv;
+          acc1[v] += a1 * wv;
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        acc0[v] += __shfl_xor_sync(0xffffffffu, acc0[v], o);
+        acc1[v] += __shfl_xor_sync(0xffffffffu, acc1[v], o);
+      }
+    }
+    // lane v writes column v
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) {
+      if (lane == v) {
+        r0 = acc0[v];
+        r1 = acc1[v];
+      }
+    }
+    if (lane < V) {
+      const float b = bias ? bias[lane] : 0.f;
+      logits[(size_t)m0 * V + lane] = r0 + b;
+      if (two) logits[(size_t)(m0 + 1) * V + lane] = r1 + b;
+    }
+  }
+}
+
+int fc_fwd(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V,
+           cudaStream_t st) {
+  if (V > 32 || V < 1) return fail(ERR_UNSUPPORTED, "fc_fwd: vocabulary > 32 not supported by the small-N kernel");
+  const size_t smem = (size_t)H * V * sizeof(float);
+  if (smem > 200 * 1024) return fail(ERR_UNSUPPORTED, "fc_fwd: H*V too large for shared memory");
+  static bool attr_done = false;
+  if (!attr_done) {
+    OS2S_CUDA(cudaFuncSetAttribute(fc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  const int grid = device_sm_count();
+  fc_fwd_kernel<32><<<grid, kFcThreads, smem, st>>>((const __nv_bfloat16*)x, w, bias, logits, M, H, V);
+  return check_launch("fc_fwd");
+}
+
+// ------------------------------------------------------------------ FC backward
+// dx[m, h] = sum_v dl[m, v] * w[h, v]   (bf16 out);  one warp per row, lanes over h.
+__global__ void __launch_bounds__(kFcThreads)
+fc_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w, __nv_bfloat16* __restrict__ dx,
+                int M, int H, int V) {
+  extern __shared__ float wsh[];  // [H][V]
+  for (int i = threadIdx.x; i < H * V; i += kFcThreads) wsh[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * kFcThreads + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * kFcThreads) >> 5;
+  for (int m = warp_global; m < M; m += n_warps) {
+    const float mine = (lane < V) ? dl[(size_t)m * V + lane] : 0.f;
+    float d[32];
+#pragma unroll
+    for (int v = 0; v < 32; ++v) d[v] = __shfl_sync(0xffffffffu, mine, v);
+    for (int h = lane; h < H; h += 32) {
+      const float* wr = &wsh[h * V];
+      float acc = 0.f;
+#pragma unroll
+      for (int v = 0; v < 32; ++v)
+        if (v < V) acc += d[v] * wr[v];
+      dx[(size_t)m * H + h] = __float2bfloat16(acc);
+    }
+  }
+}
+
+// dw[h, v] += sum_m x[m, h] * dl[m, v];  db[v] += sum_m dl[m, v].  Thread h of a block keeps V
+// partial sums over the block's row chunk, then one atomicAdd per (h, v).
+constexpr int kFcWgRows = 128;
+__global__ void __launch_bounds__(1024)
+fc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dl, float* __restrict__ dw,
+                float* __restrict__ db, int M, int H, int V) {
+  __shared__ float dsh[kFcWgRows][32];
+  const int row0 = blockIdx.x * kFcWgRows;
+  const int rows = min(kFcWgRows, M - row0);
+  for (int i = threadIdx.x; i < rows * 32; i += blockDim.x) {
+    const int r = i >> 5, v = i & 31;
+    dsh[r][v] = (v < V) ? dl[(size_t)(row0 + r) * V + v] : 0.f;
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float acc[32];
+#pragma unroll
+    for (int v = 0; v < 32; ++v) acc[v] = 0.f;
+    for (int r = 0; r < rows; ++r) {
+      const float a = __bfloat162float(x[(size_t)(row0 + r) * H + h]);
+#pragma unroll
+      for (int v = 0; v < 32; ++v) acc[v] += a * dsh[r][v];
+    }
+#pragma unroll
+    for (int v = 0; v < 32; ++v)
+      if (v < V) atomicAdd(&dw[(size_t)h * V + v], acc[v]);
+  }
+  if (threadIdx.x < V) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += dsh[r][threadIdx.x];
+    atomicAdd(&db[threadIdx.x], s);
+  }
+}
+
+int fc_bwd(const void* x, const float* dl, const float* w, void* dx, float* dw, float* db, int M, int H, int V,
+           cudaStream_t st) {
+  if (V > 32 || V < 1) return fail(ERR_UNSUPPORTED, "fc_bwd: vocabulary > 32 not supported");
+  const size_t smem = (size_t)H * V * sizeof(float);
+  if (smem > 200 * 1024) return fail(ERR_UNSUPPORTED, "fc_bwd: H*V too large for shared memory");
+  static bool attr_done = false;
+  if (!attr_done) {
+    OS2S_CUDA(cudaFuncSetAttribute(fc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  if (dx) {
+    fc_dgrad_kernel<<<device_sm_count(), kFcThreads, smem, st>>>(dl, w, (__nv_bfloat16*)dx, M, H, V);
+    int s = check_launch("fc_dgrad");
+    if (s) return s;
+  }
+  if (dw) {
+    OS2S_CUDA(cudaMemsetAsync(dw, 0, (size_t)H * V * sizeof(float), st));
+    OS2S_CUDA(cudaMemsetAsync(db, 0, (size_t)V * sizeof(float), st));
+    const int grid = (M + kFcWgRows - 1) / kFcWgRows;
+    fc_wgrad_kernel<<<grid, 1024, 0, st>>>((const __nv_bfloat16*)x, dl, dw, db, M, H, V);
+    return check_launch("fc_wgrad");
+  }
+  return OK;
+}
+
+// ------------------------------------------------------------------ CTC
+// Step 1: lse[b, t] = logsumexp_v logits[b, t, :]   (one thread per (b, t); V <= 32 floats)
+__global__ void ctc_lse_kernel(const float* __restrict__ logits, float* __restrict__ lse, int B, int T, int V,
+                               long long stride_b, long long stride_t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * T) return;
+  const int b = i / T, t = i - b * T;
+  const float* row = logits + b * stride_b + t * stride_t;
+  float m = -CUDART_INF_F;
+  for (int v = 0; v < V; ++v) m = fmaxf(m, row[v]);
+  float s = 0.f;
+  for (int v = 0; v < V; ++v) s += __expf(row[v] - m);
+  lse[i] = m + __logf(s);
+}
+
+// Step 2: alpha (blockIdx.y == 0) and beta (blockIdx.y == 1) lattices, one CTA per utterance and
+// direction.  States s = 0..S-1 over the blank-augmented label; threads stride over s; the lattice
+// row lives in shared memory (double buffered), emission rows are staged 32 time steps at a time
+// with coalesced loads.  alpha/beta rows are written to HBM [B][T][S_max] for the gradient kernel.
+constexpr int kCtcThreads = 512;
+constexpr int kCtcChunk = 32;
+__global__ void __launch_bounds__(kCtcThreads)
+ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
+                      const int* __restrict__ labels, const int* __restrict__ label_lens,
+                      const int* __restrict__ input_lens, float* __restrict__ alpha, float* __restrict__ beta,
+                      float* __restrict__ loglik, int T, int V, int L_max, int S_max, long long stride_b,
+                      long long stride_t, int blank) {
+  extern __shared__ float sh[];
+  float* lat = sh;                                  // [2][S_max]
+  float* em = sh + 2 * S_max;                       // [2][kCtcChunk][32] staged log-probs
+  int* ext = reinterpret_cast<int*>(em + 2 * kCtcChunk * 32);  // [S_max]
+  const int b = blockIdx.x;
+  const bool backward = blockIdx.y == 1;
+  const int Tb = min(input_lens[b], T);
+  const int L = min(label_lens[b], L_max);
+  const int S = 2 * L + 1;
+  const int tid = threadIdx.x;
+
+  for (int s = tid; s < S; s += kCtcThreads) ext[s] = (s & 1) ? labels[(size_t)b * L_max + (s >> 1)] : blank;
+  __syncthreads();
+  // feasibility (ignore_longer_outputs_than_inputs=True): need L + repeats <= Tb
+  __shared__ int repeats;
+  if (tid == 0) {
+    int r = 0;
+    for (int i = 1; i < L; ++i) r += (ext[2 * i + 1] == ext[2 * i - 1]);
+    repeats = r;
+  }
+  __syncthreads();
+  if (Tb <= 0 || L + repeats > Tb) {
+    if (tid == 0 && !backward) loglik[b] = CUDART_NAN_F;  // marks "skipped": loss 0, grad 0
+    return;
+  }
+
+  float* out = (backward ? beta : alpha) + (size_t)b * T * S_max;
+  const float* lg = logits + b * stride_b;
+  const float* ls = lse + (size_t)b * T;
+
+  auto stage = [&](int chunk, int buf) {
+    // chunk covers steps [chunk*32, chunk*32+32) in processing order
+    for (int i = tid; i < kCtcChunk * 32; i += kCtcThreads) {
+      const int st = i >> 5, v = i & 31;
+      const int step = chunk * kCtcChunk + st;
+      float val = kNegBig;
+      if (step < Tb && v < V) {
+        const int t = backward ? (Tb - 1 - step) : step;
+        val = lg[t * stride_t + v] - ls[t];
+      }
+      em[(buf * kCtcChunk + st) * 32 + v] = val;
+    }
+  };
+
+  const int n_chunks = (Tb + kCtcChunk - 1) / kCtcChunk;
+  stage(0, 0);
+  __syncthreads();
+  int cur = 0;
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    if (chunk + 1 < n_chunks) stage(chunk + 1, (chunk + 1) & 1);
+    const float* emc = em + (chunk & 1) * kCtcChunk * 32;
+    const int steps = min(kCtcChunk, Tb - chunk * kCtcChunk);
+    for (int st = 0; st < steps; ++st) {
+      const int step = chunk * kCtcChunk + st;
+      const int t = backward ? (Tb - 1 - step) : step;
+      const float* prev = lat + cur * S_max;
+      float* next = lat + (cur ^ 1) * S_max;
+      for (int s = tid; s < S; s += kCtcThreads) {
+        const int c = ext[s];
+        float a;
+        if (step == 0) {
+          const bool start = backward ? (s >= S - 2) : (s <= 1);
+          a = start ? 0.f : kNegBig;
+        } else if (!backward) {
+          a = prev[s];
+          if (s >= 1) a = log_add(a, prev[s - 1]);
+          if (s >= 2 && c != blank && c != ext[s - 2]) a = log_add(a, prev[s - 2]);
+        } else {
+          a = prev[s];
+          if (s + 1 < S) a = log_add(a, prev[s + 1]);
+          if (s + 2 < S && c != blank && c != ext[s + 2]) a = log_add(a, prev[s + 2]);
+        }
+        a = fmaxf(a + emc[st * 32 + c], kNegBig);
+        next[s] = a;
+        out[(size_t)t * S_max + s] = a;
+      }
+      cur ^= 1;
+      __syncthreads();
+    }
+  }
+  if (!backward && tid == 0) {
+    const float* fin = lat + cur * S_max;
+    float ll = fin[S - 1];
+    if (S > 1) ll = log_add(ll, fin[S - 2]);
+    loglik[b] = ll;
+  }
+}
+
+// Step 3: gradient wrt logits and per-utterance loss. One warp per (b, t).
+//   grad[b,t,v] = gscale * (softmax_v - sum_{s: ext[s]=v} exp(alpha+beta - logp_v - ll))   t < len
+// loss[b] = -ll (0 when skipped / NaN, mask_nans); gscale = loss_scale / B (loss_scale read from device).
+__global__ void __launch_bounds__(256)
+ctc_grad_kernel(const float* __restrict__ logits, const float* __restrict__ lse, const int* __restrict__ labels,
+                const int* __restrict__ label_lens, const int* __restrict__ input_lens,
+                const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ loglik,
+                float* __restrict__ grad, float* __restrict__ loss, const float* __restrict__ loss_scale,
+                int B, int T, int V, int L_max, int S_max, long long stride_b, long long stride_t,
+                long long gstride_b, long long gstride_t, int blank) {
+  __shared__ float acc[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= B * T) return;
+  const int b = i / T, t = i - b * T;
+  const float ll = loglik[b];
+  const bool skipped = !(ll == ll) || ll <= kNegBig * 0.5f;  // NaN or no path
+  const int Tb = min(input_lens[b], T);
+  float* g = grad + b * gstride_b + t * gstride_t;
+  if (t == 0 && lane == 0) loss[b] = skipped ? 0.f : -ll;
+  if (skipped || t >= Tb) {
+    if (lane < V) g[lane] = 0.f;
+    return;
+  }
+  const int L = min(label_lens[b], L_max);
+  const int S = 2 * L + 1;
+  acc[warp][lane] = 0.f;
+  __syncwarp();
+  const float* row = logits + b * stride_b + t * stride_t;
+  const float l = lse[(size_t)b * T + t];
+  const float* al = alpha + ((size_t)b * T + t) * S_max;
+  const float* be = beta + ((size_t)b * T + t) * S_max;
+  for (int s = lane; s < S; s += 32) {
+    const int c = (s & 1) ? labels[(size_t)b * L_max + (s >> 1)] : blank;
+    const float lp = row[c] - l;
+    const float e = __expf(al[s] + be[s] - lp - ll);
+    atomicAdd(&acc[warp][c], e);
+  }
+  __syncwarp();
+  if (lane < V) {
+    const float gscale = (loss_scale ? *loss_scale : 1.f) / (float)B;
+    const float sm = __expf(row[lane] - l);
+    g[lane] = gscale * (sm - acc[warp][lane]);
+  }
+}
+
+int ctc_loss_fwd_bwd(const float* logits, const int* labels, const int* label_lens, const int* input_lens,
+                     float* grad, float* loss, float* workspace, size_t workspace_bytes,
+                     const float* loss_scale, int B, int T, int V, int L_max, long long stride_b,
+                     long long stride_t, cudaStream_t st) {
+  if (V > 32) return fail(ERR_UNSUPPORTED, "ctc: vocabulary > 32 not supported");
+  const int S_max = 2 * L_max + 1;
+  // workspace: lse [B*T] | loglik [B] | alpha [B*T*S_max] | beta [B*T*S_max]
+  const size_t need = ((size_t)B * T + B + 2 * (size_t)B * T * S_max) * sizeof(float);
+  if (workspace_bytes < need) return fail(ERR_INVALID, "ctc: workspace too small, need " + std::to_string(need));
+  float* lse = workspace;
+  float* loglik = lse + (size_t)B * T;
+  float* alpha = loglik + B;
+  float* beta = alpha + (size_t)B * T * S_max;
+  const int blank = V - 1;
+  ctc_lse_kernel<<<(B * T + 255) / 256, 256, 0, st>>>(logits, lse, B, T, V, stride_b, stride_t);
+  const size_t smem = (2 * (size_t)S_max + 2 * kCtcChunk * 32) * sizeof(float) + (size_t)S_max * sizeof(int);
+  if (smem > 200 * 1024) return fail(ERR_UNSUPPORTED, "ctc: label sequence too long for shared memory");
+  static bool attr_done = false;
+  if (!attr_done) {
+    OS2S_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  ctc_alpha_beta_kernel<<<dim3(B, 2), kCtcThreads, smem, st>>>(logits, lse, labels, label_lens, input_lens, alpha,
+                                                               beta, loglik, T, V, L_max, S_max, stride_b,
+                                                               stride_t, blank);
+  ctc_grad_kernel<<<(B * T + 7) / 8, 256, 0, st>>>(logits, lse, labels, label_lens, input_lens, alpha, beta, loglik,
+                                                   grad, loss, loss_scale, B, T, V, L_max, S_max, stride_b, stride_t,
+                                                   (long long)T * V, (long long)V, blank);
+  return check_launch("ctc_loss_fwd_bwd");
+}
+
+size_t ctc_workspace_bytes(int B, int T, int L_max) {
+  const int S_max = 2 * L_max + 1;
+  return ((size_t)B * T + B + 2 * (size_t)B * T * S_max) * sizeof(float);
+}
+
+// ------------------------------------------------------------------ greedy decode
+// One warp per utterance: argmax per frame (first max on ties), merge repeats, drop blank.
+__global__ void ctc_greedy_kernel(const float* __restrict__ logits, const int* __restrict__ input_lens,
+                                  int* __restrict__ tokens, int* __restrict__ out_lens, float* __restrict__ neg_sum,
+                                  int B, int T, int V, long long stride_b, long long stride_t, int blank,
+                                  int merge_repeated) {
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x;
+  const int Tb = min(input_lens[b], T);
+  int count = 0;
+  int carry_prev = -1;
+  float score = 0.f;
+  for (int t0 = 0; t0 < Tb; t0 += 32) {
+    const int t = t0 + lane;
+    int c = -1;
+    float best = 0.f;
+    if (t < Tb) {
+      const float* row = logits + b * stride_b + t * stride_t;
+      best = row[0];
+      c = 0;
+      for (int v = 1; v < V; ++v) {
+        const float x = row[v];
+        if (x > best) {
+          best = x;
+          c = v;
+        }
+      }
+    }
+    int prev = __shfl_up_sync(0xffffffffu, c, 1);
+    if (lane == 0) prev = carry_prev;
+    const bool emit = (t < Tb) && (c != blank) && !(merge_repeated && c == prev);
+    const unsigned mask = __ballot_sync(0xffffffffu, emit);
+    const int pos = count + __popc(mask & ((1u << lane) - 1u));
+    if (emit) tokens[(size_t)b * T + pos] = c;
+    count += __popc(mask);
+    const int last = min(31, Tb - 1 - t0);
+    carry_prev = __shfl_sync(0xffffffffu, c, last);
+    float sc = (t < Tb) ? best : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+    score += sc;
+  }
+  if (lane == 0) {
+    out_lens[b] = count;
+    if (neg_sum) neg_sum[b] = -score;
+  }
+}
+
+int ctc_greedy(const float* logits, const int* input_lens, int* tokens, int* out_lens, float* neg_sum, int B,
+               int T, int V, long long stride_b, long long stride_t, int merge_repeated, cudaStream_t st) {
+  ctc_greedy_kernel<<<B, 32, 0, st>>>(logits, input_lens, tokens, out_lens, neg_sum, B, T, V, stride_b, stride_t,
+                                      V - 1, merge_repeated);
+  return check_launch("ctc_greedy");
+}
+
+}  // namespace os2s

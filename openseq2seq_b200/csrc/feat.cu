@@ -1,0 +1,183 @@
+// Speech2TextDataLayer log-mel featurizer on the GPU (librosa backend, input_type="logfbank").
+//
+// Reference being replaced (NumPy + librosa on 8 CPU py_func threads):
+//   open_seq2seq/data/speech2text/speech_utils.py:216-222   normalize_signal
+//   open_seq2seq/data/speech2text/speech_utils.py:364-365   dither
+//   open_seq2seq/data/speech2text/speech_utils.py:271-272   preemphasis
+//   open_seq2seq/data/speech2text/speech_utils.py:396-406   STFT(512, hop 160, hann 320) -> |.|^2 -> mel -> log
+//   open_seq2seq/data/speech2text/speech_utils.py:411-417   per-feature mean / std over time
+//   open_seq2seq/data/speech2text/speech2text.py:251-257,313-317  zero padding to [B, T_pad, F]
+// Kernel 1: per-utterance max |x| (gain).  Kernel 2: one warp per frame: gather the reflect-padded,
+// pre-emphasised, windowed frame into shared memory, radix-2 FFT, power spectrum, dense mel
+// mat-vec, log.  Kernel 3: one warp per (utterance, feature): mean / population std over the
+// utterance's frames with warp-shuffle reductions, normalise, cast to bf16, zero the padding.
+#include "common.h"
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+
+namespace os2s {
+
+__global__ void feat_absmax_kernel(const short* __restrict__ wave, const long long* __restrict__ offsets,
+                                   const int* __restrict__ n_samples, unsigned int* __restrict__ absmax) {
+  const int b = blockIdx.y;
+  const short* w = wave + offsets[b];
+  const int n = n_samples[b];
+  int m = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int v = w[i];
+    m = max(m, v < 0 ? -v : v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&absmax[b], (unsigned int)m);
+}
+
+__device__ __forceinline__ float gauss_from_index(unsigned long long seed, unsigned long long idx) {
+  // counter-based N(0,1): two splitmix64 uniforms -> Box-Muller
+  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  const float u1 = ((float)((z >> 40) & 0xFFFFFF) + 1.f) * (1.f / 16777217.f);
+  const float u2 = (float)((z >> 8) & 0xFFFFFF) * (1.f / 16777216.f);
+  return sqrtf(-2.f * __logf(u1)) * __cosf(6.28318530718f * u2);
+}
+
+constexpr int kNfftMax = 512;
+constexpr int kFeatWarps = 4;
+
+// signal value at (reflect-resolved) sample index i: normalised, dithered, then pre-emphasised.
+__device__ __forceinline__ float sample_at(const short* w, int n, int i, float gain, float dither,
+                                           unsigned long long seed, float preemph) {
+  auto base = [&](int j) {
+    float v = (float)w[j] * gain;
+    if (dither > 0.f) v += dither * gauss_from_index(seed, (unsigned long long)j);
+    return v;
+  };
+  const float cur = base(i);
+  return (i == 0) ? cur : cur - preemph * base(i - 1);
+}
+
+template <int NFFT>
+__global__ void __launch_bounds__(kFeatWarps * 32)
+feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__ offsets,
+                   const int* __restrict__ n_samples, const unsigned int* __restrict__ absmax,
+                   const float* __restrict__ mel, const float* __restrict__ window, float* __restrict__ raw,
+                   int T_pad, int F, int hop, int win, float dither, unsigned long long seed, float preemph) {
+  constexpr int NB = NFFT / 2 + 1;
+  __shared__ float re[kFeatWarps][NFFT];
+  __shared__ float im[kFeatWarps][NFFT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int frame = blockIdx.x * kFeatWarps + warp;
+  const int n = n_samples[b];
+  const int n_frames = 1 + n / hop;
+  if (frame >= n_frames) return;  // whole warp exits together
+  const short* w = wave + offsets[b];
+  const float gain = 1.f / ((float)absmax[b] + 1e-5f);
+  const unsigned long long useed = seed + (unsigned long long)b * 0x632BE59BD9B4E019ull;
+  const int lpad = (NFFT - win) / 2;
+  // bit-reversed load of the windowed frame (center=True: frame starts at frame*hop - NFFT/2)
+  constexpr int LOG2N = (NFFT == 512) ? 9 : (NFFT == 256) ? 8 : 10;
+  for (int i = lane; i < NFFT; i += 32) {
+    float v = 0.f;
+    const int wi = i - lpad;
+    if (wi >= 0 && wi < win) {
+      int j = frame * hop - NFFT / 2 + i;
+      if (j < 0) j = -j;                      // np.pad(mode="reflect")
+      if (j >= n) j = 2 * (n - 1) - j;
+      j = min(max(j, 0), n - 1);
+      v = sample_at(w, n, j, gain, dither, useed, preemph) * window[wi];
+    }
+    const int r = __brev((unsigned)i) >> (32 - LOG2N);
+    re[warp][r] = v;
+    im[warp][r] = 0.f;
+  }
+  __syncwarp();
+  // iterative radix-2 DIT FFT, NFFT/2 butterflies per stage spread over the warp
+  for (int s = 1; s <= LOG2N; ++s) {
+    const int half = 1 << (s - 1);
+    for (int i = lane; i < NFFT / 2; i += 32) {
+      const int grp = i / half, k = i - grp * half;
+      const int i0 = grp * 2 * half + k, i1 = i0 + half;
+      float sn, cs;
+      __sincosf(-3.14159265358979f * (float)k / (float)half, &sn, &cs);
+      const float xr = re[warp][i1], xi = im[warp][i1];
+      const float tr = xr * cs - xi * sn, ti = xr * sn + xi * cs;
+      const float ur = re[warp][i0], ui = im[warp][i0];
+      re[warp][i0] = ur + tr;
+      im[warp][i0] = ui + ti;
+      re[warp][i1] = ur - tr;
+      im[warp][i1] = ui - ti;
+    }
+    __syncwarp();
+  }
+  // power spectrum into re[0..NB)
+  for (int i = lane; i < NB; i += 32) {
+    const float a = re[warp][i], c = im[warp][i];
+    re[warp][i] = a * a + c * c;
+  }
+  __syncwarp();
+  // mel mat-vec: feature f = lane, lane+32; mel is [F][NB] row-major (dense)
+  for (int f = lane; f < F; f += 32) {
+    const float* mrow = mel + (size_t)f * NB;
+    float acc = 0.f;
+    for (int k = 0; k < NB; ++k) acc += mrow[k] * re[warp][k];
+    raw[((size_t)b * T_pad + frame) * F + f] = logf(acc + 1e-20f);
+  }
+}
+
+// per (b, f): mean and population std over the utterance's frames, then normalise + pad.
+__global__ void feat_norm_kernel(const float* __restrict__ raw, const int* __restrict__ n_samples,
+                                 __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                                 int* __restrict__ out_lens, int T_pad, int F, int hop, int norm_per_feature) {
+  const int b = blockIdx.y;
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (f >= F) return;
+  const int n_frames = min(1 + n_samples[b] / hop, T_pad);
+  const float* src = raw + (size_t)b * T_pad * F + f;
+  float s = 0.f;
+  for (int t = lane; t < n_frames; t += 32) s += src[(size_t)t * F];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)n_frames;
+  float q = 0.f;
+  for (int t = lane; t < n_frames; t += 32) {
+    const float d = src[(size_t)t * F] - mean;
+    q += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float inv_std = rsqrtf(q / (float)n_frames);
+  for (int t = lane; t < T_pad; t += 32) {
+    const float v = (t < n_frames) ? (src[(size_t)t * F] - mean) * inv_std : 0.f;
+    const size_t o = ((size_t)b * T_pad + t) * F + f;
+    if (out_bf16) out_bf16[o] = __float2bfloat16(v);
+    if (out_f32) out_f32[o] = v;
+  }
+  if (f == 0 && lane == 0 && out_lens) out_lens[b] = n_frames;
+}
+
+int logmel_forward(const short* wave, const long long* offsets, const int* n_samples, int B,
+                   const float* mel, const float* window, int n_fft, int win, int hop, int F, int T_pad,
+                   int max_samples, float dither, unsigned long long seed, float preemph,
+                   unsigned int* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
+                   cudaStream_t st) {
+  if (n_fft != 512) return fail(ERR_UNSUPPORTED, "logmel_forward: only n_fft = 512 is built");
+  if (win > n_fft || F > 128) return fail(ERR_INVALID, "logmel_forward: bad window / feature count");
+  OS2S_CUDA(cudaMemsetAsync(absmax_ws, 0, (size_t)B * sizeof(unsigned int), st));
+  feat_absmax_kernel<<<dim3(32, B), 256, 0, st>>>(wave, offsets, n_samples, absmax_ws);
+  const int max_frames = 1 + max_samples / hop;
+  if (max_frames > T_pad) return fail(ERR_INVALID, "logmel_forward: T_pad smaller than the frame count");
+  dim3 grid((max_frames + kFeatWarps - 1) / kFeatWarps, B);
+  feat_logmel_kernel<512><<<grid, kFeatWarps * 32, 0, st>>>(wave, offsets, n_samples, absmax_ws, mel, window, raw_ws,
+                                                           T_pad, F, hop, win, dither, seed, preemph);
+  dim3 grid2((F + 7) / 8, B);
+  feat_norm_kernel<<<grid2, 256, 0, st>>>(raw_ws, n_samples, (__nv_bfloat16*)out_bf16, out_f32, out_lens, T_pad, F,
+                                          hop, 1);
+  return check_launch("logmel_forward");
+}
+
+}  // namespace os2s

@@ -1,9 +1,14 @@
 // Internal (C++) declarations of the kernel launchers behind include/os2s.h.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "../../include/os2s.h"
+
 namespace os2s {
+
+constexpr int kMaxBranches = 12;
 
 const char* last_error_cstr();
 
@@ -16,5 +21,92 @@ int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in,
 // elementwise.cu
 int weight_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int K, int C_in, int C_out,
                           cudaStream_t st);
+struct BnBranchFwd {
+  const __nv_bfloat16* y;
+  const float* stats;   // [2][C] sums
+  const float* gamma;
+  const float* beta;
+  float* mean_invstd;   // [2][C] saved for backward
+  float* moving;        // [2][C] moving_mean, moving_variance (may be null)
+};
+struct BnFwdParams {
+  BnBranchFwd br[kMaxBranches];
+  int n_branch;
+  __nv_bfloat16* out;
+  const int* lens;      // [B] valid rows per utterance (nullptr = no mask)
+  int B, T, C;
+  float eps, momentum;  // momentum as in TF: moving = moving*momentum + batch*(1-momentum)
+  float keep;           // dropout keep probability (1 = off)
+  unsigned long long seed;
+  float relu_clip;      // <= 0: plain relu, > 0: min(relu(x), clip)
+  int apply_relu;
+};
+struct BnBranchBwd {
+  const __nv_bfloat16* y;
+  const float* mean_invstd;  // [2][C]
+  const float* gamma;
+  float* dgamma;             // [C] gradient outputs (scaled by loss scale like dA)
+  float* dbeta;              // [C]
+  __nv_bfloat16* dy;         // [M, C]
+};
+struct BnBwdParams {
+  BnBranchBwd br[kMaxBranches];
+  int n_branch;
+  const void* dA;            // bf16 or fp32 [M, C]
+  int dA_is_f32;
+  const __nv_bfloat16* a;    // forward output of this layer (post relu/dropout/mask)
+  float* red;                // [1 + n_branch][C] fp32 scratch, pre-zeroed: dbeta, dgamma_j
+  int M, C;
+  float keep;
+  int apply_relu;            // if 0: dz = dA (no activation), "a" unused
+};
+
+int bn_stats(const void* y, float* stats, int M, int C, cudaStream_t st);
+int bn_apply_fwd(const BnFwdParams& p, cudaStream_t st);
+int bn_bwd(const BnBwdParams& p, cudaStream_t st);
+
+
+// ctc.cu
+int fc_fwd(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V, cudaStream_t st);
+int fc_bwd(const void* x, const float* dl, const float* w, void* dx, float* dw, float* db, int M, int H, int V,
+           cudaStream_t st);
+size_t ctc_workspace_bytes(int B, int T, int L_max);
+int ctc_loss_fwd_bwd(const float* logits, const int* labels, const int* label_lens, const int* input_lens,
+                     float* grad, float* loss, float* workspace, size_t workspace_bytes, const float* loss_scale,
+                     int B, int T, int V, int L_max, long long stride_b, long long stride_t, cudaStream_t st);
+int ctc_greedy(const float* logits, const int* input_lens, int* tokens, int* out_lens, float* neg_sum, int B,
+               int T, int V, long long stride_b, long long stride_t, int merge_repeated, cudaStream_t st);
+
+// optim.cu
+typedef os2s_opt_hparams OptHParams;
+struct OptTable {
+  void* const* w;
+  void* const* g;
+  void* const* m;
+  void* const* wb;
+  const long long* sizes;
+  const int* chunk_tensor;
+  const long long* chunk_offset;
+  int n_tensors, n_chunks;
+};
+struct TransposeTable {
+  void* const* src;
+  void* const* dst;
+  const int* R;
+  const int* C;
+  const long long* tile_start;
+  int n_tensors;
+};
+int opt_step(const OptTable& tab, const OptHParams& hp, float* norms, int* nonfinite, float* fstate,
+             long long* istate, float* coef, float* ema, cudaStream_t st);
+int opt_chunk_elems();
+int multi_transpose(const TransposeTable& tab, long long total_tiles, cudaStream_t st);
+
+// feat.cu
+int logmel_forward(const short* wave, const long long* offsets, const int* n_samples, int B,
+                   const float* mel, const float* window, int n_fft, int win, int hop, int F, int T_pad,
+                   int max_samples, float dither, unsigned long long seed, float preemph,
+                   unsigned int* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
+                   cudaStream_t st);
 
 }  // namespace os2s
