@@ -34,6 +34,7 @@ extern "C" {
 #define OS2S_OUT_BF16 0
 #define OS2S_OUT_F32 1
 #define OS2S_OUT_F32_ACC 2 /* out(fp32) += result */
+#define OS2S_OUT_F16 3     /* fp16: conv outputs that only feed the BN kernels */
 
 const char* os2s_last_error(void);
 int os2s_version(void);
@@ -68,7 +69,9 @@ int os2s_weight_cast_transpose(const float* w_master, void* w_bf16, void* wt_bf1
  * reference: tf.layers.batch_normalization(training=True) conv_blocks.py:208-227 / :91-101,
  * residual sum :154, activation :166, tf.nn.dropout tdnn_encoder.py:255, mask :185-186,204-205. */
 
-/* stats[0..C) += sum_rows y ; stats[C..2C) += sum_rows y^2   (y bf16 [M,C]; stats pre-zeroed) */
+/* stats[0..C) += sum_rows y ; stats[C..2C) += sum_rows y^2   (y FP16 [M,C]; stats pre-zeroed).
+ * All BN entry points take the conv output y as fp16 (OS2S_OUT_F16): it is never a tensor-core
+ * operand, and fp16 keeps 3 more mantissa bits than bf16 at the same HBM traffic. */
 int os2s_bn_stats(const void* y, float* stats, int M, int C, void* stream);
 
 /* out = rowmask(dropout(act(sum_j gamma_j*(y_j-mean_j)*invstd_j + beta_j))), bf16 [B,T,C].
@@ -76,12 +79,13 @@ int os2s_bn_stats(const void* y, float* stats, int M, int C, void* stream);
  * mean_invstd[j] ([2][C]) is written for backward; moving[j] ([2][C] moving_mean, moving_variance,
  * may be NULL) is updated in place.  lens (int32 [B], may be NULL) gives valid rows per utterance;
  * rows t >= lens[b] are written as zeros.  keep = dropout keep probability (1 disables dropout);
- * apply_relu: 0 = identity, 1 = relu, with relu_clip > 0 -> min(relu(x), relu_clip). */
+ * apply_relu: 0 = identity, 1 = relu, with relu_clip > 0 -> min(relu(x), relu_clip).
+ * use_moving = 1 is inference mode (training=False): normalise with moving[j], touch no statistics. */
 int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* const* stats_host,
                       const float* const* gamma_host, const float* const* beta_host,
                       float* const* mean_invstd_host, float* const* moving_host, void* out,
                       const int* lens, int B, int T, int C, float eps, float momentum, float keep,
-                      uint64_t seed, int apply_relu, float relu_clip, void* stream);
+                      uint64_t seed, int apply_relu, float relu_clip, int use_moving, void* stream);
 
 /* Backward of the above.  dA: gradient wrt `out` (bf16, or fp32 when dA_is_f32), a: the forward
  * output (its zeros encode relu / dropout / mask).  Writes dy[j] (bf16 [M,C]) for every branch and

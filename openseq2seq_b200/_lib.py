@@ -26,6 +26,7 @@ def load():
         _build.build()
     lib = ctypes.CDLL(LIB_PATH)
     lib.os2s_last_error.restype = ctypes.c_char_p
+    lib.os2s_ctc_workspace_bytes.restype = ctypes.c_size_t
     _lib = lib
     return lib
 

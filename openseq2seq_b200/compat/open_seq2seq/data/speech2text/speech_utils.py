@@ -1,0 +1,51 @@
+"""Host-side helpers of the speech data layer (open_seq2seq/data/speech2text/speech_utils.py).
+
+The feature arithmetic of the reference (NumPy + librosa on py_func threads) runs on the GPU in
+os2s_logmel_forward; what stays on the host is only what has to: reading wav files and building the
+constant mel filterbank / window tables once.  The Slaney mel filterbank follows librosa 0.6.3's
+published definition (htk=False, area normalisation), see INTEGRATION.md."""
+import math
+
+import numpy as np
+
+
+def mel_filterbank(sr, n_fft, n_mels, fmin=0.0, fmax=None):
+    """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax): [n_mels, 1+n_fft//2] float64."""
+    fmax = sr / 2.0 if fmax is None else fmax
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, math.log(6.4) / 27.0
+
+    def hz2mel(f):
+        return min_log_mel + math.log(f / min_log_hz) / logstep if f >= min_log_hz else f / f_sp
+
+    def mel2hz(m):
+        return min_log_hz * math.exp(logstep * (m - min_log_mel)) if m >= min_log_mel else f_sp * m
+
+    pts = np.linspace(hz2mel(fmin), hz2mel(fmax), n_mels + 2)
+    edges = np.array([mel2hz(m) for m in pts])
+    freqs = np.linspace(0.0, sr / 2.0, 1 + n_fft // 2)
+    w = np.zeros((n_mels, freqs.size))
+    for i in range(n_mels):
+        up = (freqs - edges[i]) / (edges[i + 1] - edges[i])
+        down = (edges[i + 2] - freqs) / (edges[i + 2] - edges[i + 1])
+        w[i] = np.maximum(0.0, np.minimum(up, down)) * (2.0 / (edges[i + 2] - edges[i]))
+    return w
+
+
+def num_fft_for(window_size, sample_freq):
+    return 2 ** math.ceil(math.log2(window_size * sample_freq))
+
+
+def read_wav(filename, expected_sr):
+    """scipy.io.wavfile read + sample-rate check (speech_utils.py:188-195) -> int16 mono array."""
+    import scipy.io.wavfile as wave
+    sr, signal = wave.read(filename)
+    if sr != expected_sr:
+        raise ValueError("The sampling frequency set in params {} does not match the frequency {} read from "
+                         "file {}".format(expected_sr, sr, filename))
+    if signal.ndim > 1:
+        signal = signal[:, 0]
+    if signal.dtype != np.int16:
+        signal = (np.clip(signal, -1.0, 1.0) * 32767).astype(np.int16) if signal.dtype.kind == "f" \
+            else signal.astype(np.int16)
+    return signal

@@ -1,0 +1,49 @@
+"""Decoder base class (mirror of Encoder; open_seq2seq/decoders/decoder.py:16-150)."""
+import abc
+import copy
+
+import tensorflow as tf
+
+from open_seq2seq.utils.utils import check_params
+
+
+class Decoder(metaclass=abc.ABCMeta):
+    @staticmethod
+    def get_required_params():
+        return {}
+
+    @staticmethod
+    def get_optional_params():
+        return {
+            "regularizer": None, "regularizer_params": dict,
+            "initializer": None, "initializer_params": dict,
+            "dtype": [tf.float32, tf.float16, "mixed"],
+        }
+
+    def __init__(self, params, model, name="decoder", mode="train"):
+        check_params(params, self.get_required_params(), self.get_optional_params())
+        self._params = copy.deepcopy(params)
+        self._model = model
+        if "dtype" not in self._params:
+            self._params["dtype"] = model.params["dtype"] if model else tf.float32
+        self._name = name
+        self._mode = mode
+
+    def decode(self, input_dict):
+        return self._decode(input_dict)
+
+    @abc.abstractmethod
+    def _decode(self, input_dict):
+        pass
+
+    @property
+    def params(self):
+        return self._params
+
+    @property
+    def mode(self):
+        return self._mode
+
+    @property
+    def name(self):
+        return self._name

@@ -1,0 +1,73 @@
+"""optimize_loss's configuration surface (open_seq2seq/optimizers/optimizers.py:36-44,107-286),
+translated into JasperEngine.set_optimizer keyword arguments."""
+from .lr_policies import poly_decay
+from .novograd import NovoGrad
+
+
+class _Momentum(object):
+    engine_algo = "momentum"
+
+
+OPTIMIZER_CLS_NAMES = {
+    "Momentum": _Momentum,
+    "NovoGrad": NovoGrad,
+}
+
+
+def optimizer_engine_kwargs(params, last_step):
+    """Model params -> dict for JasperEngine.set_optimizer (models/model.py:475-525 wiring:
+    decay_steps defaults to last_step - begin_decay_at)."""
+    opt = params.get("optimizer", "Momentum")
+    if isinstance(opt, str):
+        if opt not in OPTIMIZER_CLS_NAMES:
+            raise ValueError("Optimizer name should be one of [{}], you provided {}.".format(
+                ", ".join(OPTIMIZER_CLS_NAMES), opt))
+        opt = OPTIMIZER_CLS_NAMES[opt]
+    algo = getattr(opt, "engine_algo", None)
+    if algo is None:
+        raise NotImplementedError("optimizer %r has no fused B200 step (NovoGrad and Momentum are built)" % (opt,))
+    op = dict(params.get("optimizer_params", {}))
+    kw = {"algo": algo}
+    if algo == "novograd":
+        for k in ("beta1", "beta2", "epsilon", "weight_decay", "grad_averaging"):
+            if k in op:
+                kw[k] = op[k]
+    else:
+        kw["momentum"] = op.get("momentum", 0.9)
+        if "weight_decay" in op:
+            kw["weight_decay"] = op["weight_decay"]
+    if params.get("max_grad_norm") is not None and params.get("larc_params") is not None:
+        raise AttributeError("LARC and gradient norm clipping should not be used together")
+    larc = params.get("larc_params")
+    if larc is not None:
+        kw["larc_eta"] = larc["larc_eta"]
+        kw["larc_mode"] = larc.get("larc_mode", "clip")
+        kw["larc_min_update"] = larc.get("min_update", 1e-7)
+        kw["larc_eps"] = larc.get("epsilon", 1e-7)
+    policy = params.get("lr_policy")
+    lp = dict(params.get("lr_policy_params", {}))
+    kw["learning_rate"] = lp.get("learning_rate", 0.01)
+    if policy is None or getattr(policy, "__name__", "") == "fixed_lr":
+        kw["decay_steps"] = 0
+    elif getattr(policy, "__name__", "") == "poly_decay" or policy is poly_decay:
+        begin = lp.get("begin_decay_at", 0)
+        kw["begin_decay_at"] = begin
+        kw["decay_steps"] = lp.get("decay_steps", max(int(last_step) - begin, 1))
+        kw["power"] = lp.get("power", 1.0)
+        kw["min_lr"] = lp.get("min_lr", 0.0)
+        kw["warmup_steps"] = lp.get("warmup_steps", 0)
+    else:
+        raise NotImplementedError("lr_policy %r is not fused on device yet (poly_decay / fixed_lr are)" % (policy,))
+    ls = params.get("loss_scaling", 1.0)
+    if isinstance(ls, str):
+        if ls.lower() != "backoff":
+            raise NotImplementedError("loss_scaling %r: only 'Backoff' is built" % ls)
+        kw["loss_scaling"] = True
+        lsp = params.get("loss_scaling_params", {}) or {}
+        for k in ("scale_min", "scale_max", "step_factor", "step_window"):
+            if k in lsp:
+                kw[k] = lsp[k]
+    else:
+        kw["loss_scaling"] = False
+        kw["initial_scale"] = float(ls)
+    return kw

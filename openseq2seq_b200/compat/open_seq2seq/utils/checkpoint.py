@@ -1,0 +1,47 @@
+"""Flat checkpoints (fp32 masters + momentum + BN moving stats + scaler/step state) with the
+reference's directory conventions (logdir/model.ckpt-<step>, `num_checkpoints` kept;
+open_seq2seq/utils/funcs.py:71-82).  The TF checkpoint FORMAT is out of scope."""
+import glob
+import os
+import re
+
+import torch
+
+
+def latest_checkpoint(ckpt_dir):
+    files = glob.glob(os.path.join(ckpt_dir, "model.ckpt-*.pt"))
+    if not files:
+        return None
+    step = lambda f: int(re.search(r"model\.ckpt-(\d+)\.pt$", f).group(1))
+    return max(files, key=step)
+
+
+def save(engine, logdir, step, keep=5, extra=None):
+    os.makedirs(logdir, exist_ok=True)
+    path = os.path.join(logdir, "model.ckpt-%d.pt" % step)
+    state = {
+        "params": {n: v.detach().cpu() for n, v in engine.named_parameters()},
+        "momentum": {n: engine.param_view(n, engine.mom).detach().cpu() for n, _ in engine.named_parameters()},
+        "moving": {k: v.detach().cpu() for k, v in engine.moving.items()},
+        "fstate": engine.fstate.cpu(), "istate": engine.istate.cpu(),
+        "ema": engine._opt["ema"].cpu(), "step": step, "extra": extra or {},
+    }
+    torch.save(state, path)
+    files = sorted(glob.glob(os.path.join(logdir, "model.ckpt-*.pt")),
+                   key=lambda f: int(re.search(r"-(\d+)\.pt$", f).group(1)))
+    for f in files[:-keep]:
+        os.remove(f)
+    return path
+
+
+def restore(engine, path):
+    state = torch.load(path, map_location="cpu")
+    engine.load_parameters(state["params"])
+    for n, v in state["momentum"].items():
+        engine.param_view(n, engine.mom).copy_(v)
+    for k, v in state["moving"].items():
+        engine.moving[k].copy_(v)
+    engine.fstate.copy_(state["fstate"])
+    engine.istate.copy_(state["istate"])
+    engine._opt["ema"].copy_(state["ema"])
+    return state["step"]

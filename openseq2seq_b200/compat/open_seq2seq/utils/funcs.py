@@ -1,0 +1,107 @@
+"""train / evaluate / infer drivers (open_seq2seq/utils/funcs.py:22-260) without TF sessions.
+
+The training loop keeps the reference's observable behaviour: print_loss_steps, checkpoints every
+save_checkpoint_steps on rank 0 (num_checkpoints kept), evaluation every eval_steps, and the
+throughput meter of `--benchmark`: after `bench_start` steps accumulate wall time and input frames
+and print "Avg objects per second" (objects = input frames, summed over ranks)."""
+import time
+
+import torch
+
+from .utils import deco_print
+
+
+def _master(model):
+    return (not model.on_horovod) or model.hvd.rank() == 0
+
+
+def evaluate_model(eval_model, max_batches=None):
+    results, losses = [], []
+    it = eval_model.get_data_layer().iterator or None
+    if it is None:
+        eval_model.get_data_layer().build_graph()
+        it = eval_model.get_data_layer().iterator
+    eng = eval_model.engine
+    was = eng.training
+    eng.set_training(False)
+    try:
+        for k, batch in enumerate(it):
+            loss, dec_out = eval_model.eval_step(batch)
+            results.append(eval_model.evaluate(batch, dec_out["outputs"][0]))
+            if loss is not None:
+                losses.append(float(loss))
+            if max_batches is not None and k + 1 >= max_batches:
+                break
+    finally:
+        eng.set_training(was)
+        eval_model.get_data_layer().build_graph()
+    out = eval_model.finalize_evaluation(results)
+    if losses:
+        out["Eval loss"] = sum(losses) / len(losses)
+        deco_print("Validation loss: {:.4f}".format(out["Eval loss"]), offset=4)
+    return out
+
+
+def train(train_model, eval_model=None, debug_port=None, custom_hooks=None):
+    p = train_model.params
+    master = _master(train_model)
+    it = train_model.get_data_layer().iterator
+    bench_start = p.get("bench_start", 10)
+    print_every = p.get("print_loss_steps")
+    save_every = p.get("save_checkpoint_steps")
+    eval_every = p.get("eval_steps") if eval_model is not None else None
+    logdir = p.get("logdir")
+    last_step = train_model.last_step
+    step = 0
+    total_time, total_objects = 0.0, 0.0
+    deco_print("Starting training ({} steps)".format(last_step))
+    t_print = time.time()
+    while step < last_step:
+        t0 = time.time()
+        batch = next(it)
+        loss, n_objects = train_model.train_step(batch)
+        step += 1
+        timed = step > bench_start
+        if timed or (print_every and step % print_every == 0):
+            torch.cuda.synchronize()
+        if timed:
+            total_time += time.time() - t0
+            total_objects += float(n_objects)
+        if print_every and step % print_every == 0 and master:
+            deco_print("Global step {}: train loss = {:.4f}, time per step = {:.3f}s".format(
+                step, float(loss), (time.time() - t_print) / print_every))
+            t_print = time.time()
+        if p.get("print_samples_steps") and step % p["print_samples_steps"] == 0 and master:
+            toks = train_model.engine.greedy_decode()
+            train_model.maybe_print_logs(batch, toks, step)
+        if save_every and logdir and step % save_every == 0 and master:
+            from . import checkpoint as ckpt
+            ckpt.save(train_model.engine, logdir, step, keep=p.get("num_checkpoints", 5))
+        if eval_every and step % eval_every == 0:
+            evaluate_model(eval_model)
+    if save_every and logdir and master:
+        from . import checkpoint as ckpt
+        ckpt.save(train_model.engine, logdir, step, keep=p.get("num_checkpoints", 5))
+    if train_model.on_horovod:
+        total_objects = train_model.hvd.sum_scalar(total_objects)
+    if master:
+        deco_print("Finished training")
+        if step > bench_start and total_time > 0:
+            deco_print("Avg time per step: {:.3f}s".format(total_time / (step - bench_start)))
+            deco_print("Avg objects per second: {:.3f}".format(total_objects / total_time))
+        else:
+            deco_print("Not enough steps for benchmarking")
+    return total_objects / total_time if total_time > 0 else None
+
+
+def evaluate(model, checkpoint):
+    return evaluate_model(model)
+
+
+def infer(model, checkpoint, output_file):
+    results = []
+    model.engine.set_training(False)
+    for batch in model.get_data_layer().iterator:
+        _, dec_out = model.eval_step(batch)
+        results.append(model.infer(batch, dec_out["outputs"][0]))
+    model.finalize_inference(results, output_file)

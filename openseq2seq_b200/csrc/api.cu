@@ -45,14 +45,15 @@ int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* cons
                       const float* const* gamma_host, const float* const* beta_host,
                       float* const* mean_invstd_host, float* const* moving_host, void* out,
                       const int* lens, int B, int T, int C, float eps, float momentum, float keep,
-                      uint64_t seed, int apply_relu, float relu_clip, void* stream) {
+                      uint64_t seed, int apply_relu, float relu_clip, int use_moving, void* stream) {
   if (n_branch < 1 || n_branch > kMaxBranches) return fail(ERR_INVALID, "os2s_bn_apply_fwd: 1..12 branches");
   if (!y_host || !stats_host || !gamma_host || !beta_host || !mean_invstd_host || !out)
     return fail(ERR_INVALID, "os2s_bn_apply_fwd: null pointer");
+  if (use_moving && !moving_host) return fail(ERR_INVALID, "os2s_bn_apply_fwd: use_moving needs moving statistics");
   if (!(keep > 0.f && keep <= 1.f)) return fail(ERR_INVALID, "os2s_bn_apply_fwd: keep must be in (0,1]");
   BnFwdParams p;
   for (int j = 0; j < n_branch; ++j) {
-    p.br[j].y = (const __nv_bfloat16*)y_host[j];
+    p.br[j].y = (const __half*)y_host[j];
     p.br[j].stats = stats_host[j];
     p.br[j].gamma = gamma_host[j];
     p.br[j].beta = beta_host[j];
@@ -64,7 +65,7 @@ int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* cons
   p.lens = lens;
   p.B = B; p.T = T; p.C = C;
   p.eps = eps; p.momentum = momentum; p.keep = keep; p.seed = seed;
-  p.relu_clip = relu_clip; p.apply_relu = apply_relu;
+  p.relu_clip = relu_clip; p.apply_relu = apply_relu; p.use_moving = use_moving;
   return bn_apply_fwd(p, (cudaStream_t)stream);
 }
 
@@ -78,7 +79,7 @@ int os2s_bn_bwd(int n_branch, const void* const* y_host, const float* const* mea
   if (apply_relu && !a) return fail(ERR_INVALID, "os2s_bn_bwd: forward output required for relu backward");
   BnBwdParams p;
   for (int j = 0; j < n_branch; ++j) {
-    p.br[j].y = (const __nv_bfloat16*)y_host[j];
+    p.br[j].y = (const __half*)y_host[j];
     p.br[j].mean_invstd = mean_invstd_host[j];
     p.br[j].gamma = gamma_host[j];
     p.br[j].dgamma = dgamma_host[j];

@@ -33,7 +33,7 @@ constexpr int kABytes = kTileM * kChunkK * 2;
 constexpr int kNumThreads = 192;
 constexpr int kSmemBudget = 220 * 1024;
 
-enum OutMode : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ACC = 2 };
+enum OutMode : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ACC = 2, OUT_F16 = 3 };
 
 struct KMajorParams {
   int B, T_out, n_mtiles, n_ntiles, N_total;
@@ -192,6 +192,19 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               v.y = pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
               v.z = pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
               v.w = pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
+              dst[q] = v;
+            }
+          } else if (p.out_mode == OUT_F16) {
+            // fp16 (2-byte elements, same addressing as bf16): used for conv outputs that are only
+            // consumed by the BN kernels -- 3 more mantissa bits than bf16 at the same traffic.
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + off + ch * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 v;
+              v.x = pack_f16(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
+              v.y = pack_f16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
+              v.z = pack_f16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
+              v.w = pack_f16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
               dst[q] = v;
             }
           } else {

@@ -3,6 +3,7 @@
 #include "kernels.h"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace os2s {
 
@@ -57,6 +58,16 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& v, float (&f)[8]) {
     f[2 * i + 1] = t.y;
   }
 }
+// conv outputs (the BN inputs "y") are stored as fp16, see OUT_F16 in conv_tc.cu
+__device__ __forceinline__ void f16x8_to_float(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
 __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
   uint4 v;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
@@ -69,7 +80,7 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
 // Thread layout: each thread owns one 8-channel vector (16-byte loads) and walks rows.
 constexpr int kStatThreads = 256;
 __global__ void __launch_bounds__(kStatThreads)
-bn_stats_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ stats, int M, int C,
+bn_stats_kernel(const __half* __restrict__ y, float* __restrict__ stats, int M, int C,
                 int rows_per_block) {
   extern __shared__ float sh[];  // [2][C]
   const int CV = C >> 3;
@@ -87,7 +98,7 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ stats, 
     for (int row = row0 + r; row < row1; row += RP) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(y + (size_t)row * C) + cv);
       float f[8];
-      bf16x8_to_float(v, f);
+      f16x8_to_float(v, f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s[i] += f[i];
@@ -110,7 +121,7 @@ int bn_stats(const void* y, float* stats, int M, int C, cudaStream_t st) {
   int rows_per_block = (M + target_blocks - 1) / target_blocks;
   if (rows_per_block < 8) rows_per_block = 8;
   const int grid = (M + rows_per_block - 1) / rows_per_block;
-  bn_stats_kernel<<<grid, kStatThreads, 2 * C * sizeof(float), st>>>((const __nv_bfloat16*)y, stats, M, C,
+  bn_stats_kernel<<<grid, kStatThreads, 2 * C * sizeof(float), st>>>((const __half*)y, stats, M, C,
                                                                     rows_per_block);
   return check_launch("bn_stats");
 }
@@ -148,13 +159,14 @@ bn_apply_fwd_kernel(const BnFwdParams p) {
   for (int i = threadIdx.x; i < p.n_branch * C; i += kApplyThreads) {
     const int j = i / C, c = i - j * C;
     const BnBranchFwd& b = p.br[j];
-    const float mean = b.stats[c] * inv_n;
-    const float var = fmaxf(b.stats[C + c] * inv_n - mean * mean, 0.f);
+    // training: batch statistics; inference (use_moving): the moving averages
+    const float mean = p.use_moving ? b.moving[c] : b.stats[c] * inv_n;
+    const float var = p.use_moving ? b.moving[C + c] : fmaxf(b.stats[C + c] * inv_n - mean * mean, 0.f);
     const float invstd = rsqrtf(var + p.eps);
     const float g = b.gamma[c];
     sh[(j * 2) * C + c] = g * invstd;
     sh[(j * 2 + 1) * C + c] = b.beta[c] - mean * g * invstd;
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == 0 && !p.use_moving) {
       b.mean_invstd[c] = mean;
       b.mean_invstd[C + c] = invstd;
       if (b.moving) {
@@ -184,7 +196,7 @@ bn_apply_fwd_kernel(const BnFwdParams p) {
       for (int j = 0; j < p.n_branch; ++j) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.br[j].y + row * C) + cv);
         float f[8];
-        bf16x8_to_float(v, f);
+        f16x8_to_float(v, f);
         const float* sc = &sh[(j * 2) * C + cv * 8];
         const float* sf = &sh[(j * 2 + 1) * C + cv * 8];
 #pragma unroll
@@ -293,7 +305,7 @@ bn_bwd_reduce_kernel(const BnBwdParams p, int rows_per_block) {
         load_dz<F32>(p, row, cv, dz);
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.br[j].y + (size_t)row * C) + cv);
         float f[8];
-        bf16x8_to_float(v, f);
+        f16x8_to_float(v, f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           dg[i] += dz[i] * (f[i] - mean[i]) * invstd[i];
@@ -343,7 +355,7 @@ bn_bwd_apply_kernel(const BnBwdParams p) {
     for (int j = 0; j < p.n_branch; ++j) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.br[j].y + row * C) + cv);
       float f[8], o[8];
-      bf16x8_to_float(v, f);
+      f16x8_to_float(v, f);
       const float* s = &sh[(size_t)j * 4 * C + cv * 8];
 #pragma unroll
       for (int i = 0; i < 8; ++i)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "../../include/os2s.h"
@@ -22,7 +23,7 @@ int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in,
 int weight_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int K, int C_in, int C_out,
                           cudaStream_t st);
 struct BnBranchFwd {
-  const __nv_bfloat16* y;
+  const __half* y;        // conv output, fp16
   const float* stats;   // [2][C] sums
   const float* gamma;
   const float* beta;
@@ -40,9 +41,10 @@ struct BnFwdParams {
   unsigned long long seed;
   float relu_clip;      // <= 0: plain relu, > 0: min(relu(x), clip)
   int apply_relu;
+  int use_moving;       // 1 = inference mode: normalise with the moving statistics
 };
 struct BnBranchBwd {
-  const __nv_bfloat16* y;
+  const __half* y;          // conv output, fp16
   const float* mean_invstd;  // [2][C]
   const float* gamma;
   float* dgamma;             // [C] gradient outputs (scaled by loss scale like dA)

@@ -1,0 +1,62 @@
+"""torch.distributed (NCCL over NVLink) stand-in for the three Horovod/MPI collectives the reference
+uses on this path:
+
+  C1 hvd.allreduce(grad) per variable   -> ONE all-reduce (sum) over the flat fp32 gradient buffer,
+                                           optionally split into buckets launched on a side stream;
+                                           the 1/N is folded into the optimizer's unscale factor
+  C2 hvd.broadcast of every global var  -> broadcast of the flat master / momentum / BN buffers
+  C3 MPI gather of scalars              -> all_reduce of a scalar
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class TorchDistHvd(object):
+    def __init__(self, rank, size, local_rank):
+        self._rank, self._size, self._local_rank = rank, size, local_rank
+
+    @classmethod
+    def init(cls):
+        rank = int(os.environ["RANK"])
+        world = int(os.environ["WORLD_SIZE"])
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        return cls(rank, world, local)
+
+    @classmethod
+    def single(cls):
+        return cls(0, 1, 0)
+
+    def size(self):
+        return self._size
+
+    def rank(self):
+        return self._rank
+
+    def local_rank(self):
+        return self._local_rank
+
+    def allreduce_(self, flat):
+        if self._size > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+
+    def broadcast_parameters(self, engine):
+        if self._size > 1:
+            for t in [engine.master, engine.mom, engine.fstate, engine.istate] + list(engine.moving.values()):
+                dist.broadcast(t, src=0)
+            engine.sync_half_copies()
+
+    def sum_scalar(self, x):
+        if self._size == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t[0])
+
+    def barrier(self):
+        if self._size > 1:
+            dist.barrier()

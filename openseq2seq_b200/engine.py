@@ -1,0 +1,735 @@
+"""JasperEngine: the B200 training path behind the OpenSeq2Seq plugin classes.
+
+It owns the device-resident state of one data-parallel replica -- fp32 master parameters, fp32
+gradients, momentum, bf16 working copies (natural + transposed layouts), BN statistics, saved
+activations -- and drives the hand-written sm_100a kernels of libos2s_b200 through the C ABI
+(include/os2s.h).  PyTorch is used only as the device allocator / stream / NCCL host.
+
+What it replaces in the reference (one training step):
+  TDNNEncoder._encode                    open_seq2seq/encoders/tdnn_encoder.py:87-265
+  conv_bn_actv / conv_bn_res_bn_actv     open_seq2seq/parts/cnns/conv_blocks.py:61-232
+  FullyConnectedTimeDecoder._decode      open_seq2seq/decoders/fc_decoders.py:105-158
+  CTCLoss._compute_loss                  open_seq2seq/losses/ctc_loss.py:44-89
+  optimize_loss + MP wrapper + NovoGrad  open_seq2seq/optimizers/{optimizers,mp_wrapper,novograd}.py
+  hvd.allreduce per gradient             open_seq2seq/optimizers/optimizers.py:77-104
+
+All launches of a step are pre-bound once per (batch, time) shape into a flat "plan" of
+(function, argument-list) pairs, so the per-step Python cost is one loop over ctypes calls and
+the step never synchronises with the host.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib as L
+
+_c_int = ctypes.c_int
+_c_float = ctypes.c_float
+_c_ll = ctypes.c_longlong
+_c_u64 = ctypes.c_uint64
+_c_size_t = ctypes.c_size_t
+_vp = ctypes.c_void_p
+
+
+class OptHParams(ctypes.Structure):
+    """Mirror of os2s_opt_hparams (include/os2s.h)."""
+    _fields_ = [
+        ("algo", _c_int), ("beta1", _c_float), ("beta2", _c_float), ("epsilon", _c_float),
+        ("weight_decay", _c_float), ("momentum", _c_float), ("grad_averaging", _c_int),
+        ("ema_persist", _c_int), ("larc_eta", _c_float), ("larc_eps", _c_float),
+        ("larc_min_update", _c_float), ("larc_mode", _c_int), ("lr0", _c_float), ("min_lr", _c_float),
+        ("power", _c_float), ("decay_steps", _c_ll), ("begin_decay_at", _c_ll), ("warmup_steps", _c_ll),
+        ("use_loss_scaler", _c_int), ("scale_min", _c_float), ("scale_max", _c_float),
+        ("step_factor", _c_float), ("step_window", _c_ll), ("world_size", _c_int),
+    ]
+
+
+def _align(n, a=128):
+    return (n + a - 1) // a * a
+
+
+def same_padding(T_in, K, stride, dilation):
+    """tf SAME padding: returns (T_out, pad_left, pad_right)."""
+    T_out = -(-T_in // stride)
+    total = max((T_out - 1) * stride + (K - 1) * dilation + 1 - T_in, 0)
+    return T_out, total // 2, total - total // 2
+
+
+class ConvLayer(object):
+    """One conv+BN(+residual)+act layer of the TDNN stack, in kernel terms."""
+
+    def __init__(self, name, K, stride, dil, c_in, c_out, keep, block, rep, block_end, res_sources,
+                 dense):
+        self.name, self.K, self.stride, self.dil = name, K, stride, dil
+        self.c_in, self.c_out, self.keep = c_in, c_out, keep
+        self.block, self.rep, self.block_end = block, rep, block_end
+        self.res_sources = res_sources  # indices into the engine's block-input list
+        self.dense = dense
+        # kernel-level geometry (stride folded into channels), filled by the engine
+        self.kK = K
+        self.kC_in = c_in
+        self.kpad = 0
+        self.lead_taps = 0
+
+
+class JasperEngine(object):
+    def __init__(self, convnet_layers, num_features, vocab_size, device="cuda", bn_momentum=0.9,
+                 bn_epsilon=1e-3, use_conv_mask=True, training=True, dropout_keep_default=1.0,
+                 opt=None, world_size=1, seed=0, relu_clip=0.0):
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.F = num_features
+        self.V = vocab_size
+        self.bn_momentum = float(bn_momentum)
+        self.bn_eps = float(bn_epsilon)
+        self.use_conv_mask = use_conv_mask
+        self.training = training
+        self.world_size = world_size
+        self.seed = seed
+        self.relu_clip = float(relu_clip)
+        self.step_count = 0
+        self._ws = {}
+        self._build_layers(convnet_layers, dropout_keep_default)
+        self._alloc_params()
+        self.set_optimizer(**(opt or {}))
+
+    # ------------------------------------------------------------------ topology
+    def _build_layers(self, cfg, keep_default):
+        layers = []
+        self.block_inputs = []  # channel count of every residual source, in order of creation
+        c_in = self.F
+        res_list = []
+        for bi, lc in enumerate(cfg):
+            if lc.get("type", "conv1d") != "conv1d":
+                raise ValueError("JasperEngine: only 'conv1d' layers are built (got %r)" % lc.get("type"))
+            if lc.get("padding", "SAME") != "SAME":
+                raise ValueError("JasperEngine: only SAME padding is built")
+            K = lc["kernel_size"][0]
+            stride = lc["stride"][0]
+            dil = lc["dilation"][0]
+            c_out = lc["num_channels"]
+            keep = lc.get("dropout_keep_prob", keep_default) if self.training else 1.0
+            residual = lc.get("residual", False)
+            dense = lc.get("residual_dense", False)
+            sources = []
+            if residual:
+                self.block_inputs.append((c_in, len(layers)))
+                idx = len(self.block_inputs) - 1
+                if dense:
+                    res_list.append(idx)
+                    sources = list(res_list)
+                else:
+                    sources = [idx]
+            if stride > 1 and (bi != 0 or lc["repeat"] != 1):
+                raise ValueError("JasperEngine: stride > 1 is only built for the first layer")
+            for ri in range(lc["repeat"]):
+                end = residual and ri == lc["repeat"] - 1
+                layers.append(ConvLayer("conv%d%d" % (bi + 1, ri + 1), K, stride, dil, c_in, c_out, keep, bi, ri,
+                                        end, sources if end else [], dense))
+                c_in = c_out
+        self.layers = layers
+        self.H = c_in
+        # which layers' OUTPUT is a residual source (needs an fp32 gradient accumulator)
+        self.src_of_layer_output = {}
+        for idx, (c, first_layer) in enumerate(self.block_inputs):
+            if first_layer == 0:
+                raise ValueError("JasperEngine: a residual block cannot be the first layer")
+            self.src_of_layer_output[first_layer - 1] = idx
+        # last consumer ordering for the fp32 accumulators: in backward order the first writer of
+        # source j is the LAST block-end layer that lists j
+        self.first_bwd_writer = {}
+        for li in range(len(layers) - 1, -1, -1):
+            for j in layers[li].res_sources:
+                self.first_bwd_writer.setdefault(j, li)
+
+    # ---------------------------------------------------------------- parameters
+    def _alloc_params(self):
+        """Flat fp32 master / grad / momentum buffers + bf16 copies; names follow SURVEY.md App. B."""
+        specs = []  # (name, shape, kind, layer)
+
+        def add(name, shape, kind, layer=None, store_shape=None):
+            specs.append({"name": name, "shape": tuple(shape), "kind": kind, "layer": layer,
+                          "store_shape": tuple(store_shape or shape)})
+
+        for lyr in self.layers:
+            if lyr.stride > 1:
+                # fold the stride into channels: x viewed [B, T/s, s*C]; taps regrouped (see engine docs)
+                if lyr.stride != 2:
+                    raise ValueError("JasperEngine: only stride 2 is built")
+                lyr.fold = True
+            else:
+                lyr.fold = False
+            add(lyr.name + "/kernel", (lyr.K, lyr.c_in, lyr.c_out), "conv", lyr)
+            add(lyr.name + "/bn/gamma", (lyr.c_out,), "gamma", lyr)
+            add(lyr.name + "/bn/beta", (lyr.c_out,), "beta", lyr)
+            for n, j in enumerate(lyr.res_sources):
+                cj = self.block_inputs[j][0]
+                rn = (lyr.name + "/res_%d" % n) if lyr.dense else (lyr.name + "/res")
+                bn = (lyr.name + "/res_bn_%d" % n) if lyr.dense else (lyr.name + "/res_bn")
+                add(rn + "/kernel", (1, cj, lyr.c_out), "conv", lyr)
+                add(bn + "/gamma", (lyr.c_out,), "gamma", lyr)
+                add(bn + "/beta", (lyr.c_out,), "beta", lyr)
+        add("fc/kernel", (self.H, self.V), "fc_w")
+        add("fc/bias", (self.V,), "fc_b")
+        off = 0
+        hoff = 0
+        for s in specs:
+            n = 1
+            for d in s["shape"]:
+                n *= d
+            s["size"] = n
+            s["store_size"] = n
+            s["offset"] = off
+            if s["kind"] == "conv":
+                s["half_offset"] = hoff
+            off += _align(n)
+            if s["kind"] == "conv":
+                hoff += _align(n)
+        self.specs = specs
+        self.by_name = {s["name"]: s for s in specs}
+        self._fix_folded_layout()
+        total = self._total
+        dev = self.device
+        self.master = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.mom = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.wb = torch.zeros(self._half_total, dtype=torch.bfloat16, device=dev)   # natural [K][Cin][Cout]
+        self.wt = torch.zeros(self._half_total, dtype=torch.bfloat16, device=dev)   # transposed [K][Cout][Cin]
+        # BN moving statistics [2][C] per BN instance (moving_mean = 0, moving_variance = 1)
+        self.moving = {}
+        for s in specs:
+            if s["kind"] == "gamma":
+                C = s["shape"][0]
+                mv = torch.zeros(2, C, dtype=torch.float32, device=dev)
+                mv[1].fill_(1.0)
+                self.moving[s["name"][:-len("/gamma")]] = mv
+        self.init_parameters(self.seed)
+
+    def _fix_folded_layout(self):
+        """Stride-2 layers: storage holds 2*K' taps (zero lead / trail taps) so that the same memory is
+        a stride-1 kernel [K', 2*C_in, C_out].  Recompute offsets with the padded sizes."""
+        off = 0
+        hoff = 0
+        for s in self.specs:
+            lyr = s["layer"]
+            if s["kind"] == "conv" and lyr is not None and lyr.fold and s["name"] == lyr.name + "/kernel":
+                K, pl_info = lyr.K, None
+                # pad_left depends on T parity; pad_to guarantees even T (asserted at run time)
+                pl = max((lyr.K - 1) * lyr.dil + 1 - lyr.stride, 0) // 2  # SAME pad_left for even T_in
+                j_min = math.floor(-pl / 2.0)
+                j_max = math.floor((K - 1 - pl) / 2.0)
+                lyr.kK = j_max - j_min + 1
+                lyr.kpad = -j_min
+                lyr.lead_taps = 2 * j_min + pl  # <= 0 -> number of leading zero taps = -lead
+                lyr.lead_taps = -lyr.lead_taps
+                lyr.kC_in = 2 * lyr.c_in
+                lyr.orig_pad_left = pl
+                s["store_size"] = 2 * lyr.kK * lyr.c_in * lyr.c_out
+                s["store_shape"] = (2 * lyr.kK, lyr.c_in, lyr.c_out)
+            elif s["kind"] == "conv" and lyr is not None and s["name"] == lyr.name + "/kernel":
+                lyr.kK, lyr.kC_in = lyr.K, lyr.c_in
+                _, lyr.kpad, _ = same_padding(1 << 20, lyr.K, 1, lyr.dil)
+                lyr.lead_taps = 0
+            s["offset"] = off
+            off += _align(s["store_size"])
+            if s["kind"] == "conv":
+                s["half_offset"] = hoff
+                hoff += _align(s["store_size"])
+        self._total = off
+        self._half_total = hoff
+
+    def _valid_slice(self, s):
+        """(start, size) of the trainable part inside the stored tensor."""
+        lyr = s["layer"]
+        if s["kind"] == "conv" and lyr is not None and lyr.fold and s["name"] == lyr.name + "/kernel":
+            per_tap = lyr.c_in * lyr.c_out
+            return lyr.lead_taps * per_tap, s["size"]
+        return 0, s["size"]
+
+    def param_view(self, name, buf=None):
+        """fp32 view (logical shape) of a parameter inside the flat master (or grad / mom) buffer."""
+        s = self.by_name[name]
+        buf = self.master if buf is None else buf
+        st, n = self._valid_slice(s)
+        return buf[s["offset"] + st:s["offset"] + st + n].view(*s["shape"])
+
+    def named_parameters(self):
+        return [(s["name"], self.param_view(s["name"])) for s in self.specs]
+
+    def init_parameters(self, seed=0):
+        """tf.contrib.layers.xavier_initializer as the Jasper config uses it:
+        encoder kernels truncated-normal (uniform=False), decoder uniform, BN gamma=1/beta=0, bias=0."""
+        gen = torch.Generator().manual_seed(seed)
+        for s in self.specs:
+            v = self.param_view(s["name"])
+            if s["kind"] == "conv":
+                K, ci, co = s["shape"]
+                n = (K * ci + K * co) / 2.0
+                std = math.sqrt(1.3 / n)
+                t = torch.empty(s["shape"])
+                torch.nn.init.trunc_normal_(t, 0.0, std, -2 * std, 2 * std, generator=gen)
+                v.copy_(t)
+            elif s["kind"] == "gamma":
+                v.fill_(1.0)
+            elif s["kind"] in ("beta", "fc_b"):
+                v.zero_()
+            elif s["kind"] == "fc_w":
+                n = (s["shape"][0] + s["shape"][1]) / 2.0
+                lim = math.sqrt(3.0 / n)
+                v.copy_((torch.rand(s["shape"], generator=gen) * 2 - 1) * lim)
+        self.sync_half_copies()
+
+    def load_parameters(self, params):
+        """params: dict name -> tensor/ndarray with the reference's variable names (relative)."""
+        for name, val in params.items():
+            if name not in self.by_name:
+                raise KeyError("unknown parameter %r" % name)
+            self.param_view(name).copy_(torch.as_tensor(val, dtype=torch.float32))
+        self.sync_half_copies()
+
+    def sync_half_copies(self):
+        """fp32 master -> bf16 natural + transposed copies for every conv kernel."""
+        st = L.stream_ptr()
+        for s in self.specs:
+            if s["kind"] != "conv":
+                continue
+            K, R, C = self._kernel_geom(s)
+            L.check(self.lib.os2s_weight_cast_transpose(
+                _vp(self.master.data_ptr() + 4 * s["offset"]), _vp(self.wb.data_ptr() + 2 * s["half_offset"]),
+                _vp(self.wt.data_ptr() + 2 * s["half_offset"]), K, R, C, st), "weight_cast_transpose")
+
+    def _kernel_geom(self, s):
+        lyr = s["layer"]
+        if lyr is not None and s["name"] == lyr.name + "/kernel":
+            return lyr.kK, lyr.kC_in, lyr.c_out
+        return s["shape"]
+
+    # ----------------------------------------------------------------- optimizer
+    def set_optimizer(self, algo="novograd", beta1=0.95, beta2=0.98, epsilon=1e-8, weight_decay=0.0,
+                      momentum=0.9, grad_averaging=False, ema_persist=False, larc_eta=0.0, larc_eps=1e-7,
+                      larc_min_update=1e-7, larc_mode="clip", learning_rate=0.01, min_lr=0.0, power=1.0,
+                      decay_steps=0, begin_decay_at=0, warmup_steps=0, loss_scaling=True, scale_min=1.0,
+                      scale_max=2.0 ** 14, step_factor=2.0, step_window=2000, initial_scale=None):
+        hp = OptHParams()
+        hp.algo = 0 if algo == "novograd" else 1
+        hp.beta1, hp.beta2, hp.epsilon = beta1, beta2, epsilon
+        hp.weight_decay, hp.momentum = weight_decay, momentum
+        hp.grad_averaging, hp.ema_persist = int(grad_averaging), int(ema_persist)
+        hp.larc_eta, hp.larc_eps, hp.larc_min_update = larc_eta, larc_eps, larc_min_update
+        hp.larc_mode = 0 if larc_mode == "clip" else 1
+        hp.lr0, hp.min_lr, hp.power = learning_rate, min_lr, power
+        hp.decay_steps, hp.begin_decay_at, hp.warmup_steps = int(decay_steps), int(begin_decay_at), int(warmup_steps)
+        hp.use_loss_scaler = int(bool(loss_scaling))
+        hp.scale_min, hp.scale_max, hp.step_factor = scale_min, scale_max, step_factor
+        hp.step_window = int(step_window)
+        hp.world_size = self.world_size
+        self.hp = hp
+        dev = self.device
+        n = len(self.specs)
+        chunk = self.lib.os2s_opt_chunk_elems()
+        ptr = lambda buf, s, esz: buf.data_ptr() + esz * s["offset"]
+        w = [ptr(self.master, s, 4) for s in self.specs]
+        g = [ptr(self.grad, s, 4) for s in self.specs]
+        m = [ptr(self.mom, s, 4) for s in self.specs]
+        wb = [(self.wb.data_ptr() + 2 * s["half_offset"]) if s["kind"] == "conv" else 0 for s in self.specs]
+        sizes = [s["store_size"] for s in self.specs]
+        ct, co = [], []
+        for i, sz in enumerate(sizes):
+            for o in range(0, sz, chunk):
+                ct.append(i)
+                co.append(o)
+        i64 = lambda x: torch.tensor(x, dtype=torch.int64, device=dev)
+        self._opt = {
+            "w": i64(w), "g": i64(g), "m": i64(m), "wb": i64(wb), "sizes": i64(sizes),
+            "ct": torch.tensor(ct, dtype=torch.int32, device=dev), "co": i64(co),
+            "norms": torch.zeros(2 * n, dtype=torch.float32, device=dev),
+            "nonfinite": torch.zeros(1, dtype=torch.int32, device=dev),
+            "coef": torch.zeros(n, dtype=torch.float32, device=dev),
+            "ema": torch.zeros(n, dtype=torch.float32, device=dev),
+            "n": n, "n_chunks": len(ct),
+        }
+        scale0 = (initial_scale if initial_scale is not None else (scale_max if loss_scaling else 1.0))
+        self.fstate = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.fstate[0] = scale0
+        self.istate = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.istate[1] = -1
+        # transposed-copy table (conv kernels only)
+        conv = [s for s in self.specs if s["kind"] == "conv"]
+        src = [self.wb.data_ptr() + 2 * s["half_offset"] for s in conv]
+        dst = [self.wt.data_ptr() + 2 * s["half_offset"] for s in conv]
+        geo = [self._kernel_geom(s) for s in conv]
+        tiles = [0]
+        for (K, R, C) in geo:
+            tiles.append(tiles[-1] + K * ((R + 31) // 32) * ((C + 31) // 32))
+        self._tr = {"src": i64(src), "dst": i64(dst),
+                    "R": torch.tensor([x[1] for x in geo], dtype=torch.int32, device=dev),
+                    "C": torch.tensor([x[2] for x in geo], dtype=torch.int32, device=dev),
+                    "tiles": i64(tiles), "n": len(conv), "total": tiles[-1]}
+        self._ws = {}
+
+    # ----------------------------------------------------------------- workspace
+    def _workspace(self, B, T):
+        key = (B, T, torch.cuda.current_stream().cuda_stream, self.training)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = _Workspace(self, B, T)
+            self._ws[key] = ws
+        return ws
+
+    # ---------------------------------------------------------------- public API
+    def forward_encoder(self, feats, feat_lens):
+        """TDNNEncoder._encode: feats bf16 [B,T,F] (zero padded), lens int32 [B] -> (bf16 [B,T',H], lens)."""
+        B, T, F = feats.shape
+        if F != self.F or feats.dtype != torch.bfloat16 or not feats.is_contiguous():
+            raise ValueError("JasperEngine: features must be contiguous bf16 [B,T,%d]" % self.F)
+        ws = self._workspace(B, T)
+        ws.run_forward(feats, feat_lens)
+        return ws.A[-1], ws.lens_out
+
+    def forward_decoder(self):
+        """FullyConnectedTimeDecoder._decode on the last encoder output -> logits fp32 [B,T',V]."""
+        ws = self._last_ws
+        ws.run_decoder()
+        return ws.logits
+
+    def forward(self, feats, feat_lens):
+        """encoder + decoder: (logits fp32 [B,T',V] batch-major, out_lens int32 [B])."""
+        _, out_lens = self.forward_encoder(feats, feat_lens)
+        return self.forward_decoder(), out_lens
+
+    def set_training(self, flag):
+        """train mode: batch statistics + dropout; eval mode: moving statistics, no dropout
+        (tdnn_encoder.py:127-128, tf.layers.batch_normalization(training=...))."""
+        self.training = bool(flag)
+
+    def loss_only(self, labels, label_lens):
+        """Per-utterance CTC loss of the last forward (no backward pass) -- eval mode."""
+        ws = self._last_ws
+        return ws.run_loss_only(labels, label_lens)
+
+    def backward_from_dlogits(self, dlogits):
+        """Backward pass from a given gradient wrt the logits (fp32 [B,T',V]); used by tests and by
+        losses other than CTC.  Gradients land in self.grad (scaled by whatever scale dlogits carries)."""
+        ws = self._last_ws
+        ws.run_backward(None, None, dlogits=dlogits)
+
+    def loss_and_backward(self, labels, label_lens):
+        """labels int32 [B,Lmax]; returns per-utterance loss (device tensor) after enqueueing backward."""
+        ws = self._last_ws
+        ws.run_backward(labels, label_lens)
+        return ws.loss
+
+    def optimizer_step(self, allreduce=None):
+        """LARC + loss-scaler + NovoGrad on the (already summed over ranks) gradients."""
+        o = self._opt
+        st = L.stream_ptr()
+        L.check(self.lib.os2s_opt_step(
+            L.ptr(o["w"]), L.ptr(o["g"]), L.ptr(o["m"]), L.ptr(o["wb"]), L.ptr(o["sizes"]), L.ptr(o["ct"]),
+            L.ptr(o["co"]), o["n"], o["n_chunks"], ctypes.byref(self.hp), L.ptr(o["norms"]),
+            L.ptr(o["nonfinite"]), L.ptr(self.fstate), L.ptr(self.istate), L.ptr(o["coef"]), L.ptr(o["ema"]),
+            st), "os2s_opt_step")
+        t = self._tr
+        L.check(self.lib.os2s_multi_transpose(L.ptr(t["src"]), L.ptr(t["dst"]), L.ptr(t["R"]), L.ptr(t["C"]),
+                                              L.ptr(t["tiles"]), t["n"], _c_ll(t["total"]), st),
+                "os2s_multi_transpose")
+        self.step_count += 1
+
+    def train_step(self, feats, feat_lens, labels, label_lens, allreduce=None):
+        self.forward(feats, feat_lens)
+        loss = self.loss_and_backward(labels, label_lens)
+        if allreduce is not None:
+            allreduce(self.grad)
+        self.optimizer_step()
+        return loss
+
+    def greedy_decode(self):
+        """tf.nn.ctc_greedy_decoder on the last forward's logits -> (tokens [B,T'], lens [B])."""
+        ws = self._last_ws
+        st = L.stream_ptr()
+        L.check(self.lib.os2s_ctc_greedy(L.ptr(ws.logits), L.ptr(ws.lens_out), L.ptr(ws.tokens), L.ptr(ws.tok_lens),
+                                         L.ptr(ws.neg_sum), ws.B, ws.T2, self.V, _c_ll(ws.T2 * self.V),
+                                         _c_ll(self.V), 1, st), "os2s_ctc_greedy")
+        return ws.tokens, ws.tok_lens
+
+    def kernel_launches_per_step(self):
+        ws = self._last_ws
+        return ws.n_launch_fwd + ws.n_launch_bwd + 4
+
+
+class _Workspace(object):
+    """Per-(B,T) activations, gradients and the pre-bound launch plan."""
+
+    def __init__(self, eng, B, T):
+        self.eng = eng
+        self.B, self.T = B, T
+        lib = eng.lib
+        dev = eng.device
+        st = L.stream_ptr()
+        first = eng.layers[0]
+        if first.fold:
+            if T % 2 != 0:
+                raise ValueError("JasperEngine: input length must be even for the stride-2 layer (pad_to)")
+            T2 = T // 2
+        else:
+            T2 = T
+        self.T2 = T2
+        M = B * T2
+        self.M = M
+        bf = lambda *shape: torch.empty(*shape, dtype=torch.bfloat16, device=dev)
+        f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        layers = eng.layers
+        nl = len(layers)
+        f16 = lambda *shape: torch.empty(*shape, dtype=torch.float16, device=dev)
+        # conv outputs (BN inputs) are fp16: never a tensor-core operand, 3 more mantissa bits than bf16
+        self.Y = [f16(B, T2, l.c_out) for l in layers]
+        self.A = [bf(B, T2, l.c_out) for l in layers]
+        self.YR = [[f16(B, T2, l.c_out) for _ in l.res_sources] for l in layers]
+        cmax = max(l.c_out for l in layers)
+        self.dY = bf(B, T2, cmax)
+        self.dA = bf(B, T2, cmax)
+        nres_max = max([len(l.res_sources) for l in layers] + [0])
+        self.dYR = [bf(B, T2, cmax) for _ in range(nres_max)]
+        self.dres = [f32(B, T2, c) for (c, _) in eng.block_inputs]
+        self.red = f32((2 + nres_max) * cmax)
+        self.lens_in = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.lens_out = torch.zeros(B, dtype=torch.int32, device=dev)
+        # BN bookkeeping: stats arena (zeroed every step) and saved mean/invstd
+        n_bn = sum(1 + len(l.res_sources) for l in layers)
+        self.stats = torch.zeros(n_bn, 2, cmax, dtype=torch.float32, device=dev)
+        self.mean_invstd = torch.zeros(n_bn, 2, cmax, dtype=torch.float32, device=dev)
+        self.logits = f32(B, T2, eng.V)
+        self.dlogits = f32(B, T2, eng.V)
+        self.loss = f32(B)
+        self.tokens = torch.zeros(B, T2, dtype=torch.int32, device=dev)
+        self.tok_lens = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.neg_sum = f32(B)
+        self.feats = None
+        self._ctc_ws = None
+        self._ctc_L = -1
+        self._build_forward_plan(st)
+        self._bwd_plan = None
+        self._bwd_L = -1
+
+    # -- helpers
+    def _p(self, t, off_elems=0, esz=None):
+        esz = t.element_size() if esz is None else esz
+        return _vp(t.data_ptr() + off_elems * esz)
+
+    def _param_ptr(self, buf, name, esz=4):
+        s = self.eng.by_name[name]
+        return _vp(buf.data_ptr() + esz * s["offset"])
+
+    def _half_ptr(self, buf, name):
+        s = self.eng.by_name[name]
+        return _vp(buf.data_ptr() + 2 * s["half_offset"])
+
+    def _build_forward_plan(self, st):
+        eng, lib = self.eng, self.eng.lib
+        B, T2, M = self.B, self.T2, self.M
+        plan = []
+        self._seed_slots = []
+        bn_idx = 0
+        self.bn_slot = {}
+        src_act = {}  # block-input index -> activation tensor
+        self.x_of_layer = []
+        x = None  # set at run time for layer 0 (features view)
+        PP = ctypes.POINTER(_vp)
+        for li, l in enumerate(eng.layers):
+            if li == 0:
+                x_ptr = None  # patched per call (feature tensor)
+            else:
+                x_ptr = self._p(self.A[li - 1])
+            # residual sources: the (masked) input of the block's first layer
+            for idx, (c, first_layer) in enumerate(eng.block_inputs):
+                if first_layer == li:
+                    src_act[idx] = self.A[li - 1]
+            self.x_of_layer.append(self.A[li - 1] if li > 0 else None)
+            call = [lib.os2s_conv1d_fwd, [x_ptr, self._half_ptr(eng.wt, l.name + "/kernel"), self._p(self.Y[li]),
+                                          B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, 3, st]]
+            plan.append(call)
+            if li == 0:
+                self._x0_call = call
+            slot_main = bn_idx
+            bn_idx += 1
+            if eng.training:
+                plan.append([lib.os2s_bn_stats, [self._p(self.Y[li]), self._p(self.stats[slot_main]), M, l.c_out,
+                                                 st]])
+            ys = [self.Y[li]]
+            names = [l.name + "/bn"]
+            slots = [slot_main]
+            for n, j in enumerate(l.res_sources):
+                rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
+                bnn = (l.name + "/res_bn_%d" % n) if l.dense else (l.name + "/res_bn")
+                cj = eng.block_inputs[j][0]
+                plan.append([lib.os2s_conv1d_fwd, [self._p(src_act[j]), self._half_ptr(eng.wt, rn + "/kernel"),
+                                                   self._p(self.YR[li][n]), B, T2, cj, l.c_out, 1, 1, 0, 3, st]])
+                slot = bn_idx
+                bn_idx += 1
+                if eng.training:
+                    plan.append([lib.os2s_bn_stats, [self._p(self.YR[li][n]), self._p(self.stats[slot]), M, l.c_out,
+                                                     st]])
+                ys.append(self.YR[li][n])
+                names.append(bnn)
+                slots.append(slot)
+            nb = len(ys)
+            arr = lambda ptrs: (ctypes.c_void_p * nb)(*[p.value if isinstance(p, _vp) else p for p in ptrs])
+            y_h = arr([self._p(y) for y in ys])
+            st_h = arr([self._p(self.stats[s]) for s in slots])
+            g_h = arr([self._param_ptr(eng.master, nm + "/gamma") for nm in names])
+            b_h = arr([self._param_ptr(eng.master, nm + "/beta") for nm in names])
+            mi_h = arr([self._p(self.mean_invstd[s]) for s in slots])
+            mv_h = arr([self._p(eng.moving[nm]) for nm in names])
+            self.bn_slot[li] = (slots, names, (y_h, st_h, g_h, b_h, mi_h, mv_h))
+            last = li == len(eng.layers) - 1
+            lens_ptr = self._p(self.lens_out) if (eng.use_conv_mask and not last) else _vp(0)
+            args = [nb, y_h, st_h, g_h, b_h, mi_h, mv_h, self._p(self.A[li]), lens_ptr, B, T2, l.c_out,
+                    _c_float(eng.bn_eps), _c_float(eng.bn_momentum), _c_float(l.keep if eng.training else 1.0),
+                    _c_u64(0), 1, _c_float(eng.relu_clip), 0 if eng.training else 1, st]
+            plan.append([lib.os2s_bn_apply_fwd, args])
+            self._seed_slots.append((args, 15, li))
+        self._fc_call = [lib.os2s_fc_fwd, [self._p(self.A[-1]), self._param_ptr(eng.master, "fc/kernel"),
+                                           self._param_ptr(eng.master, "fc/bias"), self._p(self.logits), M, eng.H,
+                                           eng.V, st]]
+        self._fwd_plan = plan
+        self.n_launch_fwd = len(plan) + 2
+        self._st = st
+
+    def run_forward(self, feats, feat_lens):
+        eng = self.eng
+        self.feats = feats
+        self.lens_in.copy_(feat_lens.to(torch.int32), non_blocking=True)
+        first = eng.layers[0]
+        s = first.stride
+        torch.div(self.lens_in + (s - 1), s, rounding_mode="floor", out=self.lens_out)
+        self.stats.zero_()
+        self._x0_call[1][0] = _vp(feats.data_ptr())
+        base = (eng.seed * 1000003 + eng.step_count) * 4099
+        for args, k, li in self._seed_slots:
+            args[k] = _c_u64((base + li) & 0xFFFFFFFFFFFFFFFF)
+        lib_check = L.check
+        for fn, args in self._fwd_plan:
+            rc = fn(*args)
+            if rc != 0:
+                lib_check(rc, fn.__name__)
+        eng._last_ws = self
+
+    def run_decoder(self):
+        fn, args = self._fc_call
+        L.check(fn(*args), "os2s_fc_fwd")
+
+    def _build_backward_plan(self, L_max):
+        eng, lib = self.eng, self.eng.lib
+        B, T2, M, st = self.B, self.T2, self.M, self._st
+        dev = eng.device
+        need = lib.os2s_ctc_workspace_bytes(B, T2, L_max)
+        if self._ctc_ws is None or self._ctc_ws.numel() < need:
+            self._ctc_ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
+        self.labels = torch.zeros(B, L_max, dtype=torch.int32, device=dev)
+        self.label_lens = torch.zeros(B, dtype=torch.int32, device=dev)
+        plan = []
+        plan.append([lib.os2s_ctc_loss_fwd_bwd,
+                     [self._p(self.logits), self._p(self.labels), self._p(self.label_lens), self._p(self.lens_out),
+                      self._p(self.dlogits), self._p(self.loss), self._p(self._ctc_ws), _c_size_t(int(need)),
+                      self._p(eng.fstate), B, T2, eng.V, L_max, _c_ll(T2 * eng.V), _c_ll(eng.V), st]])
+        plan.append([lib.os2s_fc_bwd, [self._p(self.A[-1]), self._p(self.dlogits),
+                                       self._param_ptr(eng.master, "fc/kernel"), self._p(self.dA),
+                                       self._param_ptr(eng.grad, "fc/kernel"), self._param_ptr(eng.grad, "fc/bias"),
+                                       M, eng.H, eng.V, st]])
+        written = set()  # residual-source accumulators that already hold a first contribution
+        nl = len(eng.layers)
+        for li in range(nl - 1, -1, -1):
+            l = eng.layers[li]
+            slots, names, (y_h, st_h, g_h, b_h, mi_h, mv_h) = self.bn_slot[li]
+            nb = len(slots)
+            arr = lambda ptrs: (ctypes.c_void_p * nb)(*[p.value for p in ptrs])
+            dg_h = arr([self._param_ptr(eng.grad, nm + "/gamma") for nm in names])
+            db_h = arr([self._param_ptr(eng.grad, nm + "/beta") for nm in names])
+            dys = [self.dY] + [self.dYR[n] for n in range(nb - 1)]
+            dy_h = arr([self._p(t) for t in dys])
+            if li in eng.src_of_layer_output:
+                j = eng.src_of_layer_output[li]
+                dA_ptr, dA_f32 = self._p(self.dres[j]), 1
+                if j not in written:
+                    raise RuntimeError("internal: residual source %d has no gradient writer" % j)
+            else:
+                dA_ptr, dA_f32 = self._p(self.dA), 0
+            plan.append([lib.os2s_bn_bwd, [nb, y_h, mi_h, g_h, dg_h, db_h, dy_h, dA_ptr, dA_f32, self._p(self.A[li]),
+                                           self._p(self.red), M, l.c_out, _c_float(l.keep), 1, st]])
+            self._keep = getattr(self, "_keep", []) + [dg_h, db_h, dy_h]
+            # main conv wgrad (stored layout == kernel layout, also for the folded stride-2 layer)
+            x_ptr = self._p(self.A[li - 1]) if li > 0 else None
+            wg = [lib.os2s_conv1d_wgrad, [x_ptr, self._p(self.dY), self._param_ptr(eng.grad, l.name + "/kernel"),
+                                          B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, st]]
+            plan.append(wg)
+            if li == 0:
+                self._x0_wgrad = wg
+            # residual branches: wgrad + dgrad into the fp32 accumulators
+            for n, j in enumerate(l.res_sources):
+                rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
+                cj = eng.block_inputs[j][0]
+                src = self.A[eng.block_inputs[j][1] - 1]
+                plan.append([lib.os2s_conv1d_wgrad, [self._p(src), self._p(self.dYR[n]),
+                                                     self._param_ptr(eng.grad, rn + "/kernel"), B, T2, cj, l.c_out,
+                                                     1, 1, 0, st]])
+                mode = 2 if j in written else 1
+                written.add(j)
+                plan.append([lib.os2s_conv1d_dgrad, [self._p(self.dYR[n]), self._half_ptr(eng.wb, rn + "/kernel"),
+                                                     self._p(self.dres[j]), B, T2, cj, l.c_out, 1, 1, 0, mode, st]])
+            if li > 0:
+                if (li - 1) in eng.src_of_layer_output:
+                    j = eng.src_of_layer_output[li - 1]
+                    mode = 2 if j in written else 1
+                    written.add(j)
+                    out_ptr = self._p(self.dres[j])
+                else:
+                    mode, out_ptr = 0, self._p(self.dA)
+                plan.append([lib.os2s_conv1d_dgrad, [self._p(self.dY), self._half_ptr(eng.wb, l.name + "/kernel"),
+                                                     out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
+                                                     st]])
+        self._bwd_plan = plan
+        self._bwd_L = L_max
+        self.n_launch_bwd = len(plan) + 4
+        # zero-gradient slices for structurally-zero taps of folded layers
+        self._zero_slices = []
+        for l in eng.layers:
+            if l.fold:
+                s = eng.by_name[l.name + "/kernel"]
+                st0, n = eng._valid_slice(s)
+                if st0 > 0:
+                    self._zero_slices.append(eng.grad[s["offset"]:s["offset"] + st0])
+                if st0 + n < s["store_size"]:
+                    self._zero_slices.append(eng.grad[s["offset"] + st0 + n:s["offset"] + s["store_size"]])
+
+    def run_loss_only(self, labels, label_lens):
+        L_max = int(labels.shape[1])
+        if self._bwd_plan is None or self._bwd_L != L_max:
+            self._build_backward_plan(L_max)
+        self.labels.copy_(labels.to(torch.int32), non_blocking=True)
+        self.label_lens.copy_(label_lens.to(torch.int32), non_blocking=True)
+        fn, args = self._bwd_plan[0]
+        L.check(fn(*args), "os2s_ctc_loss_fwd_bwd")
+        return self.loss
+
+    def run_backward(self, labels, label_lens, dlogits=None):
+        if dlogits is None:
+            L_max = int(labels.shape[1])
+        else:
+            L_max = self._bwd_L if self._bwd_plan is not None else 1
+        if self._bwd_plan is None or self._bwd_L != L_max:
+            self._build_backward_plan(L_max)
+        plan = self._bwd_plan
+        if dlogits is None:
+            self.labels.copy_(labels.to(torch.int32), non_blocking=True)
+            self.label_lens.copy_(label_lens.to(torch.int32), non_blocking=True)
+        else:
+            self.dlogits.copy_(dlogits)
+            plan = plan[1:]  # skip the CTC launch
+        self._x0_wgrad[1][0] = _vp(self.feats.data_ptr())
+        lib_check = L.check
+        for fn, args in plan:
+            rc = fn(*args)
+            if rc != 0:
+                lib_check(rc, fn.__name__)
+        for z in self._zero_slices:
+            z.zero_()

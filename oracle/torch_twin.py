@@ -39,9 +39,20 @@ def sequence_mask(lengths, maxlen, dtype):
     return (torch.arange(maxlen)[None, :] < lengths[:, None]).to(dtype)[:, :, None]
 
 
+def round_like_device(kind):
+    """Storage-rounding emulation for the 'what if the reference stored activations like the B200
+    path does' comparison: conv outputs fp16, layer outputs bf16 (straight-through gradient)."""
+    dt = torch.float16 if kind == "conv" else torch.bfloat16
+    return lambda t: t.to(dt).to(t.dtype)
+
+
 def tdnn_encode(x, src_len, layers, params, training=True, bn_eps=1e-3, use_conv_mask=True,
-                dropout_masks=None, collect=None, stats=None):
-    """Same contract as oracle.encoder.tdnn_encode, on torch tensors (autograd-capable)."""
+                dropout_masks=None, collect=None, stats=None, emulate_storage=False):
+    """Same contract as oracle.encoder.tdnn_encode, on torch tensors (autograd-capable).
+    emulate_storage=True rounds conv outputs to fp16 and layer outputs to bf16 where the device
+    path stores them (arithmetic stays in the tensor's dtype)."""
+    rc_ = round_like_device("conv") if emulate_storage else (lambda t: t)
+    ra_ = round_like_device("act") if emulate_storage else (lambda t: t)
     src_len = src_len.clone()
     max_len = x.shape[1]
     mask = sequence_mask(src_len, max_len, x.dtype) if use_conv_mask else None
@@ -71,7 +82,7 @@ def tdnn_encode(x, src_len, layers, params, training=True, bn_eps=1e-3, use_conv
                 feats = feats * mask
             if use_conv_mask and stride > 1:
                 mask = sequence_mask(src_len, max_len, x.dtype)
-            conv = conv1d_same(feats, params[name + "/kernel"], stride, dil)
+            conv = rc_(conv1d_same(feats, params[name + "/kernel"], stride, dil))
             if collect is not None:
                 collect[name + "/conv"] = conv
             bn, mean, var = batch_norm_train(conv, params[name + "/bn/gamma"], params[name + "/bn/beta"], bn_eps)
@@ -81,7 +92,7 @@ def tdnn_encode(x, src_len, layers, params, training=True, bn_eps=1e-3, use_conv
                 for j, res in enumerate(layer_res):
                     rname = (name + "/res_%d" % j) if dense else (name + "/res")
                     bname = (name + "/res_bn_%d" % j) if dense else (name + "/res_bn")
-                    rc = conv1d_same(res, params[rname + "/kernel"], 1, 1)
+                    rc = rc_(conv1d_same(res, params[rname + "/kernel"], 1, 1))
                     rb, mean, var = batch_norm_train(rc, params[bname + "/gamma"], params[bname + "/beta"], bn_eps)
                     if stats is not None:
                         stats[bname] = (mean.detach(), var.detach(), rc.shape[0] * rc.shape[1])
@@ -90,7 +101,11 @@ def tdnn_encode(x, src_len, layers, params, training=True, bn_eps=1e-3, use_conv
             if training and dropout_masks is not None and name in dropout_masks:
                 m, keep = dropout_masks[name]
                 out = out * m / keep
-            feats = out
+            if use_conv_mask and not (bi == len(layers) - 1 and ri == layer["repeat"] - 1):
+                # the mask the NEXT layer applies to its input (tdnn_encoder.py:185-186,204-205); applying
+                # it here is the same function and makes `feats` the tensor the device path stores
+                out = out * mask
+            feats = ra_(out)
             if collect is not None:
                 collect[name + "/out"] = feats
     return feats, src_len
@@ -164,9 +179,9 @@ def init_params(layers, num_features, vocab, seed=0):
 
 
 def forward_loss(params, layers, feats, feat_len, labels, label_lens, training=True, dropout_masks=None,
-                 collect=None):
+                 collect=None, emulate_storage=False):
     enc, out_len = tdnn_encode(feats, feat_len, layers, params, training=training,
-                               dropout_masks=dropout_masks, collect=collect)
+                               dropout_masks=dropout_masks, collect=collect, emulate_storage=emulate_storage)
     logits = fc_decode(enc, params["fc/kernel"], params["fc/bias"])
     loss = ctc_loss_mean(logits, labels, label_lens, out_len)
     return loss, logits, out_len

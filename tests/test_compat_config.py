@@ -1,0 +1,138 @@
+"""CPU tests of the drop-in boundary at the Python level: reference-style configs load through the
+`open_seq2seq` / `tensorflow` compat surface, params dicts are validated with the reference's rules,
+and the plugin classes can be constructed (no GPU work happens before compile())."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+import openseq2seq_b200.compat as compat  # noqa: E402
+
+compat.install()
+
+from open_seq2seq.utils.utils import (check_params, flatten_dict, get_base_config, nest_dict,  # noqa: E402
+                                      nested_update)
+
+REF_CFG = "/root/reference/example_configs/speech2text/jasper10x5_LibriSpeech_nvgrad.py"
+OWN_CFG = os.path.join(ROOT, "configs", "jasper10x5_dr.py")
+
+
+def test_own_jasper_config_loads_with_cli_overrides():
+    args, cfg, model_cls, module = get_base_config([
+        "--config_file=" + OWN_CFG, "--mode=train", "--batch_size_per_gpu=4",
+        "--lr_policy_params/learning_rate=0.5", "--data_layer_params/dither=0.0", "--use_horovod=False"])
+    assert model_cls.__name__ == "Speech2Text"
+    assert cfg["batch_size_per_gpu"] == 4 and cfg["lr_policy_params"]["learning_rate"] == 0.5
+    assert cfg["data_layer_params"]["dither"] == 0.0 and cfg["use_horovod"] is False
+    layers = cfg["encoder_params"]["convnet_layers"]
+    assert len(layers) == 13 and sum(l["repeat"] for l in layers) == 53
+    assert args.mode == "train"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference checkout not present (GPU box)")
+def test_reference_jasper_config_loads_unchanged_and_matches_own_config():
+    cwd = os.getcwd()
+    os.chdir("/root/reference")  # the reference config uses a path relative to its repo root
+    try:
+        _, ref, ref_model, ref_mod = get_base_config(["--config_file=" + REF_CFG, "--mode=train"])
+    finally:
+        os.chdir(cwd)
+    _, own, own_model, own_mod = get_base_config(["--config_file=" + OWN_CFG, "--mode=train"])
+    assert ref_model.__name__ == own_model.__name__ == "Speech2Text"
+    assert ref["encoder_params"]["convnet_layers"] == own["encoder_params"]["convnet_layers"]
+    for key in ("optimizer_params", "lr_policy_params", "larc_params", "dtype", "loss_scaling",
+                "batch_size_per_gpu", "num_epochs", "iter_size"):
+        assert ref[key] == own[key], key
+    assert ref["optimizer"].__name__ == own["optimizer"].__name__ == "NovoGrad"
+    skip = {"vocab_file"}
+    for k, v in ref["data_layer_params"].items():
+        if k not in skip:
+            assert own["data_layer_params"][k] == v, k
+    for k in ("dropout_keep_prob", "normalization", "data_format", "use_conv_mask", "initializer_params"):
+        assert ref["encoder_params"][k] == own["encoder_params"][k]
+    assert ref_mod["train_params"]["data_layer_params"]["max_duration"] == 16.7
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("name", ["jasper10x5_LibriSpeech_nvgrad.py", "jasper10x5_LibriSpeech_nvgrad_masks.py",
+                                  "w2lplus_large_8gpus_mp.py", "jasper-Mini-for-Jetson.py"])
+def test_other_reference_speech_configs_import_through_the_shim(name):
+    path = os.path.join("/root/reference/example_configs/speech2text", name)
+    if not os.path.exists(path):
+        pytest.skip("config not in this checkout")
+    _, cfg, model, _ = get_base_config(["--config_file=" + path, "--mode=train"])
+    assert model.__name__ == "Speech2Text" and "convnet_layers" in cfg["encoder_params"]
+
+
+def test_check_params_rules_and_errors():
+    check_params({"a": 1, "b": "x"}, {"a": int}, {"b": str})
+    with pytest.raises(ValueError, match="has to be specified"):
+        check_params({}, {"a": int}, {})
+    with pytest.raises(ValueError, match="has to be of type"):
+        check_params({"a": "1"}, {"a": int}, {})
+    with pytest.raises(ValueError, match="has to be one of"):
+        check_params({"a": 3}, {"a": [1, 2]}, {})
+    with pytest.raises(ValueError, match="Unknown parameter"):
+        check_params({"a": 1, "zz": 2}, {"a": int}, {})
+    check_params({"a": object()}, {"a": None}, {})  # None = any value
+
+
+def test_flatten_nest_update_roundtrip():
+    d = {"x": 1, "y": {"z": 2.5, "w": {"q": "s"}}, "skip": [1, 2]}
+    flat = flatten_dict(d)
+    assert flat == {"x": 1, "y/z": 2.5, "y/w/q": "s"}
+    assert nest_dict(flat) == {"x": 1, "y": {"z": 2.5, "w": {"q": "s"}}}
+    nested_update(d, {"y": {"z": 3.0}, "new": {"k": 1}})
+    assert d["y"]["z"] == 3.0 and d["y"]["w"]["q"] == "s" and d["new"] == {"k": 1}
+    with pytest.raises(ValueError):
+        nested_update({"a": 1}, {"a": {"b": 2}})
+
+
+def test_model_and_plugins_construct_without_gpu_and_validate_params():
+    import copy
+    _, cfg, model_cls, module = get_base_config(["--config_file=" + OWN_CFG, "--mode=train",
+                                                 "--use_horovod=False"])
+    cfg = copy.deepcopy(cfg)
+    nested_update(cfg, copy.deepcopy(module["train_params"]))
+    model = model_cls(params=cfg, mode="train", hvd=None)
+    assert model.get_data_layer().params["tgt_vocab_size"] == 29
+    assert model.decoder.params["tgt_vocab_size"] == 29
+    assert model.last_step == 400 * (64 // 32)
+    assert type(model.encoder).__name__ == "TDNNEncoder" and model.encoder.name == "w2l_encoder"
+    kw = model.encoder.engine_kwargs()
+    assert kw["use_conv_mask"] and kw["bn_momentum"] == 0.90 and kw["relu_clip"] == 0.0
+    bad = copy.deepcopy(cfg)
+    bad["encoder_params"]["no_such_param"] = 1
+    with pytest.raises(ValueError, match="Unknown parameter"):
+        model_cls(params=bad, mode="train", hvd=None)
+    bad = copy.deepcopy(cfg)
+    del bad["batch_size_per_gpu"]
+    with pytest.raises(ValueError, match="has to be specified"):
+        model_cls(params=bad, mode="train", hvd=None)
+
+
+def test_activation_tracing_of_config_lambdas():
+    import tensorflow as tf
+    assert tf.resolve_activation(tf.nn.relu) == (1, 0.0)
+    assert tf.resolve_activation(lambda x: tf.minimum(tf.nn.relu(x), 20.0)) == (1, 20.0)
+    assert tf.resolve_activation(None) == (0, 0.0)
+
+
+def test_optimizer_kwargs_from_jasper_params():
+    from open_seq2seq.optimizers.optimizers import optimizer_engine_kwargs
+    _, cfg, _, _ = get_base_config(["--config_file=" + OWN_CFG, "--mode=train"])
+    kw = optimizer_engine_kwargs(cfg, last_step=1000)
+    assert kw["algo"] == "novograd" and kw["beta1"] == 0.95 and kw["weight_decay"] == 0.001
+    assert kw["larc_eta"] == 0.001 and kw["larc_mode"] == "clip"
+    assert kw["decay_steps"] == 1000 and kw["power"] == 2.0 and kw["min_lr"] == 1e-5
+    assert kw["loss_scaling"] is True
+
+
+def test_levenshtein_and_wer_known_answers():
+    # known answers of the reference's own test (models/speech2text_test.py:229-256)
+    from open_seq2seq.models.speech2text import levenshtein
+    assert levenshtein("kitten", "sitting") == 3
+    assert levenshtein("", "abc") == 3 and levenshtein("abc", "abc") == 0
+    assert levenshtein("this is a test".split(), "this is test".split()) == 1
+    assert levenshtein("hello world".split(), "world hello".split()) == 2

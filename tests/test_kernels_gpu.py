@@ -1,0 +1,356 @@
+"""Per-kernel GPU parity tests: every C-ABI entry point against the CPU oracle on the same seeded
+inputs (sizes the oracle finishes in seconds) and against the committed golden fixtures."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+_vp = ctypes.c_void_p
+_f = ctypes.c_float
+_ll = ctypes.c_longlong
+
+
+def _lib():
+    from openseq2seq_b200 import _lib as L
+    return L, L.load()
+
+
+def _bf(x):
+    return torch.as_tensor(x, dtype=torch.float32).bfloat16()
+
+
+@pytest.mark.parametrize("B,T,Cin,Cout,K,dil", [
+    (2, 70, 128, 64, 5, 1),      # ragged T (not a multiple of the 128-row tile)
+    (1, 300, 256, 384, 13, 1),
+    (2, 131, 128, 256, 9, 2),    # dilation
+    (3, 64, 256, 128, 1, 1),     # 1x1 residual conv
+])
+def test_conv_fwd_dgrad_wgrad_vs_oracle(B, T, Cin, Cout, K, dil):
+    from oracle import encoder as E
+    L, lib = _lib()
+    rng = np.random.default_rng(0)
+    x = _bf(rng.standard_normal((B, T, Cin)))
+    w = _bf(rng.standard_normal((K, Cin, Cout)) / np.sqrt(K * Cin))
+    dy = _bf(rng.standard_normal((B, T, Cout)))
+    pl = ((K - 1) * dil) // 2
+    y_ref = E.conv1d_same(x.float().numpy(), w.float().numpy(), 1, dil)
+    # oracle gradients by the adjoint identities of the same restated conv
+    wf = w.float().numpy().astype(np.float64)
+    dx_ref = E.conv1d_same(dy.float().numpy(), np.ascontiguousarray(wf[::-1].transpose(0, 2, 1)), 1, dil)
+    xp = np.zeros((B, T + 2 * pl, Cin))
+    xp[:, pl:pl + T] = x.float().numpy()
+    dw_ref = np.stack([np.einsum("btc,bto->co", xp[:, k * dil:k * dil + T], dy.float().numpy().astype(np.float64))
+                       for k in range(K)])
+    xd, wd, dyd = x.cuda(), w.cuda(), dy.cuda()
+    wt = wd.permute(0, 2, 1).contiguous()
+    st = L.stream_ptr()
+    y = torch.empty(B, T, Cout, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.os2s_conv1d_fwd(L.ptr(xd), L.ptr(wt), L.ptr(y), B, T, Cin, Cout, K, dil, pl, 0, st), "fwd")
+    y16 = torch.empty(B, T, Cout, dtype=torch.float16, device="cuda")
+    L.check(lib.os2s_conv1d_fwd(L.ptr(xd), L.ptr(wt), L.ptr(y16), B, T, Cin, Cout, K, dil, pl, 3, st), "fwd16")
+    dx = torch.empty(B, T, Cin, dtype=torch.float32, device="cuda")
+    L.check(lib.os2s_conv1d_dgrad(L.ptr(dyd), L.ptr(wd), L.ptr(dx), B, T, Cin, Cout, K, dil, pl, 1, st), "dgrad")
+    if Cin % 128 == 0:
+        dw = torch.empty(K, Cin, Cout, dtype=torch.float32, device="cuda")
+        L.check(lib.os2s_conv1d_wgrad(L.ptr(xd), L.ptr(dyd), L.ptr(dw), B, T, Cin, Cout, K, dil, pl, st), "wgrad")
+    torch.cuda.synchronize()
+    assert np.abs(y.float().cpu().numpy() - y_ref).max() <= 1e-2 * np.abs(y_ref).max()
+    assert np.abs(y16.float().cpu().numpy() - y_ref).max() <= 1.5e-3 * np.abs(y_ref).max()
+    assert np.abs(dx.cpu().numpy() - dx_ref).max() <= 1e-4 * np.abs(dx_ref).max() + 1e-4
+    if Cin % 128 == 0:
+        assert np.abs(dw.cpu().numpy() - dw_ref).max() <= 1e-4 * np.abs(dw_ref).max() + 1e-4
+
+
+def test_conv_rejects_unsupported_shapes_loudly():
+    L, lib = _lib()
+    x = torch.zeros(1, 16, 48, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(1, 64, 48, dtype=torch.bfloat16, device="cuda")
+    y = torch.zeros(1, 16, 64, dtype=torch.bfloat16, device="cuda")
+    rc = lib.os2s_conv1d_fwd(L.ptr(x), L.ptr(w), L.ptr(y), 1, 16, 48, 64, 1, 1, 0, 0, L.stream_ptr())
+    assert rc == -3 and b"multiple of 64" in lib.os2s_last_error()
+    assert lib.os2s_conv1d_fwd(None, None, None, 1, 16, 64, 64, 1, 1, 0, 0, L.stream_ptr()) == -1
+
+
+def test_batchnorm_residual_relu_dropout_mask_fwd_bwd_vs_oracle():
+    from oracle import torch_twin as TT
+    L, lib = _lib()
+    B, T, C, nb = 3, 50, 128, 3
+    g = torch.Generator().manual_seed(0)
+    ys = [(torch.randn(B, T, C, generator=g) * (1 + j) + 0.3 * j).half() for j in range(nb)]
+    gam = [1 + 0.3 * torch.randn(C, generator=g) for _ in range(nb)]
+    bet = [0.2 * torch.randn(C, generator=g) for _ in range(nb)]
+    lens = torch.tensor([50, 31, 7], dtype=torch.int32)
+    dA = torch.randn(B, T, C, generator=g)
+    # oracle (fp64 autograd over the restated BN)
+    yd = [y.double().requires_grad_(True) for y in ys]
+    gd = [x.double().requires_grad_(True) for x in gam]
+    bd = [x.double().requires_grad_(True) for x in bet]
+    tot = 0
+    for j in range(nb):
+        tot = tot + TT.batch_norm_train(yd[j], gd[j], bd[j], 1e-3)[0]
+    out_ref = torch.relu(tot) * TT.sequence_mask(lens.long(), T, torch.float64)
+    out_ref.backward(dA.double())
+    # device
+    st = L.stream_ptr()
+    dev = "cuda"
+    yc = [y.to(dev) for y in ys]
+    stats = torch.zeros(nb, 2, C, device=dev)
+    for j in range(nb):
+        L.check(lib.os2s_bn_stats(L.ptr(yc[j]), L.ptr(stats[j]), B * T, C, st), "stats")
+    arr = lambda ts: (_vp * nb)(*[t.data_ptr() for t in ts])
+    gc = [x.to(dev) for x in gam]
+    bc = [x.to(dev) for x in bet]
+    mi = torch.zeros(nb, 2, C, device=dev)
+    mv = torch.zeros(nb, 2, C, device=dev)
+    mv[:, 1] = 1
+    out = torch.empty(B, T, C, dtype=torch.bfloat16, device=dev)
+    lens_c = lens.to(dev)
+    L.check(lib.os2s_bn_apply_fwd(nb, arr(yc), arr(list(stats)), arr(gc), arr(bc), arr(list(mi)), arr(list(mv)),
+                                  L.ptr(out), L.ptr(lens_c), B, T, C, _f(1e-3), _f(0.9), _f(1.0),
+                                  ctypes.c_uint64(1), 1, _f(0.0), 0, st), "apply")
+    dgam = [torch.zeros(C, device=dev) for _ in range(nb)]
+    dbet = [torch.zeros(C, device=dev) for _ in range(nb)]
+    dy = [torch.empty(B, T, C, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+    red = torch.zeros((1 + nb) * C, device=dev)
+    dAc = dA.to(dev)
+    L.check(lib.os2s_bn_bwd(nb, arr(yc), arr(list(mi)), arr(gc), arr(dgam), arr(dbet), arr(dy), L.ptr(dAc), 1,
+                            L.ptr(out), L.ptr(red), B * T, C, _f(1.0), 1, st), "bwd")
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.double().cpu() - b).abs().max() / b.abs().max())
+    assert rel(out, out_ref.detach()) < 1e-2
+    for j in range(nb):
+        assert rel(dy[j], yd[j].grad) < 2e-2
+        assert rel(dgam[j], gd[j].grad) < 2e-2
+        assert rel(dbet[j], bd[j].grad) < 2e-2
+    # moving statistics (momentum 0.9, Bessel-corrected variance)
+    n = B * T
+    m0 = ys[0].double().mean((0, 1))
+    v0 = ys[0].double().var((0, 1), unbiased=True)
+    assert rel(mv[0, 0], 0.1 * m0) < 1e-3 and rel(mv[0, 1], 0.9 + 0.1 * v0) < 1e-3
+
+
+def test_dropout_statistics_and_backward_mask():
+    L, lib = _lib()
+    B, T, C = 4, 64, 256
+    y = torch.randn(B, T, C, device="cuda").half()
+    stats = torch.zeros(2, C, device="cuda")
+    st = L.stream_ptr()
+    L.check(lib.os2s_bn_stats(L.ptr(y), L.ptr(stats), B * T, C, st), "stats")
+    one = lambda t: (_vp * 1)(t.data_ptr())
+    gam = torch.ones(C, device="cuda")
+    bet = torch.full((C,), 3.0, device="cuda")  # keep everything positive: zeros == dropped
+    mi = torch.zeros(2, C, device="cuda")
+    outs = []
+    for seed in (7, 7, 8):
+        out = torch.empty(B, T, C, dtype=torch.bfloat16, device="cuda")
+        L.check(lib.os2s_bn_apply_fwd(1, one(y), one(stats), one(gam), one(bet), one(mi), None, L.ptr(out), None,
+                                      B, T, C, _f(1e-3), _f(0.9), _f(0.7), ctypes.c_uint64(seed), 1, _f(0.0), 0, st),
+                "apply")
+        outs.append(out.float())
+    torch.cuda.synchronize()
+    kept = (outs[0] != 0).float().mean().item()
+    assert abs(kept - 0.7) < 0.01
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+    nodrop = torch.empty(B, T, C, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.os2s_bn_apply_fwd(1, one(y), one(stats), one(gam), one(bet), one(mi), None, L.ptr(nodrop), None,
+                                  B, T, C, _f(1e-3), _f(0.9), _f(1.0), ctypes.c_uint64(0), 1, _f(0.0), 0, st), "apply")
+    torch.cuda.synchronize()
+    m = outs[0] != 0
+    assert torch.allclose(outs[0][m], nodrop.float()[m] / 0.7, rtol=2e-2)
+
+
+def test_fc_fwd_bwd_vs_oracle():
+    from oracle import encoder as E
+    L, lib = _lib()
+    M, H, V = 77, 256, 29
+    rng = np.random.default_rng(1)
+    x = _bf(rng.standard_normal((M, H)))
+    w = torch.tensor(rng.standard_normal((H, V)) / 16, dtype=torch.float32)
+    b = torch.tensor(rng.standard_normal(V), dtype=torch.float32)
+    dl = torch.tensor(rng.standard_normal((M, V)), dtype=torch.float32)
+    ref = E.fc_decode(x.float().numpy()[None], w.numpy(), b.numpy())[:, 0]
+    st = L.stream_ptr()
+    xc, wc, bc, dlc = x.cuda(), w.cuda(), b.cuda(), dl.cuda()
+    logits = torch.empty(M, V, device="cuda")
+    L.check(lib.os2s_fc_fwd(L.ptr(xc), L.ptr(wc), L.ptr(bc), L.ptr(logits), M, H, V, st), "fc_fwd")
+    dx = torch.empty(M, H, dtype=torch.bfloat16, device="cuda")
+    dw = torch.empty(H, V, device="cuda")
+    db = torch.empty(V, device="cuda")
+    L.check(lib.os2s_fc_bwd(L.ptr(xc), L.ptr(dlc), L.ptr(wc), L.ptr(dx), L.ptr(dw), L.ptr(db), M, H, V, st), "fc_bwd")
+    torch.cuda.synchronize()
+    assert np.abs(logits.cpu().numpy() - ref).max() < 1e-4
+    xd = x.double().numpy()
+    assert np.abs(dx.float().cpu().numpy() - dl.double().numpy() @ w.double().numpy().T).max() < 2e-2
+    assert np.abs(dw.cpu().numpy() - xd.T @ dl.double().numpy()).max() < 1e-3
+    assert np.abs(db.cpu().numpy() - dl.double().numpy().sum(0)).max() < 1e-4
+
+
+def _run_ctc(logits_tbv, labels, label_lens, in_lens, scale=None):
+    """logits_tbv: numpy [T,B,V]; device call uses a batch-major copy with explicit strides."""
+    L, lib = _lib()
+    T, B, V = logits_tbv.shape
+    lg = torch.tensor(np.ascontiguousarray(logits_tbv.transpose(1, 0, 2)), dtype=torch.float32, device="cuda")
+    Lmax = labels.shape[1]
+    lab = torch.tensor(labels, dtype=torch.int32, device="cuda")
+    ll = torch.tensor(label_lens, dtype=torch.int32, device="cuda")
+    il = torch.tensor(in_lens, dtype=torch.int32, device="cuda")
+    grad = torch.empty(B, T, V, device="cuda")
+    loss = torch.empty(B, device="cuda")
+    need = lib.os2s_ctc_workspace_bytes(B, T, Lmax)
+    ws = torch.empty(int(need), dtype=torch.uint8, device="cuda")
+    sc = torch.tensor([scale], dtype=torch.float32, device="cuda") if scale else None
+    L.check(lib.os2s_ctc_loss_fwd_bwd(L.ptr(lg), L.ptr(lab), L.ptr(ll), L.ptr(il), L.ptr(grad), L.ptr(loss),
+                                      L.ptr(ws), ctypes.c_size_t(int(need)), L.ptr(sc), B, T, V, Lmax,
+                                      _ll(T * V), _ll(V), L.stream_ptr()), "ctc")
+    torch.cuda.synchronize()
+    return loss.cpu().numpy(), grad.cpu().numpy().transpose(1, 0, 2), lg
+
+
+def test_ctc_loss_and_greedy_on_reference_golden_vector(golden_dir):
+    """The reference's own known answers: ctc_decoder_with_lm/ctc-test.py:64-67,73."""
+    L, lib = _lib()
+    g = np.load(os.path.join(golden_dir, "ctc_test_logits.npz"))
+    lg = g["logits"]  # [184,1,29]
+    vocab = list(g["vocab"])
+    lab = np.array([[vocab.index(c) for c in "then seconds"]])
+    loss, grad, lgd = _run_ctc(lg, lab, [lab.shape[1]], [lg.shape[0]])
+    assert abs(loss[0] - (-float(g["ctc_log_prob_then_seconds"]))) < 1e-3
+    T, B, V = lg.shape
+    il = torch.tensor([T], dtype=torch.int32, device="cuda")
+    toks = torch.zeros(B, T, dtype=torch.int32, device="cuda")
+    tl = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ns = torch.zeros(B, device="cuda")
+    L.check(lib.os2s_ctc_greedy(L.ptr(lgd), L.ptr(il), L.ptr(toks), L.ptr(tl), L.ptr(ns), B, T, V, _ll(T * V), _ll(V),
+                                1, L.stream_ptr()), "greedy")
+    torch.cuda.synchronize()
+    text = "".join(vocab[c] for c in toks[0, :int(tl[0])].cpu().tolist())
+    assert text == str(g["greedy_text"]) == "then seconds"
+    assert abs(float(ns[0]) + float(g["greedy_neg_sum_logits"])) < 1e-2 or \
+        abs(float(ns[0]) - float(g["greedy_neg_sum_logits"])) < 1e-2
+
+
+def test_ctc_loss_grad_vs_oracle_random_ragged_with_repeats_and_infeasible():
+    from oracle import ctc as OC
+    rng = np.random.default_rng(3)
+    T, B, V, Lmax = 60, 5, 29, 20
+    lg = rng.standard_normal((T, B, V)).astype(np.float32) * 2
+    labels = rng.integers(0, V - 1, size=(B, Lmax))
+    labels[1, :6] = [3, 3, 3, 5, 5, 7]        # repeats
+    label_lens = [20, 6, 1, 0, 20]
+    in_lens = [60, 41, 5, 17, 21]             # last: 20 labels + repeats > 21 frames? made infeasible below
+    labels[4, :20] = 4                        # 19 repeats -> needs 39 frames > 21 -> skipped
+    ref_loss, ref_grad = OC.ctc_loss_and_grad(lg, labels, label_lens, in_lens)
+    ref_mean, ref_gmean = OC.ctc_loss_mean(lg, labels, label_lens, in_lens)
+    loss, grad, _ = _run_ctc(lg, labels, label_lens, in_lens, scale=8.0)
+    assert ref_loss[4] == 0 and loss[4] == 0
+    assert np.abs(loss - ref_loss).max() < 1e-3 * max(1.0, np.abs(ref_loss).max())
+    assert np.abs(grad / 8.0 - ref_gmean).max() < 1e-4
+    assert np.all(grad[41:, 1] == 0) and np.all(grad[:, 4] == 0)
+
+
+def test_ctc_greedy_vs_oracle_ragged():
+    from oracle import ctc as OC
+    L, lib = _lib()
+    rng = np.random.default_rng(4)
+    T, B, V = 75, 4, 29
+    lg = rng.standard_normal((T, B, V)).astype(np.float32)
+    lg[:, :, V - 1] += 1.0  # more blanks
+    lg[10:14, 0, :] = lg[9, 0, :]  # repeated frames -> merged
+    in_lens = [75, 33, 1, 64]
+    ref, ref_score = OC.ctc_greedy_decode(lg, in_lens)
+    lgd = torch.tensor(np.ascontiguousarray(lg.transpose(1, 0, 2)), device="cuda")
+    il = torch.tensor(in_lens, dtype=torch.int32, device="cuda")
+    toks = torch.zeros(B, T, dtype=torch.int32, device="cuda")
+    tl = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ns = torch.zeros(B, device="cuda")
+    L.check(lib.os2s_ctc_greedy(L.ptr(lgd), L.ptr(il), L.ptr(toks), L.ptr(tl), L.ptr(ns), B, T, V, _ll(T * V), _ll(V),
+                                1, L.stream_ptr()), "greedy")
+    torch.cuda.synchronize()
+    for b in range(B):
+        assert toks[b, :int(tl[b])].cpu().tolist() == ref[b]
+    assert np.abs(ns.cpu().numpy() - ref_score).max() < 1e-3
+
+
+def test_optimizer_chain_vs_oracle_including_overflow_skip():
+    """LARC + Backoff scaler + NovoGrad(as written) + poly_decay over several steps, 2 ranks' worth of
+    summed gradients, with an injected Inf on step 2 (skip, halve the scale, no step increment)."""
+    from oracle import optimizer as OO
+    from openseq2seq_b200.engine import JasperEngine
+    from tests.common_cfg import MINI_JASPER
+    eng = JasperEngine(MINI_JASPER, 64, 29, world_size=2,
+                       opt=dict(algo="novograd", beta1=0.95, beta2=0.98, epsilon=1e-8, weight_decay=0.001,
+                                larc_eta=0.001, learning_rate=0.02, min_lr=1e-5, power=2.0, decay_steps=10,
+                                loss_scaling=True))
+    names = [n for n, _ in eng.named_parameters()]
+    w_ref = [eng.param_view(n).detach().cpu().numpy().copy() for n in names]
+    state = OO.NovoGradState(len(names))
+    scaler = OO.BackoffScaler()
+    step = 0
+    rng = np.random.default_rng(0)
+    lr_fn = lambda s: OO.poly_decay(s, 0.02, 10, power=2.0, min_lr=1e-5)
+    for it in range(5):
+        scale = scaler.scale
+        assert abs(float(eng.fstate[0]) - scale) < 1e-6
+        per_rank = [[(rng.standard_normal(w.shape) * 0.01 * scale).astype(np.float32) for w in w_ref] for _ in range(2)]
+        if it == 2:
+            per_rank[0][3].flat[5] = np.inf
+        eng.grad.zero_()
+        for i, n in enumerate(names):
+            eng.param_view(n, eng.grad).copy_(torch.tensor(per_rank[0][i] + per_rank[1][i]))
+        eng.optimizer_step()
+        torch.cuda.synchronize()
+        skipped, lr, step = OO.train_step(w_ref, per_rank, state, scaler, step, lr_fn,
+                                          dict(beta1=0.95, beta2=0.98, epsilon=1e-8, weight_decay=0.001),
+                                          larc_params=dict(larc_eta=0.001))
+        assert int(eng.istate[3]) == int(skipped)
+        assert int(eng.istate[2]) == step
+        if not skipped:
+            assert abs(float(eng.fstate[1]) - lr) < 1e-6 * max(1.0, lr)
+        for i, n in enumerate(names):
+            got = eng.param_view(n).cpu().numpy()
+            assert np.abs(got - w_ref[i]).max() <= 2e-5 * max(1.0, np.abs(w_ref[i]).max()), (it, n)
+    assert int(eng.istate[4]) == 1 and abs(float(eng.fstate[0]) - scaler.scale) < 1e-6
+    # bf16 working copies follow the masters (natural and transposed)
+    s = eng.by_name["conv21/kernel"]
+    K, R, C = s["shape"]
+    wb = eng.wb[s["half_offset"]:s["half_offset"] + s["size"]].view(K, R, C).float()
+    wt = eng.wt[s["half_offset"]:s["half_offset"] + s["size"]].view(K, C, R).float()
+    m = eng.param_view("conv21/kernel")
+    assert torch.equal(wb, m.bfloat16().float()) and torch.equal(wt, wb.permute(0, 2, 1))
+
+
+def test_logmel_featurizer_vs_oracle():
+    from oracle import featurizer as FZ
+    L, lib = _lib()
+    rng = np.random.default_rng(1234)
+    sigs = [np.clip(3000 * rng.standard_normal(n), -32768, 32767).astype(np.int16) for n in (16000, 12345, 4000)]
+    # speech-like spectral tilt so the log-mel features are not flat noise
+    sigs = [np.clip(np.convolve(s.astype(np.float64), np.ones(8) / 8, mode="same"), -32768, 32767).astype(np.int16)
+            for s in sigs]
+    ref, ref_lens = FZ.batch_features(sigs, pad_to=16)
+    B, T_pad, F = ref.shape
+    wave = torch.tensor(np.concatenate(sigs), dtype=torch.int16, device="cuda")
+    offs = torch.tensor(np.cumsum([0] + [len(s) for s in sigs[:-1]]), dtype=torch.int64, device="cuda")
+    ns = torch.tensor([len(s) for s in sigs], dtype=torch.int32, device="cuda")
+    mel = torch.tensor(FZ.mel_filterbank(), dtype=torch.float32, device="cuda")
+    win = torch.tensor(np.hanning(320), dtype=torch.float32, device="cuda")
+    absmax = torch.zeros(B, dtype=torch.int32, device="cuda")
+    raw = torch.zeros(B * T_pad * F, device="cuda")
+    out = torch.zeros(B, T_pad, F, device="cuda")
+    outb = torch.zeros(B, T_pad, F, dtype=torch.bfloat16, device="cuda")
+    lens = torch.zeros(B, dtype=torch.int32, device="cuda")
+    L.check(lib.os2s_logmel_forward(L.ptr(wave), L.ptr(offs), L.ptr(ns), B, L.ptr(mel), L.ptr(win), 512, 320, 160, F,
+                                    T_pad, max(len(s) for s in sigs), _f(0.0), ctypes.c_uint64(0), _f(0.97),
+                                    L.ptr(absmax), L.ptr(raw), L.ptr(outb), L.ptr(out), L.ptr(lens), L.stream_ptr()),
+            "logmel")
+    torch.cuda.synchronize()
+    assert lens.cpu().tolist() == ref_lens.tolist()
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() < 2e-2  # normalised features are O(1)
+    assert np.abs(outb.float().cpu().numpy() - ref).max() < 5e-2
+    for b in range(B):
+        assert np.all(got[b, ref_lens[b]:] == 0)

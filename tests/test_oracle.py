@@ -1,0 +1,158 @@
+"""CPU tests: the oracle is pinned against the reference's own golden vectors / known answers and
+triangulated against independent implementations (torch, torchaudio)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc as OC
+from oracle import encoder as OE
+from oracle import featurizer as FZ
+from oracle import optimizer as OO
+from oracle import torch_twin as TT
+
+
+def test_ctc_oracle_reproduces_reference_golden_vector(golden_dir):
+    # known answers: /root/reference ctc_decoder_with_lm/ctc-test.py:64-67 (greedy), :73 (log prob)
+    g = np.load(os.path.join(golden_dir, "ctc_test_logits.npz"))
+    lg, vocab = g["logits"], list(g["vocab"])
+    toks, score = OC.ctc_greedy_decode(lg, [lg.shape[0]])
+    assert "".join(vocab[c] for c in toks[0]) == "then seconds"
+    assert abs(-score[0] - 7079.117) < 1e-3
+    lab = np.array([[vocab.index(c) for c in "then seconds"]])
+    loss, _ = OC.ctc_loss_and_grad(lg, lab, [lab.shape[1]], [lg.shape[0]])
+    assert abs(loss[0] - 1.1842575) < 1e-3
+
+
+def test_ctc_oracle_matches_torch_ctc_including_edge_cases():
+    rng = np.random.default_rng(0)
+    T, B, V, Lmax = 40, 4, 29, 12
+    lg = rng.standard_normal((T, B, V))
+    labels = rng.integers(0, V - 1, size=(B, Lmax))
+    labels[0, :4] = [2, 2, 2, 9]
+    label_lens = [12, 5, 0, 12]
+    in_lens = [40, 23, 9, 8]  # last is infeasible (12 labels in 8 frames)
+    loss, grad = OC.ctc_loss_and_grad(lg, labels, label_lens, in_lens)
+    x = torch.tensor(lg, requires_grad=True)
+    ref = torch.nn.functional.ctc_loss(x.log_softmax(2), torch.tensor(labels), torch.tensor(in_lens),
+                                       torch.tensor(label_lens), blank=V - 1, reduction="none", zero_infinity=True)
+    ref.sum().backward()
+    assert loss[3] == 0.0
+    assert np.abs(loss - ref.detach().numpy()).max() < 1e-9
+    assert np.abs(grad - x.grad.numpy()).max() < 1e-9
+    mean, gm = OC.ctc_loss_mean(lg, labels, label_lens, in_lens)
+    assert abs(mean - loss.mean()) < 1e-12 and np.allclose(gm, grad / B)
+
+
+def test_mel_filterbank_and_stft_match_independent_implementations():
+    import torchaudio
+    fb = torchaudio.functional.melscale_fbanks(257, 0.0, 8000.0, 64, 16000, norm="slaney", mel_scale="slaney").T
+    assert np.abs(fb.numpy() - FZ.mel_filterbank()).max() < 1e-6
+    rng = np.random.default_rng(0)
+    s = rng.standard_normal(5000)
+    win = torch.hann_window(320, periodic=False, dtype=torch.float64)
+    S = torch.stft(torch.tensor(s), n_fft=512, hop_length=160, win_length=320, window=win, center=True,
+                   pad_mode="reflect", return_complex=True).abs() ** 2
+    S2 = FZ.stft_power(s)
+    assert S2.shape == (257, 1 + 5000 // 160)
+    assert np.abs(S.numpy() - S2).max() < 1e-5 * S2.max()
+
+
+def test_featurizer_shape_and_normalisation_like_reference_test():
+    # mirrors data/speech2text/speech_utils_test.py:45-85 (shape, mean 0 / std 1) for the librosa backend
+    rng = np.random.default_rng(1)
+    sig = np.clip(3000 * rng.standard_normal(43200), -32768, 32767).astype(np.int16)
+    f, dur = FZ.logfbank_features(sig)
+    assert f.shape == (1 + 43200 // 160, 64) and abs(dur - 2.7) < 1e-9
+    assert np.abs(f.mean(0)).max() < 1e-6 and np.abs(f.std(0) - 1).max() < 1e-6
+    batch, lens = FZ.batch_features([sig, sig[:16000]], pad_to=16)
+    assert batch.shape[1] % 16 == 0 and lens.tolist() == [271, 101]
+    assert np.all(batch[1, 101:] == 0)
+
+
+def _mini_layers():
+    return [
+        {"type": "conv1d", "repeat": 1, "kernel_size": [11], "stride": [2], "num_channels": 16, "padding": "SAME",
+         "dilation": [1]},
+        {"type": "conv1d", "repeat": 2, "kernel_size": [5], "stride": [1], "num_channels": 16, "padding": "SAME",
+         "dilation": [1], "residual": True, "residual_dense": True},
+        {"type": "conv1d", "repeat": 2, "kernel_size": [7], "stride": [1], "num_channels": 24, "padding": "SAME",
+         "dilation": [1], "residual": True, "residual_dense": True},
+        {"type": "conv1d", "repeat": 1, "kernel_size": [9], "stride": [1], "num_channels": 32, "padding": "SAME",
+         "dilation": [2]},
+    ]
+
+
+def test_same_padding_rule_matches_tf_examples():
+    # conv11 K11 s2 on even T=1504 -> 4/5; stride 1 symmetric; K29 d2 -> 28/28
+    assert OE.same_padding(1504, 11, 2, 1) == (752, 4, 5)
+    assert OE.same_padding(1503, 11, 2, 1) == (752, 5, 5)
+    assert OE.same_padding(752, 29, 1, 2) == (752, 28, 28)
+    assert OE.same_padding(752, 1, 1, 1) == (752, 0, 0)
+
+
+def test_numpy_encoder_matches_torch_twin_and_torch_conv():
+    layers = _mini_layers()
+    p = TT.init_params(layers, 8, 29, seed=1)
+    torch.manual_seed(0)
+    x = torch.randn(3, 48, 8, dtype=torch.float64)
+    lens = torch.tensor([48, 30, 17])
+    x = x * TT.sequence_mask(lens, 48, x.dtype)
+    y_t, l_t = TT.tdnn_encode(x, lens, layers, {k: v.double() for k, v in p.items()})
+    y_n, l_n = OE.tdnn_encode(x.numpy(), lens.numpy(), layers, {k: v.numpy() for k, v in p.items()})
+    assert l_t.tolist() == l_n.tolist() == [24, 15, 9]
+    assert np.abs(y_t.numpy() - y_n).max() < 1e-10
+    # batch norm against torch's own implementation (biased variance, eps inside the sqrt)
+    c = torch.randn(4, 10, 6, dtype=torch.float64)
+    g, b = torch.rand(6, dtype=torch.float64) + 0.5, torch.randn(6, dtype=torch.float64)
+    ref = torch.nn.functional.batch_norm(c.reshape(-1, 6), None, None, g, b, training=True, eps=1e-3).reshape(4, 10, 6)
+    got, mean, var = OE.batch_norm_train(c.numpy(), g.numpy(), b.numpy(), 1e-3)
+    assert np.abs(got - ref.numpy()).max() < 1e-12
+    mm, mv = OE.update_moving(np.zeros(6), np.ones(6), mean, var, 40, 0.9)
+    assert np.allclose(mv, 0.9 + 0.1 * c.reshape(-1, 6).var(0, unbiased=True).numpy())
+
+
+def test_poly_decay_and_backoff_scaler_trajectories():
+    assert OO.poly_decay(0, 0.02, 100, power=2.0, min_lr=1e-5) == pytest.approx(0.02)
+    assert OO.poly_decay(50, 0.02, 100, power=2.0, min_lr=1e-5) == pytest.approx((0.02 - 1e-5) * 0.25 + 1e-5)
+    assert OO.poly_decay(500, 0.02, 100, power=2.0, min_lr=1e-5) == pytest.approx(1e-5)
+    assert OO.poly_decay(5, 0.02, 100, warmup_steps=10, begin_decay_at=20) == pytest.approx(0.01)
+    s = OO.BackoffScaler(step_window=4)
+    assert s.scale == 2.0 ** 14
+    assert s.update(False, 1.0) is False and s.scale == 2.0 ** 14     # iteration 0: since = 1
+    assert s.update(True, 1.0) is True and s.scale == 2.0 ** 13        # overflow at iteration 1
+    for _ in range(3):
+        s.update(False, 1.0)
+    assert s.scale == 2.0 ** 13
+    s.update(False, 1.0)                                               # iteration 5: since = 4 -> grow
+    assert s.scale == 2.0 ** 14
+    assert s.update(False, np.inf) is True
+
+
+def test_mp_wrapper_unscale_semantics_like_reference_test():
+    # optimizers/mp_wrapper_test.py:61-95: a gradient of 1e-8 survives because it is unscaled in fp32
+    w = [np.ones(4, dtype=np.float32)]
+    scaler = OO.BackoffScaler()
+    g_scaled = [np.full(4, 1e-8 * scaler.scale, dtype=np.float32)]
+    st = OO.NovoGradState(1)
+    before = w[0].copy()
+    skipped, lr, step = OO.train_step(w, [g_scaled], st, scaler, 0, lambda s: 0.1,
+                                      dict(beta1=0.0, beta2=0.5, epsilon=1e-8, weight_decay=0.0))
+    assert not skipped and step == 1
+    # the 1e-8 gradient is not flushed to zero: update = lr * g / sqrt(||g||^2 + eps)
+    expect = 0.1 * 1e-8 / np.sqrt(4e-16 + 1e-8)
+    assert np.allclose(before - w[0], expect, rtol=2e-2) and expect > 0
+
+
+def test_novograd_as_written_vs_corrected_ema():
+    rng = np.random.default_rng(0)
+    w1 = [rng.standard_normal(8).astype(np.float32)]
+    w2 = [w1[0].copy()]
+    s1, s2 = OO.NovoGradState(1), OO.NovoGradState(1)
+    for i in range(3):
+        g = [(rng.standard_normal(8) * (i + 1)).astype(np.float32)]
+        OO.novograd_step(w1, g, s1, 0.01, ema_persist=False)
+        OO.novograd_step(w2, g, s2, 0.01, ema_persist=True)
+    assert s1.ema[0] == 0.0 and s2.ema[0] > 0.0
+    assert not np.allclose(w1[0], w2[0])
