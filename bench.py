@@ -1,0 +1,354 @@
+"""bench.py -- Jasper 10x5 bf16 training throughput (audio-seconds/sec) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port, TF1 is
+                                                           # not installable offline)
+
+One "step" = one pass of the hot path over one batch of 32 synthetic 16 kHz / 15 s utterances per
+rank: log-mel featurizer -> Jasper 10x5 DR encoder -> FC -> CTC loss fwd/bwd -> gradient all-reduce
+(NCCL, N > 1) -> loss-scaled LARC + NovoGrad step.  `value` times K steps with the int16 waveforms
+already resident in HBM (CUDA events, barrier + synchronize on both sides, max over ranks); `e2e`
+times the same steps driven through the public plugin API with pinned HOST waveforms copied to the
+device and the loss read back every step.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+AUDIO_SECONDS = 15.0
+BATCH = 32
+SR = 16000
+TRAIN_GFLOP_PER_AUDIO_S = 100.02  # SURVEY.md section 8d (fwd+dgrad+wgrad conv/GEMM FLOPs)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1380.3), d.get("hbm_gbs", 6566.7), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
+
+
+def synth_waveforms(rank, n_utts, seconds):
+    """int16(clip(3000*N(0,1))) per rank, fixed seed."""
+    import numpy as np
+    g = np.random.default_rng(1234 + rank * 1000)
+    n = int(seconds * SR)
+    return [np.clip(3000.0 * g.standard_normal(n), -32768, 32767).astype(np.int16) for _ in range(n_utts)]
+
+
+def synth_labels(rank, n_utts):
+    import numpy as np
+    g = np.random.default_rng(4321 + rank)
+    lens = g.integers(180, 261, size=n_utts)
+    y = np.zeros((n_utts, int(lens.max())), dtype=np.int32)
+    for i, L in enumerate(lens):
+        y[i, :L] = g.integers(0, 28, size=L)
+    return y, lens.astype(np.int32)
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's CPU path: TF1 is not installable here (no wheel for py3.12, no network), so
+    this times the oracle's PyTorch-CPU fp32 port of the identical graph (oracle/torch_twin.py) on
+    all host cores, each step a bounded sample (1 utterance x 4 s) of the same workload."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import featurizer as FZ
+    from oracle import torch_twin as TT
+    import openseq2seq_b200.compat as compat
+    compat.install()
+    from open_seq2seq.utils.utils import get_base_config
+    _, cfg, _, _ = get_base_config(["--config_file=" + os.path.join(ROOT, "configs", "jasper10x5_dr.py")])
+    layers = cfg["encoder_params"]["convnet_layers"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    secs, B = 4.0, 1
+    params = TT.init_params(layers, 64, 29, seed=0)
+    for v in params.values():
+        v.requires_grad_(True)
+    mom = {}
+    waves = synth_waveforms(0, B, secs)
+    y, ylen = synth_labels(0, B)
+    y = torch.tensor(y[:, :40], dtype=torch.long)
+    ylen = torch.tensor([40] * B, dtype=torch.long)
+
+    def step():
+        feats, lens = FZ.batch_features(waves, pad_to=16)
+        x = torch.tensor(feats, dtype=torch.float32)
+        loss, _, _ = TT.forward_loss(params, layers, x, torch.tensor(lens, dtype=torch.long), y, ylen)
+        grads = torch.autograd.grad(loss, list(params.values()))
+        TT.larc_novograd_step(params, dict(zip(params.keys(), grads)), mom, lr=0.02)
+        return float(loss)
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    t0 = time.time()
+    n = 0
+    budget = 150.0
+    for _ in range(args.steps):
+        step()
+        n += 1
+        if time.time() - t0 > budget:
+            break
+    dt = time.time() - t0
+    val = n * B * secs / dt
+    sample = "%d steps of %d utterance x %.0f s (fp32, torch CPU port of the reference graph)" % (n, B, secs)
+    out = {"impl": "reference", "metric": "audio-seconds/sec Jasper-10x5 train", "value": round(val, 4),
+           "unit": "audio-s/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
+           "ms_per_step": round(1000 * dt / n, 2), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "Jasper 10x5 DR training step (featurizer+encoder+CTC+NovoGrad), CPU port"},
+           "cpu_baseline": {"value": round(val, 4), "unit": "audio-s/s", "cores": cores, "kind": "port",
+                            "sample": sample},
+           "e2e": {"value": round(val, 4), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline_quick():
+    """Bounded CPU sample timed inside the default run (rank 0, N = 1)."""
+    import torch
+    from oracle import featurizer as FZ
+    from oracle import torch_twin as TT
+    import openseq2seq_b200.compat as compat
+    compat.install()
+    from open_seq2seq.utils.utils import get_base_config
+    _, cfg, _, _ = get_base_config(["--config_file=" + os.path.join(ROOT, "configs", "jasper10x5_dr.py")])
+    layers = cfg["encoder_params"]["convnet_layers"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    secs = 4.0
+    params = TT.init_params(layers, 64, 29, seed=0)
+    for v in params.values():
+        v.requires_grad_(True)
+    mom = {}
+    waves = synth_waveforms(0, 1, secs)
+    y = torch.randint(0, 28, (1, 40))
+    ylen = torch.tensor([40])
+
+    def step():
+        feats, lens = FZ.batch_features(waves, pad_to=16)
+        x = torch.tensor(feats, dtype=torch.float32)
+        loss, _, _ = TT.forward_loss(params, layers, x, torch.tensor(lens, dtype=torch.long), y, ylen)
+        grads = torch.autograd.grad(loss, list(params.values()))
+        TT.larc_novograd_step(params, dict(zip(params.keys(), grads)), mom, lr=0.02)
+
+    step()
+    t0 = time.time()
+    n = 0
+    while n < 8 and (time.time() - t0) < 20.0:
+        step()
+        n += 1
+    dt = time.time() - t0
+    return {"value": round(n * secs / dt, 4), "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "sample": "%d training steps of 1 utterance x 4 s, fp32 torch-CPU port of the reference graph "
+                      "(oracle/torch_twin.py); TF1 not installable offline" % n}
+
+
+# --------------------------------------------------------------------------- CUDA arm
+def run_own(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import openseq2seq_b200.compat as compat
+    compat.install()
+    from open_seq2seq.utils.utils import get_base_config, nested_update
+    from openseq2seq_b200.dist import TorchDistHvd
+    import copy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        hvd = TorchDistHvd.init()
+    else:
+        torch.cuda.set_device(0)
+        hvd = TorchDistHvd.single()
+    rank, local = hvd.rank(), hvd.local_rank()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device -- the product path has no CPU fallback")
+
+    _, cfg, model_cls, module = get_base_config([
+        "--config_file=" + os.path.join(ROOT, "configs", "jasper10x5_dr.py"), "--mode=train"])
+    cfg = copy.deepcopy(cfg)
+    nested_update(cfg, copy.deepcopy(module["train_params"]))
+    cfg.pop("num_epochs", None)
+    cfg["max_steps"] = 100000  # lr schedule horizon; the bench runs K + W steps of it
+    cfg["batch_size_per_gpu"] = args.batch
+    model = model_cls(params=cfg, mode="train", hvd=hvd if world > 1 else None)
+    model.compile()
+    eng = model.engine
+    dl = model.get_data_layer()
+
+    waves = synth_waveforms(rank, args.batch, AUDIO_SECONDS)
+    n = len(waves[0])
+    host = torch.empty(args.batch * n, dtype=torch.int16).pin_memory()
+    np.concatenate(waves, out=host.numpy())
+    lens = [n] * args.batch
+    y_np, ylen_np = synth_labels(rank, args.batch)
+    y_host = torch.from_numpy(y_np).pin_memory()
+    ylen_host = torch.from_numpy(ylen_np).pin_memory()
+    y_dev, ylen_dev = y_host.cuda(), ylen_host.cuda()
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        # waveforms already in HBM (dl keeps a device staging buffer): featurizer + train step
+        feats, flens = dl.featurize_resident(seed=eng.step_count)
+        model.train_step({"source_tensors": [feats, flens], "target_tensors": [y_dev, ylen_dev]})
+
+    def step_e2e():
+        feats, flens = dl.featurize((host, lens), seed=eng.step_count)   # H2D of the int16 waveforms
+        yd = y_host.cuda(non_blocking=True)
+        yl = ylen_host.cuda(non_blocking=True)
+        loss, _ = model.train_step({"source_tensors": [feats, flens], "target_tensors": [yd, yl]})
+        loss_host.copy_(loss.reshape(1), non_blocking=False)              # D2H read of the step's loss
+        return float(loss_host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    # warm-up (also builds the launch plans and the device staging buffers)
+    last_loss = None
+    for _ in range(max(args.warmup, 3)):
+        last_loss = step_e2e()
+    for _ in range(2):
+        step_resident()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_resident, args.steps)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # roofline of the dominant kernel family (tcgen05 implicit-GEMM conv): per-launch CUDA-event
+    # timing of every conv launch of instrumented steps run right after the timed region
+    roof = eng.profile_conv_launches(lambda: step_resident(), steps=2)
+    skipped = int(eng.istate[4])
+    total_audio = world * args.batch * AUDIO_SECONDS
+    value = total_audio * args.steps / (ms / 1000.0)
+    e2e = total_audio * args.steps / (ms_e2e / 1000.0)
+    if rank != 0:
+        return
+    peak_tf, peak_hbm, peak_src = _peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_conv_summary.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = {
+        "metric": "audio-seconds/sec Jasper-10x5 bf16 train",
+        "value": round(value, 2), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Jasper 10x5 DR (configs/jasper10x5_dr.py = reference jasper10x5_LibriSpeech_nvgrad): "
+                               "featurizer + encoder + FC + CTC fwd/bwd + LARC/NovoGrad, 16 kHz x 15 s utterances",
+                   "batch_per_gpu": args.batch, "global_batch": args.batch * world, "audio_seconds_per_utt": AUDIO_SECONDS,
+                   "parallelism": "dp%d" % world,
+                   "l2_policy": "working set per step (activations ~6 GB, params/grads ~5 GB) >> 126 MB L2; no flush needed",
+                   "train_gflop_per_audio_s": TRAIN_GFLOP_PER_AUDIO_S},
+        "e2e": {"value": round(e2e, 2), "unit": "audio-s/s", "ms_per_step": round(ms_e2e / args.steps, 3),
+                "h2d_bytes_per_step": int(host.numel() * 2 + y_host.numel() * 4 + ylen_host.numel() * 4 + args.batch * 12),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(eng.kernel_launches_per_step() * args.steps),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "tapgemm_kmajor/tapgemm_mnmajor (tcgen05 implicit-GEMM conv fwd+dgrad+wgrad)",
+                     "achieved": roof["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": round(roof["tflops"] / peak_tf, 4), "traffic": traffic,
+                     "peak_source": peak_src, "launches_per_step": roof["launches"],
+                     "conv_ms_per_step": roof["ms"], "share_of_step": round(roof["ms"] / (ms / args.steps), 4),
+                     "algorithmic_tflop_per_step": roof["tflop"],
+                     "how": "CUDA events around every conv launch of 2 instrumented steps after the timed region",
+                     "by_kind": roof["by_kind"],
+                     "step_frac_of_peak": round(value / world * TRAIN_GFLOP_PER_AUDIO_S / 1000.0 / peak_tf, 4)},
+        "loss": last_loss, "skipped_steps": skipped,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_quick()
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

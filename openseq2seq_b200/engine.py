@@ -90,6 +90,7 @@ class JasperEngine(object):
         self.relu_clip = float(relu_clip)
         self.step_count = 0
         self._ws = {}
+        self._profile = None
         self._build_layers(convnet_layers, dropout_keep_default)
         self._alloc_params()
         self.set_optimizer(**(opt or {}))
@@ -453,8 +454,42 @@ class JasperEngine(object):
         return ws.tokens, ws.tok_lens
 
     def kernel_launches_per_step(self):
+        """Kernels of libos2s_b200 launched by one training step (conv + BN stats/apply + FC + CTC(3) +
+        BN bwd (2 each) + optimizer (3) + transpose (1) + featurizer (3)); memsets are not counted."""
         ws = self._last_ws
-        return ws.n_launch_fwd + ws.n_launch_bwd + 4
+        n = 0
+        for entry in ws._fwd_plan:
+            n += 1
+        n += 1  # fc fwd
+        for entry in (ws._bwd_plan or []):
+            name = entry[0].__name__
+            n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd": 2, "os2s_bn_bwd": 2}.get(name, 1)
+        return n + 3 + 1 + 3
+
+    def profile_conv_launches(self, step_fn, steps=2):
+        """Time every tensor-core conv launch of `steps` instrumented steps with CUDA events.
+        Returns achieved TFLOP/s over all conv launches (algorithmic FLOPs / summed kernel time)."""
+        self._profile = []
+        try:
+            for _ in range(steps):
+                step_fn()
+            torch.cuda.synchronize()
+            rec = self._profile
+        finally:
+            self._profile = None
+        by = {}
+        for kind, flops, e0, e1 in rec:
+            d = by.setdefault(kind, [0.0, 0.0, 0])
+            d[0] += flops
+            d[1] += e0.elapsed_time(e1)
+            d[2] += 1
+        tot_f = sum(d[0] for d in by.values())
+        tot_ms = sum(d[1] for d in by.values())
+        return {"tflops": round(tot_f / tot_ms / 1e9, 1) if tot_ms > 0 else 0.0,
+                "ms": round(tot_ms / steps, 3), "tflop": round(tot_f / steps / 1e12, 3),
+                "launches": int(sum(d[2] for d in by.values()) / steps),
+                "by_kind": {k: {"tflops": round(d[0] / d[1] / 1e9, 1), "ms_per_step": round(d[1] / steps, 3),
+                                "launches_per_step": d[2] // steps} for k, d in by.items()}}
 
 
 class _Workspace(object):
@@ -545,8 +580,9 @@ class _Workspace(object):
                 if first_layer == li:
                     src_act[idx] = self.A[li - 1]
             self.x_of_layer.append(self.A[li - 1] if li > 0 else None)
+            flops = 2.0 * B * T2 * l.K * l.c_in * l.c_out  # algorithmic (un-folded) FLOPs
             call = [lib.os2s_conv1d_fwd, [x_ptr, self._half_ptr(eng.wt, l.name + "/kernel"), self._p(self.Y[li]),
-                                          B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, 3, st]]
+                                          B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, 3, st], ("fwd", flops)]
             plan.append(call)
             if li == 0:
                 self._x0_call = call
@@ -563,7 +599,8 @@ class _Workspace(object):
                 bnn = (l.name + "/res_bn_%d" % n) if l.dense else (l.name + "/res_bn")
                 cj = eng.block_inputs[j][0]
                 plan.append([lib.os2s_conv1d_fwd, [self._p(src_act[j]), self._half_ptr(eng.wt, rn + "/kernel"),
-                                                   self._p(self.YR[li][n]), B, T2, cj, l.c_out, 1, 1, 0, 3, st]])
+                                                   self._p(self.YR[li][n]), B, T2, cj, l.c_out, 1, 1, 0, 3, st],
+                             ("fwd", 2.0 * B * T2 * cj * l.c_out)])
                 slot = bn_idx
                 bn_idx += 1
                 if eng.training:
@@ -607,15 +644,35 @@ class _Workspace(object):
         base = (eng.seed * 1000003 + eng.step_count) * 4099
         for args, k, li in self._seed_slots:
             args[k] = _c_u64((base + li) & 0xFFFFFFFFFFFFFFFF)
-        lib_check = L.check
-        for fn, args in self._fwd_plan:
-            rc = fn(*args)
-            if rc != 0:
-                lib_check(rc, fn.__name__)
+        self._exec(self._fwd_plan)
         eng._last_ws = self
 
+    def _exec(self, plan):
+        """Run a launch plan; when the engine is in profiling mode, conv launches are bracketed by
+        CUDA events on the launching stream (bench.py's roofline measurement)."""
+        prof = self.eng._profile
+        lib_check = L.check
+        if prof is None:
+            for entry in plan:
+                rc = entry[0](*entry[1])
+                if rc != 0:
+                    lib_check(rc, entry[0].__name__)
+            return
+        for entry in plan:
+            meta = entry[2] if len(entry) > 2 else None
+            if meta is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            rc = entry[0](*entry[1])
+            if rc != 0:
+                lib_check(rc, entry[0].__name__)
+            if meta is not None:
+                e1.record()
+                prof.append((meta[0], meta[1], e0, e1))
+
     def run_decoder(self):
-        fn, args = self._fc_call
+        fn, args = self._fc_call[0], self._fc_call[1]
         L.check(fn(*args), "os2s_fc_fwd")
 
     def _build_backward_plan(self, L_max):
@@ -660,7 +717,8 @@ class _Workspace(object):
             # main conv wgrad (stored layout == kernel layout, also for the folded stride-2 layer)
             x_ptr = self._p(self.A[li - 1]) if li > 0 else None
             wg = [lib.os2s_conv1d_wgrad, [x_ptr, self._p(self.dY), self._param_ptr(eng.grad, l.name + "/kernel"),
-                                          B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, st]]
+                                          B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, st],
+                  ("wgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)]
             plan.append(wg)
             if li == 0:
                 self._x0_wgrad = wg
@@ -671,11 +729,12 @@ class _Workspace(object):
                 src = self.A[eng.block_inputs[j][1] - 1]
                 plan.append([lib.os2s_conv1d_wgrad, [self._p(src), self._p(self.dYR[n]),
                                                      self._param_ptr(eng.grad, rn + "/kernel"), B, T2, cj, l.c_out,
-                                                     1, 1, 0, st]])
+                                                     1, 1, 0, st], ("wgrad", 2.0 * B * T2 * cj * l.c_out)])
                 mode = 2 if j in written else 1
                 written.add(j)
                 plan.append([lib.os2s_conv1d_dgrad, [self._p(self.dYR[n]), self._half_ptr(eng.wb, rn + "/kernel"),
-                                                     self._p(self.dres[j]), B, T2, cj, l.c_out, 1, 1, 0, mode, st]])
+                                                     self._p(self.dres[j]), B, T2, cj, l.c_out, 1, 1, 0, mode, st],
+                             ("dgrad", 2.0 * B * T2 * cj * l.c_out)])
             if li > 0:
                 if (li - 1) in eng.src_of_layer_output:
                     j = eng.src_of_layer_output[li - 1]
@@ -686,7 +745,7 @@ class _Workspace(object):
                     mode, out_ptr = 0, self._p(self.dA)
                 plan.append([lib.os2s_conv1d_dgrad, [self._p(self.dY), self._half_ptr(eng.wb, l.name + "/kernel"),
                                                      out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
-                                                     st]])
+                                                     st], ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
         self._bwd_plan = plan
         self._bwd_L = L_max
         self.n_launch_bwd = len(plan) + 4
@@ -707,7 +766,7 @@ class _Workspace(object):
             self._build_backward_plan(L_max)
         self.labels.copy_(labels.to(torch.int32), non_blocking=True)
         self.label_lens.copy_(label_lens.to(torch.int32), non_blocking=True)
-        fn, args = self._bwd_plan[0]
+        fn, args = self._bwd_plan[0][0], self._bwd_plan[0][1]
         L.check(fn(*args), "os2s_ctc_loss_fwd_bwd")
         return self.loss
 
@@ -726,10 +785,6 @@ class _Workspace(object):
             self.dlogits.copy_(dlogits)
             plan = plan[1:]  # skip the CTC launch
         self._x0_wgrad[1][0] = _vp(self.feats.data_ptr())
-        lib_check = L.check
-        for fn, args in plan:
-            rc = fn(*args)
-            if rc != 0:
-                lib_check(rc, fn.__name__)
+        self._exec(plan)
         for z in self._zero_slices:
             z.zero_()

@@ -204,3 +204,93 @@ def larc_novograd_step(params, grads, momentum, lr, beta1=0.95, beta2=0.98, epsi
             m = g if m is None else beta1 * m + g
             momentum[name] = m
             w -= lr * m
+
+
+def backward_with_saved_forward(params, layers, feats, feat_len, saved_conv, saved_out, dlogits_btv,
+                                bn_eps=1e-3, use_conv_mask=True):
+    """Reference backward pass (what TF autodiff computes) evaluated AT A GIVEN FORWARD STATE.
+
+    saved_conv: name -> conv output Y (main: 'conv21', residual branch n: 'conv25/res_0'), saved_out:
+    name -> layer output A.  ReLU gates and BN statistics are recomputed from these saved tensors
+    with the oracle's own op definitions (conv1d_same, batch_norm_train), layer by layer with local
+    autograd, so the result isolates the backward arithmetic from the forward pass's sensitivity
+    (a ReLU network's gradient is discontinuous in its forward values).  Returns name -> gradient."""
+    grads = {}
+    p = {k: v.detach().double() for k, v in params.items()}
+    # ---- topology walk (forward order)
+    plan = []
+    src_len = feat_len.clone()
+    max_len = feats.shape[1]
+    masks = {}
+    res_agg = []
+    prev = None
+    for bi, layer in enumerate(layers):
+        residual = layer.get("residual", False)
+        dense = layer.get("residual_dense", False)
+        stride = layer["stride"][0]
+        layer_res = None
+        if residual:
+            if dense:
+                res_agg.append(prev)
+                layer_res = list(res_agg)
+            else:
+                layer_res = [prev]
+        for ri in range(layer["repeat"]):
+            name = "conv%d%d" % (bi + 1, ri + 1)
+            src_len = (src_len + stride - 1) // stride
+            max_len = (max_len + stride - 1) // stride
+            last = bi == len(layers) - 1 and ri == layer["repeat"] - 1
+            m = sequence_mask(src_len, max_len, torch.float64) if (use_conv_mask and not last) else None
+            end = residual and ri == layer["repeat"] - 1
+            plan.append({"name": name, "in": prev, "K": layer["kernel_size"][0], "stride": stride,
+                         "dil": layer["dilation"][0], "mask": m, "res": layer_res if end else [], "dense": dense})
+            prev = name
+    # ---- FC
+    enc = saved_out[plan[-1]["name"]].detach().double().requires_grad_(True)
+    wk = p["fc/kernel"].clone().requires_grad_(True)
+    bk = p["fc/bias"].clone().requires_grad_(True)
+    logits = fc_decode(enc, wk, bk).transpose(0, 1)
+    logits.backward(dlogits_btv.double())
+    grads["fc/kernel"], grads["fc/bias"] = wk.grad, bk.grad
+    dA = {plan[-1]["name"]: enc.grad}
+    # ---- layers in reverse
+    for node in reversed(plan):
+        name = node["name"]
+        d_out = dA.pop(name)
+        ys = [saved_conv[name].detach().double().requires_grad_(True)]
+        gs = [p[name + "/bn/gamma"].clone().requires_grad_(True)]
+        bs = [p[name + "/bn/beta"].clone().requires_grad_(True)]
+        bnames = [name + "/bn"]
+        for n, src in enumerate(node["res"]):
+            bn_name = (name + "/res_bn_%d" % n) if node["dense"] else (name + "/res_bn")
+            cn = (name + "/res_%d" % n) if node["dense"] else (name + "/res")
+            ys.append(saved_conv[cn].detach().double().requires_grad_(True))
+            gs.append(p[bn_name + "/gamma"].clone().requires_grad_(True))
+            bs.append(p[bn_name + "/beta"].clone().requires_grad_(True))
+            bnames.append(bn_name)
+        tot = 0
+        for y, g, b in zip(ys, gs, bs):
+            tot = tot + batch_norm_train(y, g, b, bn_eps)[0]
+        out = torch.relu(tot)
+        if node["mask"] is not None:
+            out = out * node["mask"]
+        out.backward(d_out)
+        for bn_name, g, b in zip(bnames, gs, bs):
+            grads[bn_name + "/gamma"], grads[bn_name + "/beta"] = g.grad, b.grad
+        # main conv
+        x_src = feats if node["in"] is None else saved_out[node["in"]]
+        x = x_src.detach().double().requires_grad_(node["in"] is not None)
+        w = p[name + "/kernel"].clone().requires_grad_(True)
+        conv1d_same(x, w, node["stride"], node["dil"]).backward(ys[0].grad)
+        grads[name + "/kernel"] = w.grad
+        if node["in"] is not None:
+            dA[node["in"]] = dA.get(node["in"], 0) + x.grad
+        # residual 1x1 convs
+        for n, src in enumerate(node["res"]):
+            cn = (name + "/res_%d" % n) if node["dense"] else (name + "/res")
+            xr = saved_out[src].detach().double().requires_grad_(True)
+            wr = p[cn + "/kernel"].clone().requires_grad_(True)
+            conv1d_same(xr, wr, 1, 1).backward(ys[1 + n].grad)
+            grads[cn + "/kernel"] = wr.grad
+            dA[src] = dA.get(src, 0) + xr.grad
+    return grads
