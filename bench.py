@@ -76,6 +76,16 @@ class ClockSampler(object):
                 "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
 
 
+def _host_threads():
+    """Threads the CPU arm uses: the cores this process may run on (cgroup / affinity aware), capped at
+    32 -- beyond that the many small convolutions of a 4 s sample slow down from oversubscription."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 32))
+
+
 def synth_waveforms(rank, n_utts, seconds):
     """int16(clip(3000*N(0,1))) per rank, fixed seed."""
     import numpy as np
@@ -110,7 +120,7 @@ def run_reference(args):
     from open_seq2seq.utils.utils import get_base_config
     _, cfg, _, _ = get_base_config(["--config_file=" + os.path.join(ROOT, "configs", "jasper10x5_dr.py")])
     layers = cfg["encoder_params"]["convnet_layers"]
-    cores = os.cpu_count() or 1
+    cores = _host_threads()
     torch.set_num_threads(cores)
     secs, B = 4.0, 1
     params = TT.init_params(layers, 64, 29, seed=0)
@@ -164,7 +174,7 @@ def cpu_baseline_quick():
     from open_seq2seq.utils.utils import get_base_config
     _, cfg, _, _ = get_base_config(["--config_file=" + os.path.join(ROOT, "configs", "jasper10x5_dr.py")])
     layers = cfg["encoder_params"]["convnet_layers"]
-    cores = os.cpu_count() or 1
+    cores = _host_threads()
     torch.set_num_threads(cores)
     secs = 4.0
     params = TT.init_params(layers, 64, 29, seed=0)

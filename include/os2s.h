@@ -42,13 +42,18 @@ int os2s_version(void);
 /* ---- K2: tf.layers.conv1d(use_bias=False, padding=SAME), stride 1 -----------------------------
  * reference: open_seq2seq/parts/cnns/conv_blocks.py:195-206 (main), :79-85 (1x1 residual).
  * y[b,t,o] = sum_k sum_c x[b, t - pad_left + k*dil, c] * W[k,c,o]      (zero outside [0,T))
- *   x  : bf16 [B,T,C_in]          wt : bf16 [K][C_out][C_in]  (transposed working copy)
+ *   x  : bf16 [B,T,C_in]          w  : bf16 [K][C_in][C_out]  (natural TF kernel layout)
  *   y  : bf16 / fp32 [B,T,C_out]  (out_mode)
  * The stride-2 first Jasper layer is expressed by the caller as a stride-1 conv over the input
  * viewed as [B, T/2, 2*C_in] with K' = ceil(K/2) taps (see openseq2seq_b200/runtime/layers.py).
  * Constraints: C_in % 64 == 0, C_out % 64 == 0. */
-int os2s_conv1d_fwd(const void* x, const void* wt, void* y, int B, int T, int C_in, int C_out,
+int os2s_conv1d_fwd(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
                     int K, int dil, int pad_left, int out_mode, void* stream);
+
+/* Same convolution with the weights given transposed, wt : bf16 [K][C_out][C_in] (K-major B
+ * operand).  Kept for A/B measurements of the two operand layouts (tools/gpu_conv_check.py). */
+int os2s_conv1d_fwd_wt(const void* x, const void* wt, void* y, int B, int T, int C_in, int C_out,
+                       int K, int dil, int pad_left, int out_mode, void* stream);
 
 /* dgrad of the above: dx[b,t,c] = sum_k sum_o dy[b, t + pad_left - k*dil, o] * W[k,c,o]
  *   dy : bf16 [B,T,C_out]   w : bf16 [K][C_in][C_out] (natural TF layout)   dx : out_mode */
@@ -80,12 +85,15 @@ int os2s_bn_stats(const void* y, float* stats, int M, int C, void* stream);
  * may be NULL) is updated in place.  lens (int32 [B], may be NULL) gives valid rows per utterance;
  * rows t >= lens[b] are written as zeros.  keep = dropout keep probability (1 disables dropout);
  * apply_relu: 0 = identity, 1 = relu, with relu_clip > 0 -> min(relu(x), relu_clip).
- * use_moving = 1 is inference mode (training=False): normalise with moving[j], touch no statistics. */
+ * use_moving = 1 is inference mode (training=False): normalise with moving[j], touch no statistics.
+ * step_counter_dev (int64 on the device, may be NULL) is mixed into the dropout seed so that a
+ * CUDA-graph replay of the same launch draws a fresh mask every step. */
 int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* const* stats_host,
                       const float* const* gamma_host, const float* const* beta_host,
                       float* const* mean_invstd_host, float* const* moving_host, void* out,
                       const int* lens, int B, int T, int C, float eps, float momentum, float keep,
-                      uint64_t seed, int apply_relu, float relu_clip, int use_moving, void* stream);
+                      uint64_t seed, int apply_relu, float relu_clip, int use_moving,
+                      const long long* step_counter_dev, void* stream);
 
 /* Backward of the above.  dA: gradient wrt `out` (bf16, or fp32 when dA_is_f32), a: the forward
  * output (its zeros encode relu / dropout / mask).  Writes dy[j] (bf16 [M,C]) for every branch and
@@ -147,7 +155,7 @@ typedef struct os2s_opt_hparams {
  *   norms fp32 [2*n_tensors] and nonfinite int32 [1] zeroed once at creation; coef, ema fp32 [n_tensors]
  *   fstate fp32 [8]: [0] loss scale, [1] lr of the last step, [2] global grad norm
  *   istate int64 [8]: [0] scaler iteration, [1] last overflow iteration (init -1), [2] global_step,
- *                     [3] last step skipped?, [4] skipped-step count */
+ *                     [3] last step skipped?, [4] skipped-step count, [5] attempted-step count */
 int os2s_opt_chunk_elems(void);
 int os2s_opt_step(void* const* w, void* const* g, void* const* m, void* const* wb,
                   const long long* sizes, const int* chunk_tensor, const long long* chunk_offset,
@@ -164,10 +172,11 @@ int os2s_multi_transpose(void* const* src, void* const* dst, const int* Rdev, co
 
 /* ---- K1: Speech2TextDataLayer featurizer (speech_utils.py:322-441, librosa backend, logfbank) -
  * wave int16 (all utterances concatenated), offsets int64 [B], n_samples int32 [B];
- * mel fp32 [F][n_fft/2+1], window fp32 [win]; out [B,T_pad,F] bf16 and/or fp32 (either may be
+ * mel fp32 [F][n_fft/2+1], mel_band int32 [F][2] = [lo,hi) support of each filter (may be NULL =
+ * dense), window fp32 [win]; out [B,T_pad,F] bf16 and/or fp32 (either may be
  * NULL), out_lens int32 [B] = frames per utterance. absmax_ws: uint32 [B], raw_ws: fp32 [B*T_pad*F]. */
 int os2s_logmel_forward(const int16_t* wave, const long long* offsets, const int* n_samples, int B,
-                        const float* mel, const float* window, int n_fft, int win, int hop, int F,
+                        const float* mel, const int* mel_band, const float* window, int n_fft, int win, int hop, int F,
                         int T_pad, int max_samples, float dither, uint64_t seed, float preemph,
                         void* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
                         void* stream);

@@ -115,6 +115,8 @@ class Speech2TextDataLayer(DataLayer):
         win = {"hanning": np.hanning, "hamming": np.hamming, "none": np.ones}[win_name](self.n_win)
         self._dev = torch.device("cuda")
         self._mel = torch.tensor(mel, dtype=torch.float32, device=self._dev)
+        band = [[int(np.nonzero(r)[0].min()), int(np.nonzero(r)[0].max()) + 1] if np.any(r) else [0, 0] for r in mel]
+        self._band = torch.tensor(band, dtype=torch.int32, device=self._dev)
         self._win = torch.tensor(win, dtype=torch.float32, device=self._dev)
         self._ws = {}
 
@@ -158,7 +160,8 @@ class Speech2TextDataLayer(DataLayer):
         ws["n"].copy_(torch.tensor(lens, dtype=torch.int32), non_blocking=True)
         dither = float(p.get("dither", 0.0)) if p["mode"] == "train" or p.get("dither", 0.0) else 0.0
         L.check(lib.os2s_logmel_forward(
-            L.ptr(ws["wave"]), L.ptr(ws["off"]), L.ptr(ws["n"]), B, L.ptr(self._mel), L.ptr(self._win), self.n_fft,
+            L.ptr(ws["wave"]), L.ptr(ws["off"]), L.ptr(ws["n"]), B, L.ptr(self._mel), L.ptr(self._band), L.ptr(self._win),
+            self.n_fft,
             self.n_win, self.n_hop, F, T, max_n, ctypes.c_float(dither), ctypes.c_uint64(seed),
             ctypes.c_float(0.97), L.ptr(ws["absmax"]), L.ptr(ws["raw"]), L.ptr(ws["out"]), None, L.ptr(ws["lens"]),
             L.stream_ptr()), "os2s_logmel_forward")
@@ -174,7 +177,8 @@ class Speech2TextDataLayer(DataLayer):
         ws, B, T, max_n, dither = self._last
         F = self.params["num_audio_features"]
         L.check(lib.os2s_logmel_forward(
-            L.ptr(ws["wave"]), L.ptr(ws["off"]), L.ptr(ws["n"]), B, L.ptr(self._mel), L.ptr(self._win), self.n_fft,
+            L.ptr(ws["wave"]), L.ptr(ws["off"]), L.ptr(ws["n"]), B, L.ptr(self._mel), L.ptr(self._band), L.ptr(self._win),
+            self.n_fft,
             self.n_win, self.n_hop, F, T, max_n, ctypes.c_float(dither), ctypes.c_uint64(seed),
             ctypes.c_float(0.97), L.ptr(ws["absmax"]), L.ptr(ws["raw"]), L.ptr(ws["out"]), None, L.ptr(ws["lens"]),
             L.stream_ptr()), "os2s_logmel_forward")

@@ -67,6 +67,8 @@ class EncoderDecoderModel(Model):
             ckpt.restore(self.engine, checkpoint)
         if self.on_horovod:
             self._hvd.broadcast_parameters(self.engine)
+            if self.mode == "train":
+                self.engine.set_comm(self._hvd)
 
     # -------------------------------------------------------------- one step
     def _forward(self, batch):
@@ -78,17 +80,15 @@ class EncoderDecoderModel(Model):
         return enc_out, dec_out
 
     def train_step(self, batch):
-        """sess.run(train_op): forward, loss + backward, gradient all-reduce, optimizer step.
-        Returns (mean loss device tensor, number of objects in the batch as a device tensor)."""
-        was = self.engine.training
-        enc_out, dec_out = self._forward(batch)
-        loss = self._loss_computator.compute_loss({"decoder_output": dec_out,
-                                                   "target_tensors": batch["target_tensors"]})
-        if self.on_horovod:
-            self._hvd.allreduce_(self.engine.grad)
-        self.engine.optimizer_step()
-        self.loss = loss
-        return loss, batch["source_tensors"][1].sum()
+        """sess.run(train_op): forward, loss + backward, gradient all-reduce, optimizer step -- issued
+        through JasperEngine.train_step so the steady-state step is one CUDA-graph replay.  The plugin
+        objects' encode / decode / compute_loss run the same kernels phase by phase (used by eval,
+        infer and the parity tests).  Returns (mean loss, number of input frames) as device tensors."""
+        feats, lens = batch["source_tensors"]
+        y, ylen = batch["target_tensors"]
+        per_utt = self.engine.train_step(feats, lens, y, ylen)
+        self.loss = per_utt.mean()
+        return self.loss, lens.sum()
 
     def eval_step(self, batch):
         enc_out, dec_out = self._forward(batch)

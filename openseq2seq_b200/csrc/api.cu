@@ -11,16 +11,23 @@ extern "C" {
 const char* os2s_last_error(void) { return last_error_cstr(); }
 int os2s_version(void) { return 100; }
 
-int os2s_conv1d_fwd(const void* x, const void* wt, void* y, int B, int T, int C_in, int C_out,
+int os2s_conv1d_fwd(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
                     int K, int dil, int pad_left, int out_mode, void* stream) {
-  if (!x || !wt || !y) return fail(ERR_INVALID, "os2s_conv1d_fwd: null pointer");
-  return conv_kmajor(x, wt, y, B, T, C_in, C_out, K, -pad_left, dil, out_mode, (cudaStream_t)stream);
+  if (!x || !w || !y) return fail(ERR_INVALID, "os2s_conv1d_fwd: null pointer");
+  // B operand MN-major straight from the natural [K][C_in][C_out] layout
+  return conv_kmajor(x, w, y, B, T, C_in, C_out, K, -pad_left, dil, out_mode, 1, (cudaStream_t)stream);
+}
+
+int os2s_conv1d_fwd_wt(const void* x, const void* wt, void* y, int B, int T, int C_in, int C_out,
+                       int K, int dil, int pad_left, int out_mode, void* stream) {
+  if (!x || !wt || !y) return fail(ERR_INVALID, "os2s_conv1d_fwd_wt: null pointer");
+  return conv_kmajor(x, wt, y, B, T, C_in, C_out, K, -pad_left, dil, out_mode, 0, (cudaStream_t)stream);
 }
 
 int os2s_conv1d_dgrad(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
                       int K, int dil, int pad_left, int out_mode, void* stream) {
   if (!dy || !w || !dx) return fail(ERR_INVALID, "os2s_conv1d_dgrad: null pointer");
-  return conv_kmajor(dy, w, dx, B, T, C_out, C_in, K, pad_left, -dil, out_mode, (cudaStream_t)stream);
+  return conv_kmajor(dy, w, dx, B, T, C_out, C_in, K, pad_left, -dil, out_mode, 0, (cudaStream_t)stream);
 }
 
 int os2s_conv1d_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out,
@@ -45,7 +52,8 @@ int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* cons
                       const float* const* gamma_host, const float* const* beta_host,
                       float* const* mean_invstd_host, float* const* moving_host, void* out,
                       const int* lens, int B, int T, int C, float eps, float momentum, float keep,
-                      uint64_t seed, int apply_relu, float relu_clip, int use_moving, void* stream) {
+                      uint64_t seed, int apply_relu, float relu_clip, int use_moving,
+                      const long long* step_counter_dev, void* stream) {
   if (n_branch < 1 || n_branch > kMaxBranches) return fail(ERR_INVALID, "os2s_bn_apply_fwd: 1..12 branches");
   if (!y_host || !stats_host || !gamma_host || !beta_host || !mean_invstd_host || !out)
     return fail(ERR_INVALID, "os2s_bn_apply_fwd: null pointer");
@@ -66,6 +74,7 @@ int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* cons
   p.B = B; p.T = T; p.C = C;
   p.eps = eps; p.momentum = momentum; p.keep = keep; p.seed = seed;
   p.relu_clip = relu_clip; p.apply_relu = apply_relu; p.use_moving = use_moving;
+  p.step_ctr = step_counter_dev;
   return bn_apply_fwd(p, (cudaStream_t)stream);
 }
 
@@ -151,14 +160,14 @@ int os2s_multi_transpose(void* const* src, void* const* dst, const int* Rdev, co
 }
 
 int os2s_logmel_forward(const int16_t* wave, const long long* offsets, const int* n_samples, int B,
-                        const float* mel, const float* window, int n_fft, int win, int hop, int F,
+                        const float* mel, const int* mel_band, const float* window, int n_fft, int win, int hop, int F,
                         int T_pad, int max_samples, float dither, uint64_t seed, float preemph,
                         void* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
                         void* stream) {
   if (!wave || !offsets || !n_samples || !mel || !window || !absmax_ws || !raw_ws)
     return fail(ERR_INVALID, "os2s_logmel_forward: null pointer");
   if (!out_bf16 && !out_f32) return fail(ERR_INVALID, "os2s_logmel_forward: no output buffer");
-  return logmel_forward(wave, offsets, n_samples, B, mel, window, n_fft, win, hop, F, T_pad, max_samples, dither,
+  return logmel_forward(wave, offsets, n_samples, B, mel, mel_band, window, n_fft, win, hop, F, T_pad, max_samples, dither,
                         seed, preemph, (unsigned int*)absmax_ws, raw_ws, out_bf16, out_f32, out_lens,
                         (cudaStream_t)stream);
 }

@@ -69,12 +69,16 @@ struct PipeState {
 
 // Layout of the dynamic shared memory (1024-byte aligned for SWIZZLE_128B):
 //   [A stages][B stages][full bars][empty bars][tmem_full x2][tmem_empty x2][tmem ptr]
-template <int BN>
+// BMN = false: B tile is K-major, rows = n (weights stored [K][N_total][C_red])      -- dgrad
+// BMN = true : B tile is MN-major, rows = c (weights stored [K][C_red][N_total], the natural TF
+//              layout), fetched as BN/64 boxes of {64 n, 64 c}                        -- forward
+template <int BN, bool BMN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const KMajorParams p) {
   constexpr int S = num_stages<BN>();
   constexpr int kBBytes = BN * kChunkK * 2;
+  constexpr int kBoxBytes = 64 * 64 * 2;
   constexpr uint32_t kTmemCols = tmem_cols<BN>();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
@@ -123,11 +127,19 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int k = 0; k < p.K_taps; ++k) {
           const int trow = t0 + p.t_off0 + k * p.t_step;
           const int brow = k * p.N_total + n0;
+          const int crow = k * p.c_chunks * kChunkK;
           for (int c = 0; c < p.c_chunks; ++c) {
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
             mbar_expect_tx(&full_bar[ps.stage], kABytes + kBBytes);
             tma_load_3d(smem_a + ps.stage * kABytes, &map_a, &full_bar[ps.stage], c * kChunkK, trow, b);
-            tma_load_2d(smem_b + ps.stage * kBBytes, &map_b, &full_bar[ps.stage], c * kChunkK, brow);
+            if (BMN) {
+#pragma unroll
+              for (int h = 0; h < BN / 64; ++h)
+                tma_load_2d(smem_b + ps.stage * kBBytes + h * kBoxBytes, &map_b, &full_bar[ps.stage],
+                            n0 + h * 64, crow + c * kChunkK);
+            } else {
+              tma_load_2d(smem_b + ps.stage * kBBytes, &map_b, &full_bar[ps.stage], c * kChunkK, brow);
+            }
             ps.advance<S>();
           }
         }
@@ -135,7 +147,7 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(kTileM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc(kTileM, BN, 0, BMN ? 1 : 0);
       PipeState ps;
       uint32_t ti = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
@@ -151,7 +163,9 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int kk = 0; kk < kChunkK / 16; ++kk) {
             const uint64_t da = make_sdesc(a_addr + kk * 32, 0, 1024);
-            const uint64_t db = make_sdesc(b_addr + kk * 32, 0, 1024);
+            // MN-major B: 16 reduction rows = 2 KB further into every 64-wide box (as in wgrad)
+            const uint64_t db = BMN ? make_sdesc(b_addr + kk * 2048, kBoxBytes, 1024)
+                                    : make_sdesc(b_addr + kk * 32, 0, 1024);
             umma_bf16(tmem_d, da, db, idesc, (it > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[ps.stage]);
@@ -402,18 +416,18 @@ static size_t smem_bytes() {
   return (size_t)num_stages<BN>() * (kABytes + BN * kChunkK * 2) + (2 * num_stages<BN>() + 4) * 8 + 16 + 1024;
 }
 
-template <int BN>
+template <int BN, bool BMN>
 static int launch_kmajor(const CUtensorMap* ma, const CUtensorMap* mb, const KMajorParams& p,
                          cudaStream_t st) {
   static bool attr_done = false;
   const size_t smem = smem_bytes<BN>();
   if (!attr_done) {
-    OS2S_CUDA(cudaFuncSetAttribute(tapgemm_kmajor<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OS2S_CUDA(cudaFuncSetAttribute(tapgemm_kmajor<BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int tiles = p.B * p.n_mtiles * p.n_ntiles;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  tapgemm_kmajor<BN><<<grid, kNumThreads, smem, st>>>(*ma, *mb, p);
+  tapgemm_kmajor<BN, BMN><<<grid, kNumThreads, smem, st>>>(*ma, *mb, p);
   return check_launch("tapgemm_kmajor");
 }
 
@@ -452,18 +466,19 @@ static int pick_bn_mnmajor(int n) {
 //   wmat   : [K][N_total][C_red] bf16 (C_red contiguous)
 //   out    : [B, T, N_total]  (bf16, or fp32 with optional accumulate)
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
-                int K, int t_off0, int t_step, int out_mode, cudaStream_t st) {
+                int K, int t_off0, int t_step, int out_mode, int b_mn_major, cudaStream_t st) {
   if (C_red % 64 != 0) return fail(ERR_UNSUPPORTED, "conv_tc: reduction channels must be a multiple of 64");
-  const int BN = pick_bn_kmajor(N_total);
+  const int BN = b_mn_major ? pick_bn_mnmajor(N_total) : pick_bn_kmajor(N_total);
   if (BN == 0) return fail(ERR_UNSUPPORTED, "conv_tc: output channels must be a multiple of 64");
   if (B <= 0 || T <= 0 || K <= 0) return fail(ERR_INVALID, "conv_tc: bad shape");
   uint64_t adims[3] = {(uint64_t)C_red, (uint64_t)T, (uint64_t)B};
   uint64_t astr[2] = {(uint64_t)C_red * 2, (uint64_t)T * C_red * 2};
   uint32_t abox[3] = {64, 128, 1};
   const CUtensorMap* ma = get_tmap_bf16(act, 3, adims, astr, abox);
-  uint64_t bdims[2] = {(uint64_t)C_red, (uint64_t)K * N_total};
-  uint64_t bstr[1] = {(uint64_t)C_red * 2};
-  uint32_t bbox[2] = {64, (uint32_t)BN};
+  // K-major B: wmat = [K][N_total][C_red] (box {64 c, BN n}); MN-major B: wmat = [K][C_red][N_total]
+  uint64_t bdims[2] = {(uint64_t)(b_mn_major ? N_total : C_red), (uint64_t)K * (b_mn_major ? C_red : N_total)};
+  uint64_t bstr[1] = {(uint64_t)(b_mn_major ? N_total : C_red) * 2};
+  uint32_t bbox[2] = {64, (uint32_t)(b_mn_major ? 64 : BN)};
   const CUtensorMap* mb = get_tmap_bf16(wmat, 2, bdims, bstr, bbox);
   if (!ma || !mb) return ERR_CUDA;
   KMajorParams p;
@@ -480,14 +495,23 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
   p.out_row_stride = N_total;
   p.out_batch_stride = (long long)T * N_total;
   p.out_mode = out_mode;
+  if (b_mn_major) {
+    switch (BN) {
+      case 256: return launch_kmajor<256, true>(ma, mb, p, st);
+      case 192: return launch_kmajor<192, true>(ma, mb, p, st);
+      case 128: return launch_kmajor<128, true>(ma, mb, p, st);
+      case 64: return launch_kmajor<64, true>(ma, mb, p, st);
+    }
+    return fail(ERR_UNSUPPORTED, "conv_tc: no tile for N");
+  }
   switch (BN) {
-    case 256: return launch_kmajor<256>(ma, mb, p, st);
-    case 224: return launch_kmajor<224>(ma, mb, p, st);
-    case 192: return launch_kmajor<192>(ma, mb, p, st);
-    case 160: return launch_kmajor<160>(ma, mb, p, st);
-    case 128: return launch_kmajor<128>(ma, mb, p, st);
-    case 96: return launch_kmajor<96>(ma, mb, p, st);
-    case 64: return launch_kmajor<64>(ma, mb, p, st);
+    case 256: return launch_kmajor<256, false>(ma, mb, p, st);
+    case 224: return launch_kmajor<224, false>(ma, mb, p, st);
+    case 192: return launch_kmajor<192, false>(ma, mb, p, st);
+    case 160: return launch_kmajor<160, false>(ma, mb, p, st);
+    case 128: return launch_kmajor<128, false>(ma, mb, p, st);
+    case 96: return launch_kmajor<96, false>(ma, mb, p, st);
+    case 64: return launch_kmajor<64, false>(ma, mb, p, st);
   }
   return fail(ERR_UNSUPPORTED, "conv_tc: no tile for N");
 }

@@ -76,29 +76,73 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
   return v;
 }
 
-// Per-channel sum and sum of squares of y [M, C] (bf16). stats = [2][C] fp32, pre-zeroed.
-// Thread layout: each thread owns one 8-channel vector (16-byte loads) and walks rows.
-constexpr int kStatThreads = 256;
-__global__ void __launch_bounds__(kStatThreads)
-bn_stats_kernel(const __half* __restrict__ y, float* __restrict__ stats, int M, int C,
-                int rows_per_block) {
+// ---------------------------------------------------------------------------------------------
+// Row tiling shared by the four BN kernels.  The [M, C] matrix is cut into row chunks, one CTA per
+// chunk; inside a CTA thread t owns ONE 8-channel vector column cv = t % CV (16-byte accesses,
+// a warp covers 512 contiguous bytes of a row) and walks rows r, r+RP, r+2RP, ... with RP = 256/CV
+// rows in flight per pass.  Loops are unrolled 4 rows deep with all loads issued before use (4
+// independent 16-byte loads in flight per thread and tensor), there is no integer division in any
+// loop, and per-channel coefficients live in registers (single branch) or are fetched from shared
+// memory once per 4 rows (dense-residual layers).
+constexpr int kEwThreads = 256;
+constexpr int kUnroll = 4;
+
+struct RowTile {
+  int CV, RP, cv, r, row0, row1;
+  bool active;
+};
+__device__ __forceinline__ RowTile make_row_tile(int M, int C, int rows_per_block) {
+  RowTile t;
+  t.CV = C >> 3;
+  t.RP = kEwThreads / t.CV;
+  t.cv = threadIdx.x % t.CV;
+  t.r = threadIdx.x / t.CV;
+  t.active = t.r < t.RP;
+  t.row0 = blockIdx.x * rows_per_block;
+  t.row1 = min(M, t.row0 + rows_per_block);
+  return t;
+}
+static int rows_per_block_for(int M, int C, int waves) {
+  const int RP = kEwThreads / (C >> 3);
+  int target = device_sm_count() * waves;
+  int rpb = (M + target - 1) / target;
+  const int min_rows = RP * kUnroll * 2;  // at least two unrolled passes per thread
+  if (rpb < min_rows) rpb = min_rows;
+  return rpb;
+}
+
+// Per-channel sum and sum of squares of y [M, C] (fp16). stats = [2][C] fp32, pre-zeroed.
+__global__ void __launch_bounds__(kEwThreads)
+bn_stats_kernel(const __half* __restrict__ y, float* __restrict__ stats, int M, int C, int rows_per_block) {
   extern __shared__ float sh[];  // [2][C]
-  const int CV = C >> 3;
-  const int RP = kStatThreads / CV;  // rows processed per pass
-  const int cv = threadIdx.x % CV;
-  const int r = threadIdx.x / CV;
-  for (int i = threadIdx.x; i < 2 * C; i += kStatThreads) sh[i] = 0.f;
+  const RowTile t = make_row_tile(M, C, rows_per_block);
+  for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) sh[i] = 0.f;
   __syncthreads();
-  float s[8], q[8];
+  if (t.active) {
+    float s[8], q[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  if (r < RP) {
-    const int row0 = blockIdx.x * rows_per_block;
-    const int row1 = min(M, row0 + rows_per_block);
-    for (int row = row0 + r; row < row1; row += RP) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(y + (size_t)row * C) + cv);
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    const uint4* base = reinterpret_cast<const uint4*>(y) + t.cv;
+    const size_t rs = (size_t)t.CV;  // row stride in uint4
+    int row = t.row0 + t.r;
+    for (; row + (kUnroll - 1) * t.RP < t.row1; row += kUnroll * t.RP) {
+      uint4 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) v[u] = __ldg(base + (size_t)(row + u * t.RP) * rs);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        float f[8];
+        f16x8_to_float(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          q[i] += f[i] * f[i];
+        }
+      }
+    }
+    for (; row < t.row1; row += t.RP) {
       float f[8];
-      f16x8_to_float(v, f);
+      f16x8_to_float(__ldg(base + (size_t)row * rs), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s[i] += f[i];
@@ -107,22 +151,19 @@ bn_stats_kernel(const __half* __restrict__ y, float* __restrict__ stats, int M, 
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sh[cv * 8 + i], s[i]);
-      atomicAdd(&sh[C + cv * 8 + i], q[i]);
+      atomicAdd(&sh[t.cv * 8 + i], s[i]);
+      atomicAdd(&sh[C + t.cv * 8 + i], q[i]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += kStatThreads) atomicAdd(&stats[i], sh[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) atomicAdd(&stats[i], sh[i]);
 }
 
 int bn_stats(const void* y, float* stats, int M, int C, cudaStream_t st) {
   if (C % 8 != 0 || C > 2048 || C < 8) return fail(ERR_UNSUPPORTED, "bn_stats: C must be a multiple of 8, <= 2048");
-  const int target_blocks = device_sm_count() * 4;
-  int rows_per_block = (M + target_blocks - 1) / target_blocks;
-  if (rows_per_block < 8) rows_per_block = 8;
-  const int grid = (M + rows_per_block - 1) / rows_per_block;
-  bn_stats_kernel<<<grid, kStatThreads, 2 * C * sizeof(float), st>>>((const __half*)y, stats, M, C,
-                                                                    rows_per_block);
+  const int rpb = rows_per_block_for(M, C, 3);
+  const int grid = (M + rpb - 1) / rpb;
+  bn_stats_kernel<<<grid, kEwThreads, 2 * C * sizeof(float), st>>>((const __half*)y, stats, M, C, rpb);
   return check_launch("bn_stats");
 }
 
@@ -131,7 +172,6 @@ int bn_stats(const void* y, float* stats, int M, int C, cudaStream_t st) {
 // One launch covers the main branch plus all dense-residual branches of a block-ending layer
 // (conv_blocks.py:61-168); plain layers have n_branch = 1 (conv_blocks.py:170-232).
 // Block 0 additionally finalises mean / invstd (saved for backward) and the moving averages.
-
 __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
   *hi = __umulhi(a, b);
   return a * b;
@@ -150,13 +190,14 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   return ctr;
 }
 
-constexpr int kApplyThreads = 256;
-__global__ void __launch_bounds__(kApplyThreads)
-bn_apply_fwd_kernel(const BnFwdParams p) {
+
+__global__ void __launch_bounds__(kEwThreads)
+bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
   extern __shared__ float sh[];  // [n_branch][2][C]: scale, shift
   const int C = p.C;
-  const float inv_n = 1.f / (float)((long long)p.B * p.T);
-  for (int i = threadIdx.x; i < p.n_branch * C; i += kApplyThreads) {
+  const int M = p.B * p.T;
+  const float inv_n = 1.f / (float)M;
+  for (int i = threadIdx.x; i < p.n_branch * C; i += kEwThreads) {
     const int j = i / C, c = i - j * C;
     const BnBranchFwd& b = p.br[j];
     // training: batch statistics; inference (use_moving): the moving averages
@@ -170,7 +211,7 @@ bn_apply_fwd_kernel(const BnFwdParams p) {
       b.mean_invstd[c] = mean;
       b.mean_invstd[C + c] = invstd;
       if (b.moving) {
-        const float n = (float)((long long)p.B * p.T);
+        const float n = (float)M;
         const float unbiased = var * (n / fmaxf(n - 1.f, 1.f));
         b.moving[c] = b.moving[c] * p.momentum + mean * (1.f - p.momentum);
         b.moving[C + c] = b.moving[C + c] * p.momentum + unbiased * (1.f - p.momentum);
@@ -178,55 +219,88 @@ bn_apply_fwd_kernel(const BnFwdParams p) {
     }
   }
   __syncthreads();
-  const int CV = C >> 3;
-  const long long total = (long long)p.B * p.T * CV;
+  const RowTile t = make_row_tile(M, C, rows_per_block);
+  if (!t.active) return;
   const float inv_keep = 1.f / p.keep;
-  const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-  for (long long idx = (long long)blockIdx.x * kApplyThreads + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * kApplyThreads) {
-    const long long row = idx / CV;
-    const int cv = (int)(idx - row * CV);
-    const int b = (int)(row / p.T);
-    const int t = (int)(row - (long long)b * p.T);
-    float acc[8];
+  unsigned long long seed = p.seed;
+  if (p.step_ctr) seed += (unsigned long long)(*p.step_ctr) * 0x9E3779B97F4A7C15ull;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const size_t rs = (size_t)t.CV;
+  // (b, tt) of the thread's first row, advanced incrementally (no division in the loop)
+  int row = t.row0 + t.r;
+  int b = row / p.T, tt = row - b * p.T;
+  for (; row < t.row1; row += kUnroll * t.RP) {
+    float acc[kUnroll][8];
+    bool live[kUnroll];
+    int bb = b, t2 = tt;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const bool valid = (p.lens == nullptr) || (t < p.lens[b]);
-    if (valid) {
-      for (int j = 0; j < p.n_branch; ++j) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.br[j].y + row * C) + cv);
+    for (int u = 0; u < kUnroll; ++u) {
+      const int ru = row + u * t.RP;
+      live[u] = ru < t.row1 && (p.lens == nullptr || t2 < __ldg(p.lens + min(bb, p.B - 1)));
+      t2 += t.RP;
+      while (t2 >= p.T) { t2 -= p.T; ++bb; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[u][i] = 0.f;
+    }
+    for (int j = 0; j < p.n_branch; ++j) {
+      const uint4* yb = reinterpret_cast<const uint4*>(p.br[j].y) + t.cv;
+      uint4 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        v[u] = live[u] ? __ldg(yb + (size_t)(row + u * t.RP) * rs) : make_uint4(0, 0, 0, 0);
+      float sc[8], sf[8];
+      const float4* scp = reinterpret_cast<const float4*>(&sh[(j * 2) * C + t.cv * 8]);
+      const float4* sfp = reinterpret_cast<const float4*>(&sh[(j * 2 + 1) * C + t.cv * 8]);
+      *reinterpret_cast<float4*>(&sc[0]) = scp[0];
+      *reinterpret_cast<float4*>(&sc[4]) = scp[1];
+      *reinterpret_cast<float4*>(&sf[0]) = sfp[0];
+      *reinterpret_cast<float4*>(&sf[4]) = sfp[1];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
         float f[8];
-        f16x8_to_float(v, f);
-        const float* sc = &sh[(j * 2) * C + cv * 8];
-        const float* sf = &sh[(j * 2 + 1) * C + cv * 8];
+        f16x8_to_float(v[u], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += f[i] * sc[i] + sf[i];
-      }
-      if (p.apply_relu) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[i] = fmaxf(acc[i], 0.f);
-          if (p.relu_clip > 0.f) acc[i] = fminf(acc[i], p.relu_clip);
-        }
-      }
-      if (p.keep < 1.f) {
-        const uint4 r0 = philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u), key);
-        const uint4 r1 = philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 1u, 0u), key);
-        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float u = (float)(rr[i] >> 8) * (1.f / 16777216.f);  // [0,1)
-          acc[i] = (u < p.keep) ? acc[i] * inv_keep : 0.f;
-        }
+        for (int i = 0; i < 8; ++i) acc[u][i] += f[i] * sc[i] + sf[i];
       }
     }
-    reinterpret_cast<uint4*>(p.out + row * C)[cv] = float_to_bf16x8(acc);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int ru = row + u * t.RP;
+      if (ru >= t.row1) break;
+      if (live[u]) {
+        if (p.apply_relu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc[u][i] = fmaxf(acc[u][i], 0.f);
+            if (p.relu_clip > 0.f) acc[u][i] = fminf(acc[u][i], p.relu_clip);
+          }
+        }
+        if (p.keep < 1.f) {
+          const unsigned long long idx = (unsigned long long)ru * (unsigned)t.CV + (unsigned)t.cv;
+          const uint4 r0 = philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u), key);
+          const uint4 r1 = philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 1u, 0u), key);
+          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float uu = (float)(rr[i] >> 8) * (1.f / 16777216.f);  // [0,1)
+            acc[u][i] = (uu < p.keep) ? acc[u][i] * inv_keep : 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[u][i] = 0.f;
+      }
+      reinterpret_cast<uint4*>(p.out)[(size_t)ru * rs + t.cv] = float_to_bf16x8(acc[u]);
+    }
+    // advance (b, tt) by kUnroll * RP rows
+    tt += kUnroll * t.RP;
+    while (tt >= p.T) { tt -= p.T; ++b; }
   }
 }
 
 int bn_apply_fwd(const BnFwdParams& p, cudaStream_t st) {
   if (p.n_branch < 1 || p.n_branch > kMaxBranches) return fail(ERR_INVALID, "bn_apply_fwd: bad branch count");
-  if (p.C % 8 != 0) return fail(ERR_UNSUPPORTED, "bn_apply_fwd: C must be a multiple of 8");
+  if (p.C % 8 != 0 || p.C > 2048) return fail(ERR_UNSUPPORTED, "bn_apply_fwd: C must be a multiple of 8, <= 2048");
   const size_t smem = (size_t)p.n_branch * 2 * p.C * sizeof(float);
   if (smem > 200 * 1024) return fail(ERR_UNSUPPORTED, "bn_apply_fwd: too many branches x channels");
   static bool attr_done = false;
@@ -234,133 +308,183 @@ int bn_apply_fwd(const BnFwdParams& p, cudaStream_t st) {
     OS2S_CUDA(cudaFuncSetAttribute(bn_apply_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  const long long total = (long long)p.B * p.T * (p.C / 8);
-  long long blocks = (total + kApplyThreads - 1) / kApplyThreads;
-  const long long cap = (long long)device_sm_count() * 8;
-  if (blocks > cap) blocks = cap;
-  bn_apply_fwd_kernel<<<(int)blocks, kApplyThreads, smem, st>>>(p);
+  const int M = p.B * p.T;
+  const int rpb = rows_per_block_for(M, p.C, smem > 48 * 1024 ? 2 : 4);
+  const int grid = (M + rpb - 1) / rpb;
+  bn_apply_fwd_kernel<<<grid, kEwThreads, smem, st>>>(p, rpb);
   return check_launch("bn_apply_fwd");
 }
 
 // ------------------------------------------------------------------------------- backward
 // dz = dA * [a != 0] / keep           (relu + dropout + row mask folded into "a != 0")
-// pass 1: dbeta = sum dz (shared by all branches), dgamma_j = sum dz * xhat_j
-// pass 2: dy_j = gamma_j * invstd_j * (dz - dbeta/N - xhat_j * dgamma_j/N)
-
+// pass 1: dbeta = sum dz (shared by all branches), S_j = sum dz * y_j
+//         (dgamma_j = invstd_j * (S_j - mean_j * dbeta), finalised in pass 2's prologue)
+// pass 2: dy_j = gamma_j * invstd_j * (dz - dbeta/N - xhat_j * dgamma_j/N) = A_j*dz + B_j*y_j + C_j
 template <bool F32>
-__device__ __forceinline__ void load_dz(const BnBwdParams& p, long long row, int cv, float (&dz)[8]) {
-  const int C = p.C;
+__device__ __forceinline__ void load_dz_raw(const BnBwdParams& p, size_t vec_index, uint4& a_raw, float (&dz)[8]) {
+  // vec_index = row * CV + cv
   if (F32) {
-    const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dA) + row * C) + cv * 2;
+    const float4* src = reinterpret_cast<const float4*>(p.dA) + vec_index * 2;
     const float4 a0 = __ldg(src), a1 = __ldg(src + 1);
     dz[0] = a0.x; dz[1] = a0.y; dz[2] = a0.z; dz[3] = a0.w;
     dz[4] = a1.x; dz[5] = a1.y; dz[6] = a1.z; dz[7] = a1.w;
   } else {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dA) + row * C) + cv);
-    bf16x8_to_float(v, dz);
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.dA) + vec_index), dz);
   }
+  if (p.apply_relu) a_raw = __ldg(reinterpret_cast<const uint4*>(p.a) + vec_index);
+}
+__device__ __forceinline__ void gate_dz(const BnBwdParams& p, const uint4& a_raw, float (&dz)[8]) {
   if (p.apply_relu) {
-    const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.a + row * C) + cv);
     float af[8];
-    bf16x8_to_float(av, af);
+    bf16x8_to_float(a_raw, af);
     const float inv_keep = 1.f / p.keep;
 #pragma unroll
     for (int i = 0; i < 8; ++i) dz[i] = (af[i] != 0.f) ? dz[i] * inv_keep : 0.f;
   }
 }
 
+constexpr int kBwdGroup = 4;  // branches reduced per sweep over the rows
 template <bool F32>
-__global__ void __launch_bounds__(kStatThreads)
+__global__ void __launch_bounds__(kEwThreads)
 bn_bwd_reduce_kernel(const BnBwdParams p, int rows_per_block) {
   extern __shared__ float sh[];  // [1 + n_branch][C]
   const int C = p.C;
-  const int CV = C >> 3;
-  const int RP = kStatThreads / CV;
-  const int cv = threadIdx.x % CV;
-  const int r = threadIdx.x / CV;
   const int nred = (1 + p.n_branch) * C;
-  for (int i = threadIdx.x; i < nred; i += kStatThreads) sh[i] = 0.f;
+  for (int i = threadIdx.x; i < nred; i += kEwThreads) sh[i] = 0.f;
   __syncthreads();
-  if (r < RP) {
-    const int row0 = blockIdx.x * rows_per_block;
-    const int row1 = min(p.M, row0 + rows_per_block);
-    float db[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) db[i] = 0.f;
-    // branch loop outside the row loop would re-read dz; keep per-branch accumulators in smem atomics
-    // only at the end: process branches one at a time over the row range (dz is L2/L1 resident).
-    for (int j = 0; j < p.n_branch; ++j) {
-      float dg[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dg[i] = 0.f;
-      const float* mi = p.br[j].mean_invstd;
-      float mean[8], invstd[8];
+  const RowTile t = make_row_tile(p.M, C, rows_per_block);
+  if (t.active) {
+    const size_t rs = (size_t)t.CV;
+    for (int j0 = 0; j0 < p.n_branch; j0 += kBwdGroup) {
+      const int nj = min(kBwdGroup, p.n_branch - j0);
+      float db[8], S[kBwdGroup][8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        mean[i] = mi[cv * 8 + i];
-        invstd[i] = mi[C + cv * 8 + i];
-      }
-      for (int row = row0 + r; row < row1; row += RP) {
-        float dz[8];
-        load_dz<F32>(p, row, cv, dz);
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.br[j].y + (size_t)row * C) + cv);
-        float f[8];
-        f16x8_to_float(v, f);
+        db[i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          dg[i] += dz[i] * (f[i] - mean[i]) * invstd[i];
-          if (j == 0) db[i] += dz[i];
+        for (int g = 0; g < kBwdGroup; ++g) S[g][i] = 0.f;
+      }
+      for (int row = t.row0 + t.r; row < t.row1; row += 2 * t.RP) {
+        const bool two = row + t.RP < t.row1;
+        float dz0[8], dz1[8];
+        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+        uint4 y0[kBwdGroup], y1[kBwdGroup];
+        const size_t v0 = (size_t)row * rs + t.cv, v1 = v0 + (size_t)t.RP * rs;
+        load_dz_raw<F32>(p, v0, a0, dz0);
+        if (two) load_dz_raw<F32>(p, v1, a1, dz1);
+#pragma unroll
+        for (int g = 0; g < kBwdGroup; ++g) {
+          if (g < nj) {
+            const uint4* yb = reinterpret_cast<const uint4*>(p.br[j0 + g].y);
+            y0[g] = __ldg(yb + v0);
+            if (two) y1[g] = __ldg(yb + v1);
+          }
+        }
+        gate_dz(p, a0, dz0);
+        if (two) gate_dz(p, a1, dz1);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dz1[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) db[i] += dz0[i] + dz1[i];
+#pragma unroll
+        for (int g = 0; g < kBwdGroup; ++g) {
+          if (g < nj) {
+            float f[8];
+            f16x8_to_float(y0[g], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) S[g][i] += dz0[i] * f[i];
+            if (two) {
+              f16x8_to_float(y1[g], f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) S[g][i] += dz1[i] * f[i];
+            }
+          }
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&sh[(1 + j) * C + cv * 8 + i], dg[i]);
-    }
+      for (int g = 0; g < kBwdGroup; ++g) {
+        if (g < nj) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&sh[cv * 8 + i], db[i]);
+          for (int i = 0; i < 8; ++i) atomicAdd(&sh[(1 + j0 + g) * C + t.cv * 8 + i], S[g][i]);
+        }
+      }
+      if (j0 == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&sh[t.cv * 8 + i], db[i]);
+      }
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nred; i += kStatThreads) atomicAdd(&p.red[i], sh[i]);
+  for (int i = threadIdx.x; i < nred; i += kEwThreads) atomicAdd(&p.red[i], sh[i]);
 }
 
 template <bool F32>
-__global__ void __launch_bounds__(kApplyThreads)
-bn_bwd_apply_kernel(const BnBwdParams p) {
-  extern __shared__ float sh[];  // per branch: k1 = gamma*invstd, k2 = dbeta/N, k3 = dgamma/N*invstd, mean
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
+  extern __shared__ float sh[];  // per branch: A = gamma*invstd, B, Cc  (dy = A*dz + B*y + Cc)
   const int C = p.C;
   const float inv_n = 1.f / (float)p.M;
-  for (int i = threadIdx.x; i < p.n_branch * C; i += kApplyThreads) {
+  for (int i = threadIdx.x; i < p.n_branch * C; i += kEwThreads) {
     const int j = i / C, c = i - j * C;
     const BnBranchBwd& b = p.br[j];
     const float mean = b.mean_invstd[c], invstd = b.mean_invstd[C + c];
-    const float dbeta = p.red[c], dgamma = p.red[(1 + j) * C + c];
-    float* s = &sh[(size_t)j * 4 * C];
-    s[c] = b.gamma[c] * invstd;
-    s[C + c] = dbeta * inv_n;
-    s[2 * C + c] = dgamma * inv_n * invstd;
-    s[3 * C + c] = mean;
+    const float dbeta = p.red[c];
+    const float dgamma = invstd * (p.red[(1 + j) * C + c] - mean * dbeta);
+    const float A = b.gamma[c] * invstd;
+    const float Bc = -A * invstd * dgamma * inv_n;
+    float* s = &sh[(size_t)j * 3 * C];
+    s[c] = A;
+    s[C + c] = Bc;
+    s[2 * C + c] = -A * dbeta * inv_n - Bc * mean;
     if (blockIdx.x == 0) {
       b.dgamma[c] = dgamma;
       b.dbeta[c] = dbeta;
     }
   }
   __syncthreads();
-  const int CV = C >> 3;
-  const long long total = (long long)p.M * CV;
-  for (long long idx = (long long)blockIdx.x * kApplyThreads + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * kApplyThreads) {
-    const long long row = idx / CV;
-    const int cv = (int)(idx - row * CV);
-    float dz[8];
-    load_dz<F32>(p, row, cv, dz);
-    for (int j = 0; j < p.n_branch; ++j) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.br[j].y + row * C) + cv);
-      float f[8], o[8];
-      f16x8_to_float(v, f);
-      const float* s = &sh[(size_t)j * 4 * C + cv * 8];
+  const RowTile t = make_row_tile(p.M, C, rows_per_block);
+  if (!t.active) return;
+  const size_t rs = (size_t)t.CV;
+  for (int row = t.row0 + t.r; row < t.row1; row += kUnroll * t.RP) {
+    float dz[kUnroll][8];
+    uint4 araw[kUnroll];
+    bool live[kUnroll];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        o[i] = s[i] * (dz[i] - s[C + i] - (f[i] - s[3 * C + i]) * s[2 * C + i]);
-      reinterpret_cast<uint4*>(p.br[j].dy + row * C)[cv] = float_to_bf16x8(o);
+    for (int u = 0; u < kUnroll; ++u) {
+      live[u] = row + u * t.RP < t.row1;
+      araw[u] = make_uint4(0, 0, 0, 0);
+      if (live[u]) load_dz_raw<F32>(p, (size_t)(row + u * t.RP) * rs + t.cv, araw[u], dz[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (live[u]) gate_dz(p, araw[u], dz[u]);
+    for (int j = 0; j < p.n_branch; ++j) {
+      const uint4* yb = reinterpret_cast<const uint4*>(p.br[j].y) + t.cv;
+      uint4* db = reinterpret_cast<uint4*>(p.br[j].dy) + t.cv;
+      uint4 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (live[u]) v[u] = __ldg(yb + (size_t)(row + u * t.RP) * rs);
+      float A[8], Bc[8], Cc[8];
+      const float* s = &sh[(size_t)j * 3 * C + t.cv * 8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        A[i] = s[i];
+        Bc[i] = s[C + i];
+        Cc[i] = s[2 * C + i];
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (live[u]) {
+          float f[8], o[8];
+          f16x8_to_float(v[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = A[i] * dz[u][i] + Bc[i] * f[i] + Cc[i];
+          db[(size_t)(row + u * t.RP) * rs] = float_to_bf16x8(o);
+        }
+      }
     }
   }
 }
@@ -377,22 +501,18 @@ int bn_bwd(const BnBwdParams& p, cudaStream_t st) {
     attr_done = true;
   }
   const size_t smem_r = (size_t)(1 + p.n_branch) * p.C * sizeof(float);
-  const size_t smem_a = (size_t)p.n_branch * 4 * p.C * sizeof(float);
+  const size_t smem_a = (size_t)p.n_branch * 3 * p.C * sizeof(float);
   if (smem_a > 200 * 1024 || smem_r > 100 * 1024) return fail(ERR_UNSUPPORTED, "bn_bwd: too many branches x channels");
-  const int target_blocks = device_sm_count() * 4;
-  int rows_per_block = (p.M + target_blocks - 1) / target_blocks;
-  if (rows_per_block < 8) rows_per_block = 8;
-  const int grid_r = (p.M + rows_per_block - 1) / rows_per_block;
-  const long long total = (long long)p.M * (p.C / 8);
-  long long blocks = (total + kApplyThreads - 1) / kApplyThreads;
-  const long long cap = (long long)device_sm_count() * 8;
-  if (blocks > cap) blocks = cap;
+  const int rpb_r = rows_per_block_for(p.M, p.C, 2);
+  const int rpb_a = rows_per_block_for(p.M, p.C, smem_a > 48 * 1024 ? 2 : 4);
+  const int grid_r = (p.M + rpb_r - 1) / rpb_r;
+  const int grid_a = (p.M + rpb_a - 1) / rpb_a;
   if (p.dA_is_f32) {
-    bn_bwd_reduce_kernel<true><<<grid_r, kStatThreads, smem_r, st>>>(p, rows_per_block);
-    bn_bwd_apply_kernel<true><<<(int)blocks, kApplyThreads, smem_a, st>>>(p);
+    bn_bwd_reduce_kernel<true><<<grid_r, kEwThreads, smem_r, st>>>(p, rpb_r);
+    bn_bwd_apply_kernel<true><<<grid_a, kEwThreads, smem_a, st>>>(p, rpb_a);
   } else {
-    bn_bwd_reduce_kernel<false><<<grid_r, kStatThreads, smem_r, st>>>(p, rows_per_block);
-    bn_bwd_apply_kernel<false><<<(int)blocks, kApplyThreads, smem_a, st>>>(p);
+    bn_bwd_reduce_kernel<false><<<grid_r, kEwThreads, smem_r, st>>>(p, rpb_r);
+    bn_bwd_apply_kernel<false><<<grid_a, kEwThreads, smem_a, st>>>(p, rpb_a);
   }
   return check_launch("bn_bwd");
 }

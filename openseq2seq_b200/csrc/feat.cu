@@ -63,11 +63,19 @@ template <int NFFT>
 __global__ void __launch_bounds__(kFeatWarps * 32)
 feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__ offsets,
                    const int* __restrict__ n_samples, const unsigned int* __restrict__ absmax,
-                   const float* __restrict__ mel, const float* __restrict__ window, float* __restrict__ raw,
+                   const float* __restrict__ mel, const int* __restrict__ mel_band,
+                   const float* __restrict__ window, float* __restrict__ raw,
                    int T_pad, int F, int hop, int win, float dither, unsigned long long seed, float preemph) {
   constexpr int NB = NFFT / 2 + 1;
   __shared__ float re[kFeatWarps][NFFT];
   __shared__ float im[kFeatWarps][NFFT];
+  __shared__ float2 tw[NFFT / 2];  // exp(-2 pi i k / NFFT), computed once per CTA
+  for (int k = threadIdx.x; k < NFFT / 2; k += kFeatWarps * 32) {
+    float sn, cs;
+    sincospif(-2.f * (float)k / (float)NFFT, &sn, &cs);
+    tw[k] = make_float2(cs, sn);
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int frame = blockIdx.x * kFeatWarps + warp;
@@ -101,8 +109,8 @@ feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__
     for (int i = lane; i < NFFT / 2; i += 32) {
       const int grp = i / half, k = i - grp * half;
       const int i0 = grp * 2 * half + k, i1 = i0 + half;
-      float sn, cs;
-      __sincosf(-3.14159265358979f * (float)k / (float)half, &sn, &cs);
+      const float2 w2 = tw[k * (NFFT / 2 / half)];
+      const float cs = w2.x, sn = w2.y;
       const float xr = re[warp][i1], xi = im[warp][i1];
       const float tr = xr * cs - xi * sn, ti = xr * sn + xi * cs;
       const float ur = re[warp][i0], ui = im[warp][i0];
@@ -122,8 +130,11 @@ feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__
   // mel mat-vec: feature f = lane, lane+32; mel is [F][NB] row-major (dense)
   for (int f = lane; f < F; f += 32) {
     const float* mrow = mel + (size_t)f * NB;
+    // triangular filters are zero outside [lo, hi): only the support is visited when bands are given
+    const int lo = mel_band ? mel_band[2 * f] : 0;
+    const int hi = mel_band ? mel_band[2 * f + 1] : NB;
     float acc = 0.f;
-    for (int k = 0; k < NB; ++k) acc += mrow[k] * re[warp][k];
+    for (int k = lo; k < hi; ++k) acc += mrow[k] * re[warp][k];
     raw[((size_t)b * T_pad + frame) * F + f] = logf(acc + 1e-20f);
   }
 }
@@ -161,7 +172,7 @@ __global__ void feat_norm_kernel(const float* __restrict__ raw, const int* __res
 }
 
 int logmel_forward(const short* wave, const long long* offsets, const int* n_samples, int B,
-                   const float* mel, const float* window, int n_fft, int win, int hop, int F, int T_pad,
+                   const float* mel, const int* mel_band, const float* window, int n_fft, int win, int hop, int F, int T_pad,
                    int max_samples, float dither, unsigned long long seed, float preemph,
                    unsigned int* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
                    cudaStream_t st) {
@@ -172,7 +183,7 @@ int logmel_forward(const short* wave, const long long* offsets, const int* n_sam
   const int max_frames = 1 + max_samples / hop;
   if (max_frames > T_pad) return fail(ERR_INVALID, "logmel_forward: T_pad smaller than the frame count");
   dim3 grid((max_frames + kFeatWarps - 1) / kFeatWarps, B);
-  feat_logmel_kernel<512><<<grid, kFeatWarps * 32, 0, st>>>(wave, offsets, n_samples, absmax_ws, mel, window, raw_ws,
+  feat_logmel_kernel<512><<<grid, kFeatWarps * 32, 0, st>>>(wave, offsets, n_samples, absmax_ws, mel, mel_band, window, raw_ws,
                                                            T_pad, F, hop, win, dither, seed, preemph);
   dim3 grid2((F + 7) / 8, B);
   feat_norm_kernel<<<grid2, 256, 0, st>>>(raw_ws, n_samples, (__nv_bfloat16*)out_bf16, out_f32, out_lens, T_pad, F,

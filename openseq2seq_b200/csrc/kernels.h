@@ -15,7 +15,7 @@ const char* last_error_cstr();
 
 // conv_tc.cu
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
-                int K, int t_off0, int t_step, int out_mode, cudaStream_t st);
+                int K, int t_off0, int t_step, int out_mode, int b_mn_major, cudaStream_t st);
 int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out, int K,
                int dil, int pad_left, int* splits_used, cudaStream_t st);
 
@@ -42,6 +42,7 @@ struct BnFwdParams {
   float relu_clip;      // <= 0: plain relu, > 0: min(relu(x), clip)
   int apply_relu;
   int use_moving;       // 1 = inference mode: normalise with the moving statistics
+  const long long* step_ctr;  // optional device counter mixed into the dropout seed (CUDA-graph replays)
 };
 struct BnBranchBwd {
   const __half* y;          // conv output, fp16
@@ -106,7 +107,7 @@ int multi_transpose(const TransposeTable& tab, long long total_tiles, cudaStream
 
 // feat.cu
 int logmel_forward(const short* wave, const long long* offsets, const int* n_samples, int B,
-                   const float* mel, const float* window, int n_fft, int win, int hop, int F, int T_pad,
+                   const float* mel, const int* mel_band, const float* window, int n_fft, int win, int hop, int F, int T_pad,
                    int max_samples, float dither, unsigned long long seed, float preemph,
                    unsigned int* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
                    cudaStream_t st);

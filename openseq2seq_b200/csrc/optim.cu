@@ -71,7 +71,7 @@ opt_norms_kernel(const OptTable tab, float* __restrict__ norms, int* __restrict_
 // Pass 2 (one CTA): scaler / step / lr bookkeeping and the per-tensor gradient coefficient.
 //   fstate: [0] loss_scale (used by the NEXT backward)  [1] lr of this step  [2] global grad norm
 //   istate: [0] scaler iteration  [1] last overflow iteration  [2] global_step  [3] skip flag (this step)
-//           [4] number of skipped steps so far
+//           [4] number of skipped steps so far  [5] attempted steps
 __global__ void opt_prepare_kernel(const OptTable tab, const OptHParams hp, float* __restrict__ norms,
                                    int* __restrict__ nonfinite, float* __restrict__ fstate,
                                    long long* __restrict__ istate, float* __restrict__ coef,
@@ -109,6 +109,7 @@ __global__ void opt_prepare_kernel(const OptTable tab, const OptHParams hp, floa
     istate[2] = skip ? step : step + 1;
     istate[3] = skip ? 1 : 0;
     if (skip) istate[4] += 1;
+    istate[5] += 1;  // attempted steps (drives the dropout stream)
     s_scale_used = scale_used;
     s_lr = lr;
     s_skip = skip ? 1 : 0;

@@ -18,14 +18,24 @@ class TorchDistHvd(object):
         self._rank, self._size, self._local_rank = rank, size, local_rank
 
     @classmethod
-    def init(cls):
+    def init(cls, backend=None):
+        """backend: "nccl" on GPUs (default when CUDA is available); "gloo" is used by the CPU tests of
+        the host-side logic (world_size 2, no GPU)."""
         rank = int(os.environ["RANK"])
         world = int(os.environ["WORLD_SIZE"])
         local = int(os.environ.get("LOCAL_RANK", rank))
-        torch.cuda.set_device(local)
-        if not dist.is_initialized():
-            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
-        return cls(rank, world, local)
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", rank=rank, world_size=world,
+                                        device_id=torch.device("cuda", local))
+        elif not dist.is_initialized():
+            dist.init_process_group(backend, rank=rank, world_size=world)
+        obj = cls(rank, world, local)
+        obj._device = "cuda" if backend == "nccl" else "cpu"
+        return obj
 
     @classmethod
     def single(cls):
@@ -53,7 +63,7 @@ class TorchDistHvd(object):
     def sum_scalar(self, x):
         if self._size == 1:
             return x
-        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        t = torch.tensor([float(x)], dtype=torch.float64, device=getattr(self, "_device", "cuda"))
         dist.all_reduce(t)
         return float(t[0])
 

@@ -91,6 +91,10 @@ class JasperEngine(object):
         self.step_count = 0
         self._ws = {}
         self._profile = None
+        self.use_cuda_graph = True  # replay the whole step as one CUDA graph after 2 eager steps
+        self.comm = None            # object with allreduce_(tensor) (openseq2seq_b200.dist.TorchDistHvd)
+        self.bucket_bytes = 128 << 20
+        self._side = None
         self._build_layers(convnet_layers, dropout_keep_default)
         self._alloc_params()
         self.set_optimizer(**(opt or {}))
@@ -195,8 +199,9 @@ class JasperEngine(object):
         self.master = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.mom = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.wb = torch.zeros(self._half_total, dtype=torch.bfloat16, device=dev)   # natural [K][Cin][Cout]
-        self.wt = torch.zeros(self._half_total, dtype=torch.bfloat16, device=dev)   # transposed [K][Cout][Cin]
+        # one bf16 working copy in the natural TF layout [K][Cin][Cout]: it is dgrad's K-major B operand
+        # (reduction over C_out) and forward's MN-major B operand (reduction over C_in) at the same time
+        self.wb = torch.zeros(self._half_total, dtype=torch.bfloat16, device=dev)
         # BN moving statistics [2][C] per BN instance (moving_mean = 0, moving_variance = 1)
         self.moving = {}
         for s in specs:
@@ -298,7 +303,7 @@ class JasperEngine(object):
             K, R, C = self._kernel_geom(s)
             L.check(self.lib.os2s_weight_cast_transpose(
                 _vp(self.master.data_ptr() + 4 * s["offset"]), _vp(self.wb.data_ptr() + 2 * s["half_offset"]),
-                _vp(self.wt.data_ptr() + 2 * s["half_offset"]), K, R, C, st), "weight_cast_transpose")
+                _vp(0), K, R, C, st), "weight_cast_transpose")
 
     def _kernel_geom(self, s):
         lyr = s["layer"]
@@ -355,23 +360,11 @@ class JasperEngine(object):
         self.fstate[0] = scale0
         self.istate = torch.zeros(8, dtype=torch.int64, device=dev)
         self.istate[1] = -1
-        # transposed-copy table (conv kernels only)
-        conv = [s for s in self.specs if s["kind"] == "conv"]
-        src = [self.wb.data_ptr() + 2 * s["half_offset"] for s in conv]
-        dst = [self.wt.data_ptr() + 2 * s["half_offset"] for s in conv]
-        geo = [self._kernel_geom(s) for s in conv]
-        tiles = [0]
-        for (K, R, C) in geo:
-            tiles.append(tiles[-1] + K * ((R + 31) // 32) * ((C + 31) // 32))
-        self._tr = {"src": i64(src), "dst": i64(dst),
-                    "R": torch.tensor([x[1] for x in geo], dtype=torch.int32, device=dev),
-                    "C": torch.tensor([x[2] for x in geo], dtype=torch.int32, device=dev),
-                    "tiles": i64(tiles), "n": len(conv), "total": tiles[-1]}
         self._ws = {}
 
     # ----------------------------------------------------------------- workspace
     def _workspace(self, B, T):
-        key = (B, T, torch.cuda.current_stream().cuda_stream, self.training)
+        key = (B, T, self.training)
         ws = self._ws.get(key)
         if ws is None:
             ws = _Workspace(self, B, T)
@@ -399,6 +392,19 @@ class JasperEngine(object):
         _, out_lens = self.forward_encoder(feats, feat_lens)
         return self.forward_decoder(), out_lens
 
+    def set_comm(self, comm, bucket_bytes=None):
+        """Data-parallel gradient exchange (reference: hvd.allreduce per gradient,
+        optimizers/optimizers.py:77-104).  Gradients live in one flat fp32 buffer whose tail is
+        produced first by the backward pass; contiguous buckets are all-reduced (SUM) on a side stream
+        as soon as the layers that write them have been enqueued, overlapping NCCL with the remaining
+        backward kernels; the optimizer waits for the side stream."""
+        self.comm = comm if (comm is not None and comm.size() > 1) else None
+        if bucket_bytes:
+            self.bucket_bytes = int(bucket_bytes)
+        if self.comm is not None and self._side is None:
+            self._side = torch.cuda.Stream()
+        self._ws = {}
+
     def set_training(self, flag):
         """train mode: batch statistics + dropout; eval mode: moving statistics, no dropout
         (tdnn_encoder.py:127-128, tf.layers.batch_normalization(training=...))."""
@@ -421,8 +427,11 @@ class JasperEngine(object):
         ws.run_backward(labels, label_lens)
         return ws.loss
 
-    def optimizer_step(self, allreduce=None):
+    def optimizer_step(self):
         """LARC + loss-scaler + NovoGrad on the (already summed over ranks) gradients."""
+        self._launch_optimizer()
+
+    def _launch_optimizer(self):
         o = self._opt
         st = L.stream_ptr()
         L.check(self.lib.os2s_opt_step(
@@ -430,19 +439,16 @@ class JasperEngine(object):
             L.ptr(o["co"]), o["n"], o["n_chunks"], ctypes.byref(self.hp), L.ptr(o["norms"]),
             L.ptr(o["nonfinite"]), L.ptr(self.fstate), L.ptr(self.istate), L.ptr(o["coef"]), L.ptr(o["ema"]),
             st), "os2s_opt_step")
-        t = self._tr
-        L.check(self.lib.os2s_multi_transpose(L.ptr(t["src"]), L.ptr(t["dst"]), L.ptr(t["R"]), L.ptr(t["C"]),
-                                              L.ptr(t["tiles"]), t["n"], _c_ll(t["total"]), st),
-                "os2s_multi_transpose")
         self.step_count += 1
 
-    def train_step(self, feats, feat_lens, labels, label_lens, allreduce=None):
-        self.forward(feats, feat_lens)
-        loss = self.loss_and_backward(labels, label_lens)
-        if allreduce is not None:
-            allreduce(self.grad)
-        self.optimizer_step()
-        return loss
+    def train_step(self, feats, feat_lens, labels, label_lens):
+        """forward, loss + backward (with the overlapped gradient all-reduce when set_comm was called),
+        optimizer -- one call, replayed as a CUDA graph in steady state.  Returns the per-utterance
+        loss tensor (device, static buffer)."""
+        B, T, F = feats.shape
+        if F != self.F or feats.dtype != torch.bfloat16 or not feats.is_contiguous():
+            raise ValueError("JasperEngine: features must be contiguous bf16 [B,T,%d]" % self.F)
+        return self._workspace(B, T).run_train_step(feats, feat_lens, labels, label_lens)
 
     def greedy_decode(self):
         """tf.nn.ctc_greedy_decoder on the last forward's logits -> (tokens [B,T'], lens [B])."""
@@ -463,8 +469,9 @@ class JasperEngine(object):
         n += 1  # fc fwd
         for entry in (ws._bwd_plan or []):
             name = entry[0].__name__
-            n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd": 2, "os2s_bn_bwd": 2}.get(name, 1)
-        return n + 3 + 1 + 3
+            n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd": 2, "os2s_bn_bwd": 2, "zero_slices": 0,
+                  "bucket_allreduce": 0}.get(name, 1)
+        return n + 3 + 3
 
     def profile_conv_launches(self, step_fn, steps=2):
         """Time every tensor-core conv launch of `steps` instrumented steps with CUDA events.
@@ -492,6 +499,37 @@ class JasperEngine(object):
                                 "launches_per_step": d[2] // steps} for k, d in by.items()}}
 
 
+class _ZeroSlices(object):
+    """Plan entry: zero a few gradient slices (structural zeros of the folded first-layer kernel)."""
+    __name__ = "zero_slices"
+
+    def __init__(self, slices):
+        self.slices = slices
+
+    def __call__(self):
+        for z in self.slices:
+            z.zero_()
+        return 0
+
+
+class _BucketAllReduce(object):
+    """Plan entry: all-reduce (SUM) one contiguous gradient bucket on the side stream once everything
+    enqueued so far on the compute stream has finished."""
+    __name__ = "bucket_allreduce"
+
+    def __init__(self, eng, flat_slice):
+        self.eng, self.slice = eng, flat_slice
+        self.event = torch.cuda.Event()
+
+    def __call__(self):
+        eng = self.eng
+        self.event.record()
+        with torch.cuda.stream(eng._side):
+            eng._side.wait_event(self.event)
+            eng.comm.allreduce_(self.slice)
+        return 0
+
+
 class _Workspace(object):
     """Per-(B,T) activations, gradients and the pre-bound launch plan."""
 
@@ -500,7 +538,10 @@ class _Workspace(object):
         self.B, self.T = B, T
         lib = eng.lib
         dev = eng.device
-        st = L.stream_ptr()
+        # ONE mutable stream handle shared by every pre-bound call: updating its .value retargets the
+        # whole plan (needed for CUDA-graph capture, which runs on torch's capture stream)
+        st = _vp(torch.cuda.current_stream().cuda_stream)
+        self._st = st
         first = eng.layers[0]
         if first.fold:
             if T % 2 != 0:
@@ -539,7 +580,10 @@ class _Workspace(object):
         self.tokens = torch.zeros(B, T2, dtype=torch.int32, device=dev)
         self.tok_lens = torch.zeros(B, dtype=torch.int32, device=dev)
         self.neg_sum = f32(B)
-        self.feats = None
+        self.feats = torch.zeros(B, T, eng.F, dtype=torch.bfloat16, device=dev)  # static input buffer
+        self.graph = None
+        self.graph_L = -1
+        self._eager_steps = 0
         self._ctc_ws = None
         self._ctc_L = -1
         self._build_forward_plan(st)
@@ -571,21 +615,16 @@ class _Workspace(object):
         x = None  # set at run time for layer 0 (features view)
         PP = ctypes.POINTER(_vp)
         for li, l in enumerate(eng.layers):
-            if li == 0:
-                x_ptr = None  # patched per call (feature tensor)
-            else:
-                x_ptr = self._p(self.A[li - 1])
+            x_ptr = self._p(self.feats) if li == 0 else self._p(self.A[li - 1])
             # residual sources: the (masked) input of the block's first layer
             for idx, (c, first_layer) in enumerate(eng.block_inputs):
                 if first_layer == li:
                     src_act[idx] = self.A[li - 1]
             self.x_of_layer.append(self.A[li - 1] if li > 0 else None)
             flops = 2.0 * B * T2 * l.K * l.c_in * l.c_out  # algorithmic (un-folded) FLOPs
-            call = [lib.os2s_conv1d_fwd, [x_ptr, self._half_ptr(eng.wt, l.name + "/kernel"), self._p(self.Y[li]),
+            call = [lib.os2s_conv1d_fwd, [x_ptr, self._half_ptr(eng.wb, l.name + "/kernel"), self._p(self.Y[li]),
                                           B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, 3, st], ("fwd", flops)]
             plan.append(call)
-            if li == 0:
-                self._x0_call = call
             slot_main = bn_idx
             bn_idx += 1
             if eng.training:
@@ -598,7 +637,7 @@ class _Workspace(object):
                 rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
                 bnn = (l.name + "/res_bn_%d" % n) if l.dense else (l.name + "/res_bn")
                 cj = eng.block_inputs[j][0]
-                plan.append([lib.os2s_conv1d_fwd, [self._p(src_act[j]), self._half_ptr(eng.wt, rn + "/kernel"),
+                plan.append([lib.os2s_conv1d_fwd, [self._p(src_act[j]), self._half_ptr(eng.wb, rn + "/kernel"),
                                                    self._p(self.YR[li][n]), B, T2, cj, l.c_out, 1, 1, 0, 3, st],
                              ("fwd", 2.0 * B * T2 * cj * l.c_out)])
                 slot = bn_idx
@@ -622,30 +661,51 @@ class _Workspace(object):
             lens_ptr = self._p(self.lens_out) if (eng.use_conv_mask and not last) else _vp(0)
             args = [nb, y_h, st_h, g_h, b_h, mi_h, mv_h, self._p(self.A[li]), lens_ptr, B, T2, l.c_out,
                     _c_float(eng.bn_eps), _c_float(eng.bn_momentum), _c_float(l.keep if eng.training else 1.0),
-                    _c_u64(0), 1, _c_float(eng.relu_clip), 0 if eng.training else 1, st]
+                    _c_u64((eng.seed * 1000003 + 4099 * li + 17) & 0xFFFFFFFFFFFFFFFF), 1, _c_float(eng.relu_clip),
+                    0 if eng.training else 1, _vp(eng.istate.data_ptr() + 5 * 8), st]
             plan.append([lib.os2s_bn_apply_fwd, args])
-            self._seed_slots.append((args, 15, li))
         self._fc_call = [lib.os2s_fc_fwd, [self._p(self.A[-1]), self._param_ptr(eng.master, "fc/kernel"),
                                            self._param_ptr(eng.master, "fc/bias"), self._p(self.logits), M, eng.H,
                                            eng.V, st]]
         self._fwd_plan = plan
         self.n_launch_fwd = len(plan) + 2
-        self._st = st
+
+    def set_inputs(self, feats, feat_lens):
+        """Copy one batch into the static input buffers (the plans / graphs read only these)."""
+        if feats.data_ptr() != self.feats.data_ptr():
+            self.feats.copy_(feats, non_blocking=True)
+        self.lens_in.copy_(feat_lens.to(torch.int32), non_blocking=True)
+
+    def set_targets(self, labels, label_lens):
+        L_max = int(labels.shape[1])
+        L_cap = max(32, -(-L_max // 32) * 32)  # bucket label capacity so plans / graphs are reused
+        if self._bwd_plan is None or self._bwd_L != L_cap:
+            self._build_backward_plan(L_cap)
+            self.graph = None
+            self._eager_steps = 0
+        self.labels[:, :L_max].copy_(labels.to(torch.int32), non_blocking=True)
+        self.label_lens.copy_(label_lens.to(torch.int32), non_blocking=True)
+
+    def _body_forward(self):
+        eng = self.eng
+        self._st.value = torch.cuda.current_stream().cuda_stream
+        s = eng.layers[0].stride
+        torch.div(self.lens_in + (s - 1), s, rounding_mode="floor", out=self.lens_out)
+        if eng.training:
+            self.stats.zero_()
+        self._exec(self._fwd_plan)
+
+    def _body_backward(self, plan):
+        eng = self.eng
+        self._st.value = torch.cuda.current_stream().cuda_stream
+        self._exec(plan)
+        if eng.comm is not None:
+            torch.cuda.current_stream().wait_stream(eng._side)
 
     def run_forward(self, feats, feat_lens):
-        eng = self.eng
-        self.feats = feats
-        self.lens_in.copy_(feat_lens.to(torch.int32), non_blocking=True)
-        first = eng.layers[0]
-        s = first.stride
-        torch.div(self.lens_in + (s - 1), s, rounding_mode="floor", out=self.lens_out)
-        self.stats.zero_()
-        self._x0_call[1][0] = _vp(feats.data_ptr())
-        base = (eng.seed * 1000003 + eng.step_count) * 4099
-        for args, k, li in self._seed_slots:
-            args[k] = _c_u64((base + li) & 0xFFFFFFFFFFFFFFFF)
-        self._exec(self._fwd_plan)
-        eng._last_ws = self
+        self.set_inputs(feats, feat_lens)
+        self._body_forward()
+        self.eng._last_ws = self
 
     def _exec(self, plan):
         """Run a launch plan; when the engine is in profiling mode, conv launches are bracketed by
@@ -672,6 +732,7 @@ class _Workspace(object):
                 prof.append((meta[0], meta[1], e0, e1))
 
     def run_decoder(self):
+        self._st.value = torch.cuda.current_stream().cuda_stream
         fn, args = self._fc_call[0], self._fc_call[1]
         L.check(fn(*args), "os2s_fc_fwd")
 
@@ -695,6 +756,7 @@ class _Workspace(object):
                                        M, eng.H, eng.V, st]])
         written = set()  # residual-source accumulators that already hold a first contribution
         nl = len(eng.layers)
+        bucket_end = eng._total          # gradients in [bucket_start, bucket_end) are final once enqueued
         for li in range(nl - 1, -1, -1):
             l = eng.layers[li]
             slots, names, (y_h, st_h, g_h, b_h, mi_h, mv_h) = self.bn_slot[li]
@@ -715,13 +777,22 @@ class _Workspace(object):
                                            self._p(self.red), M, l.c_out, _c_float(l.keep), 1, st]])
             self._keep = getattr(self, "_keep", []) + [dg_h, db_h, dy_h]
             # main conv wgrad (stored layout == kernel layout, also for the folded stride-2 layer)
-            x_ptr = self._p(self.A[li - 1]) if li > 0 else None
+            x_ptr = self._p(self.A[li - 1]) if li > 0 else self._p(self.feats)
             wg = [lib.os2s_conv1d_wgrad, [x_ptr, self._p(self.dY), self._param_ptr(eng.grad, l.name + "/kernel"),
                                           B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, st],
                   ("wgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)]
             plan.append(wg)
-            if li == 0:
-                self._x0_wgrad = wg
+            if l.fold:
+                # structurally-zero taps of the folded stride-2 kernel get no gradient
+                s_ = eng.by_name[l.name + "/kernel"]
+                st0, n_ = eng._valid_slice(s_)
+                zs = []
+                if st0 > 0:
+                    zs.append(eng.grad[s_["offset"]:s_["offset"] + st0])
+                if st0 + n_ < s_["store_size"]:
+                    zs.append(eng.grad[s_["offset"] + st0 + n_:s_["offset"] + s_["store_size"]])
+                if zs:
+                    plan.append([_ZeroSlices(zs), []])
             # residual branches: wgrad + dgrad into the fp32 accumulators
             for n, j in enumerate(l.res_sources):
                 rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
@@ -746,45 +817,60 @@ class _Workspace(object):
                 plan.append([lib.os2s_conv1d_dgrad, [self._p(self.dY), self._half_ptr(eng.wb, l.name + "/kernel"),
                                                      out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
                                                      st], ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
+            if eng.comm is not None:
+                start = eng.by_name[l.name + "/kernel"]["offset"]
+                if (bucket_end - start) * 4 >= eng.bucket_bytes or li == 0:
+                    plan.append([_BucketAllReduce(eng, eng.grad[start:bucket_end]), []])
+                    bucket_end = start
         self._bwd_plan = plan
         self._bwd_L = L_max
         self.n_launch_bwd = len(plan) + 4
-        # zero-gradient slices for structurally-zero taps of folded layers
-        self._zero_slices = []
-        for l in eng.layers:
-            if l.fold:
-                s = eng.by_name[l.name + "/kernel"]
-                st0, n = eng._valid_slice(s)
-                if st0 > 0:
-                    self._zero_slices.append(eng.grad[s["offset"]:s["offset"] + st0])
-                if st0 + n < s["store_size"]:
-                    self._zero_slices.append(eng.grad[s["offset"] + st0 + n:s["offset"] + s["store_size"]])
 
     def run_loss_only(self, labels, label_lens):
-        L_max = int(labels.shape[1])
-        if self._bwd_plan is None or self._bwd_L != L_max:
-            self._build_backward_plan(L_max)
-        self.labels.copy_(labels.to(torch.int32), non_blocking=True)
-        self.label_lens.copy_(label_lens.to(torch.int32), non_blocking=True)
+        self.set_targets(labels, label_lens)
+        self._st.value = torch.cuda.current_stream().cuda_stream
         fn, args = self._bwd_plan[0][0], self._bwd_plan[0][1]
         L.check(fn(*args), "os2s_ctc_loss_fwd_bwd")
         return self.loss
 
     def run_backward(self, labels, label_lens, dlogits=None):
         if dlogits is None:
-            L_max = int(labels.shape[1])
+            self.set_targets(labels, label_lens)
+            plan = self._bwd_plan
         else:
-            L_max = self._bwd_L if self._bwd_plan is not None else 1
-        if self._bwd_plan is None or self._bwd_L != L_max:
-            self._build_backward_plan(L_max)
-        plan = self._bwd_plan
-        if dlogits is None:
-            self.labels.copy_(labels.to(torch.int32), non_blocking=True)
-            self.label_lens.copy_(label_lens.to(torch.int32), non_blocking=True)
-        else:
+            if self._bwd_plan is None:
+                self._build_backward_plan(32)
             self.dlogits.copy_(dlogits)
-            plan = plan[1:]  # skip the CTC launch
-        self._x0_wgrad[1][0] = _vp(self.feats.data_ptr())
-        self._exec(plan)
-        for z in self._zero_slices:
-            z.zero_()
+            plan = self._bwd_plan[1:]  # skip the CTC launch
+        self._body_backward(plan)
+
+    def run_train_step(self, feats, feat_lens, labels, label_lens):
+        """Whole training step.  After two eager steps of a given shape the step body (forward, CTC,
+        backward incl. bucketed all-reduce, optimizer) is captured into a CUDA graph and replayed."""
+        eng = self.eng
+        self.set_inputs(feats, feat_lens)
+        self.set_targets(labels, label_lens)
+        eng._last_ws = self
+        if eng.use_cuda_graph and eng._profile is None:
+            if self.graph is not None:
+                self.graph.replay()
+                eng.step_count += 1
+                return self.loss
+            if self._eager_steps >= 2:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_body()
+                self.graph = g
+                g.replay()
+                eng.step_count += 1
+                return self.loss
+        self._step_body()
+        self._eager_steps += 1
+        return self.loss
+
+    def _step_body(self):
+        self._body_forward()
+        self.run_decoder()
+        self._body_backward(self._bwd_plan)
+        self.eng._launch_optimizer()

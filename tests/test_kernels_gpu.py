@@ -49,9 +49,11 @@ def test_conv_fwd_dgrad_wgrad_vs_oracle(B, T, Cin, Cout, K, dil):
     wt = wd.permute(0, 2, 1).contiguous()
     st = L.stream_ptr()
     y = torch.empty(B, T, Cout, dtype=torch.bfloat16, device="cuda")
-    L.check(lib.os2s_conv1d_fwd(L.ptr(xd), L.ptr(wt), L.ptr(y), B, T, Cin, Cout, K, dil, pl, 0, st), "fwd")
+    L.check(lib.os2s_conv1d_fwd(L.ptr(xd), L.ptr(wd), L.ptr(y), B, T, Cin, Cout, K, dil, pl, 0, st), "fwd")
     y16 = torch.empty(B, T, Cout, dtype=torch.float16, device="cuda")
-    L.check(lib.os2s_conv1d_fwd(L.ptr(xd), L.ptr(wt), L.ptr(y16), B, T, Cin, Cout, K, dil, pl, 3, st), "fwd16")
+    L.check(lib.os2s_conv1d_fwd(L.ptr(xd), L.ptr(wd), L.ptr(y16), B, T, Cin, Cout, K, dil, pl, 3, st), "fwd16")
+    ywt = torch.empty(B, T, Cout, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.os2s_conv1d_fwd_wt(L.ptr(xd), L.ptr(wt), L.ptr(ywt), B, T, Cin, Cout, K, dil, pl, 0, st), "fwd_wt")
     dx = torch.empty(B, T, Cin, dtype=torch.float32, device="cuda")
     L.check(lib.os2s_conv1d_dgrad(L.ptr(dyd), L.ptr(wd), L.ptr(dx), B, T, Cin, Cout, K, dil, pl, 1, st), "dgrad")
     if Cin % 128 == 0:
@@ -59,6 +61,7 @@ def test_conv_fwd_dgrad_wgrad_vs_oracle(B, T, Cin, Cout, K, dil):
         L.check(lib.os2s_conv1d_wgrad(L.ptr(xd), L.ptr(dyd), L.ptr(dw), B, T, Cin, Cout, K, dil, pl, st), "wgrad")
     torch.cuda.synchronize()
     assert np.abs(y.float().cpu().numpy() - y_ref).max() <= 1e-2 * np.abs(y_ref).max()
+    assert torch.equal(y, ywt)  # the two weight-operand layouts are the same arithmetic
     assert np.abs(y16.float().cpu().numpy() - y_ref).max() <= 1.5e-3 * np.abs(y_ref).max()
     assert np.abs(dx.cpu().numpy() - dx_ref).max() <= 1e-4 * np.abs(dx_ref).max() + 1e-4
     if Cin % 128 == 0:
@@ -68,7 +71,7 @@ def test_conv_fwd_dgrad_wgrad_vs_oracle(B, T, Cin, Cout, K, dil):
 def test_conv_rejects_unsupported_shapes_loudly():
     L, lib = _lib()
     x = torch.zeros(1, 16, 48, dtype=torch.bfloat16, device="cuda")
-    w = torch.zeros(1, 64, 48, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(1, 48, 64, dtype=torch.bfloat16, device="cuda")
     y = torch.zeros(1, 16, 64, dtype=torch.bfloat16, device="cuda")
     rc = lib.os2s_conv1d_fwd(L.ptr(x), L.ptr(w), L.ptr(y), 1, 16, 48, 64, 1, 1, 0, 0, L.stream_ptr())
     assert rc == -3 and b"multiple of 64" in lib.os2s_last_error()
@@ -111,7 +114,7 @@ def test_batchnorm_residual_relu_dropout_mask_fwd_bwd_vs_oracle():
     lens_c = lens.to(dev)
     L.check(lib.os2s_bn_apply_fwd(nb, arr(yc), arr(list(stats)), arr(gc), arr(bc), arr(list(mi)), arr(list(mv)),
                                   L.ptr(out), L.ptr(lens_c), B, T, C, _f(1e-3), _f(0.9), _f(1.0),
-                                  ctypes.c_uint64(1), 1, _f(0.0), 0, st), "apply")
+                                  ctypes.c_uint64(1), 1, _f(0.0), 0, None, st), "apply")
     dgam = [torch.zeros(C, device=dev) for _ in range(nb)]
     dbet = [torch.zeros(C, device=dev) for _ in range(nb)]
     dy = [torch.empty(B, T, C, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
@@ -148,7 +151,7 @@ def test_dropout_statistics_and_backward_mask():
     for seed in (7, 7, 8):
         out = torch.empty(B, T, C, dtype=torch.bfloat16, device="cuda")
         L.check(lib.os2s_bn_apply_fwd(1, one(y), one(stats), one(gam), one(bet), one(mi), None, L.ptr(out), None,
-                                      B, T, C, _f(1e-3), _f(0.9), _f(0.7), ctypes.c_uint64(seed), 1, _f(0.0), 0, st),
+                                      B, T, C, _f(1e-3), _f(0.9), _f(0.7), ctypes.c_uint64(seed), 1, _f(0.0), 0, None, st),
                 "apply")
         outs.append(out.float())
     torch.cuda.synchronize()
@@ -157,7 +160,7 @@ def test_dropout_statistics_and_backward_mask():
     assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
     nodrop = torch.empty(B, T, C, dtype=torch.bfloat16, device="cuda")
     L.check(lib.os2s_bn_apply_fwd(1, one(y), one(stats), one(gam), one(bet), one(mi), None, L.ptr(nodrop), None,
-                                  B, T, C, _f(1e-3), _f(0.9), _f(1.0), ctypes.c_uint64(0), 1, _f(0.0), 0, st), "apply")
+                                  B, T, C, _f(1e-3), _f(0.9), _f(1.0), ctypes.c_uint64(0), 1, _f(0.0), 0, None, st), "apply")
     torch.cuda.synchronize()
     m = outs[0] != 0
     assert torch.allclose(outs[0][m], nodrop.float()[m] / 0.7, rtol=2e-2)
@@ -314,13 +317,12 @@ def test_optimizer_chain_vs_oracle_including_overflow_skip():
             got = eng.param_view(n).cpu().numpy()
             assert np.abs(got - w_ref[i]).max() <= 2e-5 * max(1.0, np.abs(w_ref[i]).max()), (it, n)
     assert int(eng.istate[4]) == 1 and abs(float(eng.fstate[0]) - scaler.scale) < 1e-6
-    # bf16 working copies follow the masters (natural and transposed)
+    # the bf16 working copy follows the master
     s = eng.by_name["conv21/kernel"]
     K, R, C = s["shape"]
     wb = eng.wb[s["half_offset"]:s["half_offset"] + s["size"]].view(K, R, C).float()
-    wt = eng.wt[s["half_offset"]:s["half_offset"] + s["size"]].view(K, C, R).float()
     m = eng.param_view("conv21/kernel")
-    assert torch.equal(wb, m.bfloat16().float()) and torch.equal(wt, wb.permute(0, 2, 1))
+    assert torch.equal(wb, m.bfloat16().float())
 
 
 def test_logmel_featurizer_vs_oracle():
@@ -343,7 +345,10 @@ def test_logmel_featurizer_vs_oracle():
     out = torch.zeros(B, T_pad, F, device="cuda")
     outb = torch.zeros(B, T_pad, F, dtype=torch.bfloat16, device="cuda")
     lens = torch.zeros(B, dtype=torch.int32, device="cuda")
-    L.check(lib.os2s_logmel_forward(L.ptr(wave), L.ptr(offs), L.ptr(ns), B, L.ptr(mel), L.ptr(win), 512, 320, 160, F,
+    melnp = FZ.mel_filterbank()
+    band = torch.tensor([[int(np.nonzero(r)[0].min()), int(np.nonzero(r)[0].max()) + 1] for r in melnp],
+                        dtype=torch.int32, device="cuda")
+    L.check(lib.os2s_logmel_forward(L.ptr(wave), L.ptr(offs), L.ptr(ns), B, L.ptr(mel), L.ptr(band), L.ptr(win), 512, 320, 160, F,
                                     T_pad, max(len(s) for s in sigs), _f(0.0), ctypes.c_uint64(0), _f(0.97),
                                     L.ptr(absmax), L.ptr(raw), L.ptr(outb), L.ptr(out), L.ptr(lens), L.stream_ptr()),
             "logmel")

@@ -39,8 +39,7 @@ import ctypes
 from openseq2seq_b200 import _lib as L
 ws.dlogits.copy_(R.cuda())
 if ws._bwd_plan is None:
-    ws._build_backward_plan(1)
-ws._x0_wgrad[1][0] = ctypes.c_void_p(ws.feats.data_ptr())
+    ws._build_backward_plan(32)
 plan = ws._bwd_plan[1:]
 print("== backward: per launch")
 li = len(eng.layers) - 1
