@@ -46,9 +46,11 @@ int os2s_version(void);
  *   y  : bf16 / fp32 [B,T,C_out]  (out_mode)
  * The stride-2 first Jasper layer is expressed by the caller as a stride-1 conv over the input
  * viewed as [B, T/2, 2*C_in] with K' = ceil(K/2) taps (see openseq2seq_b200/runtime/layers.py).
+ * bn_stats (may be NULL): fp32 [2][C_out], pre-zeroed; the epilogue adds the per-channel sum and sum of
+ * squares of the ROUNDED outputs (what os2s_bn_stats would compute), fusing the BN statistics pass.
  * Constraints: C_in % 64 == 0, C_out % 64 == 0. */
 int os2s_conv1d_fwd(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
-                    int K, int dil, int pad_left, int out_mode, void* stream);
+                    int K, int dil, int pad_left, int out_mode, float* bn_stats, void* stream);
 
 /* Same convolution with the weights given transposed, wt : bf16 [K][C_out][C_in] (K-major B
  * operand).  Kept for A/B measurements of the two operand layouts (tools/gpu_conv_check.py). */

@@ -12,22 +12,24 @@ const char* os2s_last_error(void) { return last_error_cstr(); }
 int os2s_version(void) { return 100; }
 
 int os2s_conv1d_fwd(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
-                    int K, int dil, int pad_left, int out_mode, void* stream) {
+                    int K, int dil, int pad_left, int out_mode, float* bn_stats, void* stream) {
   if (!x || !w || !y) return fail(ERR_INVALID, "os2s_conv1d_fwd: null pointer");
+  if (bn_stats && !(out_mode == OS2S_OUT_BF16 || out_mode == OS2S_OUT_F16))
+    return fail(ERR_INVALID, "os2s_conv1d_fwd: fused BN statistics need a 2-byte output mode");
   // B operand MN-major straight from the natural [K][C_in][C_out] layout
-  return conv_kmajor(x, w, y, B, T, C_in, C_out, K, -pad_left, dil, out_mode, 1, (cudaStream_t)stream);
+  return conv_kmajor(x, w, y, B, T, C_in, C_out, K, -pad_left, dil, out_mode, 1, bn_stats, (cudaStream_t)stream);
 }
 
 int os2s_conv1d_fwd_wt(const void* x, const void* wt, void* y, int B, int T, int C_in, int C_out,
                        int K, int dil, int pad_left, int out_mode, void* stream) {
   if (!x || !wt || !y) return fail(ERR_INVALID, "os2s_conv1d_fwd_wt: null pointer");
-  return conv_kmajor(x, wt, y, B, T, C_in, C_out, K, -pad_left, dil, out_mode, 0, (cudaStream_t)stream);
+  return conv_kmajor(x, wt, y, B, T, C_in, C_out, K, -pad_left, dil, out_mode, 0, nullptr, (cudaStream_t)stream);
 }
 
 int os2s_conv1d_dgrad(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
                       int K, int dil, int pad_left, int out_mode, void* stream) {
   if (!dy || !w || !dx) return fail(ERR_INVALID, "os2s_conv1d_dgrad: null pointer");
-  return conv_kmajor(dy, w, dx, B, T, C_out, C_in, K, pad_left, -dil, out_mode, 0, (cudaStream_t)stream);
+  return conv_kmajor(dy, w, dx, B, T, C_out, C_in, K, pad_left, -dil, out_mode, 0, nullptr, (cudaStream_t)stream);
 }
 
 int os2s_conv1d_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out,

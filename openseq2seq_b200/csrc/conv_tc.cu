@@ -39,15 +39,25 @@ struct KMajorParams {
   int B, T_out, n_mtiles, n_ntiles, N_total;
   int K_taps, c_chunks;
   int t_off0, t_step;
+  float* stats;                // optional [2][N_total]: += per-channel sum / sum of squares of the output
   void* out;
   long long out_row_stride;    // elements
   long long out_batch_stride;  // elements
   int out_mode;
 };
 
+// Epilogue area of the forward/dgrad kernel: per epilogue warp a 32-row x 144-byte staging buffer
+// (128 payload bytes + 16 pad: conflict-free 16-byte row writes and row-contiguous reads) and a
+// [2][BN] fp32 slice for the fused per-channel BN statistics.
+constexpr int kEpiRowBytes = 144;
+constexpr int kEpiWarpBytes = 32 * kEpiRowBytes;
+template <int BN>
+__host__ __device__ constexpr int epi_bytes() {
+  return 4 * kEpiWarpBytes + 4 * 2 * BN * 4;
+}
 template <int BN>
 __host__ __device__ constexpr int num_stages() {
-  int s = kSmemBudget / (kABytes + BN * kChunkK * 2);
+  int s = (kSmemBudget - epi_bytes<BN>()) / (kABytes + BN * kChunkK * 2);
   return s > 8 ? 8 : s;
 }
 
@@ -88,6 +98,8 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + S;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(tmem_ptr + 4);   // 16-byte aligned (barriers are 8 B each)
+  float* epi_stats = reinterpret_cast<float*>(epi_stage + 4 * kEpiWarpBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -175,70 +187,178 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // Epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32).
+    // Epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32).  Accumulators are staged
+    // through shared memory so that global stores are full 128-byte lines (4 rows per warp
+    // instruction) and -- for the forward pass -- the per-channel BN statistics of the ROUNDED
+    // outputs are accumulated on the way (one flush of 2*BN atomics per CTA and N tile).
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
+    uint8_t* stage = epi_stage + quad * kEpiWarpBytes;
+    float* sacc = epi_stats + quad * 2 * BN;
+    const bool two_byte = (p.out_mode == OUT_BF16 || p.out_mode == OUT_F16);
+    const bool do_stats = (p.stats != nullptr) && two_byte;
+    if (do_stats)
+      for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
+    int cur_nt = -1;
+    auto flush_stats = [&](int nt) {
+      // all four epilogue warps reach this point for the same tile sequence
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int tid = threadIdx.x - 64;  // 0..127
+      for (int i = tid; i < 2 * BN; i += 128) {
+        const float v = epi_stats[i] + epi_stats[2 * BN + i] + epi_stats[4 * BN + i] + epi_stats[6 * BN + i];
+        const int which = i / BN, col = i - which * BN;
+        atomicAdd(&p.stats[(size_t)which * p.N_total + nt * BN + col], v);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
+    };
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const int nt = tile / tiles_per_n;
       const int rem = tile - nt * tiles_per_n;
       const int b = rem / p.n_mtiles;
-      const int t = (rem - b * p.n_mtiles) * kTileM + row;
+      const int t0w = (rem - b * p.n_mtiles) * kTileM + quad * 32;  // first row of this warp
       const int n0 = nt * BN;
+      if (do_stats && cur_nt >= 0 && nt != cur_nt) flush_stats(cur_nt);
+      cur_nt = nt;
       const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      const bool valid = t < p.T_out;
-      const long long off = (long long)b * p.out_batch_stride + (long long)t * p.out_row_stride + n0;
+      const int nvalid = min(32, max(0, p.T_out - t0w));
+      const long long off = (long long)b * p.out_batch_stride + (long long)t0w * p.out_row_stride + n0;
+      uint8_t* myrow = stage + lane * kEpiRowBytes;
+      if (two_byte) {
+        uint16_t* out2 = reinterpret_cast<uint16_t*>(p.out) + off;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(taddr + ch * 32, r);
-        tmem_ld_wait();
-        if (valid) {
-          if (p.out_mode == OUT_BF16) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + ch * 32);
+        for (int c = 0; c < BN; c += 64) {
+          const bool wide = (BN - c) >= 64;  // 64-column chunk, or a 32-column tail
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + c, r0);
+          if (wide) tmem_ld32(taddr + c + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 v;
+            if (p.out_mode == OUT_BF16) {
+              v.x = pack_bf16(__uint_as_float(r0[q * 8 + 0]), __uint_as_float(r0[q * 8 + 1]));
+              v.y = pack_bf16(__uint_as_float(r0[q * 8 + 2]), __uint_as_float(r0[q * 8 + 3]));
+              v.z = pack_bf16(__uint_as_float(r0[q * 8 + 4]), __uint_as_float(r0[q * 8 + 5]));
+              v.w = pack_bf16(__uint_as_float(r0[q * 8 + 6]), __uint_as_float(r0[q * 8 + 7]));
+            } else {
+              v.x = pack_f16(__uint_as_float(r0[q * 8 + 0]), __uint_as_float(r0[q * 8 + 1]));
+              v.y = pack_f16(__uint_as_float(r0[q * 8 + 2]), __uint_as_float(r0[q * 8 + 3]));
+              v.z = pack_f16(__uint_as_float(r0[q * 8 + 4]), __uint_as_float(r0[q * 8 + 5]));
+              v.w = pack_f16(__uint_as_float(r0[q * 8 + 6]), __uint_as_float(r0[q * 8 + 7]));
+            }
+            *reinterpret_cast<uint4*>(myrow + q * 16) = v;
+          }
+          if (wide) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 v;
-              v.x = pack_bf16(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
-              v.y = pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
-              v.z = pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
-              v.w = pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
-              dst[q] = v;
-            }
-          } else if (p.out_mode == OUT_F16) {
-            // fp16 (2-byte elements, same addressing as bf16): used for conv outputs that are only
-            // consumed by the BN kernels -- 3 more mantissa bits than bf16 at the same traffic.
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + off + ch * 32);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 v;
-              v.x = pack_f16(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
-              v.y = pack_f16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
-              v.z = pack_f16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
-              v.w = pack_f16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
-              dst[q] = v;
-            }
-          } else {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + ch * 32);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
-                                     __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
-              if (p.out_mode == OUT_F32_ACC) {
-                const float4 o = dst[q];
-                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              if (p.out_mode == OUT_BF16) {
+                v.x = pack_bf16(__uint_as_float(r1[q * 8 + 0]), __uint_as_float(r1[q * 8 + 1]));
+                v.y = pack_bf16(__uint_as_float(r1[q * 8 + 2]), __uint_as_float(r1[q * 8 + 3]));
+                v.z = pack_bf16(__uint_as_float(r1[q * 8 + 4]), __uint_as_float(r1[q * 8 + 5]));
+                v.w = pack_bf16(__uint_as_float(r1[q * 8 + 6]), __uint_as_float(r1[q * 8 + 7]));
+              } else {
+                v.x = pack_f16(__uint_as_float(r1[q * 8 + 0]), __uint_as_float(r1[q * 8 + 1]));
+                v.y = pack_f16(__uint_as_float(r1[q * 8 + 2]), __uint_as_float(r1[q * 8 + 3]));
+                v.z = pack_f16(__uint_as_float(r1[q * 8 + 4]), __uint_as_float(r1[q * 8 + 5]));
+                v.w = pack_f16(__uint_as_float(r1[q * 8 + 6]), __uint_as_float(r1[q * 8 + 7]));
               }
-              dst[q] = v;
+              *reinterpret_cast<uint4*>(myrow + 64 + q * 16) = v;
             }
           }
+          __syncwarp();
+          const int w = wide ? 64 : 32;
+          if (do_stats && 2 * lane < w) {
+            // lane owns columns c + 2*lane, c + 2*lane + 1; rows beyond T_out are not statistics
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            for (int r = 0; r < nvalid; ++r) {
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(stage + r * kEpiRowBytes + lane * 4);
+              float x0, x1;
+              if (p.out_mode == OUT_BF16) {
+                x0 = __uint_as_float(v << 16);
+                x1 = __uint_as_float(v & 0xFFFF0000u);
+              } else {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+                x0 = f.x;
+                x1 = f.y;
+              }
+              s0 += x0; q0 += x0 * x0;
+              s1 += x1; q1 += x1 * x1;
+            }
+            sacc[c + 2 * lane] += s0;
+            sacc[c + 2 * lane + 1] += s1;
+            sacc[BN + c + 2 * lane] += q0;
+            sacc[BN + c + 2 * lane + 1] += q1;
+          }
+          // coalesced stores: `pieces` 16-byte pieces per row, 32/pieces rows per warp instruction
+          if (wide) {
+            const int pr = lane >> 3, pc = lane & 7;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = pr + 4 * i;
+              if (r < nvalid) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stage + r * kEpiRowBytes + pc * 16);
+                *reinterpret_cast<uint4*>(out2 + (long long)r * p.out_row_stride + c + pc * 8) = v;
+              }
+            }
+          } else {
+            const int pr = lane >> 2, pc = lane & 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = pr + 8 * i;
+              if (r < nvalid) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stage + r * kEpiRowBytes + pc * 16);
+                *reinterpret_cast<uint4*>(out2 + (long long)r * p.out_row_stride + c + pc * 8) = v;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        float* out4 = reinterpret_cast<float*>(p.out) + off;
+        const int pr = lane >> 3, pc = lane & 7;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(myrow + q * 16) = make_uint4(r[q * 4 + 0], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+          __syncwarp();
+          // all eight read-modify-write loads are issued before the first use (one latency, not eight)
+          float4 old[8];
+          if (p.out_mode == OUT_F32_ACC) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = pr + 4 * i;
+              old[i] = (rr < nvalid)
+                           ? *reinterpret_cast<const float4*>(out4 + (long long)rr * p.out_row_stride + c + pc * 4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = pr + 4 * i;
+            if (rr < nvalid) {
+              float4 v = *reinterpret_cast<const float4*>(stage + rr * kEpiRowBytes + pc * 16);
+              if (p.out_mode == OUT_F32_ACC) {
+                v.x += old[i].x; v.y += old[i].y; v.z += old[i].z; v.w += old[i].w;
+              }
+              *reinterpret_cast<float4*>(out4 + (long long)rr * p.out_row_stride + c + pc * 4) = v;
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
+    if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
   }
 
   tc_fence_before();
@@ -413,7 +533,8 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 // ------------------------------------------------------------------ launchers
 template <int BN>
 static size_t smem_bytes() {
-  return (size_t)num_stages<BN>() * (kABytes + BN * kChunkK * 2) + (2 * num_stages<BN>() + 4) * 8 + 16 + 1024;
+  return (size_t)num_stages<BN>() * (kABytes + BN * kChunkK * 2) + (2 * num_stages<BN>() + 4) * 8 + 16 +
+         epi_bytes<BN>() + 1024;
 }
 
 template <int BN, bool BMN>
@@ -466,7 +587,7 @@ static int pick_bn_mnmajor(int n) {
 //   wmat   : [K][N_total][C_red] bf16 (C_red contiguous)
 //   out    : [B, T, N_total]  (bf16, or fp32 with optional accumulate)
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
-                int K, int t_off0, int t_step, int out_mode, int b_mn_major, cudaStream_t st) {
+                int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st) {
   if (C_red % 64 != 0) return fail(ERR_UNSUPPORTED, "conv_tc: reduction channels must be a multiple of 64");
   const int BN = b_mn_major ? pick_bn_mnmajor(N_total) : pick_bn_kmajor(N_total);
   if (BN == 0) return fail(ERR_UNSUPPORTED, "conv_tc: output channels must be a multiple of 64");
@@ -491,6 +612,7 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
   p.c_chunks = C_red / 64;
   p.t_off0 = t_off0;
   p.t_step = t_step;
+  p.stats = stats;
   p.out = out;
   p.out_row_stride = N_total;
   p.out_batch_stride = (long long)T * N_total;

@@ -191,36 +191,62 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 
-__global__ void __launch_bounds__(kEwThreads)
-bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
-  extern __shared__ float sh[];  // [n_branch][2][C]: scale, shift
+// scale / shift of the thread's own 8 channels of branch b (batch or moving statistics); the owner
+// thread (first row slot of CTA 0) also publishes mean / invstd and updates the moving averages.
+__device__ __forceinline__ void bn_coef(const BnFwdParams& p, const BnBranchFwd& b, int c0, float inv_n, bool owner,
+                                        float (&sc)[8], float (&sf)[8]) {
   const int C = p.C;
-  const int M = p.B * p.T;
-  const float inv_n = 1.f / (float)M;
-  for (int i = threadIdx.x; i < p.n_branch * C; i += kEwThreads) {
-    const int j = i / C, c = i - j * C;
-    const BnBranchFwd& b = p.br[j];
+  float m[8], v[8], g[8], be[8];
+  const float* src_m = p.use_moving ? b.moving : b.stats;
+  *reinterpret_cast<float4*>(&m[0]) = __ldg(reinterpret_cast<const float4*>(src_m + c0));
+  *reinterpret_cast<float4*>(&m[4]) = __ldg(reinterpret_cast<const float4*>(src_m + c0) + 1);
+  *reinterpret_cast<float4*>(&v[0]) = __ldg(reinterpret_cast<const float4*>(src_m + C + c0));
+  *reinterpret_cast<float4*>(&v[4]) = __ldg(reinterpret_cast<const float4*>(src_m + C + c0) + 1);
+  *reinterpret_cast<float4*>(&g[0]) = __ldg(reinterpret_cast<const float4*>(b.gamma + c0));
+  *reinterpret_cast<float4*>(&g[4]) = __ldg(reinterpret_cast<const float4*>(b.gamma + c0) + 1);
+  *reinterpret_cast<float4*>(&be[0]) = __ldg(reinterpret_cast<const float4*>(b.beta + c0));
+  *reinterpret_cast<float4*>(&be[4]) = __ldg(reinterpret_cast<const float4*>(b.beta + c0) + 1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
     // training: batch statistics; inference (use_moving): the moving averages
-    const float mean = p.use_moving ? b.moving[c] : b.stats[c] * inv_n;
-    const float var = p.use_moving ? b.moving[C + c] : fmaxf(b.stats[C + c] * inv_n - mean * mean, 0.f);
+    const float mean = p.use_moving ? m[i] : m[i] * inv_n;
+    const float var = p.use_moving ? v[i] : fmaxf(v[i] * inv_n - mean * mean, 0.f);
     const float invstd = rsqrtf(var + p.eps);
-    const float g = b.gamma[c];
-    sh[(j * 2) * C + c] = g * invstd;
-    sh[(j * 2 + 1) * C + c] = b.beta[c] - mean * g * invstd;
-    if (blockIdx.x == 0 && !p.use_moving) {
-      b.mean_invstd[c] = mean;
-      b.mean_invstd[C + c] = invstd;
+    sc[i] = g[i] * invstd;
+    sf[i] = be[i] - mean * sc[i];
+    if (owner && !p.use_moving) {
+      b.mean_invstd[c0 + i] = mean;
+      b.mean_invstd[C + c0 + i] = invstd;
       if (b.moving) {
-        const float n = (float)M;
+        const float n = 1.f / inv_n;
         const float unbiased = var * (n / fmaxf(n - 1.f, 1.f));
-        b.moving[c] = b.moving[c] * p.momentum + mean * (1.f - p.momentum);
-        b.moving[C + c] = b.moving[C + c] * p.momentum + unbiased * (1.f - p.momentum);
+        b.moving[c0 + i] = b.moving[c0 + i] * p.momentum + mean * (1.f - p.momentum);
+        b.moving[C + c0 + i] = b.moving[C + c0 + i] * p.momentum + unbiased * (1.f - p.momentum);
       }
     }
   }
-  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
+  const int C = p.C;
+  const int M = p.B * p.T;
+  const float inv_n = 1.f / (float)M;
   const RowTile t = make_row_tile(M, C, rows_per_block);
   if (!t.active) return;
+  const bool owner = blockIdx.x == 0 && t.r == 0;
+  const int c0 = t.cv * 8;
+  // single-branch layers keep their coefficients in registers for the whole kernel; dense-residual
+  // layers recompute them per branch and 4-row group from L1-resident vectors (no shared memory,
+  // no per-CTA prologue over all channels)
+  float sc0[8], sf0[8];
+  bn_coef(p, p.br[0], c0, inv_n, owner, sc0, sf0);
+  if (owner) {
+    for (int j = 1; j < p.n_branch; ++j) {
+      float a_[8], b_[8];
+      bn_coef(p, p.br[j], c0, inv_n, true, a_, b_);
+    }
+  }
   const float inv_keep = 1.f / p.keep;
   unsigned long long seed = p.seed;
   if (p.step_ctr) seed += (unsigned long long)(*p.step_ctr) * 0x9E3779B97F4A7C15ull;
@@ -249,12 +275,12 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
       for (int u = 0; u < kUnroll; ++u)
         v[u] = live[u] ? __ldg(yb + (size_t)(row + u * t.RP) * rs) : make_uint4(0, 0, 0, 0);
       float sc[8], sf[8];
-      const float4* scp = reinterpret_cast<const float4*>(&sh[(j * 2) * C + t.cv * 8]);
-      const float4* sfp = reinterpret_cast<const float4*>(&sh[(j * 2 + 1) * C + t.cv * 8]);
-      *reinterpret_cast<float4*>(&sc[0]) = scp[0];
-      *reinterpret_cast<float4*>(&sc[4]) = scp[1];
-      *reinterpret_cast<float4*>(&sf[0]) = sfp[0];
-      *reinterpret_cast<float4*>(&sf[4]) = sfp[1];
+      if (j == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sc[i] = sc0[i]; sf[i] = sf0[i]; }
+      } else {
+        bn_coef(p, p.br[j], c0, inv_n, false, sc, sf);
+      }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         float f[8];
@@ -301,17 +327,10 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
 int bn_apply_fwd(const BnFwdParams& p, cudaStream_t st) {
   if (p.n_branch < 1 || p.n_branch > kMaxBranches) return fail(ERR_INVALID, "bn_apply_fwd: bad branch count");
   if (p.C % 8 != 0 || p.C > 2048) return fail(ERR_UNSUPPORTED, "bn_apply_fwd: C must be a multiple of 8, <= 2048");
-  const size_t smem = (size_t)p.n_branch * 2 * p.C * sizeof(float);
-  if (smem > 200 * 1024) return fail(ERR_UNSUPPORTED, "bn_apply_fwd: too many branches x channels");
-  static bool attr_done = false;
-  if (!attr_done) {
-    OS2S_CUDA(cudaFuncSetAttribute(bn_apply_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
   const int M = p.B * p.T;
-  const int rpb = rows_per_block_for(M, p.C, smem > 48 * 1024 ? 2 : 4);
+  const int rpb = rows_per_block_for(M, p.C, 4);
   const int grid = (M + rpb - 1) / rpb;
-  bn_apply_fwd_kernel<<<grid, kEwThreads, smem, st>>>(p, rpb);
+  bn_apply_fwd_kernel<<<grid, kEwThreads, 0, st>>>(p, rpb);
   return check_launch("bn_apply_fwd");
 }
 
@@ -420,32 +439,51 @@ bn_bwd_reduce_kernel(const BnBwdParams p, int rows_per_block) {
   for (int i = threadIdx.x; i < nred; i += kEwThreads) atomicAdd(&p.red[i], sh[i]);
 }
 
+// dy = A*dz + Bc*y + Cc for the thread's own 8 channels of branch b (from the pass-1 sums).
+__device__ __forceinline__ void bn_bwd_coef(const BnBwdParams& p, int j, int c0, float inv_n, bool owner,
+                                            float (&A)[8], float (&Bc)[8], float (&Cc)[8]) {
+  const int C = p.C;
+  const BnBranchBwd& b = p.br[j];
+  float mean[8], invstd[8], g[8], dbeta[8], S[8];
+  auto ld8 = [](const float* src, float (&dst)[8]) {
+    *reinterpret_cast<float4*>(&dst[0]) = __ldg(reinterpret_cast<const float4*>(src));
+    *reinterpret_cast<float4*>(&dst[4]) = __ldg(reinterpret_cast<const float4*>(src) + 1);
+  };
+  ld8(b.mean_invstd + c0, mean);
+  ld8(b.mean_invstd + C + c0, invstd);
+  ld8(b.gamma + c0, g);
+  ld8(p.red + c0, dbeta);
+  ld8(p.red + (size_t)(1 + j) * C + c0, S);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float dgamma = invstd[i] * (S[i] - mean[i] * dbeta[i]);
+    A[i] = g[i] * invstd[i];
+    Bc[i] = -A[i] * invstd[i] * dgamma * inv_n;
+    Cc[i] = -A[i] * dbeta[i] * inv_n - Bc[i] * mean[i];
+    if (owner) {
+      b.dgamma[c0 + i] = dgamma;
+      b.dbeta[c0 + i] = dbeta[i];
+    }
+  }
+}
+
 template <bool F32>
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
-  extern __shared__ float sh[];  // per branch: A = gamma*invstd, B, Cc  (dy = A*dz + B*y + Cc)
   const int C = p.C;
   const float inv_n = 1.f / (float)p.M;
-  for (int i = threadIdx.x; i < p.n_branch * C; i += kEwThreads) {
-    const int j = i / C, c = i - j * C;
-    const BnBranchBwd& b = p.br[j];
-    const float mean = b.mean_invstd[c], invstd = b.mean_invstd[C + c];
-    const float dbeta = p.red[c];
-    const float dgamma = invstd * (p.red[(1 + j) * C + c] - mean * dbeta);
-    const float A = b.gamma[c] * invstd;
-    const float Bc = -A * invstd * dgamma * inv_n;
-    float* s = &sh[(size_t)j * 3 * C];
-    s[c] = A;
-    s[C + c] = Bc;
-    s[2 * C + c] = -A * dbeta * inv_n - Bc * mean;
-    if (blockIdx.x == 0) {
-      b.dgamma[c] = dgamma;
-      b.dbeta[c] = dbeta;
-    }
-  }
-  __syncthreads();
   const RowTile t = make_row_tile(p.M, C, rows_per_block);
   if (!t.active) return;
+  const bool owner = blockIdx.x == 0 && t.r == 0;
+  const int c0 = t.cv * 8;
+  float A0[8], B0[8], C0[8];
+  bn_bwd_coef(p, 0, c0, inv_n, owner, A0, B0, C0);
+  if (owner) {
+    for (int j = 1; j < p.n_branch; ++j) {
+      float a_[8], b_[8], c_[8];
+      bn_bwd_coef(p, j, c0, inv_n, true, a_, b_, c_);
+    }
+  }
   const size_t rs = (size_t)t.CV;
   for (int row = t.row0 + t.r; row < t.row1; row += kUnroll * t.RP) {
     float dz[kUnroll][8];
@@ -468,12 +506,11 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
       for (int u = 0; u < kUnroll; ++u)
         if (live[u]) v[u] = __ldg(yb + (size_t)(row + u * t.RP) * rs);
       float A[8], Bc[8], Cc[8];
-      const float* s = &sh[(size_t)j * 3 * C + t.cv * 8];
+      if (j == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        A[i] = s[i];
-        Bc[i] = s[C + i];
-        Cc[i] = s[2 * C + i];
+        for (int i = 0; i < 8; ++i) { A[i] = A0[i]; Bc[i] = B0[i]; Cc[i] = C0[i]; }
+      } else {
+        bn_bwd_coef(p, j, c0, inv_n, false, A, Bc, Cc);
       }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
@@ -494,17 +531,15 @@ int bn_bwd(const BnBwdParams& p, cudaStream_t st) {
   if (p.C % 8 != 0 || p.C > 2048) return fail(ERR_UNSUPPORTED, "bn_bwd: C must be a multiple of 8, <= 2048");
   static bool attr_done = false;
   if (!attr_done) {
-    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
   const size_t smem_r = (size_t)(1 + p.n_branch) * p.C * sizeof(float);
-  const size_t smem_a = (size_t)p.n_branch * 3 * p.C * sizeof(float);
-  if (smem_a > 200 * 1024 || smem_r > 100 * 1024) return fail(ERR_UNSUPPORTED, "bn_bwd: too many branches x channels");
+  const size_t smem_a = 0;
+  if (smem_r > 100 * 1024) return fail(ERR_UNSUPPORTED, "bn_bwd: too many branches x channels");
   const int rpb_r = rows_per_block_for(p.M, p.C, 2);
-  const int rpb_a = rows_per_block_for(p.M, p.C, smem_a > 48 * 1024 ? 2 : 4);
+  const int rpb_a = rows_per_block_for(p.M, p.C, 4);
   const int grid_r = (p.M + rpb_r - 1) / rpb_r;
   const int grid_a = (p.M + rpb_a - 1) / rpb_a;
   if (p.dA_is_f32) {

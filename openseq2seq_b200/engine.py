@@ -19,6 +19,7 @@ the step never synchronises with the host.
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -91,7 +92,12 @@ class JasperEngine(object):
         self.step_count = 0
         self._ws = {}
         self._profile = None
-        self.use_cuda_graph = True  # replay the whole step as one CUDA graph after 2 eager steps
+        # replay the whole step as one CUDA graph after 2 eager steps (OS2S_CUDA_GRAPH=0 disables)
+        self.use_cuda_graph = os.environ.get("OS2S_CUDA_GRAPH", "1") != "0"
+        # weight-gradient kernels run on an auxiliary stream: wgrad(l) (tensor-bound, not on the critical
+        # path) overlaps bn_bwd(l-1) (HBM-bound), which co-resides on the SMs (OS2S_OVERLAP_WGRAD=0 disables)
+        self.overlap_wgrad = os.environ.get("OS2S_OVERLAP_WGRAD", "1") != "0"
+        self._aux = None
         self.comm = None            # object with allreduce_(tensor) (openseq2seq_b200.dist.TorchDistHvd)
         self.bucket_bytes = 128 << 20
         self._side = None
@@ -470,7 +476,7 @@ class JasperEngine(object):
         for entry in (ws._bwd_plan or []):
             name = entry[0].__name__
             n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd": 2, "os2s_bn_bwd": 2, "zero_slices": 0,
-                  "bucket_allreduce": 0}.get(name, 1)
+                  "bucket_allreduce": 0, "stream_record": 0, "stream_wait": 0}.get(name, 1)
         return n + 3 + 3
 
     def profile_conv_launches(self, step_fn, steps=2):
@@ -500,15 +506,41 @@ class JasperEngine(object):
 
 
 class _ZeroSlices(object):
-    """Plan entry: zero a few gradient slices (structural zeros of the folded first-layer kernel)."""
+    """Plan entry: zero a few gradient slices (structural zeros of the folded first-layer kernel), on
+    the stream that produced them (the weight-gradient stream)."""
     __name__ = "zero_slices"
 
-    def __init__(self, slices):
-        self.slices = slices
+    def __init__(self, ws, slices):
+        self.ws, self.slices = ws, slices
 
     def __call__(self):
-        for z in self.slices:
-            z.zero_()
+        with torch.cuda.stream(self.ws.aux_stream()):
+            for z in self.slices:
+                z.zero_()
+        return 0
+
+
+class _StreamRecord(object):
+    """Plan entry: record an event on the main or the aux stream of the workspace."""
+    __name__ = "stream_record"
+
+    def __init__(self, ws, which, event):
+        self.ws, self.which, self.event = ws, which, event
+
+    def __call__(self):
+        self.event.record(self.ws.aux_stream() if self.which == "aux" else torch.cuda.current_stream())
+        return 0
+
+
+class _StreamWait(object):
+    """Plan entry: make the main / aux stream wait for an event (no-op when both are the same stream)."""
+    __name__ = "stream_wait"
+
+    def __init__(self, ws, which, event):
+        self.ws, self.which, self.event = ws, which, event
+
+    def __call__(self):
+        (self.ws.aux_stream() if self.which == "aux" else torch.cuda.current_stream()).wait_event(self.event)
         return 0
 
 
@@ -562,10 +594,15 @@ class _Workspace(object):
         self.A = [bf(B, T2, l.c_out) for l in layers]
         self.YR = [[f16(B, T2, l.c_out) for _ in l.res_sources] for l in layers]
         cmax = max(l.c_out for l in layers)
-        self.dY = bf(B, T2, cmax)
         self.dA = bf(B, T2, cmax)
         nres_max = max([len(l.res_sources) for l in layers] + [0])
-        self.dYR = [bf(B, T2, cmax) for _ in range(nres_max)]
+        # conv-output gradients are ping-ponged by layer parity so that wgrad(l) (aux stream) can still
+        # read dY of layer l while bn_bwd(l-1) already writes the other buffer
+        self.dY2 = [bf(B, T2, cmax), bf(B, T2, cmax)]
+        self.dYR2 = [[bf(B, T2, cmax) for _ in range(nres_max)] for _ in range(2)]
+        self.dY = self.dY2[0]
+        self.dYR = self.dYR2[0]
+        self._st_aux = _vp(0)
         self.dres = [f32(B, T2, c) for (c, _) in eng.block_inputs]
         self.red = f32((2 + nres_max) * cmax)
         self.lens_in = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -622,14 +659,14 @@ class _Workspace(object):
                     src_act[idx] = self.A[li - 1]
             self.x_of_layer.append(self.A[li - 1] if li > 0 else None)
             flops = 2.0 * B * T2 * l.K * l.c_in * l.c_out  # algorithmic (un-folded) FLOPs
-            call = [lib.os2s_conv1d_fwd, [x_ptr, self._half_ptr(eng.wb, l.name + "/kernel"), self._p(self.Y[li]),
-                                          B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, 3, st], ("fwd", flops)]
-            plan.append(call)
             slot_main = bn_idx
             bn_idx += 1
-            if eng.training:
-                plan.append([lib.os2s_bn_stats, [self._p(self.Y[li]), self._p(self.stats[slot_main]), M, l.c_out,
-                                                 st]])
+            # training: the conv epilogue accumulates the BN statistics of its (rounded) output
+            stats_ptr = self._p(self.stats[slot_main]) if eng.training else _vp(0)
+            call = [lib.os2s_conv1d_fwd, [x_ptr, self._half_ptr(eng.wb, l.name + "/kernel"), self._p(self.Y[li]),
+                                          B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, 3, stats_ptr, st],
+                    ("fwd", flops)]
+            plan.append(call)
             ys = [self.Y[li]]
             names = [l.name + "/bn"]
             slots = [slot_main]
@@ -637,14 +674,13 @@ class _Workspace(object):
                 rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
                 bnn = (l.name + "/res_bn_%d" % n) if l.dense else (l.name + "/res_bn")
                 cj = eng.block_inputs[j][0]
-                plan.append([lib.os2s_conv1d_fwd, [self._p(src_act[j]), self._half_ptr(eng.wb, rn + "/kernel"),
-                                                   self._p(self.YR[li][n]), B, T2, cj, l.c_out, 1, 1, 0, 3, st],
-                             ("fwd", 2.0 * B * T2 * cj * l.c_out)])
                 slot = bn_idx
                 bn_idx += 1
-                if eng.training:
-                    plan.append([lib.os2s_bn_stats, [self._p(self.YR[li][n]), self._p(self.stats[slot]), M, l.c_out,
-                                                     st]])
+                stats_ptr = self._p(self.stats[slot]) if eng.training else _vp(0)
+                plan.append([lib.os2s_conv1d_fwd, [self._p(src_act[j]), self._half_ptr(eng.wb, rn + "/kernel"),
+                                                   self._p(self.YR[li][n]), B, T2, cj, l.c_out, 1, 1, 0, 3,
+                                                   stats_ptr, st],
+                             ("fwd", 2.0 * B * T2 * cj * l.c_out)])
                 ys.append(self.YR[li][n])
                 names.append(bnn)
                 slots.append(slot)
@@ -695,9 +731,20 @@ class _Workspace(object):
             self.stats.zero_()
         self._exec(self._fwd_plan)
 
+    def aux_stream(self):
+        """Stream of the weight-gradient kernels: a dedicated one, or the current stream when the
+        overlap is disabled or conv launches are being timed with events."""
+        eng = self.eng
+        if eng.overlap_wgrad and eng._profile is None:
+            if eng._aux is None:
+                eng._aux = torch.cuda.Stream()
+            return eng._aux
+        return torch.cuda.current_stream()
+
     def _body_backward(self, plan):
         eng = self.eng
         self._st.value = torch.cuda.current_stream().cuda_stream
+        self._st_aux.value = self.aux_stream().cuda_stream
         self._exec(plan)
         if eng.comm is not None:
             torch.cuda.current_stream().wait_stream(eng._side)
@@ -757,14 +804,19 @@ class _Workspace(object):
         written = set()  # residual-source accumulators that already hold a first contribution
         nl = len(eng.layers)
         bucket_end = eng._total          # gradients in [bucket_start, bucket_end) are final once enqueued
+        sa = self._st_aux                # aux-stream handle (== main stream when overlap is off / profiling)
+        ev_bn = [torch.cuda.Event() for _ in range(nl)]
+        ev_wg = [torch.cuda.Event() for _ in range(nl)]
         for li in range(nl - 1, -1, -1):
             l = eng.layers[li]
+            par = li & 1
+            dY, dYR = self.dY2[par], self.dYR2[par]
             slots, names, (y_h, st_h, g_h, b_h, mi_h, mv_h) = self.bn_slot[li]
             nb = len(slots)
             arr = lambda ptrs: (ctypes.c_void_p * nb)(*[p.value for p in ptrs])
             dg_h = arr([self._param_ptr(eng.grad, nm + "/gamma") for nm in names])
             db_h = arr([self._param_ptr(eng.grad, nm + "/beta") for nm in names])
-            dys = [self.dY] + [self.dYR[n] for n in range(nb - 1)]
+            dys = [dY] + [dYR[n] for n in range(nb - 1)]
             dy_h = arr([self._p(t) for t in dys])
             if li in eng.src_of_layer_output:
                 j = eng.src_of_layer_output[li]
@@ -773,15 +825,20 @@ class _Workspace(object):
                     raise RuntimeError("internal: residual source %d has no gradient writer" % j)
             else:
                 dA_ptr, dA_f32 = self._p(self.dA), 0
+            if li + 2 < nl:
+                # this layer's dY buffers were last read by wgrad(li + 2) on the aux stream
+                plan.append([_StreamWait(self, "main", ev_wg[li + 2]), []])
             plan.append([lib.os2s_bn_bwd, [nb, y_h, mi_h, g_h, dg_h, db_h, dy_h, dA_ptr, dA_f32, self._p(self.A[li]),
                                            self._p(self.red), M, l.c_out, _c_float(l.keep), 1, st]])
             self._keep = getattr(self, "_keep", []) + [dg_h, db_h, dy_h]
+            plan.append([_StreamRecord(self, "main", ev_bn[li]), []])
+            # ---- aux stream: weight gradients of this layer
+            plan.append([_StreamWait(self, "aux", ev_bn[li]), []])
             # main conv wgrad (stored layout == kernel layout, also for the folded stride-2 layer)
             x_ptr = self._p(self.A[li - 1]) if li > 0 else self._p(self.feats)
-            wg = [lib.os2s_conv1d_wgrad, [x_ptr, self._p(self.dY), self._param_ptr(eng.grad, l.name + "/kernel"),
-                                          B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, st],
-                  ("wgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)]
-            plan.append(wg)
+            plan.append([lib.os2s_conv1d_wgrad, [x_ptr, self._p(dY), self._param_ptr(eng.grad, l.name + "/kernel"),
+                                                 B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, sa],
+                         ("wgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
             if l.fold:
                 # structurally-zero taps of the folded stride-2 kernel get no gradient
                 s_ = eng.by_name[l.name + "/kernel"]
@@ -792,18 +849,22 @@ class _Workspace(object):
                 if st0 + n_ < s_["store_size"]:
                     zs.append(eng.grad[s_["offset"] + st0 + n_:s_["offset"] + s_["store_size"]])
                 if zs:
-                    plan.append([_ZeroSlices(zs), []])
-            # residual branches: wgrad + dgrad into the fp32 accumulators
+                    plan.append([_ZeroSlices(self, zs), []])
             for n, j in enumerate(l.res_sources):
                 rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
                 cj = eng.block_inputs[j][0]
                 src = self.A[eng.block_inputs[j][1] - 1]
-                plan.append([lib.os2s_conv1d_wgrad, [self._p(src), self._p(self.dYR[n]),
+                plan.append([lib.os2s_conv1d_wgrad, [self._p(src), self._p(dYR[n]),
                                                      self._param_ptr(eng.grad, rn + "/kernel"), B, T2, cj, l.c_out,
-                                                     1, 1, 0, st], ("wgrad", 2.0 * B * T2 * cj * l.c_out)])
+                                                     1, 1, 0, sa], ("wgrad", 2.0 * B * T2 * cj * l.c_out)])
+            plan.append([_StreamRecord(self, "aux", ev_wg[li]), []])
+            # ---- main stream (critical path): data gradients
+            for n, j in enumerate(l.res_sources):
+                rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
+                cj = eng.block_inputs[j][0]
                 mode = 2 if j in written else 1
                 written.add(j)
-                plan.append([lib.os2s_conv1d_dgrad, [self._p(self.dYR[n]), self._half_ptr(eng.wb, rn + "/kernel"),
+                plan.append([lib.os2s_conv1d_dgrad, [self._p(dYR[n]), self._half_ptr(eng.wb, rn + "/kernel"),
                                                      self._p(self.dres[j]), B, T2, cj, l.c_out, 1, 1, 0, mode, st],
                              ("dgrad", 2.0 * B * T2 * cj * l.c_out)])
             if li > 0:
@@ -814,14 +875,20 @@ class _Workspace(object):
                     out_ptr = self._p(self.dres[j])
                 else:
                     mode, out_ptr = 0, self._p(self.dA)
-                plan.append([lib.os2s_conv1d_dgrad, [self._p(self.dY), self._half_ptr(eng.wb, l.name + "/kernel"),
+                plan.append([lib.os2s_conv1d_dgrad, [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"),
                                                      out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
                                                      st], ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
             if eng.comm is not None:
                 start = eng.by_name[l.name + "/kernel"]["offset"]
                 if (bucket_end - start) * 4 >= eng.bucket_bytes or li == 0:
+                    # the bucket also holds weight gradients produced on the aux stream
+                    plan.append([_StreamWait(self, "main", ev_wg[li]), []])
                     plan.append([_BucketAllReduce(eng, eng.grad[start:bucket_end]), []])
                     bucket_end = start
+        # join: the optimizer needs every weight gradient
+        plan.append([_StreamWait(self, "main", ev_wg[0]), []])
+        if nl > 1:
+            plan.append([_StreamWait(self, "main", ev_wg[1]), []])
         self._bwd_plan = plan
         self._bwd_L = L_max
         self.n_launch_bwd = len(plan) + 4

@@ -36,7 +36,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
 def test_argument_validation_needs_no_gpu():
     from openseq2seq_b200 import _lib as L
     lib = L.load()
-    assert lib.os2s_conv1d_fwd(None, None, None, 1, 1, 64, 64, 1, 1, 0, 0, None) == -1
+    assert lib.os2s_conv1d_fwd(None, None, None, 1, 1, 64, 64, 1, 1, 0, 0, None, None) == -1
     assert b"null pointer" in lib.os2s_last_error()
     assert lib.os2s_fc_fwd(None, None, None, None, 1, 1, 1, None) == -1
 

@@ -49,9 +49,13 @@ def test_conv_fwd_dgrad_wgrad_vs_oracle(B, T, Cin, Cout, K, dil):
     wt = wd.permute(0, 2, 1).contiguous()
     st = L.stream_ptr()
     y = torch.empty(B, T, Cout, dtype=torch.bfloat16, device="cuda")
-    L.check(lib.os2s_conv1d_fwd(L.ptr(xd), L.ptr(wd), L.ptr(y), B, T, Cin, Cout, K, dil, pl, 0, st), "fwd")
+    L.check(lib.os2s_conv1d_fwd(L.ptr(xd), L.ptr(wd), L.ptr(y), B, T, Cin, Cout, K, dil, pl, 0, None, st), "fwd")
     y16 = torch.empty(B, T, Cout, dtype=torch.float16, device="cuda")
-    L.check(lib.os2s_conv1d_fwd(L.ptr(xd), L.ptr(wd), L.ptr(y16), B, T, Cin, Cout, K, dil, pl, 3, st), "fwd16")
+    fused = torch.zeros(2, Cout, device="cuda")
+    L.check(lib.os2s_conv1d_fwd(L.ptr(xd), L.ptr(wd), L.ptr(y16), B, T, Cin, Cout, K, dil, pl, 3, L.ptr(fused), st),
+            "fwd16")
+    alone = torch.zeros(2, Cout, device="cuda")
+    L.check(lib.os2s_bn_stats(L.ptr(y16), L.ptr(alone), B * T, Cout, st), "bn_stats")
     ywt = torch.empty(B, T, Cout, dtype=torch.bfloat16, device="cuda")
     L.check(lib.os2s_conv1d_fwd_wt(L.ptr(xd), L.ptr(wt), L.ptr(ywt), B, T, Cin, Cout, K, dil, pl, 0, st), "fwd_wt")
     dx = torch.empty(B, T, Cin, dtype=torch.float32, device="cuda")
@@ -62,6 +66,11 @@ def test_conv_fwd_dgrad_wgrad_vs_oracle(B, T, Cin, Cout, K, dil):
     torch.cuda.synchronize()
     assert np.abs(y.float().cpu().numpy() - y_ref).max() <= 1e-2 * np.abs(y_ref).max()
     assert torch.equal(y, ywt)  # the two weight-operand layouts are the same arithmetic
+    # BN statistics fused into the conv epilogue == the standalone statistics kernel == the oracle
+    y16d = y16.double().cpu()
+    assert torch.allclose(fused.cpu().double()[0], y16d.sum((0, 1)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(fused.cpu().double()[1], (y16d * y16d).sum((0, 1)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(fused, alone, rtol=1e-4, atol=1e-2)
     assert np.abs(y16.float().cpu().numpy() - y_ref).max() <= 1.5e-3 * np.abs(y_ref).max()
     assert np.abs(dx.cpu().numpy() - dx_ref).max() <= 1e-4 * np.abs(dx_ref).max() + 1e-4
     if Cin % 128 == 0:
@@ -73,9 +82,9 @@ def test_conv_rejects_unsupported_shapes_loudly():
     x = torch.zeros(1, 16, 48, dtype=torch.bfloat16, device="cuda")
     w = torch.zeros(1, 48, 64, dtype=torch.bfloat16, device="cuda")
     y = torch.zeros(1, 16, 64, dtype=torch.bfloat16, device="cuda")
-    rc = lib.os2s_conv1d_fwd(L.ptr(x), L.ptr(w), L.ptr(y), 1, 16, 48, 64, 1, 1, 0, 0, L.stream_ptr())
+    rc = lib.os2s_conv1d_fwd(L.ptr(x), L.ptr(w), L.ptr(y), 1, 16, 48, 64, 1, 1, 0, 0, None, L.stream_ptr())
     assert rc == -3 and b"multiple of 64" in lib.os2s_last_error()
-    assert lib.os2s_conv1d_fwd(None, None, None, 1, 16, 64, 64, 1, 1, 0, 0, L.stream_ptr()) == -1
+    assert lib.os2s_conv1d_fwd(None, None, None, 1, 16, 64, 64, 1, 1, 0, 0, None, L.stream_ptr()) == -1
 
 
 def test_batchnorm_residual_relu_dropout_mask_fwd_bwd_vs_oracle():

@@ -71,7 +71,7 @@ def run_case(name):
         dw_ref = wtt.grad.permute(2, 1, 0).contiguous()  # [K,Cin,Cout]
         if mode == "fwd":
             y = torch.full((B, T, Cout), float("nan"), device=dev).bfloat16()
-            L.check(lib.os2s_conv1d_fwd(L.ptr(x), L.ptr(w), L.ptr(y), B, T, Cin, Cout, K, dil, padl, 0, st), name)
+            L.check(lib.os2s_conv1d_fwd(L.ptr(x), L.ptr(w), L.ptr(y), B, T, Cin, Cout, K, dil, padl, 0, None, st), name)
             got, ref = y.float(), y_ref
         elif mode == "dgrad":
             dx = torch.full((B, T, Cin), float("nan"), device=dev).bfloat16()
@@ -117,10 +117,13 @@ def run_case(name):
     y = torch.empty(B, T, Cout, device=dev).bfloat16()
     dx = torch.empty(B, T, Cin, device=dev).bfloat16()
     dw = torch.empty(K, Cin, Cout, device=dev)
+    stats = torch.zeros(2, Cout, device=dev)
     flops = 2.0 * B * T * K * Cin * Cout
     res = {"case": name, "gflop": flops / 1e9}
     fns = {
-        "fwd": lambda: lib.os2s_conv1d_fwd(L.ptr(x), L.ptr(w), L.ptr(y), B, T, Cin, Cout, K, dil, padl, 0, st),
+        "fwd": lambda: lib.os2s_conv1d_fwd(L.ptr(x), L.ptr(w), L.ptr(y), B, T, Cin, Cout, K, dil, padl, 0, None, st),
+        "fwd_stats": lambda: lib.os2s_conv1d_fwd(L.ptr(x), L.ptr(w), L.ptr(y), B, T, Cin, Cout, K, dil, padl, 3,
+                                                 L.ptr(stats), st),
         "fwd_wt": lambda: lib.os2s_conv1d_fwd_wt(L.ptr(x), L.ptr(wt), L.ptr(y), B, T, Cin, Cout, K, dil, padl, 0, st),
         "dgrad": lambda: lib.os2s_conv1d_dgrad(L.ptr(dy), L.ptr(w), L.ptr(dx), B, T, Cin, Cout, K, dil, padl, 0, st),
         "wgrad": lambda: lib.os2s_conv1d_wgrad(L.ptr(x), L.ptr(dy), L.ptr(dw), B, T, Cin, Cout, K, dil, padl, st),

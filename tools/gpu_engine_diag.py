@@ -54,7 +54,7 @@ for entry in plan:
         print("fc_bwd dA(last) %.2e %.2e" % (_rel(dA, r), _rel_l2(dA, r)))
     if name == "os2s_bn_bwd":
         l = eng.layers[li]
-        dY = ws.dY.view(-1)[: ws.M * l.c_out].view(ws.B, ws.T2, l.c_out).float().cpu()
+        dY = ws.dY2[li & 1].view(-1)[: ws.M * l.c_out].view(ws.B, ws.T2, l.c_out).float().cpu()
         r = col[l.name + "/conv"].grad
         print("%-8s bn_bwd dY %.2e %.2e" % (l.name, _rel(dY, r), _rel_l2(dY, r)), end="")
         for nm in (l.name + "/bn/gamma", l.name + "/bn/beta"):
