@@ -1,0 +1,98 @@
+"""The reference's own integration test, re-hosted: train a TDNN speech2text model to convergence on
+the reference's toy speech data (8 wavs / 10 CSV rows, tests/golden/toy_speech_data) through the
+plugin API (`create`-style config dicts -> Speech2Text -> train()/evaluate()), then check the
+thresholds of open_seq2seq/models/speech2text_w2l_test.py:23-24: train loss < 5, eval loss < 30,
+WER < 0.1.  The layer widths are the tensor-core-aligned analogue of test_speech_configs/
+w2l_test_config.py (200/400 channels there, 256/384 here; stride-2 first layer so that the 64 log-mel
+features fold to 128 channels); optimizer, LARC, lr policy and activation follow that config."""
+import copy
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOY = os.path.join(ROOT, "tests", "golden", "toy_speech_data")
+
+
+def _config(tmpdir):
+    import openseq2seq_b200.compat as compat
+    compat.install()
+    import tensorflow as tf
+    from open_seq2seq.models import Speech2Text
+    from open_seq2seq.encoders import TDNNEncoder
+    from open_seq2seq.decoders import FullyConnectedCTCDecoder
+    from open_seq2seq.data import Speech2TextDataLayer
+    from open_seq2seq.losses import CTCLoss
+    from open_seq2seq.optimizers.lr_policies import poly_decay
+    import pandas as pd
+    csv = pd.read_csv(os.path.join(TOY, "toy_data.csv"))
+    csv["wav_filename"] = [os.path.join(TOY, p) for p in csv["wav_filename"]]
+    csv_path = os.path.join(str(tmpdir), "toy_abs.csv")
+    csv.to_csv(csv_path, index=False)
+    dl = {
+        "num_audio_features": 64, "input_type": "logfbank", "backend": "librosa", "norm_per_feature": True,
+        "pad_to": 16, "window": "hanning", "vocab_file": os.path.join(TOY, "vocab.txt"),
+        "dataset_files": [csv_path],
+    }
+    base = {
+        "use_horovod": False, "num_epochs": 500, "num_gpus": 1, "batch_size_per_gpu": 10,
+        "save_summaries_steps": 10, "print_loss_steps": 100, "print_samples_steps": None, "eval_steps": 1000,
+        "save_checkpoint_steps": 250, "logdir": os.path.join(str(tmpdir), "log"),
+        "optimizer": "Momentum", "optimizer_params": {"momentum": 0.90},
+        "lr_policy": poly_decay, "lr_policy_params": {"learning_rate": 0.01, "power": 2},
+        "larc_params": {"larc_eta": 0.001},
+        "dtype": "mixed", "loss_scaling": "Backoff",
+        "encoder": TDNNEncoder,
+        "encoder_params": {
+            "convnet_layers": [
+                {"type": "conv1d", "repeat": 1, "kernel_size": [11], "stride": [2], "num_channels": 256,
+                 "padding": "SAME", "dilation": [1]},
+                {"type": "conv1d", "repeat": 3, "kernel_size": [7], "stride": [1], "num_channels": 256,
+                 "padding": "SAME", "dilation": [1]},
+                {"type": "conv1d", "repeat": 1, "kernel_size": [1], "stride": [1], "num_channels": 384,
+                 "padding": "SAME", "dilation": [1]},
+            ],
+            "dropout_keep_prob": 0.9,
+            "initializer": tf.contrib.layers.xavier_initializer, "initializer_params": {"uniform": False},
+            "activation_fn": lambda x: tf.minimum(tf.nn.relu(x), 20.0),
+            "data_format": "channels_last", "bn_momentum": 0.001, "use_conv_mask": True,
+        },
+        "decoder": FullyConnectedCTCDecoder,
+        "decoder_params": {"initializer": tf.contrib.layers.xavier_initializer, "use_language_model": False},
+        "loss": CTCLoss, "loss_params": {},
+        "data_layer": Speech2TextDataLayer,
+    }
+    train_cfg = copy.deepcopy(base)
+    train_cfg["data_layer_params"] = dict(dl, shuffle=True)
+    eval_cfg = copy.deepcopy(base)
+    eval_cfg["data_layer_params"] = dict(dl, shuffle=False)
+    return Speech2Text, train_cfg, eval_cfg
+
+
+def test_w2l_style_model_converges_on_reference_toy_speech(tmp_path):
+    from open_seq2seq.utils.funcs import train, evaluate_model
+    from open_seq2seq.utils import checkpoint as ckpt
+    model_cls, train_cfg, eval_cfg = _config(tmp_path)
+    train_model = model_cls(params=train_cfg, mode="train", hvd=None)
+    train_model.compile()
+    eval_model = model_cls(params=eval_cfg, mode="eval", hvd=None)
+    eval_model.compile(force_var_reuse=True, share_with=train_model)
+    assert train_model.last_step == 500 and train_model.get_data_layer().get_size_in_samples() == 10
+    train(train_model, eval_model)
+    torch.cuda.synchronize()
+    loss = float(train_model.loss)
+    # checkpoint written by the training loop restores to identical weights (speech2text_test.py:42-55)
+    path = ckpt.latest_checkpoint(train_cfg["logdir"])
+    assert path is not None and path.endswith("model.ckpt-500.pt")
+    before = train_model.engine.master.clone()
+    ckpt.restore(train_model.engine, path)
+    assert torch.equal(before, train_model.engine.master)
+    out = evaluate_model(eval_model)
+    assert torch.equal(before, train_model.engine.master)  # evaluation does not touch the weights
+    print("toy convergence: train loss %.3f, eval loss %.3f, WER %.4f" % (loss, out["Eval loss"], out["Eval WER"]))
+    assert loss < 5.0
+    assert out["Eval loss"] < 30.0
+    assert out["Eval WER"] < 0.1
