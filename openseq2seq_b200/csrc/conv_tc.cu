@@ -371,8 +371,7 @@ struct MNMajorParams {
   int B, T, t_chunks;          // t_chunks = ceil(T / 64)
   int K_taps, dil, pad_left;
   int m_tiles, n_tiles;        // C_in / 128, C_out / BN
-  int splits, b_per_split;
-  float* dw;                   // [K][C_in][C_out] fp32, accumulated with red.add
+  float* dw;                   // [K][C_in][C_out] fp32; zeroed by the launcher, split units red.add into it
   int C_in, C_out;
 };
 
@@ -415,28 +414,40 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int units_per_split = p.K_taps * p.m_tiles * p.n_tiles;
-  const int n_units = units_per_split * p.splits;
+  // Stream-K schedule: the work of the launch is n_units * B items (one utterance of one output tile
+  // each, utterances fastest); CTA c owns the contiguous item range [c*total/G, (c+1)*total/G), i.e.
+  // every CTA does the same amount of MMA work regardless of how n_units divides by the SM count.
+  // A range is cut into segments at unit boundaries; a segment that covers all B utterances of its
+  // unit stores its tile, partial segments reduce into the (pre-zeroed) tile with red.global.add.
+  const int n_units = p.K_taps * p.m_tiles * p.n_tiles;
+  const long long total_items = (long long)n_units * p.B;
+  const long long item0 = total_items * blockIdx.x / gridDim.x;
+  const long long item1 = total_items * (blockIdx.x + 1) / gridDim.x;
 
-  // unit -> (split, tap, m tile, n tile); taps fastest so concurrent CTAs share X / dY in L2.
-  auto decode = [&](int unit, int& s, int& k, int& mi, int& ni) {
-    s = unit / units_per_split;
-    int r = unit - s * units_per_split;
-    const int mn = r / p.K_taps;
-    k = r - mn * p.K_taps;
+  // unit -> (tap, m tile, n tile); taps fastest so concurrent CTAs share X / dY in L2.
+  auto decode = [&](int unit, int& k, int& mi, int& ni) {
+    const int mn = unit / p.K_taps;
+    k = unit - mn * p.K_taps;
     mi = mn / p.n_tiles;
     ni = mn - mi * p.n_tiles;
+  };
+  // segment iterator shared by the three roles
+  auto next_segment = [&](long long& it, int& unit, int& b_lo, int& b_hi) {
+    unit = (int)(it / p.B);
+    b_lo = (int)(it - (long long)unit * p.B);
+    const long long room = item1 - it;
+    b_hi = (int)min((long long)p.B, (long long)b_lo + room);
+    it += b_hi - b_lo;
   };
 
   if (warp == 0) {
     if (elect_one()) {
       PipeState ps;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        int s, k, mi, ni;
-        decode(unit, s, k, mi, ni);
+      for (long long it = item0; it < item1;) {
+        int unit, b_lo, b_hi, k, mi, ni;
+        next_segment(it, unit, b_lo, b_hi);
+        decode(unit, k, mi, ni);
         const int tsh = k * p.dil - p.pad_left;
-        const int b_lo = s * p.b_per_split;
-        const int b_hi = min(p.B, b_lo + p.b_per_split);
         for (int b = b_lo; b < b_hi; ++b) {
           for (int tc = 0; tc < p.t_chunks; ++tc) {
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
@@ -460,17 +471,15 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       constexpr uint32_t idesc = make_idesc(kTileM, BN, 1, 1);
       PipeState ps;
       uint32_t ti = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++ti) {
-        int s, k, mi, ni;
-        decode(unit, s, k, mi, ni);
-        const int b_lo = s * p.b_per_split;
-        const int b_hi = min(p.B, b_lo + p.b_per_split);
+      for (long long it = item0; it < item1; ++ti) {
+        int unit, b_lo, b_hi;
+        next_segment(it, unit, b_lo, b_hi);
         const int n_iters = (b_hi - b_lo) * p.t_chunks;
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int it = 0; it < n_iters; ++it) {
+        for (int i = 0; i < n_iters; ++i) {
           mbar_wait(&full_bar[ps.stage], ps.phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + ps.stage * kABytes);
@@ -480,10 +489,10 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             // 16 reduction rows = 2 KB further into every 64-wide box
             const uint64_t da = make_sdesc(a_addr + kk * 2048, kBoxBytes, 1024);
             const uint64_t db = make_sdesc(b_addr + kk * 2048, kBoxBytes, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[ps.stage]);
-          if (it == n_iters - 1) umma_commit(&tfull_bar[as]);
+          if (i == n_iters - 1) umma_commit(&tfull_bar[as]);
           ps.advance<S>();
         }
       }
@@ -492,9 +501,11 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     uint32_t ti = 0;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++ti) {
-      int s, k, mi, ni;
-      decode(unit, s, k, mi, ni);
+    for (long long it = item0; it < item1; ++ti) {
+      int unit, b_lo, b_hi, k, mi, ni;
+      next_segment(it, unit, b_lo, b_hi);
+      decode(unit, k, mi, ni);
+      const bool whole = (b_lo == 0 && b_hi == p.B);
       const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -505,7 +516,7 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         uint32_t r[32];
         tmem_ld32(taddr + ch * 32, r);
         tmem_ld_wait();
-        if (p.splits == 1) {
+        if (whole) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             reinterpret_cast<float4*>(dst + ch * 32)[q] =
@@ -561,8 +572,8 @@ static int launch_mnmajor(const CUtensorMap* mx, const CUtensorMap* mdy, const M
     OS2S_CUDA(cudaFuncSetAttribute(tapgemm_mnmajor<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int units = p.K_taps * p.m_tiles * p.n_tiles * p.splits;
-  const int grid = units < device_sm_count() ? units : device_sm_count();
+  const long long items = (long long)p.K_taps * p.m_tiles * p.n_tiles * p.B;
+  const int grid = items < device_sm_count() ? (int)items : device_sm_count();
   tapgemm_mnmajor<BN><<<grid, kNumThreads, smem, st>>>(*mx, *mdy, p);
   return check_launch("tapgemm_mnmajor");
 }
@@ -665,18 +676,10 @@ int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in,
   p.dw = dw;
   p.C_in = C_in;
   p.C_out = C_out;
-  // Split the (b, t) reduction so that there are at least ~2 waves of work units.
-  const int base_units = K * p.m_tiles * p.n_tiles;
-  const int sms = device_sm_count();
-  int splits = 1;
-  while (splits < B && base_units * splits < 2 * sms) splits *= 2;
-  if (splits > B) splits = B;
-  p.b_per_split = (B + splits - 1) / splits;
-  p.splits = (B + p.b_per_split - 1) / p.b_per_split;
-  if (splits_used) *splits_used = p.splits;
-  if (p.splits > 1) {
-    OS2S_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * C_in * C_out * sizeof(float), st));
-  }
+  // stream-K: every CTA gets an equal share of (unit, utterance) items; tiles shared between CTAs are
+  // reduced with red.add into the zeroed gradient (a plain store is used when a CTA owns a whole unit)
+  if (splits_used) *splits_used = 0;
+  OS2S_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * C_in * C_out * sizeof(float), st));
   switch (BN) {
     case 256: return launch_mnmajor<256>(mx, mdy, p, st);
     case 192: return launch_mnmajor<192>(mx, mdy, p, st);

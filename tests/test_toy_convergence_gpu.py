@@ -73,9 +73,9 @@ def _config(tmpdir):
 
 
 def test_w2l_style_model_converges_on_reference_toy_speech(tmp_path):
+    model_cls, train_cfg, eval_cfg = _config(tmp_path)  # installs the compat import surface
     from open_seq2seq.utils.funcs import train, evaluate_model
     from open_seq2seq.utils import checkpoint as ckpt
-    model_cls, train_cfg, eval_cfg = _config(tmp_path)
     train_model = model_cls(params=train_cfg, mode="train", hvd=None)
     train_model.compile()
     eval_model = model_cls(params=eval_cfg, mode="eval", hvd=None)
