@@ -176,10 +176,12 @@ __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* 
   *hi = __umulhi(a, b);
   return a * b;
 }
-// Philox4x32-10 (Salmon et al.), counter = element-vector index, key = seed.
+// Philox4x32-7 (Salmon et al.; 7 rounds pass BigCrush), counter = element-vector index, key = seed.
+// One call yields 128 random bits = eight 16-bit uniforms, one per element of a 16-byte vector, so the
+// dropout mask costs ~60 integer instructions per vector and the kernel stays HBM-bound.
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < 7; ++i) {
     uint32_t hi0, hi1;
     const uint32_t lo0 = mulhilo32(0xD2511F53u, ctr.x, &hi0);
     const uint32_t lo1 = mulhilo32(0xCD9E8D57u, ctr.z, &hi1);
@@ -189,7 +191,6 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
-
 
 // scale / shift of the thread's own 8 channels of branch b (batch or moving statistics); the owner
 // thread (first row slot of CTA 0) also publishes mean / invstd and updates the moving averages.
@@ -248,6 +249,7 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
     }
   }
   const float inv_keep = 1.f / p.keep;
+  const uint32_t keep16 = (uint32_t)(p.keep * 65536.f + 0.5f);
   unsigned long long seed = p.seed;
   if (p.step_ctr) seed += (unsigned long long)(*p.step_ctr) * 0x9E3779B97F4A7C15ull;
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -304,12 +306,11 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
         if (p.keep < 1.f) {
           const unsigned long long idx = (unsigned long long)ru * (unsigned)t.CV + (unsigned)t.cv;
           const uint4 r0 = philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u), key);
-          const uint4 r1 = philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 1u, 0u), key);
-          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          const uint32_t rr[4] = {r0.x, r0.y, r0.z, r0.w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float uu = (float)(rr[i] >> 8) * (1.f / 16777216.f);  // [0,1)
-            acc[u][i] = (uu < p.keep) ? acc[u][i] * inv_keep : 0.f;
+            const uint32_t u16 = (i & 1) ? (rr[i >> 1] >> 16) : (rr[i >> 1] & 0xFFFFu);
+            acc[u][i] = (u16 < keep16) ? acc[u][i] * inv_keep : 0.f;  // P(keep) = keep16 / 65536
           }
         }
       } else {

@@ -94,6 +94,9 @@ class JasperEngine(object):
         self._profile = None
         # replay the whole step as one CUDA graph after 2 eager steps (OS2S_CUDA_GRAPH=0 disables)
         self.use_cuda_graph = os.environ.get("OS2S_CUDA_GRAPH", "1") != "0"
+        # with a communicator attached (N > 1) the step runs from the eager launch plan unless
+        # OS2S_GRAPH_DIST=1 asks for NCCL collectives to be captured into the graph as well
+        self.graph_with_comm = os.environ.get("OS2S_GRAPH_DIST", "0") == "1"
         # weight-gradient kernels run on an auxiliary stream: wgrad(l) (tensor-bound, not on the critical
         # path) overlaps bn_bwd(l-1) (HBM-bound), which co-resides on the SMs (OS2S_OVERLAP_WGRAD=0 disables)
         self.overlap_wgrad = os.environ.get("OS2S_OVERLAP_WGRAD", "1") != "0"
@@ -918,7 +921,7 @@ class _Workspace(object):
         self.set_inputs(feats, feat_lens)
         self.set_targets(labels, label_lens)
         eng._last_ws = self
-        if eng.use_cuda_graph and eng._profile is None:
+        if eng.use_cuda_graph and eng._profile is None and (eng.comm is None or eng.graph_with_comm):
             if self.graph is not None:
                 self.graph.replay()
                 eng.step_count += 1
