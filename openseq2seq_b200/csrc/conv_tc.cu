@@ -23,6 +23,7 @@
 //   warps 2-5 : epilogue, TMEM -> registers -> global; the accumulator is double buffered in TMEM so
 //   the epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.h"
+#include <cstdlib>
 #include "ptx.cuh"
 
 namespace os2s {
@@ -37,6 +38,7 @@ enum OutMode : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ACC = 2, OUT_F16 = 3 };
 
 struct KMajorParams {
   int B, T_out, n_mtiles, n_ntiles, N_total;
+  int n_tail;                  // width of the last N tile (== BN when BN divides N_total)
   int K_taps, c_chunks;
   int t_off0, t_step;
   float* stats;                // optional [2][N_total]: += per-channel sum / sum of squares of the output
@@ -76,6 +78,143 @@ struct PipeState {
     }
   }
 };
+
+// One epilogue warp: 32 rows x ncur columns, TMEM -> registers -> staging rows -> coalesced global
+// stores (+ the BN statistics of the rounded outputs when do_stats).
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const KMajorParams& p, uint8_t* stage, float* sacc, bool do_stats,
+                                              bool two_byte, uint32_t taddr, int nvalid, long long off, int ncur,
+                                              int lane) {
+  uint8_t* myrow = stage + lane * kEpiRowBytes;
+  if (two_byte) {
+    uint16_t* out2 = reinterpret_cast<uint16_t*>(p.out) + off;
+#pragma unroll 1
+    for (int c = 0; c < ncur; c += 64) {
+      const bool wide = (ncur - c) >= 64;  // 64-column chunk, or a 32-column tail
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr + c, r0);
+      if (wide) tmem_ld32(taddr + c + 32, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 v;
+        if (p.out_mode == OUT_BF16) {
+          v.x = pack_bf16(__uint_as_float(r0[q * 8 + 0]), __uint_as_float(r0[q * 8 + 1]));
+          v.y = pack_bf16(__uint_as_float(r0[q * 8 + 2]), __uint_as_float(r0[q * 8 + 3]));
+          v.z = pack_bf16(__uint_as_float(r0[q * 8 + 4]), __uint_as_float(r0[q * 8 + 5]));
+          v.w = pack_bf16(__uint_as_float(r0[q * 8 + 6]), __uint_as_float(r0[q * 8 + 7]));
+        } else {
+          v.x = pack_f16(__uint_as_float(r0[q * 8 + 0]), __uint_as_float(r0[q * 8 + 1]));
+          v.y = pack_f16(__uint_as_float(r0[q * 8 + 2]), __uint_as_float(r0[q * 8 + 3]));
+          v.z = pack_f16(__uint_as_float(r0[q * 8 + 4]), __uint_as_float(r0[q * 8 + 5]));
+          v.w = pack_f16(__uint_as_float(r0[q * 8 + 6]), __uint_as_float(r0[q * 8 + 7]));
+        }
+        *reinterpret_cast<uint4*>(myrow + q * 16) = v;
+      }
+      if (wide) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          if (p.out_mode == OUT_BF16) {
+            v.x = pack_bf16(__uint_as_float(r1[q * 8 + 0]), __uint_as_float(r1[q * 8 + 1]));
+            v.y = pack_bf16(__uint_as_float(r1[q * 8 + 2]), __uint_as_float(r1[q * 8 + 3]));
+            v.z = pack_bf16(__uint_as_float(r1[q * 8 + 4]), __uint_as_float(r1[q * 8 + 5]));
+            v.w = pack_bf16(__uint_as_float(r1[q * 8 + 6]), __uint_as_float(r1[q * 8 + 7]));
+          } else {
+            v.x = pack_f16(__uint_as_float(r1[q * 8 + 0]), __uint_as_float(r1[q * 8 + 1]));
+            v.y = pack_f16(__uint_as_float(r1[q * 8 + 2]), __uint_as_float(r1[q * 8 + 3]));
+            v.z = pack_f16(__uint_as_float(r1[q * 8 + 4]), __uint_as_float(r1[q * 8 + 5]));
+            v.w = pack_f16(__uint_as_float(r1[q * 8 + 6]), __uint_as_float(r1[q * 8 + 7]));
+          }
+          *reinterpret_cast<uint4*>(myrow + 64 + q * 16) = v;
+        }
+      }
+      __syncwarp();
+      const int w = wide ? 64 : 32;
+      if (do_stats && 2 * lane < w) {
+        // lane owns columns c + 2*lane, c + 2*lane + 1; rows beyond T_out are not statistics
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        for (int r = 0; r < nvalid; ++r) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(stage + r * kEpiRowBytes + lane * 4);
+          float x0, x1;
+          if (p.out_mode == OUT_BF16) {
+            x0 = __uint_as_float(v << 16);
+            x1 = __uint_as_float(v & 0xFFFF0000u);
+          } else {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+            x0 = f.x;
+            x1 = f.y;
+          }
+          s0 += x0; q0 += x0 * x0;
+          s1 += x1; q1 += x1 * x1;
+        }
+        sacc[c + 2 * lane] += s0;
+        sacc[c + 2 * lane + 1] += s1;
+        sacc[BN + c + 2 * lane] += q0;
+        sacc[BN + c + 2 * lane + 1] += q1;
+      }
+      // coalesced stores: `pieces` 16-byte pieces per row, 32/pieces rows per warp instruction
+      if (wide) {
+        const int pr = lane >> 3, pc = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = pr + 4 * i;
+          if (r < nvalid) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stage + r * kEpiRowBytes + pc * 16);
+            *reinterpret_cast<uint4*>(out2 + (long long)r * p.out_row_stride + c + pc * 8) = v;
+          }
+        }
+      } else {
+        const int pr = lane >> 2, pc = lane & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = pr + 8 * i;
+          if (r < nvalid) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stage + r * kEpiRowBytes + pc * 16);
+            *reinterpret_cast<uint4*>(out2 + (long long)r * p.out_row_stride + c + pc * 8) = v;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    float* out4 = reinterpret_cast<float*>(p.out) + off;
+    const int pr = lane >> 3, pc = lane & 7;
+#pragma unroll 1
+    for (int c = 0; c < ncur; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(myrow + q * 16) = make_uint4(r[q * 4 + 0], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+      __syncwarp();
+      // all eight read-modify-write loads are issued before the first use (one latency, not eight)
+      float4 old[8];
+      if (p.out_mode == OUT_F32_ACC) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = pr + 4 * i;
+          old[i] = (rr < nvalid)
+                       ? *reinterpret_cast<const float4*>(out4 + (long long)rr * p.out_row_stride + c + pc * 4)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = pr + 4 * i;
+        if (rr < nvalid) {
+          float4 v = *reinterpret_cast<const float4*>(stage + rr * kEpiRowBytes + pc * 16);
+          if (p.out_mode == OUT_F32_ACC) {
+            v.x += old[i].x; v.y += old[i].y; v.z += old[i].z; v.w += old[i].w;
+          }
+          *reinterpret_cast<float4*>(out4 + (long long)rr * p.out_row_stride + c + pc * 4) = v;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
 
 // Layout of the dynamic shared memory (1024-byte aligned for SWIZZLE_128B):
 //   [A stages][B stages][full bars][empty bars][tmem_full x2][tmem_empty x2][tmem ptr]
@@ -136,20 +275,24 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int b = rem / p.n_mtiles;
         const int t0 = (rem - b * p.n_mtiles) * kTileM;
         const int n0 = nt * BN;
+        const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
         for (int k = 0; k < p.K_taps; ++k) {
           const int trow = t0 + p.t_off0 + k * p.t_step;
           const int brow = k * p.N_total + n0;
           const int crow = k * p.c_chunks * kChunkK;
           for (int c = 0; c < p.c_chunks; ++c) {
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
-            mbar_expect_tx(&full_bar[ps.stage], kABytes + kBBytes);
+            mbar_expect_tx(&full_bar[ps.stage], kABytes + (BMN ? ncur * kChunkK * 2 : kBBytes));
             tma_load_3d(smem_a + ps.stage * kABytes, &map_a, &full_bar[ps.stage], c * kChunkK, trow, b);
             if (BMN) {
 #pragma unroll
               for (int h = 0; h < BN / 64; ++h)
-                tma_load_2d(smem_b + ps.stage * kBBytes + h * kBoxBytes, &map_b, &full_bar[ps.stage],
-                            n0 + h * 64, crow + c * kChunkK);
+                if (h * 64 < ncur)
+                  tma_load_2d(smem_b + ps.stage * kBBytes + h * kBoxBytes, &map_b, &full_bar[ps.stage],
+                              n0 + h * 64, crow + c * kChunkK);
             } else {
+              // a narrower last tile still fetches the full {64, BN} box (the extra rows are the next
+              // tap's, or zero-filled past the end) but only multiplies its own n_tail columns
               tma_load_2d(smem_b + ps.stage * kBBytes, &map_b, &full_bar[ps.stage], c * kChunkK, brow);
             }
             ps.advance<S>();
@@ -159,10 +302,11 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(kTileM, BN, 0, BMN ? 1 : 0);
       PipeState ps;
       uint32_t ti = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
+        const uint32_t idesc = make_idesc(kTileM, ncur, 0, BMN ? 1 : 0);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
@@ -203,10 +347,11 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // all four epilogue warps reach this point for the same tile sequence
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int tid = threadIdx.x - 64;  // 0..127
+      const int width = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
       for (int i = tid; i < 2 * BN; i += 128) {
         const float v = epi_stats[i] + epi_stats[2 * BN + i] + epi_stats[4 * BN + i] + epi_stats[6 * BN + i];
         const int which = i / BN, col = i - which * BN;
-        atomicAdd(&p.stats[(size_t)which * p.N_total + nt * BN + col], v);
+        if (col < width) atomicAdd(&p.stats[(size_t)which * p.N_total + nt * BN + col], v);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
@@ -218,6 +363,7 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int b = rem / p.n_mtiles;
       const int t0w = (rem - b * p.n_mtiles) * kTileM + quad * 32;  // first row of this warp
       const int n0 = nt * BN;
+      const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
       if (do_stats && cur_nt >= 0 && nt != cur_nt) flush_stats(cur_nt);
       cur_nt = nt;
       const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
@@ -226,135 +372,7 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
       const int nvalid = min(32, max(0, p.T_out - t0w));
       const long long off = (long long)b * p.out_batch_stride + (long long)t0w * p.out_row_stride + n0;
-      uint8_t* myrow = stage + lane * kEpiRowBytes;
-      if (two_byte) {
-        uint16_t* out2 = reinterpret_cast<uint16_t*>(p.out) + off;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
-          const bool wide = (BN - c) >= 64;  // 64-column chunk, or a 32-column tail
-          uint32_t r0[32], r1[32];
-          tmem_ld32(taddr + c, r0);
-          if (wide) tmem_ld32(taddr + c + 32, r1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 v;
-            if (p.out_mode == OUT_BF16) {
-              v.x = pack_bf16(__uint_as_float(r0[q * 8 + 0]), __uint_as_float(r0[q * 8 + 1]));
-              v.y = pack_bf16(__uint_as_float(r0[q * 8 + 2]), __uint_as_float(r0[q * 8 + 3]));
-              v.z = pack_bf16(__uint_as_float(r0[q * 8 + 4]), __uint_as_float(r0[q * 8 + 5]));
-              v.w = pack_bf16(__uint_as_float(r0[q * 8 + 6]), __uint_as_float(r0[q * 8 + 7]));
-            } else {
-              v.x = pack_f16(__uint_as_float(r0[q * 8 + 0]), __uint_as_float(r0[q * 8 + 1]));
-              v.y = pack_f16(__uint_as_float(r0[q * 8 + 2]), __uint_as_float(r0[q * 8 + 3]));
-              v.z = pack_f16(__uint_as_float(r0[q * 8 + 4]), __uint_as_float(r0[q * 8 + 5]));
-              v.w = pack_f16(__uint_as_float(r0[q * 8 + 6]), __uint_as_float(r0[q * 8 + 7]));
-            }
-            *reinterpret_cast<uint4*>(myrow + q * 16) = v;
-          }
-          if (wide) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 v;
-              if (p.out_mode == OUT_BF16) {
-                v.x = pack_bf16(__uint_as_float(r1[q * 8 + 0]), __uint_as_float(r1[q * 8 + 1]));
-                v.y = pack_bf16(__uint_as_float(r1[q * 8 + 2]), __uint_as_float(r1[q * 8 + 3]));
-                v.z = pack_bf16(__uint_as_float(r1[q * 8 + 4]), __uint_as_float(r1[q * 8 + 5]));
-                v.w = pack_bf16(__uint_as_float(r1[q * 8 + 6]), __uint_as_float(r1[q * 8 + 7]));
-              } else {
-                v.x = pack_f16(__uint_as_float(r1[q * 8 + 0]), __uint_as_float(r1[q * 8 + 1]));
-                v.y = pack_f16(__uint_as_float(r1[q * 8 + 2]), __uint_as_float(r1[q * 8 + 3]));
-                v.z = pack_f16(__uint_as_float(r1[q * 8 + 4]), __uint_as_float(r1[q * 8 + 5]));
-                v.w = pack_f16(__uint_as_float(r1[q * 8 + 6]), __uint_as_float(r1[q * 8 + 7]));
-              }
-              *reinterpret_cast<uint4*>(myrow + 64 + q * 16) = v;
-            }
-          }
-          __syncwarp();
-          const int w = wide ? 64 : 32;
-          if (do_stats && 2 * lane < w) {
-            // lane owns columns c + 2*lane, c + 2*lane + 1; rows beyond T_out are not statistics
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-            for (int r = 0; r < nvalid; ++r) {
-              const uint32_t v = *reinterpret_cast<const uint32_t*>(stage + r * kEpiRowBytes + lane * 4);
-              float x0, x1;
-              if (p.out_mode == OUT_BF16) {
-                x0 = __uint_as_float(v << 16);
-                x1 = __uint_as_float(v & 0xFFFF0000u);
-              } else {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
-                x0 = f.x;
-                x1 = f.y;
-              }
-              s0 += x0; q0 += x0 * x0;
-              s1 += x1; q1 += x1 * x1;
-            }
-            sacc[c + 2 * lane] += s0;
-            sacc[c + 2 * lane + 1] += s1;
-            sacc[BN + c + 2 * lane] += q0;
-            sacc[BN + c + 2 * lane + 1] += q1;
-          }
-          // coalesced stores: `pieces` 16-byte pieces per row, 32/pieces rows per warp instruction
-          if (wide) {
-            const int pr = lane >> 3, pc = lane & 7;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = pr + 4 * i;
-              if (r < nvalid) {
-                const uint4 v = *reinterpret_cast<const uint4*>(stage + r * kEpiRowBytes + pc * 16);
-                *reinterpret_cast<uint4*>(out2 + (long long)r * p.out_row_stride + c + pc * 8) = v;
-              }
-            }
-          } else {
-            const int pr = lane >> 2, pc = lane & 3;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = pr + 8 * i;
-              if (r < nvalid) {
-                const uint4 v = *reinterpret_cast<const uint4*>(stage + r * kEpiRowBytes + pc * 16);
-                *reinterpret_cast<uint4*>(out2 + (long long)r * p.out_row_stride + c + pc * 8) = v;
-              }
-            }
-          }
-          __syncwarp();
-        }
-      } else {
-        float* out4 = reinterpret_cast<float*>(p.out) + off;
-        const int pr = lane >> 3, pc = lane & 7;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(myrow + q * 16) = make_uint4(r[q * 4 + 0], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
-          __syncwarp();
-          // all eight read-modify-write loads are issued before the first use (one latency, not eight)
-          float4 old[8];
-          if (p.out_mode == OUT_F32_ACC) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = pr + 4 * i;
-              old[i] = (rr < nvalid)
-                           ? *reinterpret_cast<const float4*>(out4 + (long long)rr * p.out_row_stride + c + pc * 4)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = pr + 4 * i;
-            if (rr < nvalid) {
-              float4 v = *reinterpret_cast<const float4*>(stage + rr * kEpiRowBytes + pc * 16);
-              if (p.out_mode == OUT_F32_ACC) {
-                v.x += old[i].x; v.y += old[i].y; v.z += old[i].z; v.w += old[i].w;
-              }
-              *reinterpret_cast<float4*>(out4 + (long long)rr * p.out_row_stride + c + pc * 4) = v;
-            }
-          }
-          __syncwarp();
-        }
-      }
+      epilogue_rows<BN>(p, stage, sacc, do_stats, two_byte, taddr, nvalid, off, ncur, lane);
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
@@ -366,11 +384,192 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ------------------------------------------------------------------ forward / dgrad, CTA pairs
+// Same computation as tapgemm_kmajor on a cluster of two CTAs (cta_group::2): the pair owns a
+// 256-row x BN output tile, each CTA stages ITS 128 activation rows and only HALF of the weight
+// tile; one tcgen05.mma.cta_group::2 (M = 256) issued by the leader reads A from both CTAs and the
+// two B halves, and accumulates each CTA's 128 rows into that CTA's TMEM.  Per CTA and K chunk the
+// L2 -> SMEM traffic drops from 16 KB + BN*128 B to 16 KB + BN*64 B, the lever that matters once the
+// power cap throttles the fabric (profiles/r01_sustained_conv_vs_cublas.jsonl).
+// Barriers: TMA loads of both CTAs credit the LEADER's full barrier; the leader's MMA commits
+// multicast to both CTAs' empty / tmem-full barriers; both epilogues release the leader's tmem-empty.
+template <int BN, bool BMN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const KMajorParams p) {
+  static_assert(BN % 128 == 0, "pair tiles split B in two 64-aligned halves");
+  constexpr int HB = BN / 2;                       // B rows / columns staged by each CTA
+  constexpr int kBHalf = HB * kChunkK * 2;         // bytes
+  constexpr int kBoxBytes = 64 * 64 * 2;
+  constexpr int S = (kSmemBudget - epi_bytes<BN>()) / (kABytes + kBHalf) > 8
+                        ? 8 : (kSmemBudget - epi_bytes<BN>()) / (kABytes + kBHalf);
+  constexpr uint32_t kTmemCols = tmem_cols<BN>();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + S * kBHalf);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(tmem_ptr + 4);
+  float* epi_stats = reinterpret_cast<float*>(epi_stage + 4 * kEpiWarpBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 2);      // leader: expect_tx arrive + the peer's arrive
+      mbar_init(&empty_bar[i], 1);     // multicast commit of the leader's MMAs
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 256);  // epilogue threads of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                      // peer barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // pair tiles: 256 rows; n_mtiles here counts pair tiles per utterance
+  const int n_ptiles = (p.T_out + 2 * kTileM - 1) / (2 * kTileM);
+  const int tiles_per_n = p.B * n_ptiles;
+  const int n_tiles = tiles_per_n * p.n_ntiles;
+  const int n_iters = p.K_taps * p.c_chunks;
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      PipeState ps;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        const int nt = tile / tiles_per_n;
+        const int rem = tile - nt * tiles_per_n;
+        const int b = rem / n_ptiles;
+        const int t0 = (rem - b * n_ptiles) * 2 * kTileM + (int)rank * kTileM;
+        const int n0 = nt * BN;
+        const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
+        const int hcur = ncur / 2;                   // columns of B each CTA provides
+        for (int k = 0; k < p.K_taps; ++k) {
+          const int trow = t0 + p.t_off0 + k * p.t_step;
+          const int brow = k * p.N_total + n0 + (int)rank * hcur;
+          const int crow = k * p.c_chunks * kChunkK;
+          for (int c = 0; c < p.c_chunks; ++c) {
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            const uint32_t my_bytes = kABytes + (BMN ? hcur * kChunkK * 2 : kBHalf);
+            if (leader) mbar_expect_tx(&full_bar[ps.stage], 2 * my_bytes);
+            tma2_load_3d(smem_a + ps.stage * kABytes, &map_a, &full_bar[ps.stage], c * kChunkK, trow, b);
+            if (BMN) {
+#pragma unroll
+              for (int h = 0; h < HB / 64; ++h)
+                if (h * 64 < hcur)
+                  tma2_load_2d(smem_b + ps.stage * kBHalf + h * kBoxBytes, &map_b, &full_bar[ps.stage],
+                               n0 + (int)rank * hcur + h * 64, crow + c * kChunkK);
+            } else {
+              tma2_load_2d(smem_b + ps.stage * kBHalf, &map_b, &full_bar[ps.stage], c * kChunkK, brow);
+            }
+            if (!leader) mbar_arrive_cluster(&full_bar[ps.stage], 0);
+            ps.advance<S>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      PipeState ps;
+      uint32_t ti = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+        const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
+        const uint32_t idesc = make_idesc(2 * kTileM, ncur, 0, BMN ? 1 : 0);
+        const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int it = 0; it < n_iters; ++it) {
+          mbar_wait(&full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + ps.stage * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + ps.stage * kBHalf);
+#pragma unroll
+          for (int kk = 0; kk < kChunkK / 16; ++kk) {
+            const uint64_t da = make_sdesc(a_addr + kk * 32, 0, 1024);
+            const uint64_t db = BMN ? make_sdesc(b_addr + kk * 2048, kBoxBytes, 1024)
+                                    : make_sdesc(b_addr + kk * 32, 0, 1024);
+            umma2_bf16(tmem_d, da, db, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma2_commit(&empty_bar[ps.stage]);
+          if (it == n_iters - 1) umma2_commit(&tfull_bar[as]);
+          ps.advance<S>();
+        }
+      }
+    }
+  } else {
+    // Epilogue (both CTAs): identical to the single-CTA kernel on this CTA's 128 rows
+    const int quad = warp & 3;
+    uint8_t* stage = epi_stage + quad * kEpiWarpBytes;
+    float* sacc = epi_stats + quad * 2 * BN;
+    const bool two_byte = (p.out_mode == OUT_BF16 || p.out_mode == OUT_F16);
+    const bool do_stats = (p.stats != nullptr) && two_byte;
+    if (do_stats)
+      for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
+    int cur_nt = -1;
+    auto flush_stats = [&](int nt) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int tid = threadIdx.x - 64;
+      const int width = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
+      for (int i = tid; i < 2 * BN; i += 128) {
+        const float v = epi_stats[i] + epi_stats[2 * BN + i] + epi_stats[4 * BN + i] + epi_stats[6 * BN + i];
+        const int which = i / BN, col = i - which * BN;
+        if (col < width) atomicAdd(&p.stats[(size_t)which * p.N_total + nt * BN + col], v);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
+    };
+    uint32_t ti = 0;
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+      const int nt = tile / tiles_per_n;
+      const int rem = tile - nt * tiles_per_n;
+      const int b = rem / n_ptiles;
+      const int t0w = (rem - b * n_ptiles) * 2 * kTileM + (int)rank * kTileM + quad * 32;
+      const int n0 = nt * BN;
+      const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
+      if (do_stats && cur_nt >= 0 && nt != cur_nt) flush_stats(cur_nt);
+      cur_nt = nt;
+      const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      const int nvalid = min(32, max(0, p.T_out - t0w));
+      const long long off = (long long)b * p.out_batch_stride + (long long)t0w * p.out_row_stride + n0;
+      epilogue_rows<BN>(p, stage, sacc, do_stats, two_byte, taddr, nvalid, off, ncur, lane);
+      tc_fence_before();
+      if (leader) mbar_arrive(&tempty_bar[as]);
+      else mbar_arrive_cluster(&tempty_bar[as], 0);
+    }
+    if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                      // nobody exits while the peer may still signal its barriers
+  if (warp == 1) tmem_dealloc2(tmem_base, kTmemCols);
+}
+
 // ------------------------------------------------------------------------ wgrad
 struct MNMajorParams {
   int B, T, t_chunks;          // t_chunks = ceil(T / 64)
   int K_taps, dil, pad_left;
-  int m_tiles, n_tiles;        // C_in / 128, C_out / BN
+  int m_tiles, n_tiles;        // C_in / 128, ceil(C_out / BN)
+  int n_tail;                  // width of the last N tile
   float* dw;                   // [K][C_in][C_out] fp32; zeroed by the launcher, split units red.add into it
   int C_in, C_out;
 };
@@ -448,10 +647,11 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         next_segment(it, unit, b_lo, b_hi);
         decode(unit, k, mi, ni);
         const int tsh = k * p.dil - p.pad_left;
+        const int ncur = (ni == p.n_tiles - 1) ? p.n_tail : BN;
         for (int b = b_lo; b < b_hi; ++b) {
           for (int tc = 0; tc < p.t_chunks; ++tc) {
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
-            mbar_expect_tx(&full_bar[ps.stage], kABytes + kBBytes);
+            mbar_expect_tx(&full_bar[ps.stage], kABytes + ncur * kChunkK * 2);
             uint8_t* sa = smem_a + ps.stage * kABytes;
             uint8_t* sb = smem_b + ps.stage * kBBytes;
 #pragma unroll
@@ -460,7 +660,8 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                           tc * 64 + tsh, b);
 #pragma unroll
             for (int h = 0; h < BN / 64; ++h)
-              tma_load_3d(sb + h * kBoxBytes, &map_dy, &full_bar[ps.stage], ni * BN + h * 64, tc * 64, b);
+              if (h * 64 < ncur)
+                tma_load_3d(sb + h * kBoxBytes, &map_dy, &full_bar[ps.stage], ni * BN + h * 64, tc * 64, b);
             ps.advance<S>();
           }
         }
@@ -468,12 +669,13 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(kTileM, BN, 1, 1);
       PipeState ps;
       uint32_t ti = 0;
       for (long long it = item0; it < item1; ++ti) {
-        int unit, b_lo, b_hi;
+        int unit, b_lo, b_hi, k_, mi_, ni_;
         next_segment(it, unit, b_lo, b_hi);
+        decode(unit, k_, mi_, ni_);
+        const uint32_t idesc = make_idesc(kTileM, (ni_ == p.n_tiles - 1) ? p.n_tail : BN, 1, 1);
         const int n_iters = (b_hi - b_lo) * p.t_chunks;
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -511,8 +713,9 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
       float* dst = p.dw + ((long long)k * p.C_in + mi * kTileM + row) * p.C_out + ni * BN;
+      const int ncur = (ni == p.n_tiles - 1) ? p.n_tail : BN;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = 0; ch < ncur / 32; ++ch) {
         uint32_t r[32];
         tmem_ld32(taddr + ch * 32, r);
         tmem_ld_wait();
@@ -563,6 +766,48 @@ static int launch_kmajor(const CUtensorMap* ma, const CUtensorMap* mb, const KMa
   return check_launch("tapgemm_kmajor");
 }
 
+// CTA-pair variant: grid = 2 x (number of clusters), one cluster per SM pair.
+template <int BN, bool BMN>
+static int launch_kmajor_pair(const CUtensorMap* ma, const CUtensorMap* mb, const KMajorParams& p,
+                              cudaStream_t st) {
+  static bool attr_done = false;
+  constexpr int kStage = kABytes + (BN / 2) * kChunkK * 2;
+  constexpr int S = (kSmemBudget - epi_bytes<BN>()) / kStage > 8 ? 8 : (kSmemBudget - epi_bytes<BN>()) / kStage;
+  const size_t smem = (size_t)S * kStage + (2 * S + 4) * 8 + 16 + epi_bytes<BN>() + 1024;
+  if (!attr_done) {
+    OS2S_CUDA(cudaFuncSetAttribute(tapgemm_kmajor_pair<BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    attr_done = true;
+  }
+  const int ptiles = p.B * ((p.T_out + 2 * kTileM - 1) / (2 * kTileM)) * p.n_ntiles;
+  const int pairs = device_sm_count() / 2;
+  const int clusters = ptiles < pairs ? ptiles : pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OS2S_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_kmajor_pair<BN, BMN>, *ma, *mb, p));
+  return check_launch("tapgemm_kmajor_pair");
+}
+
+// 0 = single-CTA tiles, 1 = CTA pairs (cta_group::2) wherever the shape allows; OS2S_CONV_PAIR overrides.
+static int conv_pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("OS2S_CONV_PAIR");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode;
+}
+
 template <int BN>
 static int launch_mnmajor(const CUtensorMap* mx, const CUtensorMap* mdy, const MNMajorParams& p,
                           cudaStream_t st) {
@@ -578,19 +823,53 @@ static int launch_mnmajor(const CUtensorMap* mx, const CUtensorMap* mdy, const M
   return check_launch("tapgemm_mnmajor");
 }
 
-// Largest supported N tile dividing n (K-major B operand: any multiple of 16 up to 256).
-static int pick_bn_kmajor(int n) {
-  const int cands[] = {256, 192, 128, 224, 160, 96, 64};
-  for (int c : cands)
-    if (n % c == 0) return c;
-  return 0;
-}
-// wgrad N tile must be a multiple of 64 (one TMA box per 64 channels).
-static int pick_bn_mnmajor(int n) {
+// N tiling for forward / dgrad: tiles of width BN with a narrower last tile allowed (e.g. 640 =
+// 256 + 256 + 128).  Wide tiles matter under the power cap: L2->SMEM traffic per FLOP scales with
+// 1/BN.  The choice maximises (load balance of the static round-robin over the persistent grid, with
+// tile cost proportional to its width) x (width-weighted main-loop efficiency of the tiles).
+static float width_eff(int w) { return w >= 256 ? 1.00f : w >= 192 ? 0.97f : w >= 128 ? 0.93f : 0.75f; }
+static int pick_bn_tiles(int n, long long m_tiles, bool mn_major) {
+  // memoised: the answer only depends on (n, m_tiles, layout)
+  struct Memo { int n; long long m; bool mn; int bn; };
+  static Memo memo[64];
+  static int n_memo = 0;
+  for (int i = 0; i < n_memo; ++i)
+    if (memo[i].n == n && memo[i].m == m_tiles && memo[i].mn == mn_major) return memo[i].bn;
   const int cands[] = {256, 192, 128, 64};
-  for (int c : cands)
-    if (n % c == 0) return c;
-  return 0;
+  const int gran = mn_major ? 64 : 16;
+  const int sms = device_sm_count();
+  int best = 0;
+  float best_score = -1.f;
+  for (int bn : cands) {
+    if (n % gran != 0) continue;
+    const int nt = (n + bn - 1) / bn;
+    const int tail = n - (nt - 1) * bn;
+    if (tail % gran != 0 || (mn_major && tail % 64 != 0) || tail % 32 != 0) continue;
+    // static round-robin: tile index = nt_idx * m_tiles + m, CTA c takes c, c + G, ...
+    const long long tiles = m_tiles * nt;
+    const int G = (int)(tiles < sms ? tiles : sms);
+    double max_load = 0, total = 0;
+    for (int c = 0; c < G; ++c) {
+      double load = 0;
+      for (long long t = c; t < tiles; t += G) load += ((t / m_tiles) == nt - 1) ? tail : bn;
+      if (load > max_load) max_load = load;
+      total += load;
+    }
+    const float balance = (float)(total / (max_load * sms));
+    const float teff = ((float)(n - tail) * width_eff(bn) + (float)tail * width_eff(tail)) / (float)n;
+    const float score = balance * teff;
+    if (score > best_score) {
+      best_score = score;
+      best = bn;
+    }
+  }
+  if (n_memo < 64) memo[n_memo++] = Memo{n, m_tiles, mn_major, best};
+  return best;
+}
+// wgrad: widest tile that keeps the last tile a multiple of 64; stream-K balances the grid.
+static int pick_bn_mnmajor(int n) {
+  if (n % 64 != 0) return 0;
+  return n >= 256 ? 256 : n >= 192 ? 192 : n >= 128 ? 128 : 64;
 }
 
 // Shared driver for forward / dgrad.
@@ -600,7 +879,9 @@ static int pick_bn_mnmajor(int n) {
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
                 int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st) {
   if (C_red % 64 != 0) return fail(ERR_UNSUPPORTED, "conv_tc: reduction channels must be a multiple of 64");
-  const int BN = b_mn_major ? pick_bn_mnmajor(N_total) : pick_bn_kmajor(N_total);
+  // pairs: 256-wide tiles whose last tile is 128 or 256 wide (each CTA stages half of it)
+  const bool pair = conv_pair_mode() != 0 && N_total % 128 == 0 && N_total >= 256 && T > kTileM;
+  const int BN = pair ? 256 : pick_bn_tiles(N_total, (long long)B * ((T + kTileM - 1) / kTileM), b_mn_major != 0);
   if (BN == 0) return fail(ERR_UNSUPPORTED, "conv_tc: output channels must be a multiple of 64");
   if (B <= 0 || T <= 0 || K <= 0) return fail(ERR_INVALID, "conv_tc: bad shape");
   uint64_t adims[3] = {(uint64_t)C_red, (uint64_t)T, (uint64_t)B};
@@ -610,14 +891,15 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
   // K-major B: wmat = [K][N_total][C_red] (box {64 c, BN n}); MN-major B: wmat = [K][C_red][N_total]
   uint64_t bdims[2] = {(uint64_t)(b_mn_major ? N_total : C_red), (uint64_t)K * (b_mn_major ? C_red : N_total)};
   uint64_t bstr[1] = {(uint64_t)(b_mn_major ? N_total : C_red) * 2};
-  uint32_t bbox[2] = {64, (uint32_t)(b_mn_major ? 64 : BN)};
+  uint32_t bbox[2] = {64, (uint32_t)(b_mn_major ? 64 : (pair ? BN / 2 : BN))};
   const CUtensorMap* mb = get_tmap_bf16(wmat, 2, bdims, bstr, bbox);
   if (!ma || !mb) return ERR_CUDA;
   KMajorParams p;
   p.B = B;
   p.T_out = T;
   p.n_mtiles = (T + kTileM - 1) / kTileM;
-  p.n_ntiles = N_total / BN;
+  p.n_ntiles = (N_total + BN - 1) / BN;
+  p.n_tail = N_total - (p.n_ntiles - 1) * BN;
   p.N_total = N_total;
   p.K_taps = K;
   p.c_chunks = C_red / 64;
@@ -628,6 +910,8 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
   p.out_row_stride = N_total;
   p.out_batch_stride = (long long)T * N_total;
   p.out_mode = out_mode;
+  if (pair)
+    return b_mn_major ? launch_kmajor_pair<256, true>(ma, mb, p, st) : launch_kmajor_pair<256, false>(ma, mb, p, st);
   if (b_mn_major) {
     switch (BN) {
       case 256: return launch_kmajor<256, true>(ma, mb, p, st);
@@ -672,7 +956,8 @@ int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in,
   p.dil = dil;
   p.pad_left = pad_left;
   p.m_tiles = C_in / kTileM;
-  p.n_tiles = C_out / BN;
+  p.n_tiles = (C_out + BN - 1) / BN;
+  p.n_tail = C_out - (p.n_tiles - 1) * BN;
   p.dw = dw;
   p.C_in = C_in;
   p.C_out = C_out;

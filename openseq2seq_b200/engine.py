@@ -835,7 +835,28 @@ class _Workspace(object):
                                            self._p(self.red), M, l.c_out, _c_float(l.keep), 1, st]])
             self._keep = getattr(self, "_keep", []) + [dg_h, db_h, dy_h]
             plan.append([_StreamRecord(self, "main", ev_bn[li]), []])
-            # ---- aux stream: weight gradients of this layer
+            # ---- main stream (critical path) first: data gradients, so that bn_bwd of the next layer can
+            # start as soon as they finish while this layer's weight gradients are still running
+            for n, j in enumerate(l.res_sources):
+                rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
+                cj = eng.block_inputs[j][0]
+                mode = 2 if j in written else 1
+                written.add(j)
+                plan.append([lib.os2s_conv1d_dgrad, [self._p(dYR[n]), self._half_ptr(eng.wb, rn + "/kernel"),
+                                                     self._p(self.dres[j]), B, T2, cj, l.c_out, 1, 1, 0, mode, st],
+                             ("dgrad", 2.0 * B * T2 * cj * l.c_out)])
+            if li > 0:
+                if (li - 1) in eng.src_of_layer_output:
+                    j = eng.src_of_layer_output[li - 1]
+                    mode = 2 if j in written else 1
+                    written.add(j)
+                    out_ptr = self._p(self.dres[j])
+                else:
+                    mode, out_ptr = 0, self._p(self.dA)
+                plan.append([lib.os2s_conv1d_dgrad, [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"),
+                                                     out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
+                                                     st], ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
+            # ---- aux stream: weight gradients of this layer (enqueued after the critical-path kernels)
             plan.append([_StreamWait(self, "aux", ev_bn[li]), []])
             # main conv wgrad (stored layout == kernel layout, also for the folded stride-2 layer)
             x_ptr = self._p(self.A[li - 1]) if li > 0 else self._p(self.feats)
@@ -861,26 +882,6 @@ class _Workspace(object):
                                                      self._param_ptr(eng.grad, rn + "/kernel"), B, T2, cj, l.c_out,
                                                      1, 1, 0, sa], ("wgrad", 2.0 * B * T2 * cj * l.c_out)])
             plan.append([_StreamRecord(self, "aux", ev_wg[li]), []])
-            # ---- main stream (critical path): data gradients
-            for n, j in enumerate(l.res_sources):
-                rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
-                cj = eng.block_inputs[j][0]
-                mode = 2 if j in written else 1
-                written.add(j)
-                plan.append([lib.os2s_conv1d_dgrad, [self._p(dYR[n]), self._half_ptr(eng.wb, rn + "/kernel"),
-                                                     self._p(self.dres[j]), B, T2, cj, l.c_out, 1, 1, 0, mode, st],
-                             ("dgrad", 2.0 * B * T2 * cj * l.c_out)])
-            if li > 0:
-                if (li - 1) in eng.src_of_layer_output:
-                    j = eng.src_of_layer_output[li - 1]
-                    mode = 2 if j in written else 1
-                    written.add(j)
-                    out_ptr = self._p(self.dres[j])
-                else:
-                    mode, out_ptr = 0, self._p(self.dA)
-                plan.append([lib.os2s_conv1d_dgrad, [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"),
-                                                     out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
-                                                     st], ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
             if eng.comm is not None:
                 start = eng.by_name[l.name + "/kernel"]["offset"]
                 if (bucket_end - start) * 4 >= eng.bucket_bytes or li == 0:

@@ -28,6 +28,8 @@ def _bf(x):
     (1, 300, 256, 384, 13, 1),
     (2, 131, 128, 256, 9, 2),    # dilation
     (3, 64, 256, 128, 1, 1),     # 1x1 residual conv
+    (2, 200, 640, 640, 3, 1),    # ragged N tiling 256 + 256 + 128 (forward, dgrad and wgrad)
+    (1, 130, 384, 896, 1, 1),    # 896 = 3 x 256 + 128
 ])
 def test_conv_fwd_dgrad_wgrad_vs_oracle(B, T, Cin, Cout, K, dil):
     from oracle import encoder as E
