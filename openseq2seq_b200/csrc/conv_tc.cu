@@ -572,6 +572,7 @@ struct MNMajorParams {
   int n_tail;                  // width of the last N tile
   float* dw;                   // [K][C_in][C_out] fp32; zeroed by the launcher, split units red.add into it
   int C_in, C_out;
+  int m_off;                   // first C_in row of this launch (the pair kernel may leave a 128-row remainder)
 };
 
 template <int BN>
@@ -656,7 +657,7 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             uint8_t* sb = smem_b + ps.stage * kBBytes;
 #pragma unroll
             for (int h = 0; h < kTileM / 64; ++h)
-              tma_load_3d(sa + h * kBoxBytes, &map_x, &full_bar[ps.stage], mi * kTileM + h * 64,
+              tma_load_3d(sa + h * kBoxBytes, &map_x, &full_bar[ps.stage], p.m_off + mi * kTileM + h * 64,
                           tc * 64 + tsh, b);
 #pragma unroll
             for (int h = 0; h < BN / 64; ++h)
@@ -712,7 +713,7 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      float* dst = p.dw + ((long long)k * p.C_in + mi * kTileM + row) * p.C_out + ni * BN;
+      float* dst = p.dw + ((long long)k * p.C_in + p.m_off + mi * kTileM + row) * p.C_out + ni * BN;
       const int ncur = (ni == p.n_tiles - 1) ? p.n_tail : BN;
 #pragma unroll 1
       for (int ch = 0; ch < ncur / 32; ++ch) {
@@ -742,6 +743,194 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------ wgrad, CTA pairs
+// tapgemm_mnmajor on a cluster of two CTAs.  The M = 256 rows of the pair MMA are two independent
+// 128-row blocks of the gradient that share the dY tile: the (tap, C_in tile) row blocks are
+// enumerated taps-fastest and paired two by two, so a pair is usually two neighbouring taps of the
+// same C_in tile (A = the same X columns shifted by one dilation step) and any C_in that is a
+// multiple of 128 works.  When K * m_tiles is odd the last pair's second CTA recomputes the last block
+// and skips the store.  Each CTA stages its own X block and half of the dY tile (see
+// tapgemm_kmajor_pair for the barrier protocol).
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tapgemm_mnmajor_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                     const MNMajorParams p) {
+  static_assert(BN % 128 == 0, "pair tiles split dY in two 64-aligned halves");
+  constexpr int HB = BN / 2;
+  constexpr int kBHalf = HB * kChunkK * 2;
+  constexpr int kBoxBytes = 64 * 64 * 2;
+  constexpr int S = (kSmemBudget - 1024) / (kABytes + kBHalf) > 8 ? 8 : (kSmemBudget - 1024) / (kABytes + kBHalf);
+  constexpr uint32_t kTmemCols = tmem_cols<BN>();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + S * kBHalf);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_rb = p.K_taps * p.m_tiles;        // 128-row blocks of dW
+  const int n_pairs = (n_rb + 1) >> 1;
+  const int n_units = n_pairs * p.n_tiles;
+  const long long total_items = (long long)n_units * p.B;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const long long item0 = total_items * cluster_id / n_clusters;
+  const long long item1 = total_items * (cluster_id + 1) / n_clusters;
+
+  // unit -> (n tile, block pair) -> this CTA's (tap, C_in tile); `valid` is false for the padding block
+  bool valid = true;
+  auto decode = [&](int unit, int& k, int& mi, int& ni) {
+    ni = unit / n_pairs;
+    int blk = 2 * (unit - ni * n_pairs) + (int)rank;
+    valid = blk < n_rb;
+    if (!valid) blk = n_rb - 1;
+    mi = blk / p.K_taps;
+    k = blk - mi * p.K_taps;
+  };
+  auto next_segment = [&](long long& it, int& unit, int& b_lo, int& b_hi) {
+    unit = (int)(it / p.B);
+    b_lo = (int)(it - (long long)unit * p.B);
+    const long long room = item1 - it;
+    b_hi = (int)min((long long)p.B, (long long)b_lo + room);
+    it += b_hi - b_lo;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      PipeState ps;
+      for (long long it = item0; it < item1;) {
+        int unit, b_lo, b_hi, k, mi, ni;
+        next_segment(it, unit, b_lo, b_hi);
+        decode(unit, k, mi, ni);
+        const int tsh = k * p.dil - p.pad_left;
+        const int ncur = (ni == p.n_tiles - 1) ? p.n_tail : BN;
+        const int hcur = ncur / 2;
+        const int c0 = p.m_off + mi * kTileM;
+        const int n0 = ni * BN + (int)rank * hcur;
+        const uint32_t my_bytes = kABytes + hcur * kChunkK * 2;
+        for (int b = b_lo; b < b_hi; ++b) {
+          for (int tc = 0; tc < p.t_chunks; ++tc) {
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            if (leader) mbar_expect_tx(&full_bar[ps.stage], 2 * my_bytes);
+            uint8_t* sa = smem_a + ps.stage * kABytes;
+            uint8_t* sb = smem_b + ps.stage * kBHalf;
+#pragma unroll
+            for (int h = 0; h < kTileM / 64; ++h)
+              tma2_load_3d(sa + h * kBoxBytes, &map_x, &full_bar[ps.stage], c0 + h * 64, tc * 64 + tsh, b);
+#pragma unroll
+            for (int h = 0; h < HB / 64; ++h)
+              if (h * 64 < hcur)
+                tma2_load_3d(sb + h * kBoxBytes, &map_dy, &full_bar[ps.stage], n0 + h * 64, tc * 64, b);
+            if (!leader) mbar_arrive_cluster(&full_bar[ps.stage], 0);
+            ps.advance<S>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      PipeState ps;
+      uint32_t ti = 0;
+      for (long long it = item0; it < item1; ++ti) {
+        int unit, b_lo, b_hi, k_, mi_, ni_;
+        next_segment(it, unit, b_lo, b_hi);
+        decode(unit, k_, mi_, ni_);
+        const uint32_t idesc = make_idesc(2 * kTileM, (ni_ == p.n_tiles - 1) ? p.n_tail : BN, 1, 1);
+        const int n_iters = (b_hi - b_lo) * p.t_chunks;
+        const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int i = 0; i < n_iters; ++i) {
+          mbar_wait(&full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + ps.stage * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + ps.stage * kBHalf);
+#pragma unroll
+          for (int kk = 0; kk < 64 / 16; ++kk) {
+            const uint64_t da = make_sdesc(a_addr + kk * 2048, kBoxBytes, 1024);
+            const uint64_t db = make_sdesc(b_addr + kk * 2048, kBoxBytes, 1024);
+            umma2_bf16(tmem_d, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma2_commit(&empty_bar[ps.stage]);
+          if (i == n_iters - 1) umma2_commit(&tfull_bar[as]);
+          ps.advance<S>();
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint32_t ti = 0;
+    for (long long it = item0; it < item1; ++ti) {
+      int unit, b_lo, b_hi, k, mi, ni;
+      next_segment(it, unit, b_lo, b_hi);
+      decode(unit, k, mi, ni);
+      const bool whole = (b_lo == 0 && b_hi == p.B);
+      const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      float* dst = p.dw + ((long long)k * p.C_in + p.m_off + mi * kTileM + row) * p.C_out + ni * BN;
+      const int ncur = valid ? ((ni == p.n_tiles - 1) ? p.n_tail : BN) : 0;
+#pragma unroll 1
+      for (int ch = 0; ch < ncur / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        tmem_ld_wait();
+        if (whole) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            reinterpret_cast<float4*>(dst + ch * 32)[q] =
+                make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
+                            __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + ch * 32 + q * 4),
+                         "f"(__uint_as_float(r[q * 4 + 0])), "f"(__uint_as_float(r[q * 4 + 1])),
+                         "f"(__uint_as_float(r[q * 4 + 2])), "f"(__uint_as_float(r[q * 4 + 3]))
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+      if (leader) mbar_arrive(&tempty_bar[as]);
+      else mbar_arrive_cluster(&tempty_bar[as], 0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) tmem_dealloc2(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------ launchers
@@ -798,12 +987,13 @@ static int launch_kmajor_pair(const CUtensorMap* ma, const CUtensorMap* mb, cons
   return check_launch("tapgemm_kmajor_pair");
 }
 
-// 0 = single-CTA tiles, 1 = CTA pairs (cta_group::2) wherever the shape allows; OS2S_CONV_PAIR overrides.
+// CTA pairs (cta_group::2) are the default where the shape allows; OS2S_CONV_PAIR=0 forces single-CTA
+// tiles (A/B measurements, tools/gpu_pair_check.py), OS2S_CONV_PAIR=2 pairs even the narrow layers.
 static int conv_pair_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("OS2S_CONV_PAIR");
-    mode = e ? atoi(e) : 0;
+    mode = e ? atoi(e) : 1;
   }
   return mode;
 }
@@ -821,6 +1011,36 @@ static int launch_mnmajor(const CUtensorMap* mx, const CUtensorMap* mdy, const M
   const int grid = items < device_sm_count() ? (int)items : device_sm_count();
   tapgemm_mnmajor<BN><<<grid, kNumThreads, smem, st>>>(*mx, *mdy, p);
   return check_launch("tapgemm_mnmajor");
+}
+
+template <int BN>
+static int launch_mnmajor_pair(const CUtensorMap* mx, const CUtensorMap* mdy, const MNMajorParams& p,
+                               cudaStream_t st) {
+  static bool attr_done = false;
+  constexpr int kStage = kABytes + (BN / 2) * kChunkK * 2;
+  constexpr int S = (kSmemBudget - 1024) / kStage > 8 ? 8 : (kSmemBudget - 1024) / kStage;
+  const size_t smem = (size_t)S * kStage + (2 * S + 4) * 8 + 16 + 1024;
+  if (!attr_done) {
+    OS2S_CUDA(cudaFuncSetAttribute(tapgemm_mnmajor_pair<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const long long items = (long long)((p.K_taps * p.m_tiles + 1) / 2) * p.n_tiles * p.B;
+  const int pairs = device_sm_count() / 2;
+  const int clusters = items < pairs ? (int)items : pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OS2S_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_mnmajor_pair<BN>, *mx, *mdy, p));
+  return check_launch("tapgemm_mnmajor_pair");
 }
 
 // N tiling for forward / dgrad: tiles of width BN with a narrower last tile allowed (e.g. 640 =
@@ -880,7 +1100,9 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
                 int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st) {
   if (C_red % 64 != 0) return fail(ERR_UNSUPPORTED, "conv_tc: reduction channels must be a multiple of 64");
   // pairs: 256-wide tiles whose last tile is 128 or 256 wide (each CTA stages half of it)
-  const bool pair = conv_pair_mode() != 0 && N_total % 128 == 0 && N_total >= 256 && T > kTileM;
+  // (N = 256 is one tile wide: 96 pair tiles over 74 SM pairs quantise worse than 128-wide single tiles)
+  const bool pair = conv_pair_mode() != 0 && N_total % 128 == 0 && T > kTileM &&
+                    N_total >= (conv_pair_mode() == 2 ? 256 : 384);
   const int BN = pair ? 256 : pick_bn_tiles(N_total, (long long)B * ((T + kTileM - 1) / kTileM), b_mn_major != 0);
   if (BN == 0) return fail(ERR_UNSUPPORTED, "conv_tc: output channels must be a multiple of 64");
   if (B <= 0 || T <= 0 || K <= 0) return fail(ERR_INVALID, "conv_tc: bad shape");
@@ -961,10 +1183,19 @@ int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in,
   p.dw = dw;
   p.C_in = C_in;
   p.C_out = C_out;
+  p.m_off = 0;
   // stream-K: every CTA gets an equal share of (unit, utterance) items; tiles shared between CTAs are
   // reduced with red.add into the zeroed gradient (a plain store is used when a CTA owns a whole unit)
   if (splits_used) *splits_used = 0;
   OS2S_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * C_in * C_out * sizeof(float), st));
+  const int n_rb = K * (C_in / kTileM);
+  if (conv_pair_mode() != 0 && C_out % 128 == 0 && C_out >= 256 && (n_rb % 2 == 0 || n_rb >= 16)) {
+    // pairs of (tap, C_in tile) row blocks; an odd count pads one block (<= 1/17 of the work)
+    MNMajorParams pp = p;
+    pp.n_tiles = (C_out + 255) / 256;
+    pp.n_tail = C_out - (pp.n_tiles - 1) * 256;
+    return launch_mnmajor_pair<256>(mx, mdy, pp, st);
+  }
   switch (BN) {
     case 256: return launch_mnmajor<256>(mx, mdy, p, st);
     case 192: return launch_mnmajor<192>(mx, mdy, p, st);

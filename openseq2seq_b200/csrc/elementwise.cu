@@ -79,46 +79,52 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
 // ---------------------------------------------------------------------------------------------
 // Row tiling shared by the four BN kernels.  The [M, C] matrix is cut into row chunks, one CTA per
 // chunk; inside a CTA thread t owns ONE 8-channel vector column cv = t % CV (16-byte accesses,
-// a warp covers 512 contiguous bytes of a row) and walks rows r, r+RP, r+2RP, ... with RP = 256/CV
-// rows in flight per pass.  Loops are unrolled 4 rows deep with all loads issued before use (4
+// a warp covers 512 contiguous bytes of a row) and walks rows r, r+RP, r+2RP, ... with RP = 512/CV
+// rows in flight per pass (the CTA has exactly CV*RP threads).  Single-branch layers (43 of 53
+// launches) are a separate instantiation that fits 64 registers, i.e. two 512-thread CTAs per SM.  Loops are unrolled 4 rows deep with all loads issued before use (4
 // independent 16-byte loads in flight per thread and tensor), there is no integer division in any
 // loop, and per-channel coefficients live in registers (single branch) or are fetched from shared
 // memory once per 4 rows (dense-residual layers).
-constexpr int kEwThreads = 256;
+constexpr int kEwMaxThreads = 512;
 constexpr int kUnroll = 4;
 
 struct RowTile {
   int CV, RP, cv, r, row0, row1;
-  bool active;
 };
+// CTA size: RP whole rows of CV vector columns, as many as fit in 512 threads (every thread is active)
+static int ew_threads(int C) {
+  const int CV = C >> 3;
+  const int RP = kEwMaxThreads / CV > 0 ? kEwMaxThreads / CV : 1;
+  return CV * RP;
+}
 __device__ __forceinline__ RowTile make_row_tile(int M, int C, int rows_per_block) {
   RowTile t;
   t.CV = C >> 3;
-  t.RP = kEwThreads / t.CV;
+  t.RP = blockDim.x / t.CV;
   t.cv = threadIdx.x % t.CV;
   t.r = threadIdx.x / t.CV;
-  t.active = t.r < t.RP;
   t.row0 = blockIdx.x * rows_per_block;
   t.row1 = min(M, t.row0 + rows_per_block);
   return t;
 }
-static int rows_per_block_for(int M, int C, int waves) {
-  const int RP = kEwThreads / (C >> 3);
-  int target = device_sm_count() * waves;
+// rows per CTA for a grid of (SM count x resident CTAs per SM): one full wave, no tail wave
+static int rows_per_block_for(int M, int C, int ctas_per_sm) {
+  const int RP = ew_threads(C) / (C >> 3);
+  const int target = device_sm_count() * ctas_per_sm;
   int rpb = (M + target - 1) / target;
-  const int min_rows = RP * kUnroll * 2;  // at least two unrolled passes per thread
+  const int min_rows = RP * kUnroll;  // at least one unrolled pass per thread
   if (rpb < min_rows) rpb = min_rows;
   return rpb;
 }
 
 // Per-channel sum and sum of squares of y [M, C] (fp16). stats = [2][C] fp32, pre-zeroed.
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwMaxThreads, 2)
 bn_stats_kernel(const __half* __restrict__ y, float* __restrict__ stats, int M, int C, int rows_per_block) {
   extern __shared__ float sh[];  // [2][C]
   const RowTile t = make_row_tile(M, C, rows_per_block);
-  for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) sh[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
-  if (t.active) {
+  {
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
@@ -156,14 +162,14 @@ bn_stats_kernel(const __half* __restrict__ y, float* __restrict__ stats, int M, 
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) atomicAdd(&stats[i], sh[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[i], sh[i]);
 }
 
 int bn_stats(const void* y, float* stats, int M, int C, cudaStream_t st) {
   if (C % 8 != 0 || C > 2048 || C < 8) return fail(ERR_UNSUPPORTED, "bn_stats: C must be a multiple of 8, <= 2048");
-  const int rpb = rows_per_block_for(M, C, 3);
+  const int rpb = rows_per_block_for(M, C, 2);
   const int grid = (M + rpb - 1) / rpb;
-  bn_stats_kernel<<<grid, kEwThreads, 2 * C * sizeof(float), st>>>((const __half*)y, stats, M, C, rpb);
+  bn_stats_kernel<<<grid, ew_threads(C), 2 * C * sizeof(float), st>>>((const __half*)y, stats, M, C, rpb);
   return check_launch("bn_stats");
 }
 
@@ -228,13 +234,13 @@ __device__ __forceinline__ void bn_coef(const BnFwdParams& p, const BnBranchFwd&
   }
 }
 
-__global__ void __launch_bounds__(kEwThreads)
+template <bool ONE>
+__global__ void __launch_bounds__(kEwMaxThreads, ONE ? 2 : 1)
 bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
   const int C = p.C;
   const int M = p.B * p.T;
   const float inv_n = 1.f / (float)M;
   const RowTile t = make_row_tile(M, C, rows_per_block);
-  if (!t.active) return;
   const bool owner = blockIdx.x == 0 && t.r == 0;
   const int c0 = t.cv * 8;
   // single-branch layers keep their coefficients in registers for the whole kernel; dense-residual
@@ -242,7 +248,7 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
   // no per-CTA prologue over all channels)
   float sc0[8], sf0[8];
   bn_coef(p, p.br[0], c0, inv_n, owner, sc0, sf0);
-  if (owner) {
+  if (!ONE && owner) {
     for (int j = 1; j < p.n_branch; ++j) {
       float a_[8], b_[8];
       bn_coef(p, p.br[j], c0, inv_n, true, a_, b_);
@@ -254,11 +260,36 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
   if (p.step_ctr) seed += (unsigned long long)(*p.step_ctr) * 0x9E3779B97F4A7C15ull;
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   const size_t rs = (size_t)t.CV;
+  // activation, dropout, row mask and the 16-byte store of one row vector
+  auto finish = [&](float (&o)[8], int ru, bool live) {
+    if (live) {
+      if (p.apply_relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = fmaxf(o[i], 0.f);
+          if (p.relu_clip > 0.f) o[i] = fminf(o[i], p.relu_clip);
+        }
+      }
+      if (p.keep < 1.f) {
+        const unsigned long long idx = (unsigned long long)ru * (unsigned)t.CV + (unsigned)t.cv;
+        const uint4 r0 = philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u), key);
+        const uint32_t rr[4] = {r0.x, r0.y, r0.z, r0.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t u16 = (i & 1) ? (rr[i >> 1] >> 16) : (rr[i >> 1] & 0xFFFFu);
+          o[i] = (u16 < keep16) ? o[i] * inv_keep : 0.f;  // P(keep) = keep16 / 65536
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    }
+    reinterpret_cast<uint4*>(p.out)[(size_t)ru * rs + t.cv] = float_to_bf16x8(o);
+  };
   // (b, tt) of the thread's first row, advanced incrementally (no division in the loop)
   int row = t.row0 + t.r;
   int b = row / p.T, tt = row - b * p.T;
   for (; row < t.row1; row += kUnroll * t.RP) {
-    float acc[kUnroll][8];
     bool live[kUnroll];
     int bb = b, t2 = tt;
 #pragma unroll
@@ -267,57 +298,56 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
       live[u] = ru < t.row1 && (p.lens == nullptr || t2 < __ldg(p.lens + min(bb, p.B - 1)));
       t2 += t.RP;
       while (t2 >= p.T) { t2 -= p.T; ++bb; }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[u][i] = 0.f;
     }
-    for (int j = 0; j < p.n_branch; ++j) {
-      const uint4* yb = reinterpret_cast<const uint4*>(p.br[j].y) + t.cv;
+    if (ONE) {
+      const uint4* yb = reinterpret_cast<const uint4*>(p.br[0].y) + t.cv;
       uint4 v[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
         v[u] = live[u] ? __ldg(yb + (size_t)(row + u * t.RP) * rs) : make_uint4(0, 0, 0, 0);
-      float sc[8], sf[8];
-      if (j == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { sc[i] = sc0[i]; sf[i] = sf0[i]; }
-      } else {
-        bn_coef(p, p.br[j], c0, inv_n, false, sc, sf);
-      }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
+        const int ru = row + u * t.RP;
+        if (ru >= t.row1) break;
         float f[8];
         f16x8_to_float(v[u], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[u][i] += f[i] * sc[i] + sf[i];
+        for (int i = 0; i < 8; ++i) f[i] = f[i] * sc0[i] + sf0[i];
+        finish(f, ru, live[u]);
       }
-    }
+    } else {
+      float acc[kUnroll][8];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int ru = row + u * t.RP;
-      if (ru >= t.row1) break;
-      if (live[u]) {
-        if (p.apply_relu) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            acc[u][i] = fmaxf(acc[u][i], 0.f);
-            if (p.relu_clip > 0.f) acc[u][i] = fminf(acc[u][i], p.relu_clip);
-          }
-        }
-        if (p.keep < 1.f) {
-          const unsigned long long idx = (unsigned long long)ru * (unsigned)t.CV + (unsigned)t.cv;
-          const uint4 r0 = philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u), key);
-          const uint32_t rr[4] = {r0.x, r0.y, r0.z, r0.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t u16 = (i & 1) ? (rr[i >> 1] >> 16) : (rr[i >> 1] & 0xFFFFu);
-            acc[u][i] = (u16 < keep16) ? acc[u][i] * inv_keep : 0.f;  // P(keep) = keep16 / 65536
-          }
-        }
-      } else {
+      for (int u = 0; u < kUnroll; ++u)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[u][i] = 0.f;
+      for (int j = 0; j < p.n_branch; ++j) {
+        const uint4* yb = reinterpret_cast<const uint4*>(p.br[j].y) + t.cv;
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          v[u] = live[u] ? __ldg(yb + (size_t)(row + u * t.RP) * rs) : make_uint4(0, 0, 0, 0);
+        float sc[8], sf[8];
+        if (j == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { sc[i] = sc0[i]; sf[i] = sf0[i]; }
+        } else {
+          bn_coef(p, p.br[j], c0, inv_n, false, sc, sf);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          float f[8];
+          f16x8_to_float(v[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[u][i] += f[i] * sc[i] + sf[i];
+        }
       }
-      reinterpret_cast<uint4*>(p.out)[(size_t)ru * rs + t.cv] = float_to_bf16x8(acc[u]);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int ru = row + u * t.RP;
+        if (ru >= t.row1) break;
+        finish(acc[u], ru, live[u]);
+      }
     }
     // advance (b, tt) by kUnroll * RP rows
     tt += kUnroll * t.RP;
@@ -329,9 +359,11 @@ int bn_apply_fwd(const BnFwdParams& p, cudaStream_t st) {
   if (p.n_branch < 1 || p.n_branch > kMaxBranches) return fail(ERR_INVALID, "bn_apply_fwd: bad branch count");
   if (p.C % 8 != 0 || p.C > 2048) return fail(ERR_UNSUPPORTED, "bn_apply_fwd: C must be a multiple of 8, <= 2048");
   const int M = p.B * p.T;
-  const int rpb = rows_per_block_for(M, p.C, 4);
+  const bool one = p.n_branch == 1;
+  const int rpb = rows_per_block_for(M, p.C, one ? 2 : 1);
   const int grid = (M + rpb - 1) / rpb;
-  bn_apply_fwd_kernel<<<grid, kEwThreads, 0, st>>>(p, rpb);
+  if (one) bn_apply_fwd_kernel<true><<<grid, ew_threads(p.C), 0, st>>>(p, rpb);
+  else bn_apply_fwd_kernel<false><<<grid, ew_threads(p.C), 0, st>>>(p, rpb);
   return check_launch("bn_apply_fwd");
 }
 
@@ -363,37 +395,38 @@ __device__ __forceinline__ void gate_dz(const BnBwdParams& p, const uint4& a_raw
   }
 }
 
-constexpr int kBwdGroup = 4;  // branches reduced per sweep over the rows
-template <bool F32>
-__global__ void __launch_bounds__(kEwThreads)
+// G = branches reduced per sweep over the rows: 1 for single-branch layers (64 registers, two CTAs
+// per SM), 4 for dense-residual layers.
+template <bool F32, int G>
+__global__ void __launch_bounds__(kEwMaxThreads, G == 1 ? 2 : 1)
 bn_bwd_reduce_kernel(const BnBwdParams p, int rows_per_block) {
   extern __shared__ float sh[];  // [1 + n_branch][C]
   const int C = p.C;
   const int nred = (1 + p.n_branch) * C;
-  for (int i = threadIdx.x; i < nred; i += kEwThreads) sh[i] = 0.f;
+  for (int i = threadIdx.x; i < nred; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
   const RowTile t = make_row_tile(p.M, C, rows_per_block);
-  if (t.active) {
+  {
     const size_t rs = (size_t)t.CV;
-    for (int j0 = 0; j0 < p.n_branch; j0 += kBwdGroup) {
-      const int nj = min(kBwdGroup, p.n_branch - j0);
-      float db[8], S[kBwdGroup][8];
+    for (int j0 = 0; j0 < p.n_branch; j0 += G) {
+      const int nj = min(G, p.n_branch - j0);
+      float db[8], S[G][8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         db[i] = 0.f;
 #pragma unroll
-        for (int g = 0; g < kBwdGroup; ++g) S[g][i] = 0.f;
+        for (int g = 0; g < G; ++g) S[g][i] = 0.f;
       }
       for (int row = t.row0 + t.r; row < t.row1; row += 2 * t.RP) {
         const bool two = row + t.RP < t.row1;
         float dz0[8], dz1[8];
         uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
-        uint4 y0[kBwdGroup], y1[kBwdGroup];
+        uint4 y0[G], y1[G];
         const size_t v0 = (size_t)row * rs + t.cv, v1 = v0 + (size_t)t.RP * rs;
         load_dz_raw<F32>(p, v0, a0, dz0);
         if (two) load_dz_raw<F32>(p, v1, a1, dz1);
 #pragma unroll
-        for (int g = 0; g < kBwdGroup; ++g) {
+        for (int g = 0; g < G; ++g) {
           if (g < nj) {
             const uint4* yb = reinterpret_cast<const uint4*>(p.br[j0 + g].y);
             y0[g] = __ldg(yb + v0);
@@ -409,7 +442,7 @@ bn_bwd_reduce_kernel(const BnBwdParams p, int rows_per_block) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) db[i] += dz0[i] + dz1[i];
 #pragma unroll
-        for (int g = 0; g < kBwdGroup; ++g) {
+        for (int g = 0; g < G; ++g) {
           if (g < nj) {
             float f[8];
             f16x8_to_float(y0[g], f);
@@ -424,7 +457,7 @@ bn_bwd_reduce_kernel(const BnBwdParams p, int rows_per_block) {
         }
       }
 #pragma unroll
-      for (int g = 0; g < kBwdGroup; ++g) {
+      for (int g = 0; g < G; ++g) {
         if (g < nj) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) atomicAdd(&sh[(1 + j0 + g) * C + t.cv * 8 + i], S[g][i]);
@@ -437,7 +470,7 @@ bn_bwd_reduce_kernel(const BnBwdParams p, int rows_per_block) {
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nred; i += kEwThreads) atomicAdd(&p.red[i], sh[i]);
+  for (int i = threadIdx.x; i < nred; i += blockDim.x) atomicAdd(&p.red[i], sh[i]);
 }
 
 // dy = A*dz + Bc*y + Cc for the thread's own 8 channels of branch b (from the pass-1 sums).
@@ -468,43 +501,70 @@ __device__ __forceinline__ void bn_bwd_coef(const BnBwdParams& p, int j, int c0,
   }
 }
 
-template <bool F32>
-__global__ void __launch_bounds__(kEwThreads)
+template <bool F32, bool ONE>
+__global__ void __launch_bounds__(kEwMaxThreads, ONE ? 2 : 1)
 bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
+  constexpr int U = ONE ? 2 : kUnroll;   // rows in flight per thread (3-4 loads each when ONE)
   const int C = p.C;
   const float inv_n = 1.f / (float)p.M;
   const RowTile t = make_row_tile(p.M, C, rows_per_block);
-  if (!t.active) return;
   const bool owner = blockIdx.x == 0 && t.r == 0;
   const int c0 = t.cv * 8;
   float A0[8], B0[8], C0[8];
   bn_bwd_coef(p, 0, c0, inv_n, owner, A0, B0, C0);
-  if (owner) {
+  if (!ONE && owner) {
     for (int j = 1; j < p.n_branch; ++j) {
       float a_[8], b_[8], c_[8];
       bn_bwd_coef(p, j, c0, inv_n, true, a_, b_, c_);
     }
   }
   const size_t rs = (size_t)t.CV;
-  for (int row = t.row0 + t.r; row < t.row1; row += kUnroll * t.RP) {
-    float dz[kUnroll][8];
-    uint4 araw[kUnroll];
-    bool live[kUnroll];
+  for (int row = t.row0 + t.r; row < t.row1; row += U * t.RP) {
+    float dz[U][8];
+    uint4 araw[U];
+    bool live[U];
+    if (ONE) {
+      // all loads of the U rows (dA, a, y) are issued before the first use
+      const uint4* yb = reinterpret_cast<const uint4*>(p.br[0].y) + t.cv;
+      uint4* db = reinterpret_cast<uint4*>(p.br[0].dy) + t.cv;
+      uint4 v[U];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+      for (int u = 0; u < U; ++u) {
+        live[u] = row + u * t.RP < t.row1;
+        araw[u] = make_uint4(0, 0, 0, 0);
+        if (live[u]) {
+          load_dz_raw<F32>(p, (size_t)(row + u * t.RP) * rs + t.cv, araw[u], dz[u]);
+          v[u] = __ldg(yb + (size_t)(row + u * t.RP) * rs);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (live[u]) {
+          gate_dz(p, araw[u], dz[u]);
+          float f[8];
+          f16x8_to_float(v[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = A0[i] * dz[u][i] + B0[i] * f[i] + C0[i];
+          db[(size_t)(row + u * t.RP) * rs] = float_to_bf16x8(f);
+        }
+      }
+      continue;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
       live[u] = row + u * t.RP < t.row1;
       araw[u] = make_uint4(0, 0, 0, 0);
       if (live[u]) load_dz_raw<F32>(p, (size_t)(row + u * t.RP) * rs + t.cv, araw[u], dz[u]);
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
+    for (int u = 0; u < U; ++u)
       if (live[u]) gate_dz(p, araw[u], dz[u]);
     for (int j = 0; j < p.n_branch; ++j) {
       const uint4* yb = reinterpret_cast<const uint4*>(p.br[j].y) + t.cv;
       uint4* db = reinterpret_cast<uint4*>(p.br[j].dy) + t.cv;
-      uint4 v[kUnroll];
+      uint4 v[U];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u)
+      for (int u = 0; u < U; ++u)
         if (live[u]) v[u] = __ldg(yb + (size_t)(row + u * t.RP) * rs);
       float A[8], Bc[8], Cc[8];
       if (j == 0) {
@@ -514,7 +574,7 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
         bn_bwd_coef(p, j, c0, inv_n, false, A, Bc, Cc);
       }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+      for (int u = 0; u < U; ++u) {
         if (live[u]) {
           float f[8], o[8];
           f16x8_to_float(v[u], f);
@@ -532,23 +592,30 @@ int bn_bwd(const BnBwdParams& p, cudaStream_t st) {
   if (p.C % 8 != 0 || p.C > 2048) return fail(ERR_UNSUPPORTED, "bn_bwd: C must be a multiple of 8, <= 2048");
   static bool attr_done = false;
   if (!attr_done) {
-    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
   const size_t smem_r = (size_t)(1 + p.n_branch) * p.C * sizeof(float);
-  const size_t smem_a = 0;
   if (smem_r > 100 * 1024) return fail(ERR_UNSUPPORTED, "bn_bwd: too many branches x channels");
-  const int rpb_r = rows_per_block_for(p.M, p.C, 2);
-  const int rpb_a = rows_per_block_for(p.M, p.C, 4);
-  const int grid_r = (p.M + rpb_r - 1) / rpb_r;
-  const int grid_a = (p.M + rpb_a - 1) / rpb_a;
-  if (p.dA_is_f32) {
-    bn_bwd_reduce_kernel<true><<<grid_r, kEwThreads, smem_r, st>>>(p, rpb_r);
-    bn_bwd_apply_kernel<true><<<grid_a, kEwThreads, smem_a, st>>>(p, rpb_a);
+  const bool one = p.n_branch == 1;
+  const int rpb = rows_per_block_for(p.M, p.C, one ? 2 : 1);
+  const int grid = (p.M + rpb - 1) / rpb;
+  const int nt = ew_threads(p.C);
+  if (one) {
+    if (p.dA_is_f32) {
+      bn_bwd_reduce_kernel<true, 1><<<grid, nt, smem_r, st>>>(p, rpb);
+      bn_bwd_apply_kernel<true, true><<<grid, nt, 0, st>>>(p, rpb);
+    } else {
+      bn_bwd_reduce_kernel<false, 1><<<grid, nt, smem_r, st>>>(p, rpb);
+      bn_bwd_apply_kernel<false, true><<<grid, nt, 0, st>>>(p, rpb);
+    }
+  } else if (p.dA_is_f32) {
+    bn_bwd_reduce_kernel<true, 4><<<grid, nt, smem_r, st>>>(p, rpb);
+    bn_bwd_apply_kernel<true, false><<<grid, nt, 0, st>>>(p, rpb);
   } else {
-    bn_bwd_reduce_kernel<false><<<grid_r, kEwThreads, smem_r, st>>>(p, rpb_r);
-    bn_bwd_apply_kernel<false><<<grid_a, kEwThreads, smem_a, st>>>(p, rpb_a);
+    bn_bwd_reduce_kernel<false, 4><<<grid, nt, smem_r, st>>>(p, rpb);
+    bn_bwd_apply_kernel<false, false><<<grid, nt, 0, st>>>(p, rpb);
   }
   return check_launch("bn_bwd");
 }

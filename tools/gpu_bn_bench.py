@@ -28,7 +28,7 @@ def timeit(fn, n=10):
     return e0.elapsed_time(e1) / n
 
 
-for C, nb in [(256, 1), (768, 1), (1024, 1), (768, 4), (768, 11), (512, 7)]:
+for C, nb in [(256, 1), (384, 1), (512, 1), (640, 1), (768, 1), (1024, 1), (768, 4), (768, 11), (512, 7)]:
     ys = [torch.randn(B, T, C, device="cuda").half() for _ in range(nb)]
     # rotate through several copies so the 126 MB L2 does not serve the reads
     stats = torch.zeros(nb, 2, C, device="cuda")
