@@ -38,6 +38,14 @@ extern "C" {
 
 const char* os2s_last_error(void);
 int os2s_version(void);
+/* Kernel-variant selection for the conv entry points (all variants give bitwise-identical forward /
+ * data-gradient outputs; the switch exists for A/B measurements and the parity tests).
+ *   pair_mode: 0 = one CTA per 128-row tile, 1 = CTA pairs (cta_group::2) where the shape allows
+ *              (default), 2 = pairs for every shape that can be paired, -1 = leave unchanged
+ *   halo_mode: 0 = one activation tile per tap, 1 = one halo tile shared by all taps of a pair
+ *              tile (default), -1 = leave unchanged
+ * Initial values come from the environment (OS2S_CONV_PAIR, OS2S_CONV_HALO). */
+int os2s_conv_tuning(int pair_mode, int halo_mode);
 
 /* ---- K2: tf.layers.conv1d(use_bias=False, padding=SAME), stride 1 -----------------------------
  * reference: open_seq2seq/parts/cnns/conv_blocks.py:195-206 (main), :79-85 (1x1 residual).

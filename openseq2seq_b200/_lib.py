@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libos2s_b200.so")
+# OS2S_LIB_PATH: load another build of the same library (same-box A/B measurements of two builds)
+LIB_PATH = os.environ.get("OS2S_LIB_PATH") or os.path.join(_HERE, "lib", "libos2s_b200.so")
 
 _lib = None
 

@@ -9,7 +9,8 @@ using namespace os2s;
 extern "C" {
 
 const char* os2s_last_error(void) { return last_error_cstr(); }
-int os2s_version(void) { return 100; }
+int os2s_version(void) { return 101; }
+int os2s_conv_tuning(int pair_mode, int halo_mode) { return conv_tuning(pair_mode, halo_mode); }
 
 int os2s_conv1d_fwd(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
                     int K, int dil, int pad_left, int out_mode, float* bn_stats, void* stream) {

@@ -42,6 +42,7 @@ struct KMajorParams {
   int K_taps, c_chunks;
   int t_off0, t_step;
   float* stats;                // optional [2][N_total]: += per-channel sum / sum of squares of the output
+  int halo_rows, halo_off, sb_stages;  // halo variant: rows of the A halo tile, row offset of tap 0, B ring depth
   void* out;
   long long out_row_stride;    // elements
   long long out_batch_stride;  // elements
@@ -276,11 +277,13 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int t0 = (rem - b * p.n_mtiles) * kTileM;
         const int n0 = nt * BN;
         const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
-        for (int k = 0; k < p.K_taps; ++k) {
-          const int trow = t0 + p.t_off0 + k * p.t_step;
-          const int brow = k * p.N_total + n0;
-          const int crow = k * p.c_chunks * kChunkK;
-          for (int c = 0; c < p.c_chunks; ++c) {
+        // chunk-major, taps inner: consecutive stages read overlapping activation rows (L2 hits) and
+        // every variant of the kernel accumulates in the same order (bitwise-identical outputs)
+        for (int c = 0; c < p.c_chunks; ++c) {
+          for (int k = 0; k < p.K_taps; ++k) {
+            const int trow = t0 + p.t_off0 + k * p.t_step;
+            const int brow = k * p.N_total + n0;
+            const int crow = k * p.c_chunks * kChunkK;
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
             mbar_expect_tx(&full_bar[ps.stage], kABytes + (BMN ? ncur * kChunkK * 2 : kBBytes));
             tma_load_3d(smem_a + ps.stage * kABytes, &map_a, &full_bar[ps.stage], c * kChunkK, trow, b);
@@ -459,11 +462,11 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int n0 = nt * BN;
         const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
         const int hcur = ncur / 2;                   // columns of B each CTA provides
-        for (int k = 0; k < p.K_taps; ++k) {
-          const int trow = t0 + p.t_off0 + k * p.t_step;
-          const int brow = k * p.N_total + n0 + (int)rank * hcur;
-          const int crow = k * p.c_chunks * kChunkK;
-          for (int c = 0; c < p.c_chunks; ++c) {
+        for (int c = 0; c < p.c_chunks; ++c) {
+          for (int k = 0; k < p.K_taps; ++k) {
+            const int trow = t0 + p.t_off0 + k * p.t_step;
+            const int brow = k * p.N_total + n0 + (int)rank * hcur;
+            const int crow = k * p.c_chunks * kChunkK;
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
             const uint32_t my_bytes = kABytes + (BMN ? hcur * kChunkK * 2 : kBHalf);
             if (leader) mbar_expect_tx(&full_bar[ps.stage], 2 * my_bytes);
@@ -561,6 +564,199 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_before();
   __syncthreads();
   cluster_sync();                      // nobody exits while the peer may still signal its barriers
+  if (warp == 1) tmem_dealloc2(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------ forward / dgrad, CTA pairs + halo
+// tapgemm_kmajor_pair with the activation tile shared by all taps: per 64-channel chunk each CTA loads
+// ONE halo tile of 128 + (K-1)*|dilation| rows and tap k multiplies the 128-row window that starts
+// k*dilation rows into it (the UMMA descriptor start address moves by whole 128-byte rows; the
+// SWIZZLE_128B pattern is a function of the absolute shared-memory address, so the window needs no
+// re-layout).  Shared-memory fill traffic per chunk drops from K*(16 KB + B) to ~19 KB + K*B.
+// Two rings: A halo tiles (2 stages, one per chunk) and B tap tiles (sb_stages).
+template <int BN, bool BMN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const KMajorParams p) {
+  static_assert(BN % 128 == 0, "pair tiles split B in two 64-aligned halves");
+  constexpr int HB = BN / 2;
+  constexpr int kBHalf = HB * kChunkK * 2;
+  constexpr int kBoxBytes = 64 * 64 * 2;
+  constexpr int SA = 2;
+  constexpr int kMaxSB = 8;
+  constexpr uint32_t kTmemCols = tmem_cols<BN>();
+  const int SB = p.sb_stages;
+  const uint32_t halo_bytes = (uint32_t)p.halo_rows * 128u;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + SA * halo_bytes;
+  uint64_t* afull_bar = reinterpret_cast<uint64_t*>(smem_b + SB * kBHalf);
+  uint64_t* aempty_bar = afull_bar + SA;
+  uint64_t* bfull_bar = aempty_bar + SA;
+  uint64_t* bempty_bar = bfull_bar + kMaxSB;
+  uint64_t* tfull_bar = bempty_bar + kMaxSB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(tmem_ptr + 4);
+  float* epi_stats = reinterpret_cast<float*>(epi_stage + 4 * kEpiWarpBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < SA; ++i) {
+      mbar_init(&afull_bar[i], 2);
+      mbar_init(&aempty_bar[i], 1);
+    }
+    for (int i = 0; i < kMaxSB; ++i) {
+      mbar_init(&bfull_bar[i], 2);
+      mbar_init(&bempty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_ptiles = (p.T_out + 2 * kTileM - 1) / (2 * kTileM);
+  const int tiles_per_n = p.B * n_ptiles;
+  const int n_tiles = tiles_per_n * p.n_ntiles;
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        const int nt = tile / tiles_per_n;
+        const int rem = tile - nt * tiles_per_n;
+        const int b = rem / n_ptiles;
+        const int t0 = (rem - b * n_ptiles) * 2 * kTileM + (int)rank * kTileM;
+        const int n0 = nt * BN;
+        const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
+        const int hcur = ncur / 2;
+        const uint32_t b_bytes = BMN ? hcur * kChunkK * 2 : kBHalf;
+        for (int c = 0; c < p.c_chunks; ++c) {
+          mbar_wait(&aempty_bar[sa], pha ^ 1);
+          if (leader) mbar_expect_tx(&afull_bar[sa], 2 * halo_bytes);
+          tma2_load_3d(smem_a + sa * halo_bytes, &map_a, &afull_bar[sa], c * kChunkK, t0 + p.t_off0 - p.halo_off, b);
+          if (!leader) mbar_arrive_cluster(&afull_bar[sa], 0);
+          if (++sa == SA) { sa = 0; pha ^= 1; }
+          for (int k = 0; k < p.K_taps; ++k) {
+            const int brow = k * p.N_total + n0 + (int)rank * hcur;
+            const int crow = k * p.c_chunks * kChunkK;
+            mbar_wait(&bempty_bar[sb], phb ^ 1);
+            if (leader) mbar_expect_tx(&bfull_bar[sb], 2 * b_bytes);
+            if (BMN) {
+#pragma unroll
+              for (int h = 0; h < HB / 64; ++h)
+                if (h * 64 < hcur)
+                  tma2_load_2d(smem_b + sb * kBHalf + h * kBoxBytes, &map_b, &bfull_bar[sb],
+                               n0 + (int)rank * hcur + h * 64, crow + c * kChunkK);
+            } else {
+              tma2_load_2d(smem_b + sb * kBHalf, &map_b, &bfull_bar[sb], c * kChunkK, brow);
+            }
+            if (!leader) mbar_arrive_cluster(&bfull_bar[sb], 0);
+            if (++sb == (uint32_t)SB) { sb = 0; phb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+      uint32_t ti = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+        const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
+        const uint32_t idesc = make_idesc(2 * kTileM, ncur, 0, BMN ? 1 : 0);
+        const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int c = 0; c < p.c_chunks; ++c) {
+          mbar_wait(&afull_bar[sa], pha);
+          tc_fence_after();
+          const uint32_t a_stage = smem_u32(smem_a + sa * halo_bytes);
+          for (int k = 0; k < p.K_taps; ++k) {
+            mbar_wait(&bfull_bar[sb], phb);
+            tc_fence_after();
+            const uint32_t a_addr = a_stage + (uint32_t)(p.halo_off + k * p.t_step) * 128u;
+            const uint32_t b_addr = smem_u32(smem_b + sb * kBHalf);
+#pragma unroll
+            for (int kk = 0; kk < kChunkK / 16; ++kk) {
+              const uint64_t da = make_sdesc(a_addr + kk * 32, 0, 1024);
+              const uint64_t db = BMN ? make_sdesc(b_addr + kk * 2048, kBoxBytes, 1024)
+                                      : make_sdesc(b_addr + kk * 32, 0, 1024);
+              umma2_bf16(tmem_d, da, db, idesc, (c > 0 || k > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma2_commit(&bempty_bar[sb]);
+            if (++sb == (uint32_t)SB) { sb = 0; phb ^= 1; }
+          }
+          umma2_commit(&aempty_bar[sa]);
+          if (++sa == SA) { sa = 0; pha ^= 1; }
+        }
+        umma2_commit(&tfull_bar[as]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    uint8_t* stage = epi_stage + quad * kEpiWarpBytes;
+    float* sacc = epi_stats + quad * 2 * BN;
+    const bool two_byte = (p.out_mode == OUT_BF16 || p.out_mode == OUT_F16);
+    const bool do_stats = (p.stats != nullptr) && two_byte;
+    if (do_stats)
+      for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
+    int cur_nt = -1;
+    auto flush_stats = [&](int nt) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int tid = threadIdx.x - 64;
+      const int width = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
+      for (int i = tid; i < 2 * BN; i += 128) {
+        const float v = epi_stats[i] + epi_stats[2 * BN + i] + epi_stats[4 * BN + i] + epi_stats[6 * BN + i];
+        const int which = i / BN, col = i - which * BN;
+        if (col < width) atomicAdd(&p.stats[(size_t)which * p.N_total + nt * BN + col], v);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
+    };
+    uint32_t ti = 0;
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+      const int nt = tile / tiles_per_n;
+      const int rem = tile - nt * tiles_per_n;
+      const int b = rem / n_ptiles;
+      const int t0w = (rem - b * n_ptiles) * 2 * kTileM + (int)rank * kTileM + quad * 32;
+      const int n0 = nt * BN;
+      const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
+      if (do_stats && cur_nt >= 0 && nt != cur_nt) flush_stats(cur_nt);
+      cur_nt = nt;
+      const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      const int nvalid = min(32, max(0, p.T_out - t0w));
+      const long long off = (long long)b * p.out_batch_stride + (long long)t0w * p.out_row_stride + n0;
+      epilogue_rows<BN>(p, stage, sacc, do_stats, two_byte, taddr, nvalid, off, ncur, lane);
+      tc_fence_before();
+      if (leader) mbar_arrive(&tempty_bar[as]);
+      else mbar_arrive_cluster(&tempty_bar[as], 0);
+    }
+    if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
   if (warp == 1) tmem_dealloc2(tmem_base, kTmemCols);
 }
 
@@ -987,15 +1183,64 @@ static int launch_kmajor_pair(const CUtensorMap* ma, const CUtensorMap* mb, cons
   return check_launch("tapgemm_kmajor_pair");
 }
 
-// CTA pairs (cta_group::2) are the default where the shape allows; OS2S_CONV_PAIR=0 forces single-CTA
-// tiles (A/B measurements, tools/gpu_pair_check.py), OS2S_CONV_PAIR=2 pairs even the narrow layers.
-static int conv_pair_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("OS2S_CONV_PAIR");
-    mode = e ? atoi(e) : 1;
+// halo variant of the pair kernel: A ring = 2 halo tiles, B ring = as many half tiles as fit (<= 8)
+template <int BN, bool BMN>
+static int launch_kmajor_pair_halo(const CUtensorMap* ma, const CUtensorMap* mb, KMajorParams p, cudaStream_t st) {
+  static bool attr_done = false;
+  constexpr int kBHalf = (BN / 2) * kChunkK * 2;
+  const int halo_bytes = p.halo_rows * 128;
+  int sb = (kSmemBudget - epi_bytes<BN>() - 2 * halo_bytes - 1024) / kBHalf;
+  if (sb > 8) sb = 8;
+  if (sb < 3) return fail(ERR_UNSUPPORTED, "conv_tc: halo tile too large");
+  p.sb_stages = sb;
+  const size_t smem = (size_t)2 * halo_bytes + (size_t)sb * kBHalf + (2 * 2 + 2 * 8 + 4) * 8 + 16 + epi_bytes<BN>() + 1024;
+  if (!attr_done) {
+    OS2S_CUDA(cudaFuncSetAttribute(tapgemm_kmajor_pair_halo<BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kSmemBudget + 4096)));
+    attr_done = true;
   }
-  return mode;
+  const int ptiles = p.B * ((p.T_out + 2 * kTileM - 1) / (2 * kTileM)) * p.n_ntiles;
+  const int pairs = device_sm_count() / 2;
+  const int clusters = ptiles < pairs ? ptiles : pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OS2S_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_kmajor_pair_halo<BN, BMN>, *ma, *mb, p));
+  return check_launch("tapgemm_kmajor_pair_halo");
+}
+
+// Kernel variants (os2s_conv_tuning): CTA pairs (cta_group::2) are the default where the shape allows;
+// pair mode 0 forces single-CTA tiles, 2 pairs even the narrow layers; halo mode 1 (default) shares
+// the activation tile between the taps of the pair kernel.  Environment: OS2S_CONV_PAIR, OS2S_CONV_HALO.
+static int g_pair_mode = -1, g_halo_mode = -1;
+static int conv_pair_mode() {
+  if (g_pair_mode < 0) {
+    const char* e = getenv("OS2S_CONV_PAIR");
+    g_pair_mode = e ? atoi(e) : 1;
+  }
+  return g_pair_mode;
+}
+static int conv_halo_mode() {
+  if (g_halo_mode < 0) {
+    const char* e = getenv("OS2S_CONV_HALO");
+    g_halo_mode = e ? atoi(e) : 1;
+  }
+  return g_halo_mode;
+}
+int conv_tuning(int pair_mode, int halo_mode) {
+  if (pair_mode > 2 || halo_mode > 1) return fail(ERR_INVALID, "conv_tuning: unknown mode");
+  if (pair_mode >= 0) g_pair_mode = pair_mode;
+  if (halo_mode >= 0) g_halo_mode = halo_mode;
+  return 0;
 }
 
 template <int BN>
@@ -1108,7 +1353,11 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
   if (B <= 0 || T <= 0 || K <= 0) return fail(ERR_INVALID, "conv_tc: bad shape");
   uint64_t adims[3] = {(uint64_t)C_red, (uint64_t)T, (uint64_t)B};
   uint64_t astr[2] = {(uint64_t)C_red * 2, (uint64_t)T * C_red * 2};
-  uint32_t abox[3] = {64, 128, 1};
+  // halo tile: 128 rows + the span of the taps, rounded up to whole 8-row swizzle atoms
+  const int span = (K - 1) * (t_step < 0 ? -t_step : t_step);
+  const int halo_rows = ((kTileM + span + 7) / 8) * 8;
+  const bool halo = pair && conv_halo_mode() != 0 && K > 1 && halo_rows <= 256;
+  uint32_t abox[3] = {64, (uint32_t)(halo ? halo_rows : 128), 1};
   const CUtensorMap* ma = get_tmap_bf16(act, 3, adims, astr, abox);
   // K-major B: wmat = [K][N_total][C_red] (box {64 c, BN n}); MN-major B: wmat = [K][C_red][N_total]
   uint64_t bdims[2] = {(uint64_t)(b_mn_major ? N_total : C_red), (uint64_t)K * (b_mn_major ? C_red : N_total)};
@@ -1132,6 +1381,12 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
   p.out_row_stride = N_total;
   p.out_batch_stride = (long long)T * N_total;
   p.out_mode = out_mode;
+  p.halo_rows = halo_rows;
+  p.halo_off = t_step < 0 ? span : 0;   // row of tap 0 inside the halo tile
+  p.sb_stages = 0;
+  if (halo)
+    return b_mn_major ? launch_kmajor_pair_halo<256, true>(ma, mb, p, st)
+                      : launch_kmajor_pair_halo<256, false>(ma, mb, p, st);
   if (pair)
     return b_mn_major ? launch_kmajor_pair<256, true>(ma, mb, p, st) : launch_kmajor_pair<256, false>(ma, mb, p, st);
   if (b_mn_major) {

@@ -14,6 +14,7 @@ constexpr int kMaxBranches = 12;
 const char* last_error_cstr();
 
 // conv_tc.cu
+int conv_tuning(int pair_mode, int halo_mode);
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
                 int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st);
 int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out, int K,

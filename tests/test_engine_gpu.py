@@ -76,9 +76,15 @@ def test_forward_logits_and_greedy_match_oracle():
     assert out_lens.cpu().tolist() == ref_len.tolist()
     for b in range(feats.shape[0]):
         n = int(ref_len[b])  # padded frames are defined but irrelevant to loss / decode
-        assert _rel_l2(logits[b, :n], ref[b, :n]) < 1e-2
-        assert _rel(logits[b, :n], ref[b, :n]) < 1.5e-2
-        assert _rel(logits[b, :n], emu[b, :n]) < 1e-2  # residual = amplified rounding-flip differences
+        e_l2, e_max = _rel_l2(logits[b, :n], ref[b, :n]), _rel(logits[b, :n], ref[b, :n])
+        assert e_l2 < 1e-2, (b, e_l2)
+        assert e_max < 1.5e-2, (b, e_max)
+        # vs the storage-emulating oracle only accumulation-order effects remain: a handful of fp16 /
+        # bf16 roundings that fall the other way and are amplified by the layers above (max norm: one
+        # flipped rounding shows up undiluted, hence the same bound as against the fp64 oracle)
+        d_l2, d_max = _rel_l2(logits[b, :n], emu[b, :n]), _rel(logits[b, :n], emu[b, :n])
+        assert d_l2 < 5e-3, (b, d_l2)
+        assert d_max < 1.5e-2, (b, d_max)
     toks, tl = eng.greedy_decode()
     torch.cuda.synchronize()
     ref_toks, _ = OC.ctc_greedy_decode(ref_logits.detach().numpy(), ref_len.numpy())

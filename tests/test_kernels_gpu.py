@@ -79,6 +79,53 @@ def test_conv_fwd_dgrad_wgrad_vs_oracle(B, T, Cin, Cout, K, dil):
         assert np.abs(dw.cpu().numpy() - dw_ref).max() <= 1e-4 * np.abs(dw_ref).max() + 1e-4
 
 
+@pytest.mark.parametrize("B,T,Cin,Cout,K,dil", [
+    (2, 300, 256, 256, 11, 1),
+    (3, 752, 256, 384, 13, 1),   # odd number of (tap, C_in tile) row blocks: the pair wgrad pads one
+    (2, 1000, 768, 896, 29, 2),  # largest halo tile (128 + 56 rows), ragged last N tile
+    (1, 129, 128, 256, 3, 1),    # second CTA of the pair owns a single valid row
+    (2, 260, 896, 1024, 1, 1),
+])
+def test_conv_kernel_variants_agree(B, T, Cin, Cout, K, dil):
+    """single-CTA tiles, CTA pairs (cta_group::2) and pairs with a shared halo tile are the same
+    arithmetic in the same accumulation order: forward / data-gradient outputs must be bitwise equal
+    (weight gradients differ only by the order of the stream-K fp32 reductions)."""
+    L, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(B, T, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(K, Cin, Cout, device="cuda", generator=g) / (K * Cin) ** 0.5).bfloat16()
+    dy = torch.randn(B, T, Cout, device="cuda", generator=g).bfloat16()
+    pl = ((K - 1) * dil) // 2
+    st = L.stream_ptr()
+    outs = {}
+    try:
+        for name, (pm, hm) in {"single": (0, 0), "pair": (2, 0), "halo": (2, 1)}.items():
+            assert lib.os2s_conv_tuning(pm, hm) == 0
+            y = torch.full((B, T, Cout), float("nan"), dtype=torch.float16, device="cuda")
+            stats = torch.zeros(2, Cout, device="cuda")
+            L.check(lib.os2s_conv1d_fwd(L.ptr(x), L.ptr(w), L.ptr(y), B, T, Cin, Cout, K, dil, pl, 3, L.ptr(stats), st), name)
+            dx = torch.full((B, T, Cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+            L.check(lib.os2s_conv1d_dgrad(L.ptr(dy), L.ptr(w), L.ptr(dx), B, T, Cin, Cout, K, dil, pl, 0, st), name)
+            acc = torch.ones(B, T, Cin, device="cuda")
+            L.check(lib.os2s_conv1d_dgrad(L.ptr(dy), L.ptr(w), L.ptr(acc), B, T, Cin, Cout, K, dil, pl, 2, st), name)
+            dw = torch.full((K, Cin, Cout), float("nan"), device="cuda")
+            L.check(lib.os2s_conv1d_wgrad(L.ptr(x), L.ptr(dy), L.ptr(dw), B, T, Cin, Cout, K, dil, pl, st), name)
+            torch.cuda.synchronize()
+            outs[name] = (y, stats, dx, acc, dw)
+    finally:
+        lib.os2s_conv_tuning(1, 1)
+    ref = outs["single"]
+    assert not torch.isnan(ref[0].float()).any() and not torch.isnan(ref[4]).any()
+    for name in ("pair", "halo"):
+        y, stats, dx, acc, dw = outs[name]
+        assert torch.equal(y.view(torch.int16), ref[0].view(torch.int16)), name
+        assert torch.equal(dx.view(torch.int16), ref[2].view(torch.int16)), name
+        assert torch.equal(acc, ref[3]), name
+        assert torch.allclose(stats, ref[1], rtol=1e-5, atol=1e-3), name
+        assert (dw - ref[4]).abs().max() <= 1e-5 * ref[4].abs().max(), name
+    assert lib.os2s_conv_tuning(3, 0) != 0
+
+
 def test_conv_rejects_unsupported_shapes_loudly():
     L, lib = _lib()
     x = torch.zeros(1, 16, 48, dtype=torch.bfloat16, device="cuda")

@@ -18,6 +18,11 @@ SHAPES = [
     (4, 752, 896, 1024, 1, 1),
     (1, 129, 128, 256, 3, 1),
 ]
+MODES = {
+    "single": {"OS2S_CONV_PAIR": "0", "OS2S_CONV_HALO": "0"},
+    "pair": {"OS2S_CONV_PAIR": "2", "OS2S_CONV_HALO": "0"},
+    "halo": {"OS2S_CONV_PAIR": "2", "OS2S_CONV_HALO": "1"},
+}
 PERF = [
     (32, 752, 256, 256, 11, 1),
     (32, 752, 384, 384, 13, 1),
@@ -77,7 +82,8 @@ def child_perf():
         stats = torch.zeros(2, Cout, device="cuda")
         dw = torch.empty(K, Cin, Cout, device="cuda")
         flops = 2.0 * B * T * K * Cin * Cout
-        res = {"pair": os.environ.get("OS2S_CONV_PAIR", "0"), "shape": [Cin, Cout, K]}
+        res = {"pair": os.environ.get("OS2S_CONV_PAIR", "0"), "halo": os.environ.get("OS2S_CONV_HALO", "0"),
+               "shape": [Cin, Cout, K]}
         for name, fn in (
             ("fwd", lambda: lib.os2s_conv1d_fwd(L.ptr(x), L.ptr(w), L.ptr(y), B, T, Cin, Cout, K, dil, padl, 3, L.ptr(stats), st)),
             ("dgrad", lambda: lib.os2s_conv1d_dgrad(L.ptr(dy), L.ptr(w), L.ptr(dx), B, T, Cin, Cout, K, dil, padl, 0, st)),
@@ -105,8 +111,8 @@ def main():
         return child_perf()
     import torch
     ok = True
-    for mode in ("0", "1"):
-        env = dict(os.environ, OS2S_CONV_PAIR=("2" if mode == "1" else "0"))
+    for mode in MODES:
+        env = dict(os.environ, **MODES[mode])
         t0 = time.time()
         try:
             r = subprocess.run([sys.executable, __file__, "out", "/tmp/pair_%s.pt" % mode], env=env, timeout=240,
@@ -120,25 +126,28 @@ def main():
         print(json.dumps({"mode": mode, "secs": round(time.time() - t0, 1)}), flush=True)
     if not ok:
         return 1
-    a, b = torch.load("/tmp/pair_0.pt"), torch.load("/tmp/pair_1.pt")
+    a = torch.load("/tmp/pair_single.pt")
     allsame = True
-    for k in sorted(a):
-        if k.startswith("s") or k.startswith("w"):
-            rel = ((a[k] - b[k]).abs().max() / a[k].abs().max()).item()
-            same = rel < 1e-5 and not bool(torch.isnan(b[k]).any())
-            print(json.dumps({"tensor": k, "max_rel": rel, "ok": same}))
-        else:
-            same = torch.equal(a[k].view(torch.int16) if a[k].element_size() == 2 else a[k].view(torch.int32),
-                               b[k].view(torch.int16) if b[k].element_size() == 2 else b[k].view(torch.int32))
-            nbad = 0 if same else int((a[k].float() != b[k].float()).sum())
-            print(json.dumps({"tensor": k, "bitwise_equal": same, "mismatches": nbad,
-                              "nan": bool(torch.isnan(b[k].float()).any())}))
-        allsame &= same
+    for mode in list(MODES)[1:]:
+        b = torch.load("/tmp/pair_%s.pt" % mode)
+        print(json.dumps({"comparing": mode}))
+        for k in sorted(a):
+            if k.startswith("s") or k.startswith("w"):
+                rel = ((a[k] - b[k]).abs().max() / a[k].abs().max()).item()
+                same = rel < 1e-5 and not bool(torch.isnan(b[k]).any())
+                print(json.dumps({"tensor": k, "max_rel": rel, "ok": same}))
+            else:
+                same = torch.equal(a[k].view(torch.int16) if a[k].element_size() == 2 else a[k].view(torch.int32),
+                                   b[k].view(torch.int16) if b[k].element_size() == 2 else b[k].view(torch.int32))
+                nbad = 0 if same else int((a[k].float() != b[k].float()).sum())
+                print(json.dumps({"tensor": k, "bitwise_equal": same, "mismatches": nbad,
+                                  "nan": bool(torch.isnan(b[k].float()).any())}))
+            allsame &= same
     print(json.dumps({"pair_matches_single": allsame}), flush=True)
     if not allsame:
         return 1
-    for mode in ("0", "1"):
-        env = dict(os.environ, OS2S_CONV_PAIR=("2" if mode == "1" else "0"))
+    for mode in MODES:
+        env = dict(os.environ, **MODES[mode])
         try:
             r = subprocess.run([sys.executable, __file__, "perf"], env=env, timeout=300, capture_output=True, text=True)
             sys.stdout.write(r.stdout)
