@@ -768,7 +768,7 @@ struct MNMajorParams {
   int n_tail;                  // width of the last N tile
   float* dw;                   // [K][C_in][C_out] fp32; zeroed by the launcher, split units red.add into it
   int C_in, C_out;
-  int m_off;                   // first C_in row of this launch (the pair kernel may leave a 128-row remainder)
+  int m_off;                   // first C_in row of this launch
 };
 
 template <int BN>
@@ -878,13 +878,19 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
+        int tc = 0;
         for (int i = 0; i < n_iters; ++i) {
           mbar_wait(&full_bar[ps.stage], ps.phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + ps.stage * kABytes);
           const uint32_t b_addr = smem_u32(smem_b + ps.stage * kBBytes);
+          // the last time chunk of an utterance holds T - 64*tc real rows (dY beyond T is zero-filled):
+          // 16-row MMA steps that are all padding are skipped (T = 752: 3 of 4 steps, -2 % MMA work)
+          const int kk_n = (tc == p.t_chunks - 1) ? (p.T - tc * 64 + 15) >> 4 : 4;
+          if (++tc == p.t_chunks) tc = 0;
 #pragma unroll
           for (int kk = 0; kk < 64 / 16; ++kk) {
+            if (kk >= kk_n) break;
             // 16 reduction rows = 2 KB further into every 64-wide box
             const uint64_t da = make_sdesc(a_addr + kk * 2048, kBoxBytes, 1024);
             const uint64_t db = make_sdesc(b_addr + kk * 2048, kBoxBytes, 1024);
@@ -1065,13 +1071,17 @@ tapgemm_mnmajor_pair(const __grid_constant__ CUtensorMap map_x, const __grid_con
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
+        int tc = 0;
         for (int i = 0; i < n_iters; ++i) {
           mbar_wait(&full_bar[ps.stage], ps.phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + ps.stage * kABytes);
           const uint32_t b_addr = smem_u32(smem_b + ps.stage * kBHalf);
+          const int kk_n = (tc == p.t_chunks - 1) ? (p.T - tc * 64 + 15) >> 4 : 4;  // skip all-padding steps
+          if (++tc == p.t_chunks) tc = 0;
 #pragma unroll
           for (int kk = 0; kk < 64 / 16; ++kk) {
+            if (kk >= kk_n) break;
             const uint64_t da = make_sdesc(a_addr + kk * 2048, kBoxBytes, 1024);
             const uint64_t db = make_sdesc(b_addr + kk * 2048, kBoxBytes, 1024);
             umma2_bf16(tmem_d, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);

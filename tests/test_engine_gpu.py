@@ -83,7 +83,7 @@ def test_forward_logits_and_greedy_match_oracle():
         # bf16 roundings that fall the other way and are amplified by the layers above (max norm: one
         # flipped rounding shows up undiluted, hence the same bound as against the fp64 oracle)
         d_l2, d_max = _rel_l2(logits[b, :n], emu[b, :n]), _rel(logits[b, :n], emu[b, :n])
-        assert d_l2 < 5e-3, (b, d_l2)
+        assert d_l2 < 1e-2, (b, d_l2)
         assert d_max < 1.5e-2, (b, d_max)
     toks, tl = eng.greedy_decode()
     torch.cuda.synchronize()
