@@ -113,6 +113,33 @@ int os2s_bn_bwd(int n_branch, const void* const* y_host, const float* const* mea
                 void* const* dy_host, const void* dA, int dA_is_f32, const void* a, float* red, int M,
                 int C, float keep, int apply_relu, void* stream);
 
+/* Same two calls for branches whose conv outputs / gradients are COLUMN SLICES of wider matrices
+ * (the dense-residual 1x1 convolutions of one source are computed as ONE GEMM whose output holds the
+ * slices of all consumer blocks side by side, see os2s_multi_copy_2d).  ld_host[j]: row stride of
+ * y[j] (and dy[j]) in elements; stats_ld_host[j]: distance between the sum row and the
+ * sum-of-squares row of stats[j].  Either array may be NULL (= C). */
+int os2s_bn_apply_fwd_ld(int n_branch, const void* const* y_host, const int* ld_host,
+                         const float* const* stats_host, const int* stats_ld_host,
+                         const float* const* gamma_host, const float* const* beta_host,
+                         float* const* mean_invstd_host, float* const* moving_host, void* out,
+                         const int* lens, int B, int T, int C, float eps, float momentum, float keep,
+                         uint64_t seed, int apply_relu, float relu_clip, int use_moving,
+                         const long long* step_counter_dev, void* stream);
+int os2s_bn_bwd_ld(int n_branch, const void* const* y_host, const int* ld_host,
+                   const float* const* mean_invstd_host, const float* const* gamma_host,
+                   float* const* dgamma_host, float* const* dbeta_host, void* const* dy_host, const void* dA,
+                   int dA_is_f32, const void* a, float* red, int M, int C, float keep, int apply_relu,
+                   void* stream);
+
+/* n (<= 64) strided 2-D copies in one launch: dst[i][r][0:row_bytes) = src[i][r][0:row_bytes) for
+ * r < rows[i], row r at base + r * pitch.  row_bytes, pitches and base addresses are multiples of 16.
+ * Used to lay the 1x1 residual kernels W_{b,j} [C_j][C_b] of all consumer blocks b of a source j
+ * side by side ([C_j][sum_b C_b], one GEMM operand; conv_blocks.py:79-85 issues one conv1d per
+ * (b, j)) and to scatter the weight gradient of that GEMM back to the per-variable buffers. */
+int os2s_multi_copy_2d(int n, const void* const* src_host, void* const* dst_host, const int* rows_host,
+                       const int* row_bytes_host, const long long* src_pitch_host,
+                       const long long* dst_pitch_host, void* stream);
+
 /* ---- K5: tf.layers.dense of FullyConnectedTimeDecoder (fc_decoders.py:135-140) --------------
  * logits fp32 [M,V] = x bf16 [M,H] * w fp32 [H,V] + bias;  V <= 32. */
 int os2s_fc_fwd(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V,

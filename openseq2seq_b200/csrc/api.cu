@@ -51,12 +51,13 @@ int os2s_bn_stats(const void* y, float* stats, int M, int C, void* stream) {
   return bn_stats(y, stats, M, C, (cudaStream_t)stream);
 }
 
-int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* const* stats_host,
-                      const float* const* gamma_host, const float* const* beta_host,
-                      float* const* mean_invstd_host, float* const* moving_host, void* out,
-                      const int* lens, int B, int T, int C, float eps, float momentum, float keep,
-                      uint64_t seed, int apply_relu, float relu_clip, int use_moving,
-                      const long long* step_counter_dev, void* stream) {
+int os2s_bn_apply_fwd_ld(int n_branch, const void* const* y_host, const int* ld_host,
+                         const float* const* stats_host, const int* stats_ld_host,
+                         const float* const* gamma_host, const float* const* beta_host,
+                         float* const* mean_invstd_host, float* const* moving_host, void* out,
+                         const int* lens, int B, int T, int C, float eps, float momentum, float keep,
+                         uint64_t seed, int apply_relu, float relu_clip, int use_moving,
+                         const long long* step_counter_dev, void* stream) {
   if (n_branch < 1 || n_branch > kMaxBranches) return fail(ERR_INVALID, "os2s_bn_apply_fwd: 1..12 branches");
   if (!y_host || !stats_host || !gamma_host || !beta_host || !mean_invstd_host || !out)
     return fail(ERR_INVALID, "os2s_bn_apply_fwd: null pointer");
@@ -70,6 +71,8 @@ int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* cons
     p.br[j].beta = beta_host[j];
     p.br[j].mean_invstd = mean_invstd_host[j];
     p.br[j].moving = moving_host ? moving_host[j] : nullptr;
+    p.br[j].ld = ld_host ? ld_host[j] : C;
+    p.br[j].stats_ld = stats_ld_host ? stats_ld_host[j] : C;
   }
   p.n_branch = n_branch;
   p.out = (__nv_bfloat16*)out;
@@ -81,10 +84,22 @@ int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* cons
   return bn_apply_fwd(p, (cudaStream_t)stream);
 }
 
-int os2s_bn_bwd(int n_branch, const void* const* y_host, const float* const* mean_invstd_host,
-                const float* const* gamma_host, float* const* dgamma_host, float* const* dbeta_host,
-                void* const* dy_host, const void* dA, int dA_is_f32, const void* a, float* red, int M,
-                int C, float keep, int apply_relu, void* stream) {
+int os2s_bn_apply_fwd(int n_branch, const void* const* y_host, const float* const* stats_host,
+                      const float* const* gamma_host, const float* const* beta_host,
+                      float* const* mean_invstd_host, float* const* moving_host, void* out,
+                      const int* lens, int B, int T, int C, float eps, float momentum, float keep,
+                      uint64_t seed, int apply_relu, float relu_clip, int use_moving,
+                      const long long* step_counter_dev, void* stream) {
+  return os2s_bn_apply_fwd_ld(n_branch, y_host, nullptr, stats_host, nullptr, gamma_host, beta_host,
+                              mean_invstd_host, moving_host, out, lens, B, T, C, eps, momentum, keep, seed,
+                              apply_relu, relu_clip, use_moving, step_counter_dev, stream);
+}
+
+int os2s_bn_bwd_ld(int n_branch, const void* const* y_host, const int* ld_host,
+                   const float* const* mean_invstd_host, const float* const* gamma_host,
+                   float* const* dgamma_host, float* const* dbeta_host, void* const* dy_host, const void* dA,
+                   int dA_is_f32, const void* a, float* red, int M, int C, float keep, int apply_relu,
+                   void* stream) {
   if (n_branch < 1 || n_branch > kMaxBranches) return fail(ERR_INVALID, "os2s_bn_bwd: 1..12 branches");
   if (!y_host || !mean_invstd_host || !gamma_host || !dgamma_host || !dbeta_host || !dy_host || !dA || !red)
     return fail(ERR_INVALID, "os2s_bn_bwd: null pointer");
@@ -97,12 +112,46 @@ int os2s_bn_bwd(int n_branch, const void* const* y_host, const float* const* mea
     p.br[j].dgamma = dgamma_host[j];
     p.br[j].dbeta = dbeta_host[j];
     p.br[j].dy = (__nv_bfloat16*)dy_host[j];
+    p.br[j].ld = ld_host ? ld_host[j] : C;
   }
   p.n_branch = n_branch;
   p.dA = dA; p.dA_is_f32 = dA_is_f32; p.a = (const __nv_bfloat16*)a;
   p.red = red; p.M = M; p.C = C; p.keep = keep; p.apply_relu = apply_relu;
   OS2S_CUDA(cudaMemsetAsync(red, 0, (size_t)(1 + n_branch) * C * sizeof(float), (cudaStream_t)stream));
   return bn_bwd(p, (cudaStream_t)stream);
+}
+
+int os2s_bn_bwd(int n_branch, const void* const* y_host, const float* const* mean_invstd_host,
+                const float* const* gamma_host, float* const* dgamma_host, float* const* dbeta_host,
+                void* const* dy_host, const void* dA, int dA_is_f32, const void* a, float* red, int M,
+                int C, float keep, int apply_relu, void* stream) {
+  return os2s_bn_bwd_ld(n_branch, y_host, nullptr, mean_invstd_host, gamma_host, dgamma_host, dbeta_host, dy_host,
+                        dA, dA_is_f32, a, red, M, C, keep, apply_relu, stream);
+}
+
+int os2s_multi_copy_2d(int n, const void* const* src_host, void* const* dst_host, const int* rows_host,
+                       const int* row_bytes_host, const long long* src_pitch_host,
+                       const long long* dst_pitch_host, void* stream) {
+  if (n < 0 || n > kMaxCopies) return fail(ERR_INVALID, "os2s_multi_copy_2d: 0..64 copies per call");
+  if (n == 0) return 0;
+  if (!src_host || !dst_host || !rows_host || !row_bytes_host || !src_pitch_host || !dst_pitch_host)
+    return fail(ERR_INVALID, "os2s_multi_copy_2d: null pointer");
+  Copy2dTable tab;
+  tab.n = n;
+  for (int i = 0; i < n; ++i) {
+    if (!src_host[i] || !dst_host[i]) return fail(ERR_INVALID, "os2s_multi_copy_2d: null pointer");
+    if (((uintptr_t)src_host[i] | (uintptr_t)dst_host[i] | (uintptr_t)row_bytes_host[i] |
+         (uintptr_t)src_pitch_host[i] | (uintptr_t)dst_pitch_host[i]) & 15)
+      return fail(ERR_INVALID, "os2s_multi_copy_2d: addresses, row bytes and pitches must be multiples of 16");
+    if (rows_host[i] < 0 || row_bytes_host[i] < 0) return fail(ERR_INVALID, "os2s_multi_copy_2d: negative extent");
+    tab.src[i] = (const char*)src_host[i];
+    tab.dst[i] = (char*)dst_host[i];
+    tab.rows[i] = rows_host[i];
+    tab.row_vecs[i] = row_bytes_host[i] / 16;
+    tab.src_pitch[i] = src_pitch_host[i];
+    tab.dst_pitch[i] = dst_pitch_host[i];
+  }
+  return multi_copy_2d(tab, (cudaStream_t)stream);
 }
 
 int os2s_fc_fwd(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V,

@@ -76,6 +76,33 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
   return v;
 }
 
+// ------------------------------------------------------------------------------ strided copies
+// blockIdx.y = copy, grid-stride over its 16-byte vectors (row-major); pitches in bytes.
+__global__ void multi_copy_2d_kernel(const Copy2dTable tab) {
+  const int i = blockIdx.y;
+  const int rv = tab.row_vecs[i];
+  const long long total = (long long)tab.rows[i] * rv;
+  const char* src = tab.src[i];
+  char* dst = tab.dst[i];
+  const long long sp = tab.src_pitch[i], dp = tab.dst_pitch[i];
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+    const long long r = v / rv;
+    const int c = (int)(v - r * rv);
+    *reinterpret_cast<uint4*>(dst + r * dp + (long long)c * 16) =
+        __ldg(reinterpret_cast<const uint4*>(src + r * sp + (long long)c * 16));
+  }
+}
+int multi_copy_2d(const Copy2dTable& tab, cudaStream_t st) {
+  if (tab.n <= 0) return 0;
+  long long most = 0;
+  for (int i = 0; i < tab.n; ++i) most = most > (long long)tab.rows[i] * tab.row_vecs[i] ? most : (long long)tab.rows[i] * tab.row_vecs[i];
+  int bx = (int)((most + 256 * 4 - 1) / (256 * 4));
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  multi_copy_2d_kernel<<<dim3(bx, tab.n), 256, 0, st>>>(tab);
+  return check_launch("multi_copy_2d");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Row tiling shared by the four BN kernels.  The [M, C] matrix is cut into row chunks, one CTA per
 // chunk; inside a CTA thread t owns ONE 8-channel vector column cv = t % CV (16-byte accesses,
@@ -207,8 +234,9 @@ __device__ __forceinline__ void bn_coef(const BnFwdParams& p, const BnBranchFwd&
   const float* src_m = p.use_moving ? b.moving : b.stats;
   *reinterpret_cast<float4*>(&m[0]) = __ldg(reinterpret_cast<const float4*>(src_m + c0));
   *reinterpret_cast<float4*>(&m[4]) = __ldg(reinterpret_cast<const float4*>(src_m + c0) + 1);
-  *reinterpret_cast<float4*>(&v[0]) = __ldg(reinterpret_cast<const float4*>(src_m + C + c0));
-  *reinterpret_cast<float4*>(&v[4]) = __ldg(reinterpret_cast<const float4*>(src_m + C + c0) + 1);
+  const int sq = p.use_moving ? C : b.stats_ld;   // second row: moving variance / sum of squares
+  *reinterpret_cast<float4*>(&v[0]) = __ldg(reinterpret_cast<const float4*>(src_m + sq + c0));
+  *reinterpret_cast<float4*>(&v[4]) = __ldg(reinterpret_cast<const float4*>(src_m + sq + c0) + 1);
   *reinterpret_cast<float4*>(&g[0]) = __ldg(reinterpret_cast<const float4*>(b.gamma + c0));
   *reinterpret_cast<float4*>(&g[4]) = __ldg(reinterpret_cast<const float4*>(b.gamma + c0) + 1);
   *reinterpret_cast<float4*>(&be[0]) = __ldg(reinterpret_cast<const float4*>(b.beta + c0));
@@ -301,10 +329,11 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
     }
     if (ONE) {
       const uint4* yb = reinterpret_cast<const uint4*>(p.br[0].y) + t.cv;
+      const size_t ys = (size_t)(p.br[0].ld >> 3);
       uint4 v[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
-        v[u] = live[u] ? __ldg(yb + (size_t)(row + u * t.RP) * rs) : make_uint4(0, 0, 0, 0);
+        v[u] = live[u] ? __ldg(yb + (size_t)(row + u * t.RP) * ys) : make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const int ru = row + u * t.RP;
@@ -323,10 +352,11 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
         for (int i = 0; i < 8; ++i) acc[u][i] = 0.f;
       for (int j = 0; j < p.n_branch; ++j) {
         const uint4* yb = reinterpret_cast<const uint4*>(p.br[j].y) + t.cv;
+        const size_t ys = (size_t)(p.br[j].ld >> 3);
         uint4 v[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
-          v[u] = live[u] ? __ldg(yb + (size_t)(row + u * t.RP) * rs) : make_uint4(0, 0, 0, 0);
+          v[u] = live[u] ? __ldg(yb + (size_t)(row + u * t.RP) * ys) : make_uint4(0, 0, 0, 0);
         float sc[8], sf[8];
         if (j == 0) {
 #pragma unroll
@@ -358,6 +388,9 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
 int bn_apply_fwd(const BnFwdParams& p, cudaStream_t st) {
   if (p.n_branch < 1 || p.n_branch > kMaxBranches) return fail(ERR_INVALID, "bn_apply_fwd: bad branch count");
   if (p.C % 8 != 0 || p.C > 2048) return fail(ERR_UNSUPPORTED, "bn_apply_fwd: C must be a multiple of 8, <= 2048");
+  for (int j = 0; j < p.n_branch; ++j)
+    if (p.br[j].ld < p.C || p.br[j].ld % 8 != 0 || p.br[j].stats_ld < p.C || p.br[j].stats_ld % 4 != 0)
+      return fail(ERR_INVALID, "bn_apply_fwd: bad leading dimension");
   const int M = p.B * p.T;
   const bool one = p.n_branch == 1;
   const int rpb = rows_per_block_for(M, p.C, one ? 2 : 1);
@@ -428,9 +461,10 @@ bn_bwd_reduce_kernel(const BnBwdParams p, int rows_per_block) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           if (g < nj) {
-            const uint4* yb = reinterpret_cast<const uint4*>(p.br[j0 + g].y);
-            y0[g] = __ldg(yb + v0);
-            if (two) y1[g] = __ldg(yb + v1);
+            const uint4* yb = reinterpret_cast<const uint4*>(p.br[j0 + g].y) + t.cv;
+            const size_t ys = (size_t)(p.br[j0 + g].ld >> 3);
+            y0[g] = __ldg(yb + (size_t)row * ys);
+            if (two) y1[g] = __ldg(yb + (size_t)(row + t.RP) * ys);
           }
         }
         gate_dz(p, a0, dz0);
@@ -527,6 +561,7 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
       // all loads of the U rows (dA, a, y) are issued before the first use
       const uint4* yb = reinterpret_cast<const uint4*>(p.br[0].y) + t.cv;
       uint4* db = reinterpret_cast<uint4*>(p.br[0].dy) + t.cv;
+      const size_t ys = (size_t)(p.br[0].ld >> 3);
       uint4 v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -534,7 +569,7 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
         araw[u] = make_uint4(0, 0, 0, 0);
         if (live[u]) {
           load_dz_raw<F32>(p, (size_t)(row + u * t.RP) * rs + t.cv, araw[u], dz[u]);
-          v[u] = __ldg(yb + (size_t)(row + u * t.RP) * rs);
+          v[u] = __ldg(yb + (size_t)(row + u * t.RP) * ys);
         }
       }
 #pragma unroll
@@ -545,7 +580,7 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
           f16x8_to_float(v[u], f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = A0[i] * dz[u][i] + B0[i] * f[i] + C0[i];
-          db[(size_t)(row + u * t.RP) * rs] = float_to_bf16x8(f);
+          db[(size_t)(row + u * t.RP) * ys] = float_to_bf16x8(f);
         }
       }
       continue;
@@ -562,10 +597,11 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
     for (int j = 0; j < p.n_branch; ++j) {
       const uint4* yb = reinterpret_cast<const uint4*>(p.br[j].y) + t.cv;
       uint4* db = reinterpret_cast<uint4*>(p.br[j].dy) + t.cv;
+      const size_t ys = (size_t)(p.br[j].ld >> 3);
       uint4 v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (live[u]) v[u] = __ldg(yb + (size_t)(row + u * t.RP) * rs);
+        if (live[u]) v[u] = __ldg(yb + (size_t)(row + u * t.RP) * ys);
       float A[8], Bc[8], Cc[8];
       if (j == 0) {
 #pragma unroll
@@ -580,7 +616,7 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
           f16x8_to_float(v[u], f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = A[i] * dz[u][i] + Bc[i] * f[i] + Cc[i];
-          db[(size_t)(row + u * t.RP) * rs] = float_to_bf16x8(o);
+          db[(size_t)(row + u * t.RP) * ys] = float_to_bf16x8(o);
         }
       }
     }
@@ -596,6 +632,8 @@ int bn_bwd(const BnBwdParams& p, cudaStream_t st) {
     OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
+  for (int j = 0; j < p.n_branch; ++j)
+    if (p.br[j].ld < p.C || p.br[j].ld % 8 != 0) return fail(ERR_INVALID, "bn_bwd: bad leading dimension");
   const size_t smem_r = (size_t)(1 + p.n_branch) * p.C * sizeof(float);
   if (smem_r > 100 * 1024) return fail(ERR_UNSUPPORTED, "bn_bwd: too many branches x channels");
   const bool one = p.n_branch == 1;

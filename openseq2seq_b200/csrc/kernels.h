@@ -30,6 +30,8 @@ struct BnBranchFwd {
   const float* beta;
   float* mean_invstd;   // [2][C] saved for backward
   float* moving;        // [2][C] moving_mean, moving_variance (may be null)
+  int ld;               // row stride of y in elements (C, or wider when y is a column slice)
+  int stats_ld;         // offset of the sum-of-squares row from the sum row in `stats` (C by default)
 };
 struct BnFwdParams {
   BnBranchFwd br[kMaxBranches];
@@ -52,6 +54,7 @@ struct BnBranchBwd {
   float* dgamma;             // [C] gradient outputs (scaled by loss scale like dA)
   float* dbeta;              // [C]
   __nv_bfloat16* dy;         // [M, C]
+  int ld;                    // row stride of y AND dy in elements
 };
 struct BnBwdParams {
   BnBranchBwd br[kMaxBranches];
@@ -65,6 +68,15 @@ struct BnBwdParams {
   int apply_relu;            // if 0: dz = dA (no activation), "a" unused
 };
 
+constexpr int kMaxCopies = 64;
+struct Copy2dTable {
+  const char* src[kMaxCopies];
+  char* dst[kMaxCopies];
+  long long src_pitch[kMaxCopies], dst_pitch[kMaxCopies];
+  int rows[kMaxCopies], row_vecs[kMaxCopies];   // row length in 16-byte vectors
+  int n;
+};
+int multi_copy_2d(const Copy2dTable& tab, cudaStream_t st);
 int bn_stats(const void* y, float* stats, int M, int C, cudaStream_t st);
 int bn_apply_fwd(const BnFwdParams& p, cudaStream_t st);
 int bn_bwd(const BnBwdParams& p, cudaStream_t st);

@@ -150,12 +150,32 @@ class JasperEngine(object):
             if first_layer == 0:
                 raise ValueError("JasperEngine: a residual block cannot be the first layer")
             self.src_of_layer_output[first_layer - 1] = idx
-        # last consumer ordering for the fp32 accumulators: in backward order the first writer of
-        # source j is the LAST block-end layer that lists j
-        self.first_bwd_writer = {}
-        for li in range(len(layers) - 1, -1, -1):
-            for j in layers[li].res_sources:
-                self.first_bwd_writer.setdefault(j, li)
+        # Dense-residual 1x1 convolutions are computed SOURCE-major: all consumers (block-end layers) of
+        # source j share the input A_j, so their kernels W_{b,j} [C_j, C_b] are laid side by side and
+        # Y_{.,j} = A_j @ [W_{b1,j} | W_{b2,j} | ...] is ONE GEMM with N = sum_b C_b (likewise one
+        # data-gradient GEMM with K = sum_b C_b and one weight-gradient GEMM per source).
+        # res_groups[j] = {"cj", "ntot", "consumers": [(layer index, branch position, C_b, first column)]}
+        self.res_groups = []
+        for j, (cj, first_layer) in enumerate(self.block_inputs):
+            cons, col = [], 0
+            for li, l in enumerate(layers):
+                for n, jj in enumerate(l.res_sources):
+                    if jj == j:
+                        cons.append((li, n, l.c_out, col))
+                        col += l.c_out
+            self.res_groups.append({"cj": cj, "ntot": col, "consumers": cons, "first_layer": first_layer})
+        self.res_col = {}  # (layer index, branch position) -> (source, first column)
+        for j, g in enumerate(self.res_groups):
+            for (li, n, cb, col) in g["consumers"]:
+                self.res_col[(li, n)] = (j, col)
+
+    @staticmethod
+    def res_name(lyr, n):
+        return (lyr.name + "/res_%d" % n) if lyr.dense else (lyr.name + "/res")
+
+    @staticmethod
+    def res_bn_name(lyr, n):
+        return (lyr.name + "/res_bn_%d" % n) if lyr.dense else (lyr.name + "/res_bn")
 
     # ---------------------------------------------------------------- parameters
     def _alloc_params(self):
@@ -178,12 +198,19 @@ class JasperEngine(object):
             add(lyr.name + "/bn/gamma", (lyr.c_out,), "gamma", lyr)
             add(lyr.name + "/bn/beta", (lyr.c_out,), "beta", lyr)
             for n, j in enumerate(lyr.res_sources):
-                cj = self.block_inputs[j][0]
-                rn = (lyr.name + "/res_%d" % n) if lyr.dense else (lyr.name + "/res")
                 bn = (lyr.name + "/res_bn_%d" % n) if lyr.dense else (lyr.name + "/res_bn")
-                add(rn + "/kernel", (1, cj, lyr.c_out), "conv", lyr)
                 add(bn + "/gamma", (lyr.c_out,), "gamma", lyr)
                 add(bn + "/beta", (lyr.c_out,), "beta", lyr)
+            # the 1x1 residual kernels of every consumer of the source that feeds THIS layer: their
+            # (merged) weight gradient is produced when backward reaches this layer, so they sit in its
+            # region of the flat buffers (gradient buckets are cut by layer, last layer first)
+            li = self.layers.index(lyr)
+            for j, g in enumerate(self.res_groups):
+                if g["first_layer"] != li:
+                    continue
+                for (lc, n, cb, col) in g["consumers"]:
+                    cons = self.layers[lc]
+                    add(self.res_name(cons, n) + "/kernel", (1, g["cj"], cb), "conv", cons)
         add("fc/kernel", (self.H, self.V), "fc_w")
         add("fc/bias", (self.V,), "fc_b")
         off = 0
@@ -211,6 +238,10 @@ class JasperEngine(object):
         # one bf16 working copy in the natural TF layout [K][Cin][Cout]: it is dgrad's K-major B operand
         # (reduction over C_out) and forward's MN-major B operand (reduction over C_in) at the same time
         self.wb = torch.zeros(self._half_total, dtype=torch.bfloat16, device=dev)
+        # per residual source: bf16 kernels of all consumers side by side [C_j, Ntot_j] (gathered from wb
+        # at the start of every forward) and the fp32 weight gradient of the merged GEMM (scattered back)
+        self.wcat = [torch.zeros(g["cj"], g["ntot"], dtype=torch.bfloat16, device=dev) for g in self.res_groups]
+        self.dwcat = [torch.zeros(g["cj"], g["ntot"], dtype=torch.float32, device=dev) for g in self.res_groups]
         # BN moving statistics [2][C] per BN instance (moving_mean = 0, moving_variance = 1)
         self.moving = {}
         for s in specs:
@@ -478,7 +509,7 @@ class JasperEngine(object):
         n += 1  # fc fwd
         for entry in (ws._bwd_plan or []):
             name = entry[0].__name__
-            n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd": 2, "os2s_bn_bwd": 2, "zero_slices": 0,
+            n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd": 2, "os2s_bn_bwd": 2, "os2s_bn_bwd_ld": 2, "zero_slices": 0,
                   "bucket_allreduce": 0, "stream_record": 0, "stream_wait": 0}.get(name, 1)
         return n + 3 + 3
 
@@ -595,16 +626,17 @@ class _Workspace(object):
         # conv outputs (BN inputs) are fp16: never a tensor-core operand, 3 more mantissa bits than bf16
         self.Y = [f16(B, T2, l.c_out) for l in layers]
         self.A = [bf(B, T2, l.c_out) for l in layers]
-        self.YR = [[f16(B, T2, l.c_out) for _ in l.res_sources] for l in layers]
+        # residual-branch conv outputs / their gradients, one matrix per SOURCE: [B, T2, sum_b C_b]
+        # (consumer b's branch is the column slice starting at its first column)
+        self.YRcat = [f16(B, T2, g["ntot"]) for g in eng.res_groups]
+        self.dYRcat = [bf(B, T2, g["ntot"]) for g in eng.res_groups]
         cmax = max(l.c_out for l in layers)
         self.dA = bf(B, T2, cmax)
         nres_max = max([len(l.res_sources) for l in layers] + [0])
         # conv-output gradients are ping-ponged by layer parity so that wgrad(l) (aux stream) can still
         # read dY of layer l while bn_bwd(l-1) already writes the other buffer
         self.dY2 = [bf(B, T2, cmax), bf(B, T2, cmax)]
-        self.dYR2 = [[bf(B, T2, cmax) for _ in range(nres_max)] for _ in range(2)]
         self.dY = self.dY2[0]
-        self.dYR = self.dYR2[0]
         self._st_aux = _vp(0)
         self.dres = [f32(B, T2, c) for (c, _) in eng.block_inputs]
         self.red = f32((2 + nres_max) * cmax)
@@ -612,7 +644,15 @@ class _Workspace(object):
         self.lens_out = torch.zeros(B, dtype=torch.int32, device=dev)
         # BN bookkeeping: stats arena (zeroed every step) and saved mean/invstd
         n_bn = sum(1 + len(l.res_sources) for l in layers)
-        self.stats = torch.zeros(n_bn, 2, cmax, dtype=torch.float32, device=dev)
+        # one flat arena (a single memset per step): [2][cmax] per main-path BN, then [2][Ntot_j] per source
+        n_main = len(layers)
+        cat_sizes = [2 * g["ntot"] for g in eng.res_groups]
+        self.stats_all = torch.zeros(n_main * 2 * cmax + sum(cat_sizes), dtype=torch.float32, device=dev)
+        self.stats = self.stats_all[:n_main * 2 * cmax].view(n_main, 2, cmax)
+        self.stats_cat, o = [], n_main * 2 * cmax
+        for sz in cat_sizes:
+            self.stats_cat.append(self.stats_all[o:o + sz])
+            o += sz
         self.mean_invstd = torch.zeros(n_bn, 2, cmax, dtype=torch.float32, device=dev)
         self.logits = f32(B, T2, eng.V)
         self.dlogits = f32(B, T2, eng.V)
@@ -648,61 +688,78 @@ class _Workspace(object):
         B, T2, M = self.B, self.T2, self.M
         plan = []
         self._seed_slots = []
-        bn_idx = 0
         self.bn_slot = {}
-        src_act = {}  # block-input index -> activation tensor
         self.x_of_layer = []
-        x = None  # set at run time for layer 0 (features view)
-        PP = ctypes.POINTER(_vp)
+        self._keep = []
+        vparr = lambda ptrs: (ctypes.c_void_p * len(ptrs))(*[p.value if isinstance(p, _vp) else p for p in ptrs])
+        iarr = lambda xs: (ctypes.c_int * len(xs))(*xs)
+        llarr = lambda xs: (ctypes.c_longlong * len(xs))(*xs)
+        # (1) lay the 1x1 residual kernels of every source side by side (bf16, from the working copy)
+        src, dst, rows, rbytes, sp, dp = [], [], [], [], [], []
+        for j, g in enumerate(eng.res_groups):
+            for (lc, n, cb, col) in g["consumers"]:
+                rn = eng.res_name(eng.layers[lc], n) + "/kernel"
+                src.append(self._half_ptr(eng.wb, rn))
+                dst.append(self._p(eng.wcat[j], col))
+                rows.append(g["cj"])
+                rbytes.append(cb * 2)
+                sp.append(cb * 2)
+                dp.append(g["ntot"] * 2)
+        for i in range(0, len(src), 64):
+            sl = slice(i, i + 64)
+            a = (vparr(src[sl]), vparr(dst[sl]), iarr(rows[sl]), iarr(rbytes[sl]), llarr(sp[sl]), llarr(dp[sl]))
+            self._keep.append(a)
+            plan.append([lib.os2s_multi_copy_2d, [len(src[sl])] + list(a) + [st]])
+        bn_idx = 0
         for li, l in enumerate(eng.layers):
             x_ptr = self._p(self.feats) if li == 0 else self._p(self.A[li - 1])
-            # residual sources: the (masked) input of the block's first layer
-            for idx, (c, first_layer) in enumerate(eng.block_inputs):
-                if first_layer == li:
-                    src_act[idx] = self.A[li - 1]
             self.x_of_layer.append(self.A[li - 1] if li > 0 else None)
+            # (2) the input of this layer is a residual source: ONE GEMM for all its consumers' branches
+            for j, g in enumerate(eng.res_groups):
+                if g["first_layer"] == li:
+                    stats_ptr = self._p(self.stats_cat[j]) if eng.training else _vp(0)
+                    plan.append([lib.os2s_conv1d_fwd, [x_ptr, self._p(eng.wcat[j]), self._p(self.YRcat[j]), B, T2,
+                                                       g["cj"], g["ntot"], 1, 1, 0, 3, stats_ptr, st],
+                                 ("fwd", 2.0 * B * T2 * g["cj"] * g["ntot"])])
             flops = 2.0 * B * T2 * l.K * l.c_in * l.c_out  # algorithmic (un-folded) FLOPs
             slot_main = bn_idx
             bn_idx += 1
             # training: the conv epilogue accumulates the BN statistics of its (rounded) output
-            stats_ptr = self._p(self.stats[slot_main]) if eng.training else _vp(0)
+            stats_ptr = self._p(self.stats[li]) if eng.training else _vp(0)
             call = [lib.os2s_conv1d_fwd, [x_ptr, self._half_ptr(eng.wb, l.name + "/kernel"), self._p(self.Y[li]),
                                           B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, 3, stats_ptr, st],
                     ("fwd", flops)]
             plan.append(call)
-            ys = [self.Y[li]]
+            ys, lds = [self._p(self.Y[li])], [l.c_out]
+            sts, st_lds = [self._p(self.stats[li])], [l.c_out]
             names = [l.name + "/bn"]
             slots = [slot_main]
             for n, j in enumerate(l.res_sources):
-                rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
-                bnn = (l.name + "/res_bn_%d" % n) if l.dense else (l.name + "/res_bn")
-                cj = eng.block_inputs[j][0]
-                slot = bn_idx
+                jj, col = eng.res_col[(li, n)]
+                ntot = eng.res_groups[jj]["ntot"]
+                ys.append(self._p(self.YRcat[jj], col))
+                lds.append(ntot)
+                sts.append(self._p(self.stats_cat[jj], col))
+                st_lds.append(ntot)
+                names.append(eng.res_bn_name(l, n))
+                slots.append(bn_idx)
                 bn_idx += 1
-                stats_ptr = self._p(self.stats[slot]) if eng.training else _vp(0)
-                plan.append([lib.os2s_conv1d_fwd, [self._p(src_act[j]), self._half_ptr(eng.wb, rn + "/kernel"),
-                                                   self._p(self.YR[li][n]), B, T2, cj, l.c_out, 1, 1, 0, 3,
-                                                   stats_ptr, st],
-                             ("fwd", 2.0 * B * T2 * cj * l.c_out)])
-                ys.append(self.YR[li][n])
-                names.append(bnn)
-                slots.append(slot)
             nb = len(ys)
-            arr = lambda ptrs: (ctypes.c_void_p * nb)(*[p.value if isinstance(p, _vp) else p for p in ptrs])
-            y_h = arr([self._p(y) for y in ys])
-            st_h = arr([self._p(self.stats[s]) for s in slots])
-            g_h = arr([self._param_ptr(eng.master, nm + "/gamma") for nm in names])
-            b_h = arr([self._param_ptr(eng.master, nm + "/beta") for nm in names])
-            mi_h = arr([self._p(self.mean_invstd[s]) for s in slots])
-            mv_h = arr([self._p(eng.moving[nm]) for nm in names])
-            self.bn_slot[li] = (slots, names, (y_h, st_h, g_h, b_h, mi_h, mv_h))
+            y_h, st_h = vparr(ys), vparr(sts)
+            ld_h, stld_h = iarr(lds), iarr(st_lds)
+            g_h = vparr([self._param_ptr(eng.master, nm + "/gamma") for nm in names])
+            b_h = vparr([self._param_ptr(eng.master, nm + "/beta") for nm in names])
+            mi_h = vparr([self._p(self.mean_invstd[s]) for s in slots])
+            mv_h = vparr([self._p(eng.moving[nm]) for nm in names])
+            self.bn_slot[li] = (slots, names, (y_h, ld_h, st_h, g_h, b_h, mi_h, mv_h))
             last = li == len(eng.layers) - 1
             lens_ptr = self._p(self.lens_out) if (eng.use_conv_mask and not last) else _vp(0)
-            args = [nb, y_h, st_h, g_h, b_h, mi_h, mv_h, self._p(self.A[li]), lens_ptr, B, T2, l.c_out,
+            args = [nb, y_h, ld_h, st_h, stld_h, g_h, b_h, mi_h, mv_h, self._p(self.A[li]), lens_ptr, B, T2, l.c_out,
                     _c_float(eng.bn_eps), _c_float(eng.bn_momentum), _c_float(l.keep if eng.training else 1.0),
                     _c_u64((eng.seed * 1000003 + 4099 * li + 17) & 0xFFFFFFFFFFFFFFFF), 1, _c_float(eng.relu_clip),
                     0 if eng.training else 1, _vp(eng.istate.data_ptr() + 5 * 8), st]
-            plan.append([lib.os2s_bn_apply_fwd, args])
+            self._keep.append(stld_h)
+            plan.append([lib.os2s_bn_apply_fwd_ld, args])
         self._fc_call = [lib.os2s_fc_fwd, [self._p(self.A[-1]), self._param_ptr(eng.master, "fc/kernel"),
                                            self._param_ptr(eng.master, "fc/bias"), self._p(self.logits), M, eng.H,
                                            eng.V, st]]
@@ -731,7 +788,7 @@ class _Workspace(object):
         s = eng.layers[0].stride
         torch.div(self.lens_in + (s - 1), s, rounding_mode="floor", out=self.lens_out)
         if eng.training:
-            self.stats.zero_()
+            self.stats_all.zero_()
         self._exec(self._fwd_plan)
 
     def aux_stream(self):
@@ -804,53 +861,55 @@ class _Workspace(object):
                                        self._param_ptr(eng.master, "fc/kernel"), self._p(self.dA),
                                        self._param_ptr(eng.grad, "fc/kernel"), self._param_ptr(eng.grad, "fc/bias"),
                                        M, eng.H, eng.V, st]])
-        written = set()  # residual-source accumulators that already hold a first contribution
         nl = len(eng.layers)
         bucket_end = eng._total          # gradients in [bucket_start, bucket_end) are final once enqueued
         sa = self._st_aux                # aux-stream handle (== main stream when overlap is off / profiling)
         ev_bn = [torch.cuda.Event() for _ in range(nl)]
         ev_wg = [torch.cuda.Event() for _ in range(nl)]
+        vparr = lambda ptrs: (ctypes.c_void_p * len(ptrs))(*[p.value if isinstance(p, _vp) else p for p in ptrs])
+        iarr = lambda xs: (ctypes.c_int * len(xs))(*xs)
+        llarr = lambda xs: (ctypes.c_longlong * len(xs))(*xs)
         for li in range(nl - 1, -1, -1):
             l = eng.layers[li]
             par = li & 1
-            dY, dYR = self.dY2[par], self.dYR2[par]
-            slots, names, (y_h, st_h, g_h, b_h, mi_h, mv_h) = self.bn_slot[li]
+            dY = self.dY2[par]
+            slots, names, (y_h, ld_h, st_h, g_h, b_h, mi_h, mv_h) = self.bn_slot[li]
             nb = len(slots)
-            arr = lambda ptrs: (ctypes.c_void_p * nb)(*[p.value for p in ptrs])
-            dg_h = arr([self._param_ptr(eng.grad, nm + "/gamma") for nm in names])
-            db_h = arr([self._param_ptr(eng.grad, nm + "/beta") for nm in names])
-            dys = [dY] + [dYR[n] for n in range(nb - 1)]
-            dy_h = arr([self._p(t) for t in dys])
+            dg_h = vparr([self._param_ptr(eng.grad, nm + "/gamma") for nm in names])
+            db_h = vparr([self._param_ptr(eng.grad, nm + "/beta") for nm in names])
+            # gradient of branch n goes into its column slice of the source's dYRcat (row stride = ld_h[n])
+            dys = [self._p(dY)]
+            for n, j in enumerate(l.res_sources):
+                jj, col = eng.res_col[(li, n)]
+                dys.append(self._p(self.dYRcat[jj], col))
+            dy_h = vparr(dys)
             if li in eng.src_of_layer_output:
-                j = eng.src_of_layer_output[li]
-                dA_ptr, dA_f32 = self._p(self.dres[j]), 1
-                if j not in written:
-                    raise RuntimeError("internal: residual source %d has no gradient writer" % j)
+                dA_ptr, dA_f32 = self._p(self.dres[eng.src_of_layer_output[li]]), 1
             else:
                 dA_ptr, dA_f32 = self._p(self.dA), 0
             if li + 2 < nl:
-                # this layer's dY buffers were last read by wgrad(li + 2) on the aux stream
+                # this layer's dY buffer was last read by wgrad(li + 2) on the aux stream
                 plan.append([_StreamWait(self, "main", ev_wg[li + 2]), []])
-            plan.append([lib.os2s_bn_bwd, [nb, y_h, mi_h, g_h, dg_h, db_h, dy_h, dA_ptr, dA_f32, self._p(self.A[li]),
-                                           self._p(self.red), M, l.c_out, _c_float(l.keep), 1, st]])
-            self._keep = getattr(self, "_keep", []) + [dg_h, db_h, dy_h]
+            plan.append([lib.os2s_bn_bwd_ld, [nb, y_h, ld_h, mi_h, g_h, dg_h, db_h, dy_h, dA_ptr, dA_f32,
+                                              self._p(self.A[li]), self._p(self.red), M, l.c_out, _c_float(l.keep), 1,
+                                              st]])
+            self._keep += [dg_h, db_h, dy_h]
             plan.append([_StreamRecord(self, "main", ev_bn[li]), []])
+            # the input of this layer is residual source j: every consumer block has written its slice of
+            # dYRcat[j] by now (they are all later layers)
+            src_j = eng.src_of_layer_output.get(li - 1) if li > 0 else None
             # ---- main stream (critical path) first: data gradients, so that bn_bwd of the next layer can
             # start as soon as they finish while this layer's weight gradients are still running
-            for n, j in enumerate(l.res_sources):
-                rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
-                cj = eng.block_inputs[j][0]
-                mode = 2 if j in written else 1
-                written.add(j)
-                plan.append([lib.os2s_conv1d_dgrad, [self._p(dYR[n]), self._half_ptr(eng.wb, rn + "/kernel"),
-                                                     self._p(self.dres[j]), B, T2, cj, l.c_out, 1, 1, 0, mode, st],
-                             ("dgrad", 2.0 * B * T2 * cj * l.c_out)])
+            if src_j is not None:
+                g = eng.res_groups[src_j]
+                # all residual branches that read source j: ONE GEMM, reduction over sum_b C_b (first writer
+                # of the fp32 accumulator; the main-path gradient below adds to it)
+                plan.append([lib.os2s_conv1d_dgrad, [self._p(self.dYRcat[src_j]), self._p(eng.wcat[src_j]),
+                                                     self._p(self.dres[src_j]), B, T2, g["cj"], g["ntot"], 1, 1, 0, 1,
+                                                     st], ("dgrad", 2.0 * B * T2 * g["cj"] * g["ntot"])])
             if li > 0:
-                if (li - 1) in eng.src_of_layer_output:
-                    j = eng.src_of_layer_output[li - 1]
-                    mode = 2 if j in written else 1
-                    written.add(j)
-                    out_ptr = self._p(self.dres[j])
+                if src_j is not None:
+                    mode, out_ptr = 2, self._p(self.dres[src_j])
                 else:
                     mode, out_ptr = 0, self._p(self.dA)
                 plan.append([lib.os2s_conv1d_dgrad, [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"),
@@ -874,13 +933,27 @@ class _Workspace(object):
                     zs.append(eng.grad[s_["offset"] + st0 + n_:s_["offset"] + s_["store_size"]])
                 if zs:
                     plan.append([_ZeroSlices(self, zs), []])
-            for n, j in enumerate(l.res_sources):
-                rn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
-                cj = eng.block_inputs[j][0]
-                src = self.A[eng.block_inputs[j][1] - 1]
-                plan.append([lib.os2s_conv1d_wgrad, [self._p(src), self._p(dYR[n]),
-                                                     self._param_ptr(eng.grad, rn + "/kernel"), B, T2, cj, l.c_out,
-                                                     1, 1, 0, sa], ("wgrad", 2.0 * B * T2 * cj * l.c_out)])
+            if src_j is not None:
+                # weight gradients of all 1x1 kernels that read source j: one GEMM into [C_j, Ntot_j], then
+                # scattered to the per-variable gradient buffers (which live in this layer's region)
+                g = eng.res_groups[src_j]
+                plan.append([lib.os2s_conv1d_wgrad, [x_ptr, self._p(self.dYRcat[src_j]), self._p(eng.dwcat[src_j]),
+                                                     B, T2, g["cj"], g["ntot"], 1, 1, 0, sa],
+                             ("wgrad", 2.0 * B * T2 * g["cj"] * g["ntot"])])
+                src, dst, rows, rbytes, sp, dp = [], [], [], [], [], []
+                for (lc, n, cb, col) in g["consumers"]:
+                    rn = eng.res_name(eng.layers[lc], n) + "/kernel"
+                    src.append(self._p(eng.dwcat[src_j], col))
+                    dst.append(self._param_ptr(eng.grad, rn))
+                    rows.append(g["cj"])
+                    rbytes.append(cb * 4)
+                    sp.append(g["ntot"] * 4)
+                    dp.append(cb * 4)
+                for i in range(0, len(src), 64):
+                    sl = slice(i, i + 64)
+                    a = (vparr(src[sl]), vparr(dst[sl]), iarr(rows[sl]), iarr(rbytes[sl]), llarr(sp[sl]), llarr(dp[sl]))
+                    self._keep.append(a)
+                    plan.append([lib.os2s_multi_copy_2d, [len(src[sl])] + list(a) + [sa]])
             plan.append([_StreamRecord(self, "aux", ev_wg[li]), []])
             if eng.comm is not None:
                 start = eng.by_name[l.name + "/kernel"]["offset"]

@@ -87,9 +87,19 @@ def test_forward_logits_and_greedy_match_oracle():
         assert d_max < 1.5e-2, (b, d_max)
     toks, tl = eng.greedy_decode()
     torch.cuda.synchronize()
-    ref_toks, _ = OC.ctc_greedy_decode(ref_logits.detach().numpy(), ref_len.numpy())
+    # integer work is exact: the decode kernel on the engine's logits == the oracle decoder on the same logits
+    own_toks, _ = OC.ctc_greedy_decode(logits.float().cpu().transpose(0, 1).numpy(), ref_len.numpy())
     for b in range(feats.shape[0]):
-        assert toks[b, :int(tl[b])].cpu().tolist() == ref_toks[b]
+        assert toks[b, :int(tl[b])].cpu().tolist() == own_toks[b]
+    # against the fp64 oracle's logits the per-frame argmax must agree wherever the oracle's top-2 margin
+    # exceeds the logit tolerance (a random-init net has near-ties that any rounding may flip)
+    for b in range(feats.shape[0]):
+        n = int(ref_len[b])
+        top2 = ref[b, :n].topk(2, dim=-1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 2 * 1.5e-2 * ref[b, :n].abs().max()
+        same = logits[b, :n].float().cpu().argmax(-1) == ref[b, :n].argmax(-1)
+        assert bool(same[clear].all())
+        assert float(same.float().mean()) > 0.9
 
 
 def test_ctc_loss_value_matches_oracle():
@@ -111,7 +121,8 @@ def _saved_forward(eng):
         out[l.name] = ws.A[li].float().cpu()
         for n in range(len(l.res_sources)):
             cn = (l.name + "/res_%d" % n) if l.dense else (l.name + "/res")
-            conv[cn] = ws.YR[li][n].float().cpu()
+            j, col = eng.res_col[(li, n)]   # the branch is a column slice of its source's merged GEMM output
+            conv[cn] = ws.YRcat[j][:, :, col:col + l.c_out].float().cpu()
     return conv, out
 
 
