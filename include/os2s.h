@@ -72,6 +72,20 @@ int os2s_conv1d_dgrad(const void* dy, const void* w, void* dx, int B, int T, int
 
 /* wgrad: dw[k,c,o] = sum_{b,t} x[b, t - pad_left + k*dil, c] * dy[b,t,o]   (fp32 [K][C_in][C_out])
  * Overwrites dw.  Constraints: C_in % 128 == 0, C_out % 64 == 0. */
+/* Data gradient whose output dx is the gradient dA of a single-branch BN + ReLU + dropout layer
+ * (conv_blocks.py:208-227 followed by tdnn_encoder.py:255): dx is written as bf16 and the epilogue
+ * also accumulates that layer's batch-norm backward reductions,
+ *   red[0][c] += sum_rows dz,  red[1][c] += sum_rows dz * y,   dz = dx * [a != 0] / keep,
+ * (a = the layer's forward output, y = its conv output, both [B,T,C_in]; red fp32 [2][C_in], zeroed by
+ * the caller), so that os2s_bn_bwd_apply can skip the separate reduction pass over dA, a and y. */
+int os2s_conv1d_dgrad_bnred(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
+                            int K, int dil, int pad_left, const void* a, const void* y, float keep, float* red,
+                            void* stream);
+/* Second half of os2s_bn_bwd for one branch when `red` already holds the two sums (see above). */
+int os2s_bn_bwd_apply(const void* y, const float* mean_invstd, const float* gamma, float* dgamma, float* dbeta,
+                      void* dy, const void* dA, const void* a, const float* red, int M, int C, float keep,
+                      void* stream);
+
 int os2s_conv1d_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out,
                       int K, int dil, int pad_left, void* stream);
 

@@ -33,6 +33,15 @@ int os2s_conv1d_dgrad(const void* dy, const void* w, void* dx, int B, int T, int
   return conv_kmajor(dy, w, dx, B, T, C_out, C_in, K, pad_left, -dil, out_mode, 0, nullptr, (cudaStream_t)stream);
 }
 
+int os2s_conv1d_dgrad_bnred(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
+                            int K, int dil, int pad_left, const void* a, const void* y, float keep, float* red,
+                            void* stream) {
+  if (!dy || !w || !dx || !a || !y || !red) return fail(ERR_INVALID, "os2s_conv1d_dgrad_bnred: null pointer");
+  if (!(keep > 0.f && keep <= 1.f)) return fail(ERR_INVALID, "os2s_conv1d_dgrad_bnred: keep must be in (0,1]");
+  return conv_kmajor(dy, w, dx, B, T, C_out, C_in, K, pad_left, -dil, OS2S_OUT_BF16, 0, red, (cudaStream_t)stream, a, y,
+                     1.f / keep);
+}
+
 int os2s_conv1d_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out,
                       int K, int dil, int pad_left, void* stream) {
   if (!x || !dy || !dw) return fail(ERR_INVALID, "os2s_conv1d_wgrad: null pointer");
@@ -119,6 +128,25 @@ int os2s_bn_bwd_ld(int n_branch, const void* const* y_host, const int* ld_host,
   p.red = red; p.M = M; p.C = C; p.keep = keep; p.apply_relu = apply_relu;
   OS2S_CUDA(cudaMemsetAsync(red, 0, (size_t)(1 + n_branch) * C * sizeof(float), (cudaStream_t)stream));
   return bn_bwd(p, (cudaStream_t)stream);
+}
+
+int os2s_bn_bwd_apply(const void* y, const float* mean_invstd, const float* gamma, float* dgamma, float* dbeta,
+                      void* dy, const void* dA, const void* a, const float* red, int M, int C, float keep,
+                      void* stream) {
+  if (!y || !mean_invstd || !gamma || !dgamma || !dbeta || !dy || !dA || !a || !red)
+    return fail(ERR_INVALID, "os2s_bn_bwd_apply: null pointer");
+  BnBwdParams p;
+  p.br[0].y = (const __half*)y;
+  p.br[0].mean_invstd = mean_invstd;
+  p.br[0].gamma = gamma;
+  p.br[0].dgamma = dgamma;
+  p.br[0].dbeta = dbeta;
+  p.br[0].dy = (__nv_bfloat16*)dy;
+  p.br[0].ld = C;
+  p.n_branch = 1;
+  p.dA = dA; p.dA_is_f32 = 0; p.a = (const __nv_bfloat16*)a;
+  p.red = const_cast<float*>(red); p.M = M; p.C = C; p.keep = keep; p.apply_relu = 1;
+  return bn_bwd(p, (cudaStream_t)stream, /*reduce=*/false);
 }
 
 int os2s_bn_bwd(int n_branch, const void* const* y_host, const float* const* mean_invstd_host,

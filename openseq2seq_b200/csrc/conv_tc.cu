@@ -42,6 +42,12 @@ struct KMajorParams {
   int K_taps, c_chunks;
   int t_off0, t_step;
   float* stats;                // optional [2][N_total]: += per-channel sum / sum of squares of the output
+  // data-gradient launches only: when bwd_a is set the output is dA of a BN+ReLU+dropout layer and the
+  // epilogue accumulates that layer's BN-backward reductions into `stats` instead:
+  //   stats[0][c] += sum_rows dz,  stats[1][c] += sum_rows dz * y,   dz = dA * [a != 0] * bwd_inv_keep
+  const void* bwd_a;           // bf16 [B, T, N_total]: forward output of that layer (zeros = relu/dropout/mask)
+  const void* bwd_y;           // fp16 [B, T, N_total]: its conv output (the BN input)
+  float bwd_inv_keep;
   int halo_rows, halo_off, sb_stages;  // halo variant: rows of the A halo tile, row offset of tap 0, B ring depth
   void* out;
   long long out_row_stride;    // elements
@@ -132,7 +138,39 @@ __device__ __forceinline__ void epilogue_rows(const KMajorParams& p, uint8_t* st
       }
       __syncwarp();
       const int w = wide ? 64 : 32;
-      if (do_stats && 2 * lane < w) {
+      if (do_stats && p.bwd_a != nullptr && 2 * lane < w) {
+        // BN-backward reductions of the layer whose output gradient this tile is: lane owns two
+        // columns; a and y are read straight from global memory
+        const uint32_t* ga = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.bwd_a) + off + c) + lane;
+        const uint32_t* gy = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.bwd_y) + off + c) + lane;
+        const long long rs2 = p.out_row_stride >> 1;   // row stride in 2-element words
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        {
+          // all 32 rows of the warp's slab at once: 64 independent 4-byte loads in flight per lane, one
+          // memory round trip per 64-column chunk (the last tile's epilogue is not hidden by a main loop)
+          uint32_t av[32], yv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = i < nvalid;
+            av[i] = ok ? __ldg(ga + (long long)i * rs2) : 0u;
+            yv[i] = ok ? __ldg(gy + (long long)i * rs2) : 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(stage + i * kEpiRowBytes + lane * 4);
+            const float2 yf = __half22float2(*reinterpret_cast<const __half2*>(&yv[i]));
+            // rows >= nvalid have av == 0 -> dz == 0
+            const float dz0 = (av[i] & 0x7FFFu) ? __uint_as_float(v << 16) * p.bwd_inv_keep : 0.f;
+            const float dz1 = (av[i] & 0x7FFF0000u) ? __uint_as_float(v & 0xFFFF0000u) * p.bwd_inv_keep : 0.f;
+            s0 += dz0; q0 += dz0 * yf.x;
+            s1 += dz1; q1 += dz1 * yf.y;
+          }
+        }
+        sacc[c + 2 * lane] += s0;
+        sacc[c + 2 * lane + 1] += s1;
+        sacc[BN + c + 2 * lane] += q0;
+        sacc[BN + c + 2 * lane + 1] += q1;
+      } else if (do_stats && 2 * lane < w) {
         // lane owns columns c + 2*lane, c + 2*lane + 1; rows beyond T_out are not statistics
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
         for (int r = 0; r < nvalid; ++r) {
@@ -1352,7 +1390,8 @@ static int pick_bn_mnmajor(int n) {
 //   wmat   : [K][N_total][C_red] bf16 (C_red contiguous)
 //   out    : [B, T, N_total]  (bf16, or fp32 with optional accumulate)
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
-                int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st) {
+                int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st,
+                const void* bwd_a, const void* bwd_y, float bwd_inv_keep) {
   if (C_red % 64 != 0) return fail(ERR_UNSUPPORTED, "conv_tc: reduction channels must be a multiple of 64");
   // pairs: 256-wide tiles whose last tile is 128 or 256 wide (each CTA stages half of it)
   // (N = 256 is one tile wide: 96 pair tiles over 74 SM pairs quantise worse than 128-wide single tiles)
@@ -1387,6 +1426,9 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
   p.t_off0 = t_off0;
   p.t_step = t_step;
   p.stats = stats;
+  p.bwd_a = bwd_a;
+  p.bwd_y = bwd_y;
+  p.bwd_inv_keep = bwd_inv_keep;
   p.out = out;
   p.out_row_stride = N_total;
   p.out_batch_stride = (long long)T * N_total;

@@ -24,28 +24,39 @@ __device__ __forceinline__ float log_add(float a, float b) {
 
 // ------------------------------------------------------------------ FC forward (small-N GEMM)
 // logits[m, v] = sum_h x[m, h] * w[h, v] + bias[v];  x bf16 [M, H], w fp32 [H, V] staged in smem.
-// One warp computes two rows at a time; lane l owns h = l, l+32, ...; V <= 32.
-constexpr int kFcThreads = 256;
+// HBM-bound (49 MB of activations for 1.4 GFLOP): one 768-thread CTA per SM, a warp takes two rows at a
+// time, stages them in shared memory with 16-byte coalesced loads (all loads of a row pair in flight
+// before the first use), then lane l owns h = l, l+32, ... (row stride V = 29 floats: conflict-free).
+constexpr int kFcThreads = 768;
+constexpr int kFcWarps = kFcThreads / 32;
 template <int VMAX>
 __global__ void __launch_bounds__(kFcThreads)
 fc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
               float* __restrict__ logits, int M, int H, int V) {
-  extern __shared__ float wsh[];  // [H][V]
+  extern __shared__ float wsh[];  // [H][V] fp32, then per warp 2 rows of x (bf16)
+  __nv_bfloat16* xsh = reinterpret_cast<__nv_bfloat16*>(wsh + (((size_t)H * V + 3) & ~(size_t)3));
   for (int i = threadIdx.x; i < H * V; i += kFcThreads) wsh[i] = w[i];
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warp_global = (blockIdx.x * kFcThreads + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * kFcThreads) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __nv_bfloat16* xw = xsh + (size_t)warp * 2 * H;
+  const int warp_global = blockIdx.x * kFcWarps + warp;
+  const int n_warps = gridDim.x * kFcWarps;
+  const int hv = H >> 3;  // 16-byte vectors per row
   for (int m0 = warp_global * 2; m0 < M; m0 += n_warps * 2) {
     const bool two = (m0 + 1) < M;
+    const uint4* g0 = reinterpret_cast<const uint4*>(x + (size_t)m0 * H);
+    const uint4* g1 = reinterpret_cast<const uint4*>(x + (size_t)(two ? m0 + 1 : m0) * H);
+    for (int i = lane; i < hv; i += 32) {
+      reinterpret_cast<uint4*>(xw)[i] = __ldg(g0 + i);
+      reinterpret_cast<uint4*>(xw + H)[i] = __ldg(g1 + i);
+    }
+    __syncwarp();
     float acc0[VMAX], acc1[VMAX];
 #pragma unroll
     for (int v = 0; v < VMAX; ++v) acc0[v] = acc1[v] = 0.f;
-    const __nv_bfloat16* x0 = x + (size_t)m0 * H;
-    const __nv_bfloat16* x1 = x + (size_t)(two ? m0 + 1 : m0) * H;
     for (int h = lane; h < H; h += 32) {
-      const float a0 = __bfloat162float(x0[h]);
-      const float a1 = __bfloat162float(x1[h]);
+      const float a0 = __bfloat162float(xw[h]);
+      const float a1 = __bfloat162float(xw[H + h]);
       const float* wr = &wsh[h * V];
 #pragma unroll
       for (int v = 0; v < VMAX; ++v) {
@@ -56,6 +67,7 @@ fc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, 
         }
       }
     }
+    __syncwarp();
 #pragma unroll
     for (int v = 0; v < VMAX; ++v) {
 #pragma unroll
@@ -81,14 +93,19 @@ fc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, 
   }
 }
 
+static size_t fc_smem_bytes(int H, int V) {
+  return ((((size_t)H * V + 3) & ~(size_t)3) * sizeof(float)) + (size_t)kFcWarps * 2 * H * sizeof(__nv_bfloat16);
+}
+
 int fc_fwd(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V,
            cudaStream_t st) {
   if (V > 32 || V < 1) return fail(ERR_UNSUPPORTED, "fc_fwd: vocabulary > 32 not supported by the small-N kernel");
-  const size_t smem = (size_t)H * V * sizeof(float);
-  if (smem > 200 * 1024) return fail(ERR_UNSUPPORTED, "fc_fwd: H*V too large for shared memory");
+  if (H % 8 != 0) return fail(ERR_UNSUPPORTED, "fc_fwd: H must be a multiple of 8");
+  const size_t smem = fc_smem_bytes(H, V);
+  if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "fc_fwd: H*V too large for shared memory");
   static bool attr_done = false;
   if (!attr_done) {
-    OS2S_CUDA(cudaFuncSetAttribute(fc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(fc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_done = true;
   }
   const int grid = device_sm_count();
@@ -97,18 +114,22 @@ int fc_fwd(const void* x, const float* w, const float* bias, float* logits, int 
 }
 
 // ------------------------------------------------------------------ FC backward
-// dx[m, h] = sum_v dl[m, v] * w[h, v]   (bf16 out);  one warp per row, lanes over h.
+// dx[m, h] = sum_v dl[m, v] * w[h, v]   (bf16 out);  one warp per row, lanes over h; the row is
+// assembled in shared memory and written with 16-byte coalesced stores.
 __global__ void __launch_bounds__(kFcThreads)
 fc_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w, __nv_bfloat16* __restrict__ dx,
                 int M, int H, int V) {
-  extern __shared__ float wsh[];  // [H][V]
+  extern __shared__ float wsh[];  // [H][V], then per warp one output row (bf16)
+  __nv_bfloat16* xsh = reinterpret_cast<__nv_bfloat16*>(wsh + (((size_t)H * V + 3) & ~(size_t)3));
   for (int i = threadIdx.x; i < H * V; i += kFcThreads) wsh[i] = w[i];
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warp_global = (blockIdx.x * kFcThreads + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * kFcThreads) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __nv_bfloat16* xw = xsh + (size_t)warp * 2 * H;
+  const int warp_global = blockIdx.x * kFcWarps + warp;
+  const int n_warps = gridDim.x * kFcWarps;
+  const int hv = H >> 3;
   for (int m = warp_global; m < M; m += n_warps) {
-    const float mine = (lane < V) ? dl[(size_t)m * V + lane] : 0.f;
+    const float mine = (lane < V) ? __ldg(dl + (size_t)m * V + lane) : 0.f;
     float d[32];
 #pragma unroll
     for (int v = 0; v < 32; ++v) d[v] = __shfl_sync(0xffffffffu, mine, v);
@@ -118,53 +139,74 @@ fc_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w, __nv_
 #pragma unroll
       for (int v = 0; v < 32; ++v)
         if (v < V) acc += d[v] * wr[v];
-      dx[(size_t)m * H + h] = __float2bfloat16(acc);
+      xw[h] = __float2bfloat16(acc);
     }
+    __syncwarp();
+    uint4* g = reinterpret_cast<uint4*>(dx + (size_t)m * H);
+    for (int i = lane; i < hv; i += 32) g[i] = reinterpret_cast<const uint4*>(xw)[i];
+    __syncwarp();
   }
 }
 
-// dw[h, v] += sum_m x[m, h] * dl[m, v];  db[v] += sum_m dl[m, v].  Thread h of a block keeps V
-// partial sums over the block's row chunk, then one atomicAdd per (h, v).
-constexpr int kFcWgRows = 128;
-__global__ void __launch_bounds__(1024)
+// dw[h, v] += sum_m x[m, h] * dl[m, v];  db[v] += sum_m dl[m, v].  Grid = (row chunks, H / 256): thread
+// h of a CTA keeps V partial sums over the CTA's row chunk (dl rows broadcast from shared memory),
+// then one atomicAdd per (h, v) -- chunks are sized for ~2 CTAs per SM so the atomics stay few.
+constexpr int kFcWgTile = 64;   // dl rows staged per pass
+__global__ void __launch_bounds__(256)
 fc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dl, float* __restrict__ dw,
-                float* __restrict__ db, int M, int H, int V) {
-  __shared__ float dsh[kFcWgRows][32];
-  const int row0 = blockIdx.x * kFcWgRows;
-  const int rows = min(kFcWgRows, M - row0);
-  for (int i = threadIdx.x; i < rows * 32; i += blockDim.x) {
-    const int r = i >> 5, v = i & 31;
-    dsh[r][v] = (v < V) ? dl[(size_t)(row0 + r) * V + v] : 0.f;
-  }
-  __syncthreads();
-  for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    float acc[32];
+                float* __restrict__ db, int M, int H, int V, int rows_per_cta) {
+  __shared__ float dsh[kFcWgTile][32];
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int row1 = min(M, row0 + rows_per_cta);
+  const int h = blockIdx.y * 256 + threadIdx.x;
+  float acc[32];
 #pragma unroll
-    for (int v = 0; v < 32; ++v) acc[v] = 0.f;
-    for (int r = 0; r < rows; ++r) {
-      const float a = __bfloat162float(x[(size_t)(row0 + r) * H + h]);
-#pragma unroll
-      for (int v = 0; v < 32; ++v) acc[v] += a * dsh[r][v];
+  for (int v = 0; v < 32; ++v) acc[v] = 0.f;
+  float dbs = 0.f;
+  for (int r0 = row0; r0 < row1; r0 += kFcWgTile) {
+    const int rows = min(kFcWgTile, row1 - r0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * 32; i += 256) {
+      const int r = i >> 5, v = i & 31;
+      dsh[r][v] = (v < V) ? __ldg(dl + (size_t)(r0 + r) * V + v) : 0.f;
     }
+    __syncthreads();
+    if (h < H) {
+      const __nv_bfloat16* xp = x + (size_t)r0 * H + h;
+#pragma unroll 8
+      for (int r = 0; r < rows; ++r) {
+        const float a = __bfloat162float(xp[(size_t)r * H]);
+        const float4* drow = reinterpret_cast<const float4*>(dsh[r]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 dv = drow[q];
+          acc[4 * q + 0] += a * dv.x;
+          acc[4 * q + 1] += a * dv.y;
+          acc[4 * q + 2] += a * dv.z;
+          acc[4 * q + 3] += a * dv.w;
+        }
+      }
+    }
+    if (blockIdx.y == 0 && threadIdx.x < V)
+      for (int r = 0; r < rows; ++r) dbs += dsh[r][threadIdx.x];
+  }
+  if (h < H) {
 #pragma unroll
     for (int v = 0; v < 32; ++v)
       if (v < V) atomicAdd(&dw[(size_t)h * V + v], acc[v]);
   }
-  if (threadIdx.x < V) {
-    float s = 0.f;
-    for (int r = 0; r < rows; ++r) s += dsh[r][threadIdx.x];
-    atomicAdd(&db[threadIdx.x], s);
-  }
+  if (blockIdx.y == 0 && threadIdx.x < V) atomicAdd(&db[threadIdx.x], dbs);
 }
 
 int fc_bwd(const void* x, const float* dl, const float* w, void* dx, float* dw, float* db, int M, int H, int V,
            cudaStream_t st) {
   if (V > 32 || V < 1) return fail(ERR_UNSUPPORTED, "fc_bwd: vocabulary > 32 not supported");
-  const size_t smem = (size_t)H * V * sizeof(float);
-  if (smem > 200 * 1024) return fail(ERR_UNSUPPORTED, "fc_bwd: H*V too large for shared memory");
+  if (H % 8 != 0) return fail(ERR_UNSUPPORTED, "fc_bwd: H must be a multiple of 8");
+  const size_t smem = fc_smem_bytes(H, V);
+  if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "fc_bwd: H*V too large for shared memory");
   static bool attr_done = false;
   if (!attr_done) {
-    OS2S_CUDA(cudaFuncSetAttribute(fc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(fc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_done = true;
   }
   if (dx) {
@@ -175,8 +217,12 @@ int fc_bwd(const void* x, const float* dl, const float* w, void* dx, float* dw, 
   if (dw) {
     OS2S_CUDA(cudaMemsetAsync(dw, 0, (size_t)H * V * sizeof(float), st));
     OS2S_CUDA(cudaMemsetAsync(db, 0, (size_t)V * sizeof(float), st));
-    const int grid = (M + kFcWgRows - 1) / kFcWgRows;
-    fc_wgrad_kernel<<<grid, 1024, 0, st>>>((const __nv_bfloat16*)x, dl, dw, db, M, H, V);
+    const int hy = (H + 255) / 256;
+    int chunks = (2 * device_sm_count() + hy - 1) / hy;   // ~2 CTAs per SM in total
+    int rows_per_cta = (M + chunks - 1) / chunks;
+    rows_per_cta = ((rows_per_cta + kFcWgTile - 1) / kFcWgTile) * kFcWgTile;
+    chunks = (M + rows_per_cta - 1) / rows_per_cta;
+    fc_wgrad_kernel<<<dim3(chunks, hy), 256, 0, st>>>((const __nv_bfloat16*)x, dl, dw, db, M, H, V, rows_per_cta);
     return check_launch("fc_wgrad");
   }
   return OK;
@@ -198,11 +244,14 @@ __global__ void ctc_lse_kernel(const float* __restrict__ logits, float* __restri
 }
 
 // Step 2: alpha (blockIdx.y == 0) and beta (blockIdx.y == 1) lattices, one CTA per utterance and
-// direction.  States s = 0..S-1 over the blank-augmented label; threads stride over s; the lattice
-// row lives in shared memory (double buffered), emission rows are staged 32 time steps at a time
-// with coalesced loads.  alpha/beta rows are written to HBM [B][T][S_max] for the gradient kernel.
+// direction.  The T time steps are serial, so the step latency is everything: thread i owns states
+// s = i, i + 512, ... (NS of them) and keeps their labels and skip-transition flags in registers for
+// the whole utterance; a step is three independent shared-memory loads of the previous row, one
+// max, three exp, one log, the emission (staged 32 steps at a time with coalesced loads), one shared
+// and one HBM store, and one barrier.  alpha/beta rows go to HBM [B][T][S_max] for the gradient kernel.
 constexpr int kCtcThreads = 512;
 constexpr int kCtcChunk = 32;
+template <int NS>
 __global__ void __launch_bounds__(kCtcThreads)
 ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
                       const int* __restrict__ labels, const int* __restrict__ label_lens,
@@ -210,8 +259,10 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
                       float* __restrict__ loglik, int T, int V, int L_max, int S_max, long long stride_b,
                       long long stride_t, int blank) {
   extern __shared__ float sh[];
-  float* lat = sh;                                  // [2][S_max]
-  float* em = sh + 2 * S_max;                       // [2][kCtcChunk][32] staged log-probs
+  // lattice rows carry 2 guard cells on both sides (-inf), so neighbour loads need no bounds checks
+  const int LP = S_max + 4;
+  float* lat = sh;                                  // [2][LP]
+  float* em = sh + 2 * LP;                          // [2][kCtcChunk][32] staged log-probs
   int* ext = reinterpret_cast<int*>(em + 2 * kCtcChunk * 32);  // [S_max]
   const int b = blockIdx.x;
   const bool backward = blockIdx.y == 1;
@@ -221,6 +272,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
   const int tid = threadIdx.x;
 
   for (int s = tid; s < S; s += kCtcThreads) ext[s] = (s & 1) ? labels[(size_t)b * L_max + (s >> 1)] : blank;
+  for (int i = tid; i < 2 * LP; i += kCtcThreads) lat[i] = kNegBig;
   __syncthreads();
   // feasibility (ignore_longer_outputs_than_inputs=True): need L + repeats <= Tb
   __shared__ int repeats;
@@ -238,6 +290,20 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
   float* out = (backward ? beta : alpha) + (size_t)b * T * S_max;
   const float* lg = logits + b * stride_b;
   const float* ls = lse + (size_t)b * T;
+
+  // per-thread constants of the owned states
+  const int d = backward ? 1 : -1;        // direction of the "previous" neighbours
+  int cls[NS];
+  bool own[NS], skip[NS], start[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int s = tid + j * kCtcThreads;
+    own[j] = s < S;
+    cls[j] = own[j] ? ext[s] : 0;
+    const int s2 = s + 2 * d;
+    skip[j] = own[j] && s2 >= 0 && s2 < S && cls[j] != blank && cls[j] != ext[s2];
+    start[j] = own[j] && (backward ? (s >= S - 2) : (s <= 1));
+  }
 
   auto stage = [&](int chunk, int buf) {
     // chunk covers steps [chunk*32, chunk*32+32) in processing order
@@ -264,33 +330,33 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
     for (int st = 0; st < steps; ++st) {
       const int step = chunk * kCtcChunk + st;
       const int t = backward ? (Tb - 1 - step) : step;
-      const float* prev = lat + cur * S_max;
-      float* next = lat + (cur ^ 1) * S_max;
-      for (int s = tid; s < S; s += kCtcThreads) {
-        const int c = ext[s];
+      const float* prev = lat + cur * LP + 2;
+      float* next = lat + (cur ^ 1) * LP + 2;
+      float* orow = out + (size_t)t * S_max;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        if (!own[j]) continue;
+        const int s = tid + j * kCtcThreads;
         float a;
         if (step == 0) {
-          const bool start = backward ? (s >= S - 2) : (s <= 1);
-          a = start ? 0.f : kNegBig;
-        } else if (!backward) {
-          a = prev[s];
-          if (s >= 1) a = log_add(a, prev[s - 1]);
-          if (s >= 2 && c != blank && c != ext[s - 2]) a = log_add(a, prev[s - 2]);
+          a = start[j] ? 0.f : kNegBig;
         } else {
-          a = prev[s];
-          if (s + 1 < S) a = log_add(a, prev[s + 1]);
-          if (s + 2 < S && c != blank && c != ext[s + 2]) a = log_add(a, prev[s + 2]);
+          const float a0 = prev[s];
+          const float a1 = prev[s + d];
+          const float a2 = skip[j] ? prev[s + 2 * d] : kNegBig;
+          const float m = fmaxf(a0, fmaxf(a1, a2));
+          a = m + __logf(__expf(a0 - m) + __expf(a1 - m) + __expf(a2 - m));
         }
-        a = fmaxf(a + emc[st * 32 + c], kNegBig);
+        a = fmaxf(a + emc[st * 32 + cls[j]], kNegBig);
         next[s] = a;
-        out[(size_t)t * S_max + s] = a;
+        orow[s] = a;
       }
       cur ^= 1;
       __syncthreads();
     }
   }
   if (!backward && tid == 0) {
-    const float* fin = lat + cur * S_max;
+    const float* fin = lat + cur * LP + 2;
     float ll = fin[S - 1];
     if (S > 1) ll = log_add(ll, fin[S - 2]);
     loglik[b] = ll;
@@ -358,16 +424,29 @@ int ctc_loss_fwd_bwd(const float* logits, const int* labels, const int* label_le
   float* beta = alpha + (size_t)B * T * S_max;
   const int blank = V - 1;
   ctc_lse_kernel<<<(B * T + 255) / 256, 256, 0, st>>>(logits, lse, B, T, V, stride_b, stride_t);
-  const size_t smem = (2 * (size_t)S_max + 2 * kCtcChunk * 32) * sizeof(float) + (size_t)S_max * sizeof(int);
-  if (smem > 200 * 1024) return fail(ERR_UNSUPPORTED, "ctc: label sequence too long for shared memory");
+  const size_t smem = (2 * (size_t)(S_max + 4) + 2 * kCtcChunk * 32) * sizeof(float) + (size_t)S_max * sizeof(int);
+  if (smem > 200 * 1024 || S_max > 4 * kCtcThreads)
+    return fail(ERR_UNSUPPORTED, "ctc: label sequence too long for the lattice kernel");
   static bool attr_done = false;
   if (!attr_done) {
-    OS2S_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  ctc_alpha_beta_kernel<<<dim3(B, 2), kCtcThreads, smem, st>>>(logits, lse, labels, label_lens, input_lens, alpha,
-                                                               beta, loglik, T, V, L_max, S_max, stride_b,
-                                                               stride_t, blank);
+  // states per thread: 1 (S <= 512), 2 (<= 1024) or 4 (<= 2048)
+  if (S_max <= kCtcThreads)
+    ctc_alpha_beta_kernel<1><<<dim3(B, 2), kCtcThreads, smem, st>>>(logits, lse, labels, label_lens, input_lens, alpha,
+                                                                    beta, loglik, T, V, L_max, S_max, stride_b,
+                                                                    stride_t, blank);
+  else if (S_max <= 2 * kCtcThreads)
+    ctc_alpha_beta_kernel<2><<<dim3(B, 2), kCtcThreads, smem, st>>>(logits, lse, labels, label_lens, input_lens, alpha,
+                                                                    beta, loglik, T, V, L_max, S_max, stride_b,
+                                                                    stride_t, blank);
+  else
+    ctc_alpha_beta_kernel<4><<<dim3(B, 2), kCtcThreads, smem, st>>>(logits, lse, labels, label_lens, input_lens, alpha,
+                                                                    beta, loglik, T, V, L_max, S_max, stride_b,
+                                                                    stride_t, blank);
   ctc_grad_kernel<<<(B * T + 7) / 8, 256, 0, st>>>(logits, lse, labels, label_lens, input_lens, alpha, beta, loglik,
                                                    grad, loss, loss_scale, B, T, V, L_max, S_max, stride_b, stride_t,
                                                    (long long)T * V, (long long)V, blank);

@@ -623,7 +623,7 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
   }
 }
 
-int bn_bwd(const BnBwdParams& p, cudaStream_t st) {
+int bn_bwd(const BnBwdParams& p, cudaStream_t st, bool reduce) {
   if (p.n_branch < 1 || p.n_branch > kMaxBranches) return fail(ERR_INVALID, "bn_bwd: bad branch count");
   if (p.C % 8 != 0 || p.C > 2048) return fail(ERR_UNSUPPORTED, "bn_bwd: C must be a multiple of 8, <= 2048");
   static bool attr_done = false;
@@ -640,7 +640,11 @@ int bn_bwd(const BnBwdParams& p, cudaStream_t st) {
   const int rpb = rows_per_block_for(p.M, p.C, one ? 2 : 1);
   const int grid = (p.M + rpb - 1) / rpb;
   const int nt = ew_threads(p.C);
-  if (one) {
+  if (!reduce) {
+    // the reductions were accumulated by the data-gradient kernel that produced dA (single branch, bf16)
+    if (!one || p.dA_is_f32) return fail(ERR_INVALID, "bn_bwd: apply-only needs one branch and a bf16 dA");
+    bn_bwd_apply_kernel<false, true><<<grid, nt, 0, st>>>(p, rpb);
+  } else if (one) {
     if (p.dA_is_f32) {
       bn_bwd_reduce_kernel<true, 1><<<grid, nt, smem_r, st>>>(p, rpb);
       bn_bwd_apply_kernel<true, true><<<grid, nt, 0, st>>>(p, rpb);

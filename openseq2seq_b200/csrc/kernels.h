@@ -16,7 +16,8 @@ const char* last_error_cstr();
 // conv_tc.cu
 int conv_tuning(int pair_mode, int halo_mode);
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
-                int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st);
+                int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st,
+                const void* bwd_a = nullptr, const void* bwd_y = nullptr, float bwd_inv_keep = 1.f);
 int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out, int K,
                int dil, int pad_left, int* splits_used, cudaStream_t st);
 
@@ -79,7 +80,7 @@ struct Copy2dTable {
 int multi_copy_2d(const Copy2dTable& tab, cudaStream_t st);
 int bn_stats(const void* y, float* stats, int M, int C, cudaStream_t st);
 int bn_apply_fwd(const BnFwdParams& p, cudaStream_t st);
-int bn_bwd(const BnBwdParams& p, cudaStream_t st);
+int bn_bwd(const BnBwdParams& p, cudaStream_t st, bool reduce = true);
 
 
 // ctc.cu

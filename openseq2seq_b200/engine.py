@@ -100,6 +100,10 @@ class JasperEngine(object):
         # weight-gradient kernels run on an auxiliary stream: wgrad(l) (tensor-bound, not on the critical
         # path) overlaps bn_bwd(l-1) (HBM-bound), which co-resides on the SMs (OS2S_OVERLAP_WGRAD=0 disables)
         self.overlap_wgrad = os.environ.get("OS2S_OVERLAP_WGRAD", "1") != "0"
+        # BN-backward reductions of plain (single-branch) layers are accumulated in the epilogue of the
+        # data-gradient kernel that produces their dA (OS2S_FUSE_BNRED=0 keeps the separate reduction pass)
+        self.fuse_bn_reduce = os.environ.get("OS2S_FUSE_BNRED", "1") != "0"
+        self.fuse_bn_min_channels = 384
         self._aux = None
         self.comm = None            # object with allreduce_(tensor) (openseq2seq_b200.dist.TorchDistHvd)
         self.bucket_bytes = 128 << 20
@@ -509,7 +513,7 @@ class JasperEngine(object):
         n += 1  # fc fwd
         for entry in (ws._bwd_plan or []):
             name = entry[0].__name__
-            n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd": 2, "os2s_bn_bwd": 2, "os2s_bn_bwd_ld": 2, "zero_slices": 0,
+            n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd": 2, "os2s_bn_bwd": 2, "os2s_bn_bwd_ld": 2, "os2s_bn_bwd_apply": 1, "zero_slices": 0,
                   "bucket_allreduce": 0, "stream_record": 0, "stream_wait": 0}.get(name, 1)
         return n + 3 + 3
 
@@ -551,6 +555,18 @@ class _ZeroSlices(object):
         with torch.cuda.stream(self.ws.aux_stream()):
             for z in self.slices:
                 z.zero_()
+        return 0
+
+
+class _ZeroMain(object):
+    """Plan entry: zero a scratch tensor on the main stream."""
+    __name__ = "zero_slices"
+
+    def __init__(self, t):
+        self.t = t
+
+    def __call__(self):
+        self.t.zero_()
         return 0
 
 
@@ -654,6 +670,17 @@ class _Workspace(object):
             self.stats_cat.append(self.stats_all[o:o + sz])
             o += sz
         self.mean_invstd = torch.zeros(n_bn, 2, cmax, dtype=torch.float32, device=dev)
+        # [2][C] BN-backward sums of every plain layer whose dA comes from a conv data-gradient kernel
+        self.fused_red = {}
+        offs, o = {}, 0
+        for li, l in enumerate(layers):
+            plain = (not l.res_sources) and (li not in eng.src_of_layer_output) and li + 1 < len(layers)
+            if eng.fuse_bn_reduce and plain and l.c_out >= eng.fuse_bn_min_channels and l.c_out % 64 == 0:
+                offs[li] = o
+                o += 2 * l.c_out
+        self.red_all = torch.zeros(max(o, 1), dtype=torch.float32, device=dev)
+        for li, off in offs.items():
+            self.fused_red[li] = self.red_all[off:off + 2 * layers[li].c_out]
         self.logits = f32(B, T2, eng.V)
         self.dlogits = f32(B, T2, eng.V)
         self.loss = f32(B)
@@ -862,6 +889,8 @@ class _Workspace(object):
                                        self._param_ptr(eng.grad, "fc/kernel"), self._param_ptr(eng.grad, "fc/bias"),
                                        M, eng.H, eng.V, st]])
         nl = len(eng.layers)
+        if self.fused_red:
+            plan.append([_ZeroMain(self.red_all), []])
         bucket_end = eng._total          # gradients in [bucket_start, bucket_end) are final once enqueued
         sa = self._st_aux                # aux-stream handle (== main stream when overlap is off / profiling)
         ev_bn = [torch.cuda.Event() for _ in range(nl)]
@@ -890,9 +919,19 @@ class _Workspace(object):
             if li + 2 < nl:
                 # this layer's dY buffer was last read by wgrad(li + 2) on the aux stream
                 plan.append([_StreamWait(self, "main", ev_wg[li + 2]), []])
-            plan.append([lib.os2s_bn_bwd_ld, [nb, y_h, ld_h, mi_h, g_h, dg_h, db_h, dy_h, dA_ptr, dA_f32,
-                                              self._p(self.A[li]), self._p(self.red), M, l.c_out, _c_float(l.keep), 1,
-                                              st]])
+            if li in self.fused_red:
+                # the two reductions were accumulated by dgrad(li + 1) below (enqueued earlier)
+                nm = names[0]
+                plan.append([lib.os2s_bn_bwd_apply, [self._p(self.Y[li]), self._p(self.mean_invstd[slots[0]]),
+                                                     self._param_ptr(eng.master, nm + "/gamma"),
+                                                     self._param_ptr(eng.grad, nm + "/gamma"),
+                                                     self._param_ptr(eng.grad, nm + "/beta"), self._p(dY), dA_ptr,
+                                                     self._p(self.A[li]), self._p(self.fused_red[li]), M, l.c_out,
+                                                     _c_float(l.keep), st]])
+            else:
+                plan.append([lib.os2s_bn_bwd_ld, [nb, y_h, ld_h, mi_h, g_h, dg_h, db_h, dy_h, dA_ptr, dA_f32,
+                                                  self._p(self.A[li]), self._p(self.red), M, l.c_out, _c_float(l.keep),
+                                                  1, st]])
             self._keep += [dg_h, db_h, dy_h]
             plan.append([_StreamRecord(self, "main", ev_bn[li]), []])
             # the input of this layer is residual source j: every consumer block has written its slice of
@@ -912,9 +951,18 @@ class _Workspace(object):
                     mode, out_ptr = 2, self._p(self.dres[src_j])
                 else:
                     mode, out_ptr = 0, self._p(self.dA)
-                plan.append([lib.os2s_conv1d_dgrad, [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"),
-                                                     out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
-                                                     st], ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
+                if (li - 1) in self.fused_red:
+                    # dA of the plain layer below + its BN-backward sums in the same kernel
+                    lp = eng.layers[li - 1]
+                    plan.append([lib.os2s_conv1d_dgrad_bnred,
+                                 [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"), out_ptr, B, T2, l.kC_in,
+                                  l.c_out, l.kK, l.dil, l.kpad, self._p(self.A[li - 1]), self._p(self.Y[li - 1]),
+                                  _c_float(lp.keep), self._p(self.fused_red[li - 1]), st],
+                                 ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
+                else:
+                    plan.append([lib.os2s_conv1d_dgrad, [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"),
+                                                         out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
+                                                         st], ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
             # ---- aux stream: weight gradients of this layer (enqueued after the critical-path kernels)
             plan.append([_StreamWait(self, "aux", ev_bn[li]), []])
             # main conv wgrad (stored layout == kernel layout, also for the folded stride-2 layer)

@@ -24,7 +24,7 @@ def _rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-12))
 
 
-def _setup(B=3, T=96, F=64, V=29, seed=0):
+def _setup(B=3, T=96, F=64, V=29, seed=0, fuse_min_channels=None):
     from openseq2seq_b200.engine import JasperEngine
     from oracle import torch_twin as TT
     torch.manual_seed(seed)
@@ -48,6 +48,10 @@ def _setup(B=3, T=96, F=64, V=29, seed=0):
                        opt=dict(loss_scaling=False, learning_rate=0.01))
     for l in eng.layers:
         l.keep = 1.0
+    if fuse_min_channels is not None:
+        # the production threshold (384 channels) is above this toy net's widths: lower it so that the
+        # dgrad kernels that also accumulate the BN-backward reductions are the ones under test
+        eng.fuse_bn_min_channels = fuse_min_channels
     eng._ws = {}
     eng.load_parameters(params)
     L = 12
@@ -126,15 +130,18 @@ def _saved_forward(eng):
     return conv, out
 
 
-def test_parameter_gradients_match_oracle_backward_at_the_same_forward_state():
+@pytest.mark.parametrize("fuse_min_channels", [None, 64])
+def test_parameter_gradients_match_oracle_backward_at_the_same_forward_state(fuse_min_channels):
     """Backward pass (BN bwd, dgrad, wgrad, dense-residual fp32 accumulation, FC bwd) against the
     oracle's backward evaluated at the engine's own saved forward state, for loss = <logits, R>.
     (A ReLU network's gradient is discontinuous in the forward values -- ~0.4% of gates sit within
     bf16 rounding of zero -- so comparing gradients across two different forward passes measures that
     sensitivity, not the kernels; the CTC gradient itself is pinned in test_kernels_gpu.)"""
     from oracle import torch_twin as TT
-    eng, params, feats, lens, labels, label_lens = _setup()
+    eng, params, feats, lens, labels, label_lens = _setup(fuse_min_channels=fuse_min_channels)
     logits, out_lens = eng.forward(feats.cuda().bfloat16().contiguous(), lens.cuda())
+    if fuse_min_channels is not None:
+        assert len(eng._last_ws.fused_red) >= 2   # the fused path is really the one that runs
     g = torch.Generator().manual_seed(9)
     R = torch.randn(logits.shape, generator=g)
     R = R * TT.sequence_mask(out_lens.cpu().long(), logits.shape[1], R.dtype)  # no gradient on padded frames

@@ -126,6 +126,65 @@ def test_conv_kernel_variants_agree(B, T, Cin, Cout, K, dil):
     assert lib.os2s_conv_tuning(3, 0) != 0
 
 
+@pytest.mark.parametrize("B,T,Cin,Cout,K,dil,modes", [
+    (2, 300, 384, 384, 13, 1, [(0, 0), (1, 1)]),   # single-CTA and pair + halo epilogues
+    (3, 131, 256, 128, 3, 1, [(1, 1)]),            # narrow layer: single-CTA kernel, ragged rows
+    (2, 260, 640, 896, 1, 1, [(1, 0)]),            # 1x1, pair kernel without halo
+])
+def test_dgrad_with_fused_bn_backward_reductions(B, T, Cin, Cout, K, dil, modes):
+    """os2s_conv1d_dgrad_bnred == os2s_conv1d_dgrad (bitwise dx) and its epilogue sums equal
+    sum dz and sum dz*y computed from the stored tensors; os2s_bn_bwd_apply on those sums == os2s_bn_bwd."""
+    L, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dy = torch.randn(B, T, Cout, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(K, Cin, Cout, device="cuda", generator=g) / (K * Cout) ** 0.5).bfloat16()
+    y = torch.randn(B, T, Cin, device="cuda", generator=g).half()
+    a = torch.relu(torch.randn(B, T, Cin, device="cuda", generator=g)).bfloat16()   # ~half zeros
+    a[:, T - 7:] = 0                                                                   # masked tail rows
+    keep = 0.8
+    pl = ((K - 1) * dil) // 2
+    st = L.stream_ptr()
+    try:
+        for pm, hm in modes:
+            assert lib.os2s_conv_tuning(pm, hm) == 0
+            dx0 = torch.empty(B, T, Cin, dtype=torch.bfloat16, device="cuda")
+            L.check(lib.os2s_conv1d_dgrad(L.ptr(dy), L.ptr(w), L.ptr(dx0), B, T, Cin, Cout, K, dil, pl, 0, st), "dgrad")
+            dx1 = torch.empty_like(dx0)
+            red = torch.zeros(2, Cin, device="cuda")
+            L.check(lib.os2s_conv1d_dgrad_bnred(L.ptr(dy), L.ptr(w), L.ptr(dx1), B, T, Cin, Cout, K, dil, pl, L.ptr(a),
+                                                L.ptr(y), _f(keep), L.ptr(red), st), "dgrad_bnred")
+            torch.cuda.synchronize()
+            assert torch.equal(dx0.view(torch.int16), dx1.view(torch.int16))
+            dz = dx1.double() * (a != 0).double() / keep
+            ref0, ref1 = dz.sum((0, 1)), (dz * y.double()).sum((0, 1))
+            scale0, scale1 = dz.abs().sum((0, 1)).max(), (dz * y.double()).abs().sum((0, 1)).max()
+            assert (red[0].double() - ref0).abs().max() <= 1e-5 * scale0
+            assert (red[1].double() - ref1).abs().max() <= 1e-5 * scale1
+    finally:
+        lib.os2s_conv_tuning(1, 1)
+    # apply-only BN backward on the fused sums == the two-pass kernel
+    M = B * T
+    mi = torch.stack([y.float().mean((0, 1)), 1.0 / torch.sqrt(y.float().var((0, 1), unbiased=False) + 1e-3)]).contiguous()
+    gam = (1.0 + 0.1 * torch.randn(Cin, device="cuda", generator=g)).contiguous()
+    outs = []
+    for fused in (False, True):
+        dyo = torch.empty(B, T, Cin, dtype=torch.bfloat16, device="cuda")
+        dg, db = torch.zeros(Cin, device="cuda"), torch.zeros(Cin, device="cuda")
+        if fused:
+            L.check(lib.os2s_bn_bwd_apply(L.ptr(y), L.ptr(mi), L.ptr(gam), L.ptr(dg), L.ptr(db), L.ptr(dyo), L.ptr(dx1),
+                                          L.ptr(a), L.ptr(red), M, Cin, _f(keep), st), "bn_bwd_apply")
+        else:
+            scratch = torch.zeros(2 * Cin, device="cuda")
+            arr = lambda t: (_vp * 1)(t.data_ptr())
+            L.check(lib.os2s_bn_bwd(1, arr(y), arr(mi), arr(gam), arr(dg), arr(db), arr(dyo), L.ptr(dx1), 0, L.ptr(a),
+                                    L.ptr(scratch), M, Cin, _f(keep), 1, st), "bn_bwd")
+        torch.cuda.synchronize()
+        outs.append((dyo.float(), dg, db))
+    assert (outs[0][0] - outs[1][0]).abs().max() <= 2e-2 * outs[0][0].abs().max()
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=1e-4 * float(outs[0][1].abs().max()))
+    assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-4, atol=1e-4 * float(outs[0][2].abs().max()))
+
+
 def test_conv_rejects_unsupported_shapes_loudly():
     L, lib = _lib()
     x = torch.zeros(1, 16, 48, dtype=torch.bfloat16, device="cuda")
