@@ -183,7 +183,7 @@ int os2s_ctc_greedy(const float* logits, const int* input_lens, int* tokens, int
 /* ---- K8: optimizer chain (mp_wrapper.py, optimizers.py LARC, automatic_loss_scaler.py,
  *          novograd.py, lr_policies.py poly_decay) as three launches ---------------------------- */
 typedef struct os2s_opt_hparams {
-  int algo;              /* 0 = NovoGrad, 1 = Momentum SGD */
+  int algo;              /* 0 = NovoGrad, 1 = Momentum SGD, 2 = Adam (tf.train.AdamOptimizer; os2s_opt_step2) */
   float beta1, beta2, epsilon, weight_decay, momentum;
   int grad_averaging;
   int ema_persist;       /* 0 = reference as written (v_t = |g_t|^2), 1 = corrected NovoGrad EMA */
@@ -196,6 +196,12 @@ typedef struct os2s_opt_hparams {
   float scale_min, scale_max, step_factor;
   long long step_window;
   int world_size;        /* gradients are SUMS over this many ranks */
+  /* learning-rate policy (lr_policies.py): 0 = poly_decay (:95-131), 1 = cosine_decay (:134-170; the
+   * reference passes min_lr as tf.train.cosine_decay's alpha, i.e. a FRACTION of lr0 -- kept),
+   * 2 = exp_decay (:55-92, no warm-up), 3 = fixed_lr (:15-27) */
+  int lr_policy;
+  float decay_rate;      /* exp_decay */
+  int staircase;         /* exp_decay: use_staircase_decay */
 } os2s_opt_hparams;
 
 /* Tensor table (all device memory, owned by the caller):
@@ -204,7 +210,8 @@ typedef struct os2s_opt_hparams {
  *   sizes    : int64 [n_tensors];  chunk_tensor int32 / chunk_offset int64 [n_chunks] with chunks of
  *              os2s_opt_chunk_elems() elements
  *   norms fp32 [2*n_tensors] and nonfinite int32 [1] zeroed once at creation; coef, ema fp32 [n_tensors]
- *   fstate fp32 [8]: [0] loss scale, [1] lr of the last step, [2] global grad norm
+ *   fstate fp32 [8]: [0] loss scale, [1] lr of the last step, [2] global grad norm, [3] Adam's lr_t,
+ *                    [4] loss scale the current gradients carry
  *   istate int64 [8]: [0] scaler iteration, [1] last overflow iteration (init -1), [2] global_step,
  *                     [3] last step skipped?, [4] skipped-step count, [5] attempted-step count */
 int os2s_opt_chunk_elems(void);
@@ -213,6 +220,19 @@ int os2s_opt_step(void* const* w, void* const* g, void* const* m, void* const* w
                   int n_tensors, int n_chunks, const os2s_opt_hparams* hp, float* norms,
                   int* nonfinite, float* fstate, long long* istate, float* coef, float* ema,
                   void* stream);
+
+/* Same step with (a) a second per-parameter state array v (fp32, like m): required for algo = 2 (Adam:
+ * m <- b1*m + (1-b1)*g, v <- b2*v + (1-b2)*g^2, w <- w - lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps),
+ * t = number of applied steps), ignored (may be NULL) otherwise; (b) reg: device fp32 [n_tensors] of
+ * per-variable L2-regulariser scales (tf.contrib.layers.l2_regularizer(scale): gradient scale*w added
+ * to the unscaled fp32 gradient before LARC, mp_wrapper.py:81-89; 0 for variables built without a
+ * regularizer), may be NULL. */
+int os2s_opt_step2(void* const* w, void* const* g, void* const* m, void* const* v, void* const* wb,
+                   const float* reg, const long long* sizes, const int* chunk_tensor,
+                   const long long* chunk_offset, int n_tensors, int n_chunks, const os2s_opt_hparams* hp,
+                   float* norms,
+                   int* nonfinite, float* fstate, long long* istate, float* coef, float* ema,
+                   void* stream);
 
 /* wt[k][c][r] = w[k][r][c] for n tensors in one launch (bf16). src/dst: device arrays of device
  * pointers; K,R,C: host int arrays. tile_start: device int64 [n+1] prefix of K*ceil(R/32)*ceil(C/32);

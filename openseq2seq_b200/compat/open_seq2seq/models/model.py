@@ -67,8 +67,8 @@ class Model(metaclass=abc.ABCMeta):
         p["summaries"] = p.get("summaries", [])
         if "dtype" not in p:
             p["dtype"] = tf.float32
-        if p["iter_size"] != 1:
-            raise NotImplementedError("iter_size > 1 (gradient accumulation) is a 'next' item, not built yet")
+        if int(p["iter_size"]) < 1:
+            raise ValueError("iter_size must be >= 1")
         self._hvd = hvd if (p["use_horovod"] and hvd is not None) else None
         self.on_horovod = self._hvd is not None
         self._gpu_ids = [0]

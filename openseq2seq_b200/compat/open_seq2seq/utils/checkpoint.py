@@ -23,6 +23,11 @@ def save(engine, logdir, step, keep=5, extra=None):
         "params": {n: v.detach().cpu() for n, v in engine.named_parameters()},
         "momentum": {n: engine.param_view(n, engine.mom).detach().cpu() for n, _ in engine.named_parameters()},
         "moving": {k: v.detach().cpu() for k, v in engine.moving.items()},
+        # Adam second moments / a partially filled iter_size accumulator, when the run has them
+        "momentum2": ({n: engine.param_view(n, engine.mom2).detach().cpu() for n, _ in engine.named_parameters()}
+                      if engine.mom2 is not None else None),
+        "grad_acc": engine.grad_acc.detach().cpu() if engine.grad_acc is not None else None,
+        "micro": engine._micro,
         "fstate": engine.fstate.cpu(), "istate": engine.istate.cpu(),
         "ema": engine._opt["ema"].cpu(), "step": step, "extra": extra or {},
     }
@@ -41,6 +46,12 @@ def restore(engine, path):
         engine.param_view(n, engine.mom).copy_(v)
     for k, v in state["moving"].items():
         engine.moving[k].copy_(v)
+    if state.get("momentum2") is not None and engine.mom2 is not None:
+        for n, v in state["momentum2"].items():
+            engine.param_view(n, engine.mom2).copy_(v)
+    if state.get("grad_acc") is not None and engine.grad_acc is not None:
+        engine.grad_acc.copy_(state["grad_acc"])
+        engine._micro = int(state.get("micro", 0))
     engine.fstate.copy_(state["fstate"])
     engine.istate.copy_(state["istate"])
     engine._opt["ema"].copy_(state["ema"])

@@ -218,17 +218,30 @@ int os2s_ctc_greedy(const float* logits, const int* input_lens, int* tokens, int
 
 int os2s_opt_chunk_elems(void) { return opt_chunk_elems(); }
 
+int os2s_opt_step2(void* const* w, void* const* g, void* const* m, void* const* v, void* const* wb,
+                   const float* reg, const long long* sizes, const int* chunk_tensor,
+                   const long long* chunk_offset, int n_tensors, int n_chunks, const os2s_opt_hparams* hp,
+                   float* norms,
+                   int* nonfinite, float* fstate, long long* istate, float* coef, float* ema,
+                   void* stream) {
+  if (!w || !g || !m || !wb || !sizes || !chunk_tensor || !chunk_offset || !hp || !norms || !nonfinite ||
+      !fstate || !istate || !coef || !ema)
+    return fail(ERR_INVALID, "os2s_opt_step: null pointer");
+  if (hp->world_size < 1) return fail(ERR_INVALID, "os2s_opt_step: world_size < 1");
+  if (hp->algo < 0 || hp->algo > 2) return fail(ERR_INVALID, "os2s_opt_step: unknown algorithm");
+  if (hp->algo == 2 && !v) return fail(ERR_INVALID, "os2s_opt_step: Adam needs the second-moment array (os2s_opt_step2)");
+  if (hp->lr_policy < 0 || hp->lr_policy > 3) return fail(ERR_INVALID, "os2s_opt_step: unknown lr policy");
+  OptTable tab{w, g, m, wb, v, reg, sizes, chunk_tensor, chunk_offset, n_tensors, n_chunks};
+  return opt_step(tab, *hp, norms, nonfinite, fstate, istate, coef, ema, (cudaStream_t)stream);
+}
+
 int os2s_opt_step(void* const* w, void* const* g, void* const* m, void* const* wb,
                   const long long* sizes, const int* chunk_tensor, const long long* chunk_offset,
                   int n_tensors, int n_chunks, const os2s_opt_hparams* hp, float* norms,
                   int* nonfinite, float* fstate, long long* istate, float* coef, float* ema,
                   void* stream) {
-  if (!w || !g || !m || !wb || !sizes || !chunk_tensor || !chunk_offset || !hp || !norms || !nonfinite ||
-      !fstate || !istate || !coef || !ema)
-    return fail(ERR_INVALID, "os2s_opt_step: null pointer");
-  if (hp->world_size < 1) return fail(ERR_INVALID, "os2s_opt_step: world_size < 1");
-  OptTable tab{w, g, m, wb, sizes, chunk_tensor, chunk_offset, n_tensors, n_chunks};
-  return opt_step(tab, *hp, norms, nonfinite, fstate, istate, coef, ema, (cudaStream_t)stream);
+  return os2s_opt_step2(w, g, m, nullptr, wb, nullptr, sizes, chunk_tensor, chunk_offset, n_tensors, n_chunks, hp, norms,
+                        nonfinite, fstate, istate, coef, ema, stream);
 }
 
 int os2s_multi_transpose(void* const* src, void* const* dst, const int* Rdev, const int* Cdev,

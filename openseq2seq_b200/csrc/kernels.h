@@ -101,6 +101,8 @@ struct OptTable {
   void* const* g;
   void* const* m;
   void* const* wb;
+  void* const* v;   // Adam second moments (nullptr otherwise)
+  const float* reg; // per-tensor L2-regulariser scale (nullptr = none)
   const long long* sizes;
   const int* chunk_tensor;
   const long long* chunk_offset;

@@ -1,12 +1,14 @@
 // Fused multi-tensor optimizer step: unscale -> (gradients already all-reduced) -> LARC -> NaN/Inf
-// check -> Backoff loss-scaler update -> NovoGrad (on TF Momentum) -> fp32 master -> bf16 copies.
+// check -> Backoff loss-scaler update -> NovoGrad (on TF Momentum) / Momentum / Adam -> fp32 master ->
+// bf16 copies.
 //
 // Reference chain being replaced (hundreds of tiny TF ops per step):
 //   open_seq2seq/optimizers/mp_wrapper.py:44-122          loss scale, fp32 masters, skip on overflow
 //   open_seq2seq/optimizers/optimizers.py:333-377         LARC
 //   open_seq2seq/optimizers/automatic_loss_scaler.py:31-106  check_grads + BackoffScaler
 //   open_seq2seq/optimizers/novograd.py:93-126            NovoGrad (+ tf.train.MomentumOptimizer)
-//   open_seq2seq/optimizers/lr_policies.py:95-131         poly_decay
+//   open_seq2seq/optimizers/lr_policies.py:15-170         fixed_lr, exp_decay, poly_decay, cosine_decay
+//   tf.train.AdamOptimizer (optimizers.py:36-44 "Adam")   m, v moments with the lr_t bias correction
 // Everything (loss scale, step counters, learning rate, skip decision) lives in device memory, so a
 // training step never synchronises with the host.
 #include "common.h"
@@ -21,8 +23,12 @@ constexpr int kOptThreads = 256;
 
 // Pass 1: per-tensor sum g^2, sum w^2 and a global non-finite flag.
 __global__ void __launch_bounds__(kOptThreads)
-opt_norms_kernel(const OptTable tab, float* __restrict__ norms, int* __restrict__ nonfinite) {
+opt_norms_kernel(const OptTable tab, const OptHParams hp, const float* __restrict__ fstate,
+                 float* __restrict__ norms, int* __restrict__ nonfinite) {
   const int tid = tab.chunk_tensor[blockIdx.x];
+  // L2 regulariser (mp_wrapper.py:81-89: its gradient reg*w is added to the UNSCALED fp32 gradient before
+  // LARC): in units of the scaled, rank-summed gradient G that is G + (reg * loss_scale * world) * w
+  const float kreg = tab.reg ? tab.reg[tid] * fstate[0] * (float)hp.world_size : 0.f;
   const long long off = tab.chunk_offset[blockIdx.x];
   const long long n = tab.sizes[tid];
   const float* g = reinterpret_cast<const float*>(tab.g[tid]) + off;
@@ -32,17 +38,20 @@ opt_norms_kernel(const OptTable tab, float* __restrict__ norms, int* __restrict_
   bool bad = false;
   const int len4 = ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(w)) & 15) == 0 ? (len & ~3) : 0;
   for (int i = threadIdx.x * 4; i < len4; i += kOptThreads * 4) {
-    const float4 gv = *reinterpret_cast<const float4*>(g + i);
+    float4 gv = *reinterpret_cast<const float4*>(g + i);
     const float4 wv = *reinterpret_cast<const float4*>(w + i);
+    bad |= !(isfinite(gv.x) && isfinite(gv.y) && isfinite(gv.z) && isfinite(gv.w));
+    gv.x += kreg * wv.x; gv.y += kreg * wv.y; gv.z += kreg * wv.z; gv.w += kreg * wv.w;
     sg += gv.x * gv.x + gv.y * gv.y + gv.z * gv.z + gv.w * gv.w;
     sw += wv.x * wv.x + wv.y * wv.y + wv.z * wv.z + wv.w * wv.w;
-    bad |= !(isfinite(gv.x) && isfinite(gv.y) && isfinite(gv.z) && isfinite(gv.w));
   }
   for (int i = len4 + threadIdx.x; i < len; i += kOptThreads) {
-    const float gv = g[i], wv = w[i];
+    const float wv = w[i];
+    float gv = g[i];
+    bad |= !isfinite(gv);
+    gv += kreg * wv;
     sg += gv * gv;
     sw += wv * wv;
-    bad |= !isfinite(gv);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -86,9 +95,26 @@ __global__ void opt_prepare_kernel(const OptTable tab, const OptHParams hp, floa
     float lr0 = hp.lr0;
     if (hp.warmup_steps > 0 && step < hp.warmup_steps) lr0 = lr0 * (float)step / (float)hp.warmup_steps;
     float lr = lr0;
-    if (step >= hp.begin_decay_at && hp.decay_steps > 0) {
+    if (hp.lr_policy == 2) {
+      // exp_decay (lr_policies.py:55-92): no warm-up, tf.train.exponential_decay, floor at min_lr
+      lr = hp.lr0;
+      if (step >= hp.begin_decay_at && hp.decay_steps > 0) {
+        float e = (float)(step - hp.begin_decay_at) / (float)hp.decay_steps;
+        if (hp.staircase) e = floorf(e);
+        lr = hp.lr0 * powf(hp.decay_rate, e);
+      }
+      lr = fmaxf(lr, hp.min_lr);
+    } else if (hp.lr_policy == 3) {
+      lr = hp.lr0;  // fixed_lr
+    } else if (step >= hp.begin_decay_at && hp.decay_steps > 0) {
       const long long s = min(step - hp.begin_decay_at, hp.decay_steps);
-      lr = (lr0 - hp.min_lr) * powf(1.f - (float)s / (float)hp.decay_steps, hp.power) + hp.min_lr;
+      if (hp.lr_policy == 1) {
+        // tf.train.cosine_decay with alpha = min_lr (as the reference calls it, lr_policies.py:160-166)
+        const float cosd = 0.5f * (1.f + cospif((float)s / (float)hp.decay_steps));
+        lr = lr0 * ((1.f - hp.min_lr) * cosd + hp.min_lr);
+      } else {
+        lr = (lr0 - hp.min_lr) * powf(1.f - (float)s / (float)hp.decay_steps, hp.power) + hp.min_lr;
+      }
     }
     // BackoffScaler.update_op (automatic_loss_scaler.py:78-106)
     float scale = scale_used;
@@ -104,6 +130,12 @@ __global__ void opt_prepare_kernel(const OptTable tab, const OptHParams hp, floa
     const bool skip = overflow;  // mp_wrapper.py:115-120
     fstate[0] = scale;
     fstate[1] = lr;
+    fstate[4] = scale_used;  // the update kernel needs the scale this step's gradients carry
+    if (hp.algo == 2) {
+      // tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), t = applied steps incl. this one
+      const float t = (float)(step + 1);
+      fstate[3] = lr * sqrtf(1.f - powf(hp.beta2, t)) / (1.f - powf(hp.beta1, t));
+    }
     istate[0] = iteration;
     istate[1] = last_of;
     istate[2] = skip ? step : step + 1;
@@ -174,11 +206,28 @@ opt_update_kernel(const OptTable tab, const OptHParams hp, const float* __restri
   __nv_bfloat16* wb = tab.wb[tid] ? reinterpret_cast<__nv_bfloat16*>(tab.wb[tid]) + off : nullptr;
   const float c = coef[tid];
   const float lr = fstate[1];
+  const float kreg = tab.reg ? tab.reg[tid] * fstate[4] * (float)hp.world_size : 0.f;
   const float wd = hp.weight_decay * ((hp.algo == 0 && hp.grad_averaging) ? (1.f - hp.beta1) : 1.f);
   const float mom = (hp.algo == 0) ? hp.beta1 : hp.momentum;
+  if (hp.algo == 2) {
+    float* v = reinterpret_cast<float*>(tab.v[tid]) + off;
+    const float lr_t = fstate[3];
+    for (int i = threadIdx.x; i < len; i += kOptThreads) {
+      const float wv = w[i];
+      const float gh = c * (g[i] + kreg * wv) + wd * wv;
+      const float mv = hp.beta1 * m[i] + (1.f - hp.beta1) * gh;
+      const float vv = hp.beta2 * v[i] + (1.f - hp.beta2) * gh * gh;
+      const float nw = wv - lr_t * mv / (sqrtf(vv) + hp.epsilon);
+      m[i] = mv;
+      v[i] = vv;
+      w[i] = nw;
+      if (wb) wb[i] = __float2bfloat16(nw);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < len; i += kOptThreads) {
     const float wv = w[i];
-    const float gh = c * g[i] + wd * wv;
+    const float gh = c * (g[i] + kreg * wv) + wd * wv;
     const float mv = mom * m[i] + gh;
     const float nw = wv - lr * mv;
     m[i] = mv;
@@ -190,7 +239,7 @@ opt_update_kernel(const OptTable tab, const OptHParams hp, const float* __restri
 int opt_step(const OptTable& tab, const OptHParams& hp, float* norms, int* nonfinite, float* fstate,
              long long* istate, float* coef, float* ema, cudaStream_t st) {
   if (tab.n_tensors <= 0 || tab.n_chunks <= 0) return fail(ERR_INVALID, "opt_step: empty table");
-  opt_norms_kernel<<<tab.n_chunks, kOptThreads, 0, st>>>(tab, norms, nonfinite);
+  opt_norms_kernel<<<tab.n_chunks, kOptThreads, 0, st>>>(tab, hp, fstate, norms, nonfinite);
   opt_prepare_kernel<<<1, 1024, 0, st>>>(tab, hp, norms, nonfinite, fstate, istate, coef, ema);
   opt_update_kernel<<<tab.n_chunks, kOptThreads, 0, st>>>(tab, hp, fstate, istate, coef);
   return check_launch("opt_step");

@@ -43,6 +43,7 @@ class OptHParams(ctypes.Structure):
         ("power", _c_float), ("decay_steps", _c_ll), ("begin_decay_at", _c_ll), ("warmup_steps", _c_ll),
         ("use_loss_scaler", _c_int), ("scale_min", _c_float), ("scale_max", _c_float),
         ("step_factor", _c_float), ("step_window", _c_ll), ("world_size", _c_int),
+        ("lr_policy", _c_int), ("decay_rate", _c_float), ("staircase", _c_int),
     ]
 
 
@@ -92,6 +93,7 @@ class JasperEngine(object):
         self.step_count = 0
         self._ws = {}
         self._profile = None
+        self._suppress_comm = False
         # replay the whole step as one CUDA graph after 2 eager steps (OS2S_CUDA_GRAPH=0 disables)
         self.use_cuda_graph = os.environ.get("OS2S_CUDA_GRAPH", "1") != "0"
         # with a communicator attached (N > 1) the step runs from the eager launch plan unless
@@ -360,9 +362,26 @@ class JasperEngine(object):
                       momentum=0.9, grad_averaging=False, ema_persist=False, larc_eta=0.0, larc_eps=1e-7,
                       larc_min_update=1e-7, larc_mode="clip", learning_rate=0.01, min_lr=0.0, power=1.0,
                       decay_steps=0, begin_decay_at=0, warmup_steps=0, loss_scaling=True, scale_min=1.0,
-                      scale_max=2.0 ** 14, step_factor=2.0, step_window=2000, initial_scale=None):
+                      scale_max=2.0 ** 14, step_factor=2.0, step_window=2000, initial_scale=None,
+                      lr_policy="poly_decay", decay_rate=1.0, use_staircase_decay=False, iter_size=1,
+                      l2_regularizer_scale=0.0):
+        """algo: "novograd" | "momentum" | "adam"; lr_policy: "poly_decay" | "cosine_decay" | "exp_decay" |
+        "fixed_lr" (lr_policies.py); l2_regularizer_scale: tf.contrib.layers.l2_regularizer(scale) on the
+        variables the reference builds with it (conv / dense kernels and BN gammas, conv_blocks.py:203,219;
+        fc_decoders.py:138); iter_size > 1 accumulates g / iter_size over that many calls of
+        train_step and updates on the last one (optimizers.py:212-259)."""
         hp = OptHParams()
-        hp.algo = 0 if algo == "novograd" else 1
+        if algo not in ("novograd", "momentum", "adam"):
+            raise ValueError("JasperEngine: optimizer %r has no fused step (novograd / momentum / adam)" % (algo,))
+        policies = {"poly_decay": 0, "cosine_decay": 1, "exp_decay": 2, "fixed_lr": 3}
+        if lr_policy not in policies:
+            raise ValueError("JasperEngine: lr_policy %r is not built (%s)" % (lr_policy, ", ".join(sorted(policies))))
+        hp.algo = {"novograd": 0, "momentum": 1, "adam": 2}[algo]
+        hp.lr_policy, hp.decay_rate, hp.staircase = policies[lr_policy], float(decay_rate), int(bool(use_staircase_decay))
+        self.iter_size = int(iter_size)
+        if self.iter_size < 1:
+            raise ValueError("JasperEngine: iter_size must be >= 1")
+        self._micro = 0
         hp.beta1, hp.beta2, hp.epsilon = beta1, beta2, epsilon
         hp.weight_decay, hp.momentum = weight_decay, momentum
         hp.grad_averaging, hp.ema_persist = int(grad_averaging), int(ema_persist)
@@ -390,8 +409,14 @@ class JasperEngine(object):
                 ct.append(i)
                 co.append(o)
         i64 = lambda x: torch.tensor(x, dtype=torch.int64, device=dev)
+        # Adam: second moments, laid out like the momentum buffer; gradient accumulator for iter_size > 1
+        self.mom2 = torch.zeros(self._total, dtype=torch.float32, device=dev) if algo == "adam" else None
+        self.grad_acc = torch.zeros(self._total, dtype=torch.float32, device=dev) if self.iter_size > 1 else None
+        v = [ptr(self.mom2, s, 4) for s in self.specs] if algo == "adam" else [0] * n
+        reg = [float(l2_regularizer_scale) if s["kind"] in ("conv", "gamma", "fc_w") else 0.0 for s in self.specs]
+        self._reg = torch.tensor(reg, dtype=torch.float32, device=dev) if l2_regularizer_scale else None
         self._opt = {
-            "w": i64(w), "g": i64(g), "m": i64(m), "wb": i64(wb), "sizes": i64(sizes),
+            "w": i64(w), "g": i64(g), "m": i64(m), "v": i64(v), "wb": i64(wb), "sizes": i64(sizes),
             "ct": torch.tensor(ct, dtype=torch.int32, device=dev), "co": i64(co),
             "norms": torch.zeros(2 * n, dtype=torch.float32, device=dev),
             "nonfinite": torch.zeros(1, dtype=torch.int32, device=dev),
@@ -478,8 +503,9 @@ class JasperEngine(object):
     def _launch_optimizer(self):
         o = self._opt
         st = L.stream_ptr()
-        L.check(self.lib.os2s_opt_step(
-            L.ptr(o["w"]), L.ptr(o["g"]), L.ptr(o["m"]), L.ptr(o["wb"]), L.ptr(o["sizes"]), L.ptr(o["ct"]),
+        L.check(self.lib.os2s_opt_step2(
+            L.ptr(o["w"]), L.ptr(o["g"]), L.ptr(o["m"]), L.ptr(o["v"]) if self.mom2 is not None else _vp(0),
+            L.ptr(o["wb"]), L.ptr(self._reg) if self._reg is not None else _vp(0), L.ptr(o["sizes"]), L.ptr(o["ct"]),
             L.ptr(o["co"]), o["n"], o["n_chunks"], ctypes.byref(self.hp), L.ptr(o["norms"]),
             L.ptr(o["nonfinite"]), L.ptr(self.fstate), L.ptr(self.istate), L.ptr(o["coef"]), L.ptr(o["ema"]),
             st), "os2s_opt_step")
@@ -605,6 +631,8 @@ class _BucketAllReduce(object):
 
     def __call__(self):
         eng = self.eng
+        if eng._suppress_comm:
+            return 0
         self.event.record()
         with torch.cuda.stream(eng._side):
             eng._side.wait_event(self.event)
@@ -1043,6 +1071,8 @@ class _Workspace(object):
         self.set_inputs(feats, feat_lens)
         self.set_targets(labels, label_lens)
         eng._last_ws = self
+        if eng.iter_size > 1:
+            return self._accumulating_step()
         if eng.use_cuda_graph and eng._profile is None and (eng.comm is None or eng.graph_with_comm):
             if self.graph is not None:
                 self.graph.replay()
@@ -1059,6 +1089,32 @@ class _Workspace(object):
                 return self.loss
         self._step_body()
         self._eager_steps += 1
+        return self.loss
+
+    def _accumulating_step(self):
+        """iter_size > 1 (optimizers.py:212-259): every call adds g / iter_size to the accumulator; the
+        iter_size-th call reduces the ACCUMULATED gradient over the ranks, runs LARC + the optimizer on it
+        and clears the accumulator.  The loss scale is constant inside a window (it only changes in the
+        optimizer step), so scaled gradients are accumulated and unscaled once.  Runs from the eager plan."""
+        eng = self.eng
+        eng._suppress_comm = True   # no per-bucket all-reduce of the micro-step gradients
+        try:
+            self._body_forward()
+            self.run_decoder()
+            self._body_backward(self._bwd_plan)
+        finally:
+            eng._suppress_comm = False
+        eng.grad_acc.add_(eng.grad, alpha=1.0 / eng.iter_size)
+        eng._micro += 1
+        if eng._micro < eng.iter_size:
+            eng.istate[5] += 1      # attempted-step counter: a fresh dropout stream for the next micro-step
+            return self.loss
+        eng._micro = 0
+        eng.grad.copy_(eng.grad_acc)
+        eng.grad_acc.zero_()
+        if eng.comm is not None:
+            eng.comm.allreduce_(eng.grad)
+        eng._launch_optimizer()
         return self.loss
 
     def _step_body(self):

@@ -37,6 +37,34 @@ def poly_decay(step, learning_rate, decay_steps, power=1.0, begin_decay_at=0, mi
     return (lr0 - min_lr) * (1.0 - float(s) / float(decay_steps)) ** power + min_lr
 
 
+def cosine_decay(step, learning_rate, decay_steps, power=1.0, begin_decay_at=0, min_lr=0.0, warmup_steps=0):
+    """lr_policies.py:134-170: tf.train.cosine_decay with alpha = min_lr (a FRACTION of the learning
+    rate -- that is what the reference passes)."""
+    lr0 = float(learning_rate)
+    if warmup_steps > 0 and step < warmup_steps:
+        lr0 = lr0 * float(step) / float(warmup_steps)
+    if step < begin_decay_at:
+        return lr0
+    s = min(step - begin_decay_at, decay_steps)
+    cosd = 0.5 * (1.0 + np.cos(np.pi * float(s) / float(decay_steps)))
+    return lr0 * ((1.0 - min_lr) * cosd + min_lr)
+
+
+def exp_decay(step, learning_rate, decay_steps, decay_rate, use_staircase_decay, begin_decay_at=0, min_lr=0.0):
+    """lr_policies.py:55-92: tf.train.exponential_decay from begin_decay_at on, floored at min_lr."""
+    if step < begin_decay_at:
+        return max(float(learning_rate), min_lr)
+    e = float(step - begin_decay_at) / float(decay_steps)
+    if use_staircase_decay:
+        e = np.floor(e)
+    return max(float(learning_rate) * decay_rate ** e, min_lr)
+
+
+def fixed_lr(step, learning_rate):
+    """lr_policies.py:15-27."""
+    return float(learning_rate)
+
+
 class BackoffScaler(object):
     """automatic_loss_scaler.py:50-110."""
 
@@ -104,6 +132,42 @@ def novograd_step(weights, grads, state, lr, beta1=0.95, beta2=0.98, epsilon=1e-
         w -= np.float32(lr) * state.momentum[i]
 
 
+def momentum_step(weights, grads, state, lr, momentum=0.9, weight_decay=0.0):
+    """tf.train.MomentumOptimizer (use_nesterov=False): accum <- m*accum + g; w <- w - lr*accum."""
+    for i, (w, g) in enumerate(zip(weights, grads)):
+        g = g.astype(np.float32)
+        if weight_decay > 0.0:
+            g = g + np.float32(weight_decay) * w
+        if state.momentum[i] is None:
+            state.momentum[i] = np.zeros_like(w, dtype=np.float32)
+        state.momentum[i] = np.float32(momentum) * state.momentum[i] + g
+        w -= np.float32(lr) * state.momentum[i]
+
+
+class AdamState(object):
+    def __init__(self, n):
+        self.m = [None] * n
+        self.v = [None] * n
+        self.t = 0
+
+
+def adam_step(weights, grads, state, lr, beta1=0.9, beta2=0.999, epsilon=1e-8, weight_decay=0.0):
+    """tf.train.AdamOptimizer (the reference's "Adam", optimizers.py:36-44):
+    lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m <- b1 m + (1-b1) g; v <- b2 v + (1-b2) g^2; w <- w - lr_t m/(sqrt(v)+eps)."""
+    state.t += 1
+    lr_t = np.float32(lr) * np.float32(np.sqrt(1.0 - beta2 ** state.t) / (1.0 - beta1 ** state.t))
+    for i, (w, g) in enumerate(zip(weights, grads)):
+        g = g.astype(np.float32)
+        if weight_decay > 0.0:
+            g = g + np.float32(weight_decay) * w
+        if state.m[i] is None:
+            state.m[i] = np.zeros_like(w, dtype=np.float32)
+            state.v[i] = np.zeros_like(w, dtype=np.float32)
+        state.m[i] = np.float32(beta1) * state.m[i] + np.float32(1.0 - beta1) * g
+        state.v[i] = np.float32(beta2) * state.v[i] + np.float32(1.0 - beta2) * g * g
+        w -= lr_t * state.m[i] / (np.sqrt(state.v[i]) + np.float32(epsilon))
+
+
 def check_grads(grads):
     """automatic_loss_scaler.py:31-47."""
     has_nan = any(bool(np.isnan(g).any()) for g in grads)
@@ -112,7 +176,7 @@ def check_grads(grads):
 
 
 def train_step(weights, scaled_grads_per_rank, state, scaler, step, lr_fn, opt_params, larc_params=None,
-               ema_persist=False):
+               ema_persist=False, algo="novograd", reg_scales=None):
     """One optimize_loss step (optimizers.py:208-281 + mp_wrapper.py:44-122).
 
     scaled_grads_per_rank: list over ranks of lists of gradients of (loss * scaler.scale) wrt the
@@ -124,6 +188,9 @@ def train_step(weights, scaled_grads_per_rank, state, scaler, step, lr_fn, opt_p
     for i in range(len(weights)):
         g = [scaled_grads_per_rank[r][i].astype(np.float32) * (np.float32(1.0) / scale) for r in range(n_rank)]
         grads.append(np.sum(g, axis=0, dtype=np.float32) / np.float32(n_rank) if n_rank > 1 else g[0])
+    if reg_scales is not None:
+        # deferred regulariser gradient on the fp32 copy, added after the un-scaling (mp_wrapper.py:81-95)
+        grads = [g + np.float32(r) * w if r else g for g, w, r in zip(grads, weights, reg_scales)]
     lr = lr_fn(step)
     if larc_params is not None:
         grads = larc(grads, weights, lr, **larc_params)
@@ -131,5 +198,12 @@ def train_step(weights, scaled_grads_per_rank, state, scaler, step, lr_fn, opt_p
     skipped = scaler.update(has_nan, amax)
     if skipped:
         return True, lr, step
-    novograd_step(weights, grads, state, lr, ema_persist=ema_persist, **opt_params)
+    if algo == "novograd":
+        novograd_step(weights, grads, state, lr, ema_persist=ema_persist, **opt_params)
+    elif algo == "momentum":
+        momentum_step(weights, grads, state, lr, **opt_params)
+    elif algo == "adam":
+        adam_step(weights, grads, state, lr, **opt_params)
+    else:
+        raise ValueError(algo)
     return False, lr, step + 1

@@ -41,8 +41,19 @@ def test_argument_validation_needs_no_gpu():
     assert lib.os2s_fc_fwd(None, None, None, None, 1, 1, 1, None) == -1
 
 
-def test_opt_hparams_struct_layout_matches_header():
+def test_opt_hparams_struct_layout_matches_header(tmp_path):
+    """The ctypes mirror of os2s_opt_hparams has the layout the C compiler gives the header's struct
+    (checked by compiling a probe against include/os2s.h with gcc)."""
+    import subprocess
     from openseq2seq_b200.engine import OptHParams
-    # 4-byte fields with 8-byte long longs: the C compiler's natural layout
-    assert ctypes.sizeof(OptHParams) == 120
-    assert OptHParams.decay_steps.offset == 64 and OptHParams.step_window.offset == 104
+    fields = [f[0] for f in OptHParams._fields_]
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "os2s.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(os2s_opt_hparams));\n' +
+                   "".join('  printf("%%zu\\n", offsetof(os2s_opt_hparams, %s));\n' % f for f in fields) +
+                   "  return 0;\n}\n")
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert ctypes.sizeof(OptHParams) == out[0]
+    assert [getattr(OptHParams, f).offset for f in fields] == out[1:]

@@ -106,6 +106,38 @@ def test_forward_logits_and_greedy_match_oracle():
         assert float(same.float().mean()) > 0.9
 
 
+def test_iter_size_accumulates_and_updates_on_the_last_call():
+    """optimizers.py:212-259 (pinned by optimizers_test.py:21-80): with iter_size = 2 the first call only
+    accumulates g / 2 (no parameter changes), the second call applies the accumulated gradient -- on the
+    same batch twice that is exactly the iter_size = 1 update (dropout off, identical BN batch statistics)."""
+    def run(iter_size, calls):
+        eng, params, feats, lens, labels, label_lens = _setup()
+        eng.set_optimizer(algo="novograd", learning_rate=0.01, loss_scaling=False, larc_eta=0.001, iter_size=iter_size)
+        eng.load_parameters(params)
+        x, xl = feats.cuda().bfloat16().contiguous(), lens.cuda()
+        snaps = []
+        for _ in range(calls):
+            eng.train_step(x, xl, labels.cuda(), label_lens.cuda())
+            torch.cuda.synchronize()
+            snaps.append({n: v.clone() for n, v in eng.named_parameters()})
+        return params, snaps
+
+    params, one = run(1, 1)
+    _, two = run(2, 2)
+    for n in params:
+        assert torch.equal(two[0][n].cpu(), params[n].float()), n          # first micro-step: untouched
+    # gradients are reduced with fp32 atomics (summation order varies run to run), and NovoGrad divides
+    # every tensor's gradient by its norm: compare the UPDATES tensor by tensor in the L2 sense
+    worst = {}
+    for n in params:
+        u1 = (one[0][n].cpu() - params[n]).double()
+        u2 = (two[1][n].cpu() - params[n]).double()
+        assert float(u1.norm()) > 0, n
+        worst[n] = float((u1 - u2).norm() / u1.norm())
+    bad = {k: round(v, 4) for k, v in worst.items() if v > 2e-2}
+    assert not bad, "accumulated update differs: %r" % bad
+
+
 def test_ctc_loss_value_matches_oracle():
     from oracle import torch_twin as TT
     eng, params, feats, lens, labels, label_lens = _setup()

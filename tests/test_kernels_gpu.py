@@ -442,6 +442,61 @@ def test_optimizer_chain_vs_oracle_including_overflow_skip():
     assert torch.equal(wb, m.bfloat16().float())
 
 
+@pytest.mark.parametrize("algo,policy", [("adam", "cosine_decay"), ("momentum", "exp_decay"), ("novograd", "fixed_lr")])
+def test_optimizer_variants_vs_oracle(algo, policy):
+    """Adam / Momentum / NovoGrad with the cosine / exponential / fixed policies, an L2 regulariser on
+    kernels and BN gammas (added to the unscaled gradient before LARC) and a static loss scale."""
+    from oracle import optimizer as OO
+    from openseq2seq_b200.engine import JasperEngine
+    from tests.common_cfg import MINI_JASPER
+    opt_kw = {"adam": dict(beta1=0.9, beta2=0.999, epsilon=1e-8),
+              "momentum": dict(momentum=0.9),
+              "novograd": dict(beta1=0.95, beta2=0.98, epsilon=1e-8, weight_decay=0.001)}[algo]
+    pol_kw = {"cosine_decay": dict(decay_steps=8, min_lr=0.1, warmup_steps=3),
+              "exp_decay": dict(decay_steps=2, decay_rate=0.5, use_staircase_decay=True, begin_decay_at=1, min_lr=1e-4),
+              "fixed_lr": dict()}[policy]
+    lr0, reg = 0.01, 1e-3
+    eng = JasperEngine(MINI_JASPER, 64, 29, world_size=1,
+                       opt=dict(algo=algo, larc_eta=0.001, learning_rate=lr0, loss_scaling=False, initial_scale=128.0,
+                                lr_policy=policy, l2_regularizer_scale=reg, **opt_kw, **pol_kw))
+    names = [n for n, _ in eng.named_parameters()]
+    kinds = [eng.by_name[n]["kind"] for n in names]
+    # non-zero betas / bias: with warm-up the first step has lr = 0 and LARC's ratio for an all-zero
+    # variable would be 0/0 (the reference would skip that step on the NaN; not what is under test here)
+    for n, k in zip(names, kinds):
+        if k in ("beta", "fc_b"):
+            eng.param_view(n).fill_(0.05)
+    reg_scales = [reg if k in ("conv", "gamma", "fc_w") else 0.0 for k in kinds]
+    w_ref = [eng.param_view(n).detach().cpu().numpy().copy() for n in names]
+    state = OO.AdamState(len(names)) if algo == "adam" else OO.NovoGradState(len(names))
+
+    class _Static(object):
+        scale = 128.0
+
+        def update(self, has_nan, amax):
+            return bool(has_nan) or bool(np.isinf(amax))
+
+    lr_fn = {"cosine_decay": lambda s: OO.cosine_decay(s, lr0, 8, min_lr=0.1, warmup_steps=3),
+             "exp_decay": lambda s: OO.exp_decay(s, lr0, 2, 0.5, True, begin_decay_at=1, min_lr=1e-4),
+             "fixed_lr": lambda s: OO.fixed_lr(s, lr0)}[policy]
+    rng = np.random.default_rng(1)
+    step = 0
+    for it in range(6):
+        per_rank = [[(rng.standard_normal(w.shape) * 0.01 * 128.0).astype(np.float32) for w in w_ref]]
+        eng.grad.zero_()
+        for i, n in enumerate(names):
+            eng.param_view(n, eng.grad).copy_(torch.tensor(per_rank[0][i]))
+        eng.optimizer_step()
+        torch.cuda.synchronize()
+        skipped, lr, step = OO.train_step(w_ref, per_rank, state, _Static(), step, lr_fn, opt_kw,
+                                          larc_params=dict(larc_eta=0.001), algo=algo, reg_scales=reg_scales)
+        assert not skipped and int(eng.istate[2]) == step
+        assert abs(float(eng.fstate[1]) - lr) < 1e-6 * max(1.0, lr), (it, float(eng.fstate[1]), lr)
+        for i, n in enumerate(names):
+            got = eng.param_view(n).cpu().numpy()
+            assert np.abs(got - w_ref[i]).max() <= 3e-5 * max(1.0, np.abs(w_ref[i]).max()), (it, n)
+
+
 def test_logmel_featurizer_vs_oracle():
     from oracle import featurizer as FZ
     L, lib = _lib()

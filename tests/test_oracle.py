@@ -156,3 +156,32 @@ def test_novograd_as_written_vs_corrected_ema():
         OO.novograd_step(w2, g, s2, 0.01, ema_persist=True)
     assert s1.ema[0] == 0.0 and s2.ema[0] > 0.0
     assert not np.allclose(w1[0], w2[0])
+
+
+def test_lr_policies_and_adam_against_closed_forms():
+    """cosine / exponential policies as tf.train.{cosine,exponential}_decay define them (the reference
+    passes min_lr as cosine_decay's alpha) and Adam against torch.optim.Adam (eps -> 0 limit, where the
+    TF and torch placements of epsilon coincide)."""
+    import torch
+    from oracle import optimizer as OO
+    assert OO.cosine_decay(0, 1.0, 10) == 1.0
+    assert abs(OO.cosine_decay(5, 1.0, 10, min_lr=0.2) - (0.8 * 0.5 + 0.2)) < 1e-12
+    assert abs(OO.cosine_decay(50, 1.0, 10, min_lr=0.2) - 0.2) < 1e-12
+    assert abs(OO.cosine_decay(1, 1.0, 10, warmup_steps=4) - 0.25 * (0.5 * (1 + np.cos(np.pi * 0.1)))) < 1e-12
+    assert OO.exp_decay(0, 0.1, 10, 0.5, True, begin_decay_at=3) == 0.1
+    assert abs(OO.exp_decay(13, 0.1, 10, 0.5, True, begin_decay_at=3) - 0.05) < 1e-12
+    assert abs(OO.exp_decay(8, 0.1, 10, 0.5, False, begin_decay_at=3) - 0.1 * 0.5 ** 0.5) < 1e-12
+    assert OO.exp_decay(1000, 0.1, 10, 0.5, True, min_lr=1e-3) == 1e-3
+    rng = np.random.default_rng(0)
+    w = [rng.standard_normal((5, 7)).astype(np.float32), rng.standard_normal(11).astype(np.float32)]
+    tw = [torch.tensor(x.copy(), requires_grad=True) for x in w]
+    opt = torch.optim.Adam(tw, lr=0.01, betas=(0.9, 0.999), eps=1e-12)
+    st = OO.AdamState(2)
+    for _ in range(4):
+        g = [rng.standard_normal(x.shape).astype(np.float32) for x in w]
+        for t, gg in zip(tw, g):
+            t.grad = torch.tensor(gg)
+        opt.step()
+        OO.adam_step(w, g, st, 0.01, epsilon=1e-12)
+    for a, b in zip(w, tw):
+        assert np.abs(a - b.detach().numpy()).max() < 1e-5
