@@ -252,6 +252,21 @@ int os2s_logmel_forward(const int16_t* wave, const long long* offsets, const int
                         void* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
                         void* stream);
 
+/* Same kernels with the backend conventions selectable (speech_utils.py:444-535, the default
+ * "psf" backend of the Wave2Letter(+) configs, input_type = "logfbank"):
+ *   psf_backend = 1: signal re-quantised to int16 and zero-padded so that the frame count is a multiple
+ *     of pad_to (:473-488), psf.logfbank = rectangular frames [f*hop, f*hop+win), pre-emphasis, |rfft|^2/n_fft,
+ *     the caller's filterbank `mel` (python_speech_features.get_filterbanks), zeros -> eps, log;
+ *     pass window = ones(win);
+ *   norm_per_feature = 0: ONE mean / population std per utterance over frames x features (:531-533, and
+ *     norm_per_feature=False of the librosa backend :411-417).
+ * out_lens[b] = frames of utterance b under the selected convention. */
+int os2s_features_forward(const int16_t* wave, const long long* offsets, const int* n_samples, int B,
+                          const float* mel, const int* mel_band, const float* window, int n_fft, int win, int hop,
+                          int F, int T_pad, int max_samples, float dither, uint64_t seed, float preemph,
+                          int psf_backend, int pad_to, int norm_per_feature, void* absmax_ws, float* raw_ws,
+                          void* out_bf16, float* out_f32, int* out_lens, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

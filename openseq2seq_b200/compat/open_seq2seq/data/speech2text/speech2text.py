@@ -100,19 +100,26 @@ class Speech2TextDataLayer(DataLayer):
     # ---------------------------------------------------------------- featurizer
     def _setup_device_tables(self):
         p = self.params
-        if p.get("backend", "psf") != "librosa" or p["input_type"] != "logfbank":
-            raise NotImplementedError("Speech2TextDataLayer: the GPU featurizer implements backend='librosa', "
-                                      "input_type='logfbank' (the Jasper configuration)")
-        if not p.get("norm_per_feature", False):
-            raise NotImplementedError("Speech2TextDataLayer: norm_per_feature=False is not built")
+        self._psf = p.get("backend", "psf") == "psf"
+        if p["input_type"] != "logfbank":
+            raise NotImplementedError("Speech2TextDataLayer: the GPU featurizer implements input_type='logfbank' "
+                                      "(both backends); 'spectrogram' / 'mfcc' are not built")
+        # psf normalises with one mean / std per utterance; librosa per feature unless norm_per_feature=False
+        self._per_feature = (not self._psf) and bool(p.get("norm_per_feature", False))
         sr = p["sample_freq"]
         self.n_win = int(sr * p["window_size"])
         self.n_hop = int(sr * p["window_stride"])
-        self.n_fft = p.get("num_fft") or speech_utils.num_fft_for(p["window_size"], sr)
         F = p["num_audio_features"]
-        mel = speech_utils.mel_filterbank(sr, self.n_fft, F, 0.0, int(sr / 2))
-        win_name = p.get("window", "hanning")
-        win = {"hanning": np.hanning, "hamming": np.hamming, "none": np.ones}[win_name](self.n_win)
+        if self._psf:
+            # psf.logfbank(nfft=512, winfunc = rectangular) (speech_utils.py:514-522)
+            self.n_fft = 512
+            mel = speech_utils.psf_filterbank(F, self.n_fft, sr, 0.0, sr / 2.0)
+            win = np.ones(self.n_win)
+        else:
+            self.n_fft = p.get("num_fft") or speech_utils.num_fft_for(p["window_size"], sr)
+            mel = speech_utils.mel_filterbank(sr, self.n_fft, F, 0.0, int(sr / 2))
+            win_name = p.get("window", "hanning")
+            win = {"hanning": np.hanning, "hamming": np.hamming, "none": np.ones}[win_name](self.n_win)
         self._dev = torch.device("cuda")
         self._mel = torch.tensor(mel, dtype=torch.float32, device=self._dev)
         band = [[int(np.nonzero(r)[0].min()), int(np.nonzero(r)[0].max()) + 1] if np.any(r) else [0, 0] for r in mel]
@@ -137,8 +144,11 @@ class Speech2TextDataLayer(DataLayer):
         B = len(lens)
         F = p["num_audio_features"]
         max_n = int(max(lens))
-        T = 1 + max_n // self.n_hop
         pad_to = p.get("pad_to", 8)
+        if self._psf:
+            T = speech_utils.psf_num_frames(max_n, self.n_win, self.n_hop, pad_to)
+        else:
+            T = 1 + max_n // self.n_hop
         if pad_to > 0 and T % pad_to:
             T += pad_to - T % pad_to
         key = (B, T, int(host.numel()))
@@ -159,12 +169,15 @@ class Speech2TextDataLayer(DataLayer):
         ws["off"].copy_(torch.from_numpy(offs), non_blocking=True)
         ws["n"].copy_(torch.tensor(lens, dtype=torch.int32), non_blocking=True)
         dither = float(p.get("dither", 0.0)) if p["mode"] == "train" or p.get("dither", 0.0) else 0.0
-        L.check(lib.os2s_logmel_forward(
+        if self._psf:
+            dither = 0.0   # get_speech_features_psf takes no dither (speech_utils.py:444-449): silently unused
+        L.check(lib.os2s_features_forward(
             L.ptr(ws["wave"]), L.ptr(ws["off"]), L.ptr(ws["n"]), B, L.ptr(self._mel), L.ptr(self._band), L.ptr(self._win),
             self.n_fft,
             self.n_win, self.n_hop, F, T, max_n, ctypes.c_float(dither), ctypes.c_uint64(seed),
-            ctypes.c_float(0.97), L.ptr(ws["absmax"]), L.ptr(ws["raw"]), L.ptr(ws["out"]), None, L.ptr(ws["lens"]),
-            L.stream_ptr()), "os2s_logmel_forward")
+            ctypes.c_float(0.97), int(self._psf), int(self.params.get("pad_to", 8)), int(self._per_feature),
+            L.ptr(ws["absmax"]), L.ptr(ws["raw"]), L.ptr(ws["out"]), None, L.ptr(ws["lens"]),
+            L.stream_ptr()), "os2s_features_forward")
         self.h2d_bytes = host.numel() * 2 + B * 12
         self._last = (ws, B, T, max_n, dither)
         return ws["out"], ws["lens"]
@@ -176,12 +189,13 @@ class Speech2TextDataLayer(DataLayer):
         lib = L.load()
         ws, B, T, max_n, dither = self._last
         F = self.params["num_audio_features"]
-        L.check(lib.os2s_logmel_forward(
+        L.check(lib.os2s_features_forward(
             L.ptr(ws["wave"]), L.ptr(ws["off"]), L.ptr(ws["n"]), B, L.ptr(self._mel), L.ptr(self._band), L.ptr(self._win),
             self.n_fft,
             self.n_win, self.n_hop, F, T, max_n, ctypes.c_float(dither), ctypes.c_uint64(seed),
-            ctypes.c_float(0.97), L.ptr(ws["absmax"]), L.ptr(ws["raw"]), L.ptr(ws["out"]), None, L.ptr(ws["lens"]),
-            L.stream_ptr()), "os2s_logmel_forward")
+            ctypes.c_float(0.97), int(self._psf), int(self.params.get("pad_to", 8)), int(self._per_feature),
+            L.ptr(ws["absmax"]), L.ptr(ws["raw"]), L.ptr(ws["out"]), None, L.ptr(ws["lens"]),
+            L.stream_ptr()), "os2s_features_forward")
         return ws["out"], ws["lens"]
 
     # ------------------------------------------------------------------ batching

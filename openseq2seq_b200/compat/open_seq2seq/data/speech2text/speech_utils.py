@@ -32,6 +32,30 @@ def mel_filterbank(sr, n_fft, n_mels, fmin=0.0, fmax=None):
     return w
 
 
+def psf_filterbank(nfilt, nfft, samplerate, lowfreq=0.0, highfreq=None):
+    """python_speech_features.base.get_filterbanks (the psf backend's logfbank, speech_utils.py:514-522):
+    HTK mel scale, nfilt + 2 points evenly spaced in mel, bins floor((nfft+1)*hz/sr), plain triangles."""
+    highfreq = highfreq or samplerate / 2.0
+    hz2mel = lambda hz: 2595.0 * np.log10(1.0 + hz / 700.0)
+    mel2hz = lambda mel: 700.0 * (10.0 ** (mel / 2595.0) - 1.0)
+    bins = np.floor((nfft + 1) * mel2hz(np.linspace(hz2mel(lowfreq), hz2mel(highfreq), nfilt + 2)) / samplerate)
+    fb = np.zeros((nfilt, nfft // 2 + 1))
+    for j in range(nfilt):
+        for i in range(int(bins[j]), int(bins[j + 1])):
+            fb[j, i] = (i - bins[j]) / (bins[j + 1] - bins[j])
+        for i in range(int(bins[j + 1]), int(bins[j + 2])):
+            fb[j, i] = (bins[j + 2] - i) / (bins[j + 2] - bins[j + 1])
+    return fb
+
+
+def psf_num_frames(n, n_win, n_hop, pad_to):
+    """frames of the psf backend for an n-sample utterance (speech_utils.py:478-488)."""
+    length = 1 if n <= n_win else 1 + -(-(n - n_win) // n_hop)
+    if pad_to > 0 and length % pad_to:
+        length += pad_to - length % pad_to
+    return length
+
+
 def num_fft_for(window_size, sample_freq):
     return 2 ** math.ceil(math.log2(window_size * sample_freq))
 

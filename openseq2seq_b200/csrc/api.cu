@@ -265,4 +265,19 @@ int os2s_logmel_forward(const int16_t* wave, const long long* offsets, const int
                         (cudaStream_t)stream);
 }
 
+int os2s_features_forward(const int16_t* wave, const long long* offsets, const int* n_samples, int B,
+                          const float* mel, const int* mel_band, const float* window, int n_fft, int win, int hop,
+                          int F, int T_pad, int max_samples, float dither, uint64_t seed, float preemph,
+                          int psf_backend, int pad_to, int norm_per_feature, void* absmax_ws, float* raw_ws,
+                          void* out_bf16, float* out_f32, int* out_lens, void* stream) {
+  if (!wave || !offsets || !n_samples || !mel || !window || !absmax_ws || !raw_ws)
+    return fail(ERR_INVALID, "os2s_features_forward: null pointer");
+  if (!out_bf16 && !out_f32) return fail(ERR_INVALID, "os2s_features_forward: no output buffer");
+  if (psf_backend && dither != 0.f) return fail(ERR_INVALID, "os2s_features_forward: the psf backend has no dither");
+  if (pad_to < 0) return fail(ERR_INVALID, "os2s_features_forward: pad_to < 0");
+  return logmel_forward(wave, offsets, n_samples, B, mel, mel_band, window, n_fft, win, hop, F, T_pad, max_samples, dither,
+                        seed, preemph, (unsigned int*)absmax_ws, raw_ws, out_bf16, out_f32, out_lens,
+                        (cudaStream_t)stream, psf_backend, pad_to, norm_per_feature);
+}
+
 }  // extern "C"

@@ -47,6 +47,26 @@ __device__ __forceinline__ float gauss_from_index(unsigned long long seed, unsig
 constexpr int kNfftMax = 512;
 constexpr int kFeatWarps = 4;
 
+// Backend differences (speech_utils.py:322-441 librosa vs :444-535 python_speech_features):
+//   librosa: frames = 1 + n/hop, centred with reflect padding, float signal (+ dither), log(x + 1e-20),
+//            per-feature normalisation;
+//   psf    : signal re-quantised to int16 and zero-padded so that frames % pad_to == 0 (the padding is
+//            pre-emphasised with the signal), frame f = samples [f*hop, f*hop + win), power / n_fft,
+//            zeros -> eps before the log, ONE mean / std per utterance.
+struct FeatOpts {
+  int psf;            // 0 = librosa conventions, 1 = psf conventions
+  int pad_to;         // psf: frames per utterance are a multiple of this
+  int per_feature;    // normalisation: 1 = per feature over time, 0 = one mean/std per utterance
+  float power_scale;  // multiplies |X|^2
+};
+__device__ __forceinline__ int frames_of(const FeatOpts& o, int n, int hop, int win) {
+  if (!o.psf) return 1 + n / hop;
+  int len = 1 + (n - win + hop - 1) / hop;      // 1 + ceil((n - win) / hop) for n >= win
+  if (n <= win) len = 1;
+  if (o.pad_to > 0 && len % o.pad_to) len += o.pad_to - len % o.pad_to;
+  return len;
+}
+
 // signal value at (reflect-resolved) sample index i: normalised, dithered, then pre-emphasised.
 __device__ __forceinline__ float sample_at(const short* w, int n, int i, float gain, float dither,
                                            unsigned long long seed, float preemph) {
@@ -59,13 +79,24 @@ __device__ __forceinline__ float sample_at(const short* w, int n, int i, float g
   return (i == 0) ? cur : cur - preemph * base(i - 1);
 }
 
+// psf: q[i] = (int16)(float(x[i] * gain) * 32767) (truncation), zero for i >= n; the zero padding up to
+// n_padded belongs to the signal when it is pre-emphasised, so sample n is -preemph * q[n-1].
+__device__ __forceinline__ float sample_at_psf(const short* w, int n, int n_padded, int i, float gain, float preemph) {
+  if (i < 0 || i >= n_padded) return 0.f;
+  const float cur = (i < n) ? truncf(((float)w[i] * gain) * 32767.0f) : 0.f;
+  if (i == 0) return cur;
+  const float prev = (i - 1 < n) ? truncf(((float)w[i - 1] * gain) * 32767.0f) : 0.f;
+  return cur - preemph * prev;
+}
+
 template <int NFFT>
 __global__ void __launch_bounds__(kFeatWarps * 32)
 feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__ offsets,
                    const int* __restrict__ n_samples, const unsigned int* __restrict__ absmax,
                    const float* __restrict__ mel, const int* __restrict__ mel_band,
                    const float* __restrict__ window, float* __restrict__ raw,
-                   int T_pad, int F, int hop, int win, float dither, unsigned long long seed, float preemph) {
+                   int T_pad, int F, int hop, int win, float dither, unsigned long long seed, float preemph,
+                   const FeatOpts opts) {
   constexpr int NB = NFFT / 2 + 1;
   __shared__ float re[kFeatWarps][NFFT];
   __shared__ float im[kFeatWarps][NFFT];
@@ -80,8 +111,16 @@ feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__
   const int b = blockIdx.y;
   const int frame = blockIdx.x * kFeatWarps + warp;
   const int n = n_samples[b];
-  const int n_frames = 1 + n / hop;
+  const int n_frames = frames_of(opts, n, hop, win);
   if (frame >= n_frames) return;  // whole warp exits together
+  // psf: the zero padding that makes the frame count a multiple of pad_to is part of the signal
+  // (speech_utils.py:481-488 pads the int16 signal before psf pre-emphasises it; framesig's own zero
+  // padding of the last frame comes after the pre-emphasis)
+  int n_padded = n;
+  if (opts.psf) {
+    const int len0 = (n <= win) ? 1 : 1 + (n - win + hop - 1) / hop;
+    n_padded = n + (n_frames - len0) * hop;
+  }
   const short* w = wave + offsets[b];
   const float gain = 1.f / ((float)absmax[b] + 1e-5f);
   const unsigned long long useed = seed + (unsigned long long)b * 0x632BE59BD9B4E019ull;
@@ -92,11 +131,16 @@ feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__
     float v = 0.f;
     const int wi = i - lpad;
     if (wi >= 0 && wi < win) {
-      int j = frame * hop - NFFT / 2 + i;
-      if (j < 0) j = -j;                      // np.pad(mode="reflect")
-      if (j >= n) j = 2 * (n - 1) - j;
-      j = min(max(j, 0), n - 1);
-      v = sample_at(w, n, j, gain, dither, useed, preemph) * window[wi];
+      if (opts.psf) {
+        // frame f = samples [f*hop, f*hop + win); the position inside the FFT buffer does not change |X|
+        v = sample_at_psf(w, n, n_padded, frame * hop + wi, gain, preemph) * window[wi];
+      } else {
+        int j = frame * hop - NFFT / 2 + i;
+        if (j < 0) j = -j;                      // np.pad(mode="reflect")
+        if (j >= n) j = 2 * (n - 1) - j;
+        j = min(max(j, 0), n - 1);
+        v = sample_at(w, n, j, gain, dither, useed, preemph) * window[wi];
+      }
     }
     const int r = __brev((unsigned)i) >> (32 - LOG2N);
     re[warp][r] = v;
@@ -135,19 +179,22 @@ feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__
     const int hi = mel_band ? mel_band[2 * f + 1] : NB;
     float acc = 0.f;
     for (int k = lo; k < hi; ++k) acc += mrow[k] * re[warp][k];
-    raw[((size_t)b * T_pad + frame) * F + f] = logf(acc + 1e-20f);
+    acc *= opts.power_scale;
+    // librosa path: log(S + 1e-20) (speech_utils.py:406); psf: zeros -> float eps, then log (base.fbank)
+    raw[((size_t)b * T_pad + frame) * F + f] = opts.psf ? logf(acc == 0.f ? 2.220446049250313e-16f : acc)
+                                                        : logf(acc + 1e-20f);
   }
 }
 
 // per (b, f): mean and population std over the utterance's frames, then normalise + pad.
 __global__ void feat_norm_kernel(const float* __restrict__ raw, const int* __restrict__ n_samples,
                                  __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
-                                 int* __restrict__ out_lens, int T_pad, int F, int hop, int norm_per_feature) {
+                                 int* __restrict__ out_lens, int T_pad, int F, int hop, int win, const FeatOpts opts) {
   const int b = blockIdx.y;
   const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (f >= F) return;
-  const int n_frames = min(1 + n_samples[b] / hop, T_pad);
+  const int n_frames = min(frames_of(opts, n_samples[b], hop, win), T_pad);
   const float* src = raw + (size_t)b * T_pad * F + f;
   float s = 0.f;
   for (int t = lane; t < n_frames; t += 32) s += src[(size_t)t * F];
@@ -171,23 +218,81 @@ __global__ void feat_norm_kernel(const float* __restrict__ raw, const int* __res
   if (f == 0 && lane == 0 && out_lens) out_lens[b] = n_frames;
 }
 
+// one mean / population std per utterance over all frames x features (psf backend, or
+// norm_per_feature = False): one CTA per utterance, three passes over its L2-resident [frames, F] slab.
+__global__ void __launch_bounds__(256)
+feat_norm_global_kernel(const float* __restrict__ raw, const int* __restrict__ n_samples,
+                        __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                        int* __restrict__ out_lens, int T_pad, int F, int hop, int win, const FeatOpts opts) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const int b = blockIdx.x;
+  const int n_frames = min(frames_of(opts, n_samples[b], hop, win), T_pad);
+  const int n = n_frames * F;
+  const float* src = raw + (size_t)b * T_pad * F;
+  auto block_sum = [&](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < 8; ++i) s += red[i];
+      bc = s;
+    }
+    __syncthreads();
+    return bc;
+  };
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += src[i];
+  const float mean = block_sum(s) / (float)n;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float d = src[i] - mean;
+    q += d * d;
+  }
+  const float inv_std = rsqrtf(block_sum(q) / (float)n);
+  for (int i = threadIdx.x; i < T_pad * F; i += 256) {
+    const float v = (i < n) ? (src[i] - mean) * inv_std : 0.f;
+    const size_t o = (size_t)b * T_pad * F + i;
+    if (out_bf16) out_bf16[o] = __float2bfloat16(v);
+    if (out_f32) out_f32[o] = v;
+  }
+  if (threadIdx.x == 0 && out_lens) out_lens[b] = n_frames;
+}
+
 int logmel_forward(const short* wave, const long long* offsets, const int* n_samples, int B,
                    const float* mel, const int* mel_band, const float* window, int n_fft, int win, int hop, int F, int T_pad,
                    int max_samples, float dither, unsigned long long seed, float preemph,
                    unsigned int* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
-                   cudaStream_t st) {
+                   cudaStream_t st, int psf_backend, int pad_to, int norm_per_feature) {
   if (n_fft != 512) return fail(ERR_UNSUPPORTED, "logmel_forward: only n_fft = 512 is built");
   if (win > n_fft || F > 128) return fail(ERR_INVALID, "logmel_forward: bad window / feature count");
+  FeatOpts opts;
+  opts.psf = psf_backend ? 1 : 0;
+  opts.pad_to = pad_to;
+  opts.per_feature = norm_per_feature ? 1 : 0;
+  opts.power_scale = psf_backend ? 1.f / (float)n_fft : 1.f;
   OS2S_CUDA(cudaMemsetAsync(absmax_ws, 0, (size_t)B * sizeof(unsigned int), st));
   feat_absmax_kernel<<<dim3(32, B), 256, 0, st>>>(wave, offsets, n_samples, absmax_ws);
-  const int max_frames = 1 + max_samples / hop;
+  int max_frames = 1 + max_samples / hop;
+  if (psf_backend) {
+    max_frames = max_samples <= win ? 1 : 1 + (max_samples - win + hop - 1) / hop;
+    if (pad_to > 0 && max_frames % pad_to) max_frames += pad_to - max_frames % pad_to;
+  }
   if (max_frames > T_pad) return fail(ERR_INVALID, "logmel_forward: T_pad smaller than the frame count");
   dim3 grid((max_frames + kFeatWarps - 1) / kFeatWarps, B);
   feat_logmel_kernel<512><<<grid, kFeatWarps * 32, 0, st>>>(wave, offsets, n_samples, absmax_ws, mel, mel_band, window, raw_ws,
-                                                           T_pad, F, hop, win, dither, seed, preemph);
-  dim3 grid2((F + 7) / 8, B);
-  feat_norm_kernel<<<grid2, 256, 0, st>>>(raw_ws, n_samples, (__nv_bfloat16*)out_bf16, out_f32, out_lens, T_pad, F,
-                                          hop, 1);
+                                                           T_pad, F, hop, win, dither, seed, preemph, opts);
+  if (norm_per_feature) {
+    dim3 grid2((F + 7) / 8, B);
+    feat_norm_kernel<<<grid2, 256, 0, st>>>(raw_ws, n_samples, (__nv_bfloat16*)out_bf16, out_f32, out_lens, T_pad, F,
+                                            hop, win, opts);
+  } else {
+    feat_norm_global_kernel<<<B, 256, 0, st>>>(raw_ws, n_samples, (__nv_bfloat16*)out_bf16, out_f32, out_lens, T_pad,
+                                               F, hop, win, opts);
+  }
   return check_launch("logmel_forward");
 }
 

@@ -126,6 +126,7 @@ int logmel_forward(const short* wave, const long long* offsets, const int* n_sam
                    const float* mel, const int* mel_band, const float* window, int n_fft, int win, int hop, int F, int T_pad,
                    int max_samples, float dither, unsigned long long seed, float preemph,
                    unsigned int* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
-                   cudaStream_t st);
+                   cudaStream_t st,
+                   int psf_backend = 0, int pad_to = 0, int norm_per_feature = 1);
 
 }  // namespace os2s

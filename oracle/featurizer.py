@@ -136,3 +136,67 @@ def batch_features(signals_int16, pad_to=16, **kw):
     for i, f in enumerate(feats):
         out[i, :f.shape[0]] = f
     return out, lens
+
+
+# ---------------------------------------------------------------------------------------------
+# psf backend (speech_utils.py:444-535, the default backend: used by the Wave2Letter(+) configs and
+# the reference's toy tests).  The arithmetic lives in python_speech_features (unpinned in
+# requirements.txt:9, not under /root/reference, not installed); its published algorithm (v0.6,
+# base.py / sigproc.py) is restated:
+#   sigproc.preemphasis(x, c)        = append(x[0], x[1:] - c*x[:-1])
+#   sigproc.framesig(sig, L, S, win) : numframes = 1 + ceil((len - L)/S) (1 if len <= L), signal zero-padded
+#                                      to (numframes-1)*S + L, frames * win(L)
+#   sigproc.powspec(frames, NFFT)    = 1/NFFT * |rfft(frames, NFFT)|^2
+#   base.get_filterbanks(nfilt, nfft, sr, lo, hi): HTK mel (2595*log10(1+f/700)), nfilt+2 points evenly
+#       spaced in mel, bin = floor((nfft+1)*hz/sr), unnormalised triangles between consecutive bins
+#   base.fbank(): preemphasis -> framesig (winfunc: rectangular by default, as the reference calls it) ->
+#       powspec -> energies = pspec . fb^T, zeros replaced by float eps;  logfbank = log(fbank)
+# Pins in the reference's own tests (speech_utils_test.py:45-85): output shape and global mean 0 / std 1.
+
+
+def psf_mel_filterbank(nfilt=64, nfft=512, samplerate=16000, lowfreq=0.0, highfreq=None):
+    """python_speech_features.base.get_filterbanks -> [nfilt, nfft//2 + 1] float64."""
+    highfreq = highfreq or samplerate / 2.0
+    hz2mel = lambda hz: 2595.0 * np.log10(1.0 + hz / 700.0)
+    mel2hz = lambda mel: 700.0 * (10.0 ** (mel / 2595.0) - 1.0)
+    melpoints = np.linspace(hz2mel(lowfreq), hz2mel(highfreq), nfilt + 2)
+    bins = np.floor((nfft + 1) * mel2hz(melpoints) / samplerate)
+    fb = np.zeros((nfilt, nfft // 2 + 1))
+    for j in range(nfilt):
+        for i in range(int(bins[j]), int(bins[j + 1])):
+            fb[j, i] = (i - bins[j]) / (bins[j + 1] - bins[j])
+        for i in range(int(bins[j + 1]), int(bins[j + 2])):
+            fb[j, i] = (bins[j + 2] - i) / (bins[j + 2] - bins[j + 1])
+    return fb
+
+
+def psf_quantize_and_pad(signal_int16, sample_freq=16000, window_size=20e-3, window_stride=10e-3, pad_to=8):
+    """speech_utils.py:473-488: re-quantise the normalised signal to int16 and zero-pad it so that the
+    number of frames is a multiple of pad_to."""
+    signal = (normalize_signal(np.asarray(signal_int16).astype(np.float32)) * 32767.0).astype(np.int16)
+    n_win, n_hop = int(sample_freq * window_size), int(sample_freq * window_stride)
+    length = 1 + int(math.ceil((1.0 * signal.shape[0] - n_win) / n_hop))
+    if pad_to > 0 and length % pad_to != 0:
+        signal = np.pad(signal, (0, (pad_to - length % pad_to) * n_hop), mode="constant")
+    return signal
+
+
+def psf_logfbank_features(signal_int16, sample_freq=16000, num_features=64, window_size=20e-3,
+                          window_stride=10e-3, pad_to=8, nfft=512, preemph=0.97):
+    """get_speech_features_psf(features_type='logfbank') without augmentation -> ([frames, F] f64, seconds)."""
+    duration = len(signal_int16) * 1.0 / sample_freq
+    signal = psf_quantize_and_pad(signal_int16, sample_freq, window_size, window_stride, pad_to).astype(np.float64)
+    n_win, n_hop = int(sample_freq * window_size), int(sample_freq * window_stride)
+    signal = preemphasis(signal, preemph)
+    slen = len(signal)
+    numframes = 1 if slen <= n_win else 1 + int(math.ceil((1.0 * slen - n_win) / n_hop))
+    padded = np.concatenate([signal, np.zeros((numframes - 1) * n_hop + n_win - slen)])
+    idx = np.arange(n_win)[None, :] + n_hop * np.arange(numframes)[:, None]
+    frames = padded[idx]                                    # rectangular window
+    pspec = (1.0 / nfft) * np.abs(np.fft.rfft(frames, nfft, axis=1)) ** 2
+    fb = psf_mel_filterbank(num_features, nfft, sample_freq, 0.0, sample_freq / 2.0)
+    feat = np.dot(pspec, fb.T)
+    feat = np.where(feat == 0, np.finfo(float).eps, feat)
+    features = np.log(feat)
+    features = (features - np.mean(features)) / np.std(features)   # global normalisation (:531-533)
+    return features, duration

@@ -129,6 +129,24 @@ def test_optimizer_kwargs_from_jasper_params():
     assert kw["loss_scaling"] is True
 
 
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference checkout not present (GPU box)")
+def test_optimizer_and_data_layer_kwargs_from_reference_w2lplus_config():
+    """example_configs/speech2text/w2lplus_large_8gpus_mp.py unchanged: Momentum + poly_decay + LARC + an L2
+    regulariser + the default (python_speech_features) feature backend all map onto built pieces."""
+    from open_seq2seq.optimizers.optimizers import optimizer_engine_kwargs
+    path = "/root/reference/example_configs/speech2text/w2lplus_large_8gpus_mp.py"
+    _, cfg, _, mod = get_base_config(["--config_file=" + path, "--mode=train"])
+    kw = optimizer_engine_kwargs(cfg, last_step=2000)
+    assert kw["algo"] == "momentum" and kw["momentum"] == 0.9
+    assert kw["l2_regularizer_scale"] == cfg["regularizer_params"]["scale"] > 0
+    assert kw["larc_eta"] == cfg["larc_params"]["larc_eta"] and kw["loss_scaling"] is True
+    assert kw["iter_size"] == 1 and kw["decay_steps"] == 2000
+    dl = mod["train_params"]["data_layer_params"]
+    assert dl.get("backend", "psf") == "psf" and dl["input_type"] == "logfbank"
+    widths = {l["num_channels"] for l in cfg["encoder_params"]["convnet_layers"]}
+    assert all(w % 64 == 0 for w in widths)   # every layer is covered by the tensor-core tiles
+
+
 def test_levenshtein_and_wer_known_answers():
     # known answers of the reference's own test (models/speech2text_test.py:229-256)
     from open_seq2seq.models.speech2text import levenshtein

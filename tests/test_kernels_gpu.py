@@ -531,3 +531,54 @@ def test_logmel_featurizer_vs_oracle():
     assert np.abs(outb.float().cpu().numpy() - ref).max() < 5e-2
     for b in range(B):
         assert np.all(got[b, ref_lens[b]:] == 0)
+
+
+@pytest.mark.parametrize("mode", ["psf", "librosa_global_norm"])
+def test_featurizer_psf_backend_and_global_normalisation_vs_oracle(mode):
+    """os2s_features_forward: python_speech_features conventions (int16 re-quantisation, frame count a
+    multiple of pad_to with the padding pre-emphasised, rectangular frames, power / n_fft, HTK filterbank,
+    one mean/std per utterance) and the librosa backend with norm_per_feature=False."""
+    from oracle import featurizer as FZ
+    L, lib = _lib()
+    rng = np.random.default_rng(99)
+    sigs = [np.clip(3000 * rng.standard_normal(n), -32768, 32767).astype(np.int16) for n in (16000, 12345, 4001, 2000)]
+    sigs = [np.clip(np.convolve(s.astype(np.float64), np.ones(8) / 8, mode="same"), -32768, 32767).astype(np.int16)
+            for s in sigs]
+    F = 64
+    if mode == "psf":
+        feats = [FZ.psf_logfbank_features(s, num_features=F, pad_to=8)[0] for s in sigs]
+        melnp, win = FZ.psf_mel_filterbank(F, 512, 16000, 0.0, 8000.0), np.ones(320)
+        psf, per_feature = 1, 0
+    else:
+        feats = [FZ.logfbank_features(s, num_features=F, norm_per_feature=False)[0] for s in sigs]
+        melnp, win = FZ.mel_filterbank(), np.hanning(320)
+        psf, per_feature = 0, 0
+    ref_lens = [f.shape[0] for f in feats]
+    if mode == "psf":
+        assert all(n % 8 == 0 for n in ref_lens)
+        assert ref_lens[0] == 104   # 1 + ceil((16000 - 320) / 160) = 99 -> 104
+    B, T_pad = len(sigs), -(-max(ref_lens) // 16) * 16
+    wave = torch.tensor(np.concatenate(sigs), dtype=torch.int16, device="cuda")
+    offs = torch.tensor(np.cumsum([0] + [len(s) for s in sigs[:-1]]), dtype=torch.int64, device="cuda")
+    ns = torch.tensor([len(s) for s in sigs], dtype=torch.int32, device="cuda")
+    mel = torch.tensor(melnp, dtype=torch.float32, device="cuda")
+    band = torch.tensor([[int(np.nonzero(r)[0].min()), int(np.nonzero(r)[0].max()) + 1] if np.any(r) else [0, 0]
+                         for r in melnp], dtype=torch.int32, device="cuda")
+    wint = torch.tensor(win, dtype=torch.float32, device="cuda")
+    absmax = torch.zeros(B, dtype=torch.int32, device="cuda")
+    raw = torch.zeros(B * T_pad * F, device="cuda")
+    out = torch.full((B, T_pad, F), float("nan"), device="cuda")
+    lens = torch.zeros(B, dtype=torch.int32, device="cuda")
+    L.check(lib.os2s_features_forward(L.ptr(wave), L.ptr(offs), L.ptr(ns), B, L.ptr(mel), L.ptr(band), L.ptr(wint), 512, 320,
+                                      160, F, T_pad, max(len(s) for s in sigs), _f(0.0), ctypes.c_uint64(0), _f(0.97),
+                                      psf, 8, per_feature, L.ptr(absmax), L.ptr(raw), None, L.ptr(out), L.ptr(lens),
+                                      L.stream_ptr()), "features")
+    torch.cuda.synchronize()
+    assert lens.cpu().tolist() == ref_lens
+    got = out.cpu().numpy()
+    for b in range(B):
+        n = ref_lens[b]
+        assert np.abs(got[b, :n] - feats[b]).max() < 2e-2, (mode, b, np.abs(got[b, :n] - feats[b]).max())
+        assert np.all(got[b, n:] == 0)
+        # the reference's own pin for this backend (speech_utils_test.py:72-73): mean 0, std 1
+        assert abs(float(got[b, :n].mean())) < 1e-4 and abs(float(got[b, :n].std()) - 1.0) < 1e-4

@@ -185,3 +185,33 @@ def test_lr_policies_and_adam_against_closed_forms():
         OO.adam_step(w, g, st, 0.01, epsilon=1e-12)
     for a, b in zip(w, tw):
         assert np.abs(a - b.detach().numpy()).max() < 1e-5
+
+
+def test_psf_backend_shape_and_normalisation_pins(golden_dir):
+    """speech_utils_test.py:45-73 for features_type='logfbank': shape (ceil8(1 + (n - win)//stride), F)
+    and global mean 0 / std 1 to 6 places, on the reference's own toy wavs; plus the filterbank against
+    an independent construction (torchaudio's HTK triangles differ only by psf's bin flooring, so the
+    check is structural: partition of unity between the first and last centre bins)."""
+    import scipy.io.wavfile as wave
+    from oracle import featurizer as FZ
+    wav_dir = os.path.join(golden_dir, "toy_speech_data", "wav_files")
+    names = ['46gc040q.wav', '206o0103.wav', '48rc041b.wav']   # the three files the reference test uses
+    for name in names:
+        sr, sig = wave.read(os.path.join(wav_dir, name))
+        for num_features in (64, 40):
+            for stride in (10e-3, 5e-3, 40e-3):
+                for win in (20e-3, 30e-3):
+                    n_win, n_hop = int(sr * win), int(sr * stride)
+                    length = 1 + (sig.shape[0] - n_win) // n_hop
+                    if length % 8:
+                        length += 8 - length % 8
+                    f, dur = FZ.psf_logfbank_features(sig, sr, num_features, win, stride, pad_to=8)
+                    assert f.shape == (length, num_features)
+                    assert abs(np.mean(f)) < 1e-6 and abs(np.std(f) - 1.0) < 1e-6
+                    assert abs(dur - len(sig) / sr) < 1e-12
+    fb = FZ.psf_mel_filterbank(64, 512, 16000, 0.0, 8000.0)
+    assert fb.shape == (64, 257) and fb.min() >= 0.0 and fb.max() <= 1.0
+    peaks = fb.argmax(1)
+    assert np.all(np.diff(peaks) >= 0)
+    inner = fb[:, peaks[0]:peaks[-1] + 1].sum(0)
+    assert np.allclose(inner, 1.0, atol=1e-12)

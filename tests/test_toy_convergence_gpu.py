@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOY = os.path.join(ROOT, "tests", "golden", "toy_speech_data")
 
 
-def _config(tmpdir):
+def _config(tmpdir, backend="librosa"):
     import openseq2seq_b200.compat as compat
     compat.install()
     import tensorflow as tf
@@ -32,11 +32,19 @@ def _config(tmpdir):
     csv["wav_filename"] = [os.path.join(TOY, p) for p in csv["wav_filename"]]
     csv_path = os.path.join(str(tmpdir), "toy_abs.csv")
     csv.to_csv(csv_path, index=False)
-    dl = {
-        "num_audio_features": 64, "input_type": "logfbank", "backend": "librosa", "norm_per_feature": True,
-        "pad_to": 16, "window": "hanning", "vocab_file": os.path.join(TOY, "vocab.txt"),
-        "dataset_files": [csv_path],
-    }
+    if backend == "librosa":
+        dl = {
+            "num_audio_features": 64, "input_type": "logfbank", "backend": "librosa", "norm_per_feature": True,
+            "pad_to": 16, "window": "hanning", "vocab_file": os.path.join(TOY, "vocab.txt"),
+            "dataset_files": [csv_path],
+        }
+    else:
+        # exactly the data-layer section of test_speech_configs/w2l_test_config.py:80-90 (default backend =
+        # python_speech_features, default pad_to = 8, one mean/std per utterance), 64 features instead of 40
+        dl = {
+            "num_audio_features": 64, "input_type": "logfbank", "vocab_file": os.path.join(TOY, "vocab.txt"),
+            "dataset_files": [csv_path],
+        }
     base = {
         "use_horovod": False, "num_epochs": 500, "num_gpus": 1, "batch_size_per_gpu": 10,
         "save_summaries_steps": 10, "print_loss_steps": 100, "print_samples_steps": None, "eval_steps": 1000,
@@ -72,8 +80,9 @@ def _config(tmpdir):
     return Speech2Text, train_cfg, eval_cfg
 
 
-def test_w2l_style_model_converges_on_reference_toy_speech(tmp_path):
-    model_cls, train_cfg, eval_cfg = _config(tmp_path)  # installs the compat import surface
+@pytest.mark.parametrize("backend", ["librosa", "psf"])
+def test_w2l_style_model_converges_on_reference_toy_speech(tmp_path, backend):
+    model_cls, train_cfg, eval_cfg = _config(tmp_path, backend)  # installs the compat import surface
     from open_seq2seq.utils.funcs import train, evaluate_model
     from open_seq2seq.utils import checkpoint as ckpt
     train_model = model_cls(params=train_cfg, mode="train", hvd=None)
@@ -92,7 +101,7 @@ def test_w2l_style_model_converges_on_reference_toy_speech(tmp_path):
     assert torch.equal(before, train_model.engine.master)
     out = evaluate_model(eval_model)
     assert torch.equal(before, train_model.engine.master)  # evaluation does not touch the weights
-    print("toy convergence: train loss %.3f, eval loss %.3f, WER %.4f" % (loss, out["Eval loss"], out["Eval WER"]))
+    print("toy convergence (%s backend): train loss %.3f, eval loss %.3f, WER %.4f" % (backend, loss, out["Eval loss"], out["Eval WER"]))
     assert loss < 5.0
     assert out["Eval loss"] < 30.0
     assert out["Eval WER"] < 0.1
