@@ -27,6 +27,10 @@ class TorchDistHvd(object):
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
+            # the all-reduce overlaps persistent one-CTA-per-SM conv kernels: every SM NCCL occupies is one
+            # the convolutions lose, and 16 channels already saturate NVLink for 128 MB buckets
+            # (tools/n2_sweep.sh: 43.5 -> 42.8 ms/step at N = 2); the user's own setting wins
+            os.environ.setdefault("NCCL_MAX_CTAS", "16")
             torch.cuda.set_device(local)
             if not dist.is_initialized():
                 dist.init_process_group("nccl", rank=rank, world_size=world,
