@@ -166,6 +166,26 @@ def create_logdir(args, base_config):
     return None, None
 
 
+def adjust_for_benchmark(train_config, args):
+    """--benchmark (reference utils.py:846-865): no samples / summaries / checkpoints, empty logdir,
+    max_steps = bench_steps instead of num_epochs, bench_start default 10."""
+    deco_print("Adjusting config for benchmarking")
+    train_config["print_samples_steps"] = None
+    train_config["print_loss_steps"] = 1
+    train_config["save_summaries_steps"] = None
+    train_config["save_checkpoint_steps"] = None
+    train_config["logdir"] = str("")
+    if "num_epochs" in train_config:
+        del train_config["num_epochs"]
+    train_config["max_steps"] = args.bench_steps
+    if args.bench_start:
+        train_config["bench_start"] = args.bench_start
+    elif "bench_start" not in train_config:
+        train_config["bench_start"] = 10
+    train_config["data_layer_params"]["shuffle"] = False
+    deco_print("New benchmarking config: max_steps={} shuffle=False".format(args.bench_steps))
+
+
 def create_model(args, base_config, config_module, base_model, hvd=None, checkpoint=None):
     """utils.py:791-882: merge mode-specific params, apply --benchmark rewrites, build + compile."""
     train_config = copy.deepcopy(base_config)
@@ -182,21 +202,8 @@ def create_model(args, base_config, config_module, base_model, hvd=None, checkpo
         if key in config_module:
             nested_update(infer_config, copy.deepcopy(config_module[key]))
     if args.benchmark:
-        deco_print("Adjusting config for benchmarking")
-        train_config["print_samples_steps"] = None
-        train_config["print_loss_steps"] = 1
-        train_config["save_summaries_steps"] = None
-        train_config["save_checkpoint_steps"] = None
-        train_config["logdir"] = None
-        if "num_epochs" in train_config:
-            del train_config["num_epochs"]
-        train_config["max_steps"] = args.bench_steps
-        if args.bench_start:
-            train_config["bench_start"] = args.bench_start
-        elif "bench_start" not in train_config:
-            train_config["bench_start"] = 10
-        train_config["data_layer_params"]["shuffle"] = False
-        deco_print("New benchmarking config: max_steps={} shuffle=False".format(args.bench_steps))
+        adjust_for_benchmark(train_config, args)
+        args.mode = "train"
     if args.mode == "train_eval":
         train_model = base_model(params=train_config, mode="train", hvd=hvd)
         train_model.compile()

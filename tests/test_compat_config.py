@@ -1,6 +1,7 @@
 """CPU tests of the drop-in boundary at the Python level: reference-style configs load through the
 `open_seq2seq` / `tensorflow` compat surface, params dicts are validated with the reference's rules,
 and the plugin classes can be constructed (no GPU work happens before compile())."""
+import copy
 import os
 import sys
 
@@ -154,3 +155,19 @@ def test_levenshtein_and_wer_known_answers():
     assert levenshtein("", "abc") == 3 and levenshtein("abc", "abc") == 0
     assert levenshtein("this is a test".split(), "this is test".split()) == 1
     assert levenshtein("hello world".split(), "world hello".split()) == 2
+
+
+def test_benchmark_flag_rewrites_the_train_config_like_the_reference():
+    """utils.py:846-865: --benchmark empties logdir (a str, so Model's params check still passes), drops
+    num_epochs for max_steps = bench_steps and silences samples / summaries / checkpoints."""
+    import argparse
+    from open_seq2seq.models import Speech2Text
+    from open_seq2seq.utils.utils import adjust_for_benchmark
+    _, cfg, _, mod = get_base_config(["--config_file=" + OWN_CFG, "--mode=train"])
+    train_cfg = copy.deepcopy(cfg)
+    nested_update(train_cfg, copy.deepcopy(mod["train_params"]))
+    adjust_for_benchmark(train_cfg, argparse.Namespace(bench_steps=30, bench_start=None))
+    assert train_cfg["logdir"] == "" and train_cfg["max_steps"] == 30 and "num_epochs" not in train_cfg
+    assert train_cfg["bench_start"] == 10 and train_cfg["save_checkpoint_steps"] is None
+    assert train_cfg["data_layer_params"]["shuffle"] is False
+    check_params(train_cfg, Speech2Text.get_required_params(), Speech2Text.get_optional_params())
