@@ -9,16 +9,20 @@ import torch
 
 
 def latest_checkpoint(ckpt_dir):
-    files = glob.glob(os.path.join(ckpt_dir, "model.ckpt-*.pt"))
+    """Highest-step checkpoint of a directory (model.ckpt-<step>.pt, or val_loss=<x>-step-<step>.pt in
+    best_models)."""
+    files = glob.glob(os.path.join(ckpt_dir, "*-*.pt"))
     if not files:
         return None
-    step = lambda f: int(re.search(r"model\.ckpt-(\d+)\.pt$", f).group(1))
+    step = lambda f: int(re.search(r"-(\d+)\.pt$", f).group(1))
     return max(files, key=step)
 
 
-def save(engine, logdir, step, keep=5, extra=None):
+def save(engine, logdir, step, keep=5, extra=None, prefix="model.ckpt"):
+    """prefix: file stem; the evaluation hook's best-model copies use "val_loss=<loss>-step"
+    (utils/hooks.py:228-236) inside logdir/best_models."""
     os.makedirs(logdir, exist_ok=True)
-    path = os.path.join(logdir, "model.ckpt-%d.pt" % step)
+    path = os.path.join(logdir, "%s-%d.pt" % (prefix, step))
     state = {
         "params": {n: v.detach().cpu() for n, v in engine.named_parameters()},
         "momentum": {n: engine.param_view(n, engine.mom).detach().cpu() for n, _ in engine.named_parameters()},
@@ -32,10 +36,11 @@ def save(engine, logdir, step, keep=5, extra=None):
         "ema": engine._opt["ema"].cpu(), "step": step, "extra": extra or {},
     }
     torch.save(state, path)
-    files = sorted(glob.glob(os.path.join(logdir, "model.ckpt-*.pt")),
-                   key=lambda f: int(re.search(r"-(\d+)\.pt$", f).group(1)))
+    # keep the `keep` most recently written files of this directory (tf.train.Saver(max_to_keep))
+    files = sorted(glob.glob(os.path.join(logdir, "*-*.pt")), key=os.path.getmtime)
     for f in files[:-keep]:
-        os.remove(f)
+        if f != path:
+            os.remove(f)
     return path
 
 

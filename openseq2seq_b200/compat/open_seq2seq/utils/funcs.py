@@ -4,6 +4,7 @@ The training loop keeps the reference's observable behaviour: print_loss_steps, 
 save_checkpoint_steps on rank 0 (num_checkpoints kept), evaluation every eval_steps, and the
 throughput meter of `--benchmark`: after `bench_start` steps accumulate wall time and input frames
 and print "Avg objects per second" (objects = input frames, summed over ranks)."""
+import os
 import time
 
 import torch
@@ -52,7 +53,10 @@ def train(train_model, eval_model=None, debug_port=None, custom_hooks=None):
     eval_every = p.get("eval_steps") if eval_model is not None else None
     logdir = p.get("logdir")
     last_step = train_model.last_step
-    step = 0
+    # resume (--continue_learning restored the engine state): continue from the restored global step
+    step = int(train_model.engine.istate[2]) if hasattr(train_model.engine, "istate") else 0
+    first_step = step
+    best_eval_loss = 1e9   # RunEvaluationHook._best_eval_loss (utils/hooks.py:182)
     total_time, total_objects = 0.0, 0.0
     deco_print("Starting training ({} steps)".format(last_step))
     t_print = time.time()
@@ -61,8 +65,8 @@ def train(train_model, eval_model=None, debug_port=None, custom_hooks=None):
         batch = next(it)
         loss, n_objects = train_model.train_step(batch)
         step += 1
-        timed = step > bench_start
-        if timed or (print_every and step % print_every == 0):
+        timed = step - first_step > bench_start
+        if (timed or (print_every and step % print_every == 0)) and torch.cuda.is_available():
             torch.cuda.synchronize()
         if timed:
             total_time += time.time() - t0
@@ -77,8 +81,16 @@ def train(train_model, eval_model=None, debug_port=None, custom_hooks=None):
         if save_every and logdir and step % save_every == 0 and master:
             from . import checkpoint as ckpt
             ckpt.save(train_model.engine, logdir, step, keep=p.get("num_checkpoints", 5))
-        if eval_every and step % eval_every == 0:
-            evaluate_model(eval_model)
+        if eval_every and (step % eval_every == 0 or step == last_step):
+            # RunEvaluationHook (utils/hooks.py:192-245): every eval_steps and at the last step; the best
+            # validation loss so far gets its own checkpoint under logdir/best_models
+            out = evaluate_model(eval_model)
+            eval_loss = out.get("Eval loss")
+            if save_every and logdir and master and eval_loss is not None and eval_loss < best_eval_loss:
+                from . import checkpoint as ckpt
+                best_eval_loss = eval_loss
+                ckpt.save(train_model.engine, os.path.join(logdir, "best_models"), step,
+                          keep=p.get("num_checkpoints", 5), prefix="val_loss={:.4f}-step".format(eval_loss))
     if save_every and logdir and master:
         from . import checkpoint as ckpt
         ckpt.save(train_model.engine, logdir, step, keep=p.get("num_checkpoints", 5))
@@ -86,8 +98,8 @@ def train(train_model, eval_model=None, debug_port=None, custom_hooks=None):
         total_objects = train_model.hvd.sum_scalar(total_objects)
     if master:
         deco_print("Finished training")
-        if step > bench_start and total_time > 0:
-            deco_print("Avg time per step: {:.3f}s".format(total_time / (step - bench_start)))
+        if step - first_step > bench_start and total_time > 0:
+            deco_print("Avg time per step: {:.3f}s".format(total_time / (step - first_step - bench_start)))
             deco_print("Avg objects per second: {:.3f}".format(total_objects / total_time))
         else:
             deco_print("Not enough steps for benchmarking")

@@ -145,6 +145,12 @@ def check_logdir(args, base_config, restore_best_checkpoint=False):
             return None
         if args.mode in ("infer", "eval", "interactive_infer"):
             if os.path.isdir(logdir) and os.listdir(logdir) != []:
+                best_dir = os.path.join(ckpt_dir, "best_models")
+                if restore_best_checkpoint and os.path.isdir(best_dir):
+                    deco_print("Restoring from the best checkpoint")
+                    ckpt_dir = best_dir
+                else:
+                    deco_print("Restoring from the latest checkpoint")
                 ckpt = latest_checkpoint(ckpt_dir)
                 if ckpt is None:
                     raise IOError("There is no valid checkpoint in the {}. Can't load model".format(ckpt_dir))
