@@ -27,6 +27,9 @@ BATCH = 32
 SR = 16000
 TRAIN_GFLOP_PER_AUDIO_S = 100.02  # SURVEY.md section 8d (fwd+dgrad+wgrad conv/GEMM FLOPs)
 NOMINAL_BF16_TFLOPS = 2250.0   # dense bf16, B200 data sheet (at the 1965 MHz boost clock)
+METRIC = "audio-seconds/sec Jasper-10x5 bf16 train"
+WORKLOAD = ("Jasper 10x5 DR (configs/jasper10x5_dr.py = reference jasper10x5_LibriSpeech_nvgrad): "
+            "featurizer + encoder + FC + CTC fwd/bwd + LARC/NovoGrad, 16 kHz x 15 s utterances")
 
 
 def _peaks():
@@ -154,11 +157,16 @@ def run_reference(args):
     dt = time.time() - t0
     val = n * B * secs / dt
     sample = "%d steps of %d utterance x %.0f s (fp32, torch CPU port of the reference graph)" % (n, B, secs)
-    out = {"impl": "reference", "metric": "audio-seconds/sec Jasper-10x5 train", "value": round(val, 4),
+    # same metric / unit / workload as the own arm; each step is a bounded sample of that workload (the
+    # reference's CPU path computes in fp32)
+    out = {"impl": "reference", "metric": METRIC, "value": round(val, 4),
            "unit": "audio-s/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
            "ms_per_step": round(1000 * dt / n, 2), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "Jasper 10x5 DR training step (featurizer+encoder+CTC+NovoGrad), CPU port"},
+           "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B,
+                      "audio_seconds_per_utt": secs, "parallelism": "cpu",
+                      "sample": "bounded sample of the workload: " + sample,
+                      "train_gflop_per_audio_s": TRAIN_GFLOP_PER_AUDIO_S},
            "cpu_baseline": {"value": round(val, 4), "unit": "audio-s/s", "cores": cores, "kind": "port",
                             "sample": sample},
            "e2e": {"value": round(val, 4), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -315,12 +323,11 @@ def run_own(args):
         except Exception:
             traffic = None
     out = {
-        "metric": "audio-seconds/sec Jasper-10x5 bf16 train",
+        "metric": METRIC,
         "value": round(value, 2), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Jasper 10x5 DR (configs/jasper10x5_dr.py = reference jasper10x5_LibriSpeech_nvgrad): "
-                               "featurizer + encoder + FC + CTC fwd/bwd + LARC/NovoGrad, 16 kHz x 15 s utterances",
+        "config": {"workload": WORKLOAD,
                    "batch_per_gpu": args.batch, "global_batch": args.batch * world, "audio_seconds_per_utt": AUDIO_SECONDS,
                    "parallelism": "dp%d" % world,
                    "l2_policy": "working set per step (activations ~6 GB, params/grads ~5 GB) >> 126 MB L2; no flush needed",
