@@ -205,10 +205,14 @@ def test_psf_backend_shape_and_normalisation_pins(golden_dir):
                     length = 1 + (sig.shape[0] - n_win) // n_hop
                     if length % 8:
                         length += 8 - length % 8
-                    f, dur = FZ.psf_logfbank_features(sig, sr, num_features, win, stride, pad_to=8)
-                    assert f.shape == (length, num_features)
-                    assert abs(np.mean(f)) < 1e-6 and abs(np.std(f) - 1.0) < 1e-6
-                    assert abs(dur - len(sig) / sr) < 1e-12
+                    for fn in (FZ.psf_logfbank_features, FZ.psf_spectrogram_features, FZ.psf_mfcc_features):
+                        f, dur = fn(sig, sr, num_features, win, stride, pad_to=8)
+                        assert f.shape == (length, num_features)
+                        assert abs(np.mean(f)) < 1e-6 and abs(np.std(f) - 1.0) < 1e-6
+                        assert abs(dur - len(sig) / sr) < 1e-12
+                # the reference's assertion on too many spectrogram bins (speech_utils_test.py:74-85)
+                with pytest.raises(AssertionError):
+                    FZ.psf_spectrogram_features(sig, sr, int(sr * win) // 2 + 2, win, stride, pad_to=8)
     fb = FZ.psf_mel_filterbank(64, 512, 16000, 0.0, 8000.0)
     assert fb.shape == (64, 257) and fb.min() >= 0.0 and fb.max() <= 1.0
     peaks = fb.argmax(1)
