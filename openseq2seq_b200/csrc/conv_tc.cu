@@ -11,12 +11,20 @@
 //
 //  * tapgemm_kmajor  (forward and dgrad):  D[t, n] = sum_k sum_c A[b, t + off0 + k*step, c] * Wk[n, c]
 //      A tile  : 128 rows(t) x 64 c, K-major, SWIZZLE_128B        (TMA 3-D box {64,128,1})
-//      B tile  : BN rows(n)  x 64 c, K-major, SWIZZLE_128B        (TMA 2-D box {64,BN})
-//      forward : Wk = W^T[k] stored [K][C_out][C_in];   off0 = -pad_left, step = +dilation
-//      dgrad   : Wk = W[k]   stored [K][C_in][C_out];   off0 = +pad_left, step = -dilation
+//      B tile  : the ONE bf16 weight copy in the natural TF layout W[k][C_in][C_out]:
+//      forward : read MN-major (boxes {64 n, 64 c}, b_major = 1); off0 = -pad_left, step = +dilation
+//      dgrad   : read K-major  (box {64 c, BN n});                off0 = +pad_left, step = -dilation
 //  * tapgemm_mnmajor (wgrad): dW[k][ci, co] += sum_{b,t} X[b, t + k*dil - pad_left, ci] * dY[b, t, co]
 //      both operands are MN-major (the reduction index t is the smem row), so X and dY are used in
-//      their natural NWC layout with no transposed copies.
+//      their natural NWC layout with no transposed copies; stream-K over (tile, utterance) items.
+//  * tapgemm_kmajor_pair / tapgemm_mnmajor_pair: the same computations on clusters of two CTAs
+//      (tcgen05.mma.cta_group::2, M = 256): each CTA stages its own 128 A rows and HALF of the B tile.
+//  * tapgemm_kmajor_pair_halo: additionally ONE activation halo tile per 64-channel chunk shared by all
+//      taps (the UMMA descriptor start address moves by whole 128-byte rows).
+//  All forward / dgrad variants accumulate chunk-major, taps inner, so their outputs are bitwise equal
+//  (os2s_conv_tuning selects the variant; tests/test_kernels_gpu.py::test_conv_kernel_variants_agree).
+//  Epilogue extras: BN statistics of the rounded output (forward), BN-backward sums of the layer whose
+//  dA the tile is (dgrad), fp32 accumulate mode.
 //
 // Warp roles (192 threads, persistent CTAs, 1 CTA / SM):
 //   warp 0 : TMA producer (one elected lane)        warp 1 : tcgen05.mma issuer (one elected lane)
