@@ -97,6 +97,9 @@ base_params = {
 train_params = {
     "data_layer": Speech2TextDataLayer,
     "data_layer_params": {
+        "augmentation": {
+            "speed_perturbation_ratio": [0.9, 1., 1.1],
+        },
         # 16 kHz / 15 s LibriSpeech-shaped synthetic utterances
         "dataset_files": ["synthetic:64:15.0:1234"],
         "max_duration": 16.7,

@@ -34,7 +34,23 @@ extern "C" {
 #define OS2S_OUT_BF16 0
 #define OS2S_OUT_F32 1
 #define OS2S_OUT_F32_ACC 2 /* out(fp32) += result */
-#define OS2S_OUT_F16 3     /* fp16: conv outputs that only feed the BN kernels */
+#define OS2S_OUT_F16 3     /* fp16, saturating: conv outputs that only feed the BN kernels */
+#define OS2S_OUT_F16_GRAD 4 /* fp16, overflow -> inf: gradients in OS2S_HALF_F16 mode */
+
+/* Storage formats: bit flags of the `dtypes` argument of the *_p entry points (the entry points without the
+ * suffix are the same calls with dtypes = 0).
+ *   OS2S_HALF_F16 : every 16-bit tensor of the path -- layer inputs / outputs (x, a, the features), the weight
+ *                   working copies and all activation gradients (dy, dA) -- is fp16 instead of bf16: the
+ *                   reference's own "mixed" mode (fp16 storage + fp32 masters + loss scaling, mp_wrapper.py).
+ *                   It is one switch, not per tensor: tcgen05.mma kind::f16 faults (illegal instruction) when
+ *                   its two operands have different formats, and every tensor above meets every other one in
+ *                   some MMA (x*w forward, dy*w data gradient, x*dy weight gradient).  fp16 gradient stores
+ *                   do not saturate (OS2S_OUT_F16_GRAD): an overflow becomes inf and the Backoff scaler skips.
+ *   OS2S_CONV_F32 : conv outputs y (the BN inputs, never a tensor-core operand) are fp32 instead of fp16.
+ * With both flags the full 54-layer Jasper 10x5 reproduces the fp32 reference's logits to < 1e-2 (L2) at
+ * random initialisation; DESIGN.md section 4 has the measured error of every combination. */
+#define OS2S_HALF_F16 1
+#define OS2S_CONV_F32 2
 
 const char* os2s_last_error(void);
 int os2s_version(void);
@@ -53,12 +69,16 @@ int os2s_conv_tuning(int pair_mode, int halo_mode);
  *   x  : bf16 [B,T,C_in]          w  : bf16 [K][C_in][C_out]  (natural TF kernel layout)
  *   y  : bf16 / fp32 [B,T,C_out]  (out_mode)
  * The stride-2 first Jasper layer is expressed by the caller as a stride-1 conv over the input
- * viewed as [B, T/2, 2*C_in] with K' = ceil(K/2) taps (see openseq2seq_b200/runtime/layers.py).
+ * viewed as [B, T/2, 2*C_in] with K' = ceil(K/2) taps (see JasperEngine._fix_folded_layout in openseq2seq_b200/engine.py).
  * bn_stats (may be NULL): fp32 [2][C_out], pre-zeroed; the epilogue adds the per-channel sum and sum of
  * squares of the ROUNDED outputs (what os2s_bn_stats would compute), fusing the BN statistics pass.
  * Constraints: C_in % 64 == 0, C_out % 64 == 0. */
 int os2s_conv1d_fwd(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
                     int K, int dil, int pad_left, int out_mode, float* bn_stats, void* stream);
+/* dtypes & OS2S_HALF_F16: x and w are fp16.  bn_stats may be combined with OS2S_OUT_F32 (statistics of the fp32
+ * outputs) as well as with the 2-byte modes. */
+int os2s_conv1d_fwd_p(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
+                      int K, int dil, int pad_left, int out_mode, float* bn_stats, int dtypes, void* stream);
 
 /* Same convolution with the weights given transposed, wt : bf16 [K][C_out][C_in] (K-major B
  * operand).  Kept for A/B measurements of the two operand layouts (tools/gpu_conv_check.py). */
@@ -69,9 +89,10 @@ int os2s_conv1d_fwd_wt(const void* x, const void* wt, void* y, int B, int T, int
  *   dy : bf16 [B,T,C_out]   w : bf16 [K][C_in][C_out] (natural TF layout)   dx : out_mode */
 int os2s_conv1d_dgrad(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
                       int K, int dil, int pad_left, int out_mode, void* stream);
+/* dtypes & OS2S_HALF_F16: dy and w are fp16; pass out_mode = OS2S_OUT_F16_GRAD for an fp16 dx. */
+int os2s_conv1d_dgrad_p(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
+                        int K, int dil, int pad_left, int out_mode, int dtypes, void* stream);
 
-/* wgrad: dw[k,c,o] = sum_{b,t} x[b, t - pad_left + k*dil, c] * dy[b,t,o]   (fp32 [K][C_in][C_out])
- * Overwrites dw.  Constraints: C_in % 128 == 0, C_out % 64 == 0. */
 /* Data gradient whose output dx is the gradient dA of a single-branch BN + ReLU + dropout layer
  * (conv_blocks.py:208-227 followed by tdnn_encoder.py:255): dx is written as bf16 and the epilogue
  * also accumulates that layer's batch-norm backward reductions,
@@ -81,18 +102,32 @@ int os2s_conv1d_dgrad(const void* dy, const void* w, void* dx, int B, int T, int
 int os2s_conv1d_dgrad_bnred(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
                             int K, int dil, int pad_left, const void* a, const void* y, float keep, float* red,
                             void* stream);
+/* dtypes & OS2S_CONV_F32: y is fp32; dtypes & OS2S_HALF_F16: dy, w and dx are fp16 (a is only tested for
+ * zero bits, so either format is accepted). */
+int os2s_conv1d_dgrad_bnred_p(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
+                              int K, int dil, int pad_left, const void* a, const void* y, float keep, float* red,
+                              int dtypes, void* stream);
 /* Second half of os2s_bn_bwd for one branch when `red` already holds the two sums (see above). */
 int os2s_bn_bwd_apply(const void* y, const float* mean_invstd, const float* gamma, float* dgamma, float* dbeta,
                       void* dy, const void* dA, const void* a, const float* red, int M, int C, float keep,
                       void* stream);
+int os2s_bn_bwd_apply_p(const void* y, const float* mean_invstd, const float* gamma, float* dgamma, float* dbeta,
+                        void* dy, const void* dA, const void* a, const float* red, int M, int C, float keep,
+                        int dtypes, void* stream);
 
+/* wgrad: dw[k,c,o] = sum_{b,t} x[b, t - pad_left + k*dil, c] * dy[b,t,o]   (fp32 [K][C_in][C_out])
+ * Overwrites dw.  Constraints: C_in % 128 == 0, C_out % 64 == 0.  (_p: dtypes & OS2S_HALF_F16: x and dy are fp16.) */
 int os2s_conv1d_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out,
                       int K, int dil, int pad_left, void* stream);
+int os2s_conv1d_wgrad_p(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out,
+                        int K, int dil, int pad_left, int dtypes, void* stream);
 
 /* W fp32 [K][C_in][C_out] -> w bf16 (same layout) and wt bf16 [K][C_out][C_in]. Either output may
  * be NULL.  Replaces the fp32->fp16 assign of mp_wrapper.py:104-109 when used standalone. */
 int os2s_weight_cast_transpose(const float* w_master, void* w_bf16, void* wt_bf16, int K, int C_in,
                                int C_out, void* stream);
+int os2s_weight_cast_transpose_p(const float* w_master, void* w_half, void* wt_half, int K, int C_in,
+                                 int C_out, int dtypes, void* stream);
 
 /* ---- K3/K4: batch norm (training) + residual sum + ReLU + dropout + sequence mask ------------
  * reference: tf.layers.batch_normalization(training=True) conv_blocks.py:208-227 / :91-101,
@@ -144,6 +179,21 @@ int os2s_bn_bwd_ld(int n_branch, const void* const* y_host, const int* ld_host,
                    float* const* dgamma_host, float* const* dbeta_host, void* const* dy_host, const void* dA,
                    int dA_is_f32, const void* a, float* red, int M, int C, float keep, int apply_relu,
                    void* stream);
+/* The _ld calls with selectable storage formats: OS2S_CONV_F32 -> every y[j] is fp32 (ld still in
+ * elements); OS2S_HALF_F16 -> `out` is written as fp16 (forward); a 16-bit dA is read and every dy[j] is
+ * written as fp16 (backward; `a` is only tested for zero bits). */
+int os2s_bn_apply_fwd_p(int n_branch, const void* const* y_host, const int* ld_host,
+                        const float* const* stats_host, const int* stats_ld_host,
+                        const float* const* gamma_host, const float* const* beta_host,
+                        float* const* mean_invstd_host, float* const* moving_host, void* out,
+                        const int* lens, int B, int T, int C, float eps, float momentum, float keep,
+                        uint64_t seed, int apply_relu, float relu_clip, int use_moving,
+                        const long long* step_counter_dev, int dtypes, void* stream);
+int os2s_bn_bwd_p(int n_branch, const void* const* y_host, const int* ld_host,
+                  const float* const* mean_invstd_host, const float* const* gamma_host,
+                  float* const* dgamma_host, float* const* dbeta_host, void* const* dy_host, const void* dA,
+                  int dA_is_f32, const void* a, float* red, int M, int C, float keep, int apply_relu,
+                  int dtypes, void* stream);
 
 /* n (<= 64) strided 2-D copies in one launch: dst[i][r][0:row_bytes) = src[i][r][0:row_bytes) for
  * r < rows[i], row r at base + r * pitch.  row_bytes, pitches and base addresses are multiples of 16.
@@ -161,6 +211,11 @@ int os2s_fc_fwd(const void* x, const float* w, const float* bias, float* logits,
 /* dx bf16 [M,H] (may be NULL), dw fp32 [H,V], db fp32 [V] (dw/db overwritten; may be NULL). */
 int os2s_fc_bwd(const void* x, const float* dlogits, const float* w, void* dx, float* dw, float* db,
                 int M, int H, int V, void* stream);
+/* dtypes & OS2S_HALF_F16: x is fp16 and dx is written as fp16. */
+int os2s_fc_fwd_p(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V,
+                  int dtypes, void* stream);
+int os2s_fc_bwd_p(const void* x, const float* dlogits, const float* w, void* dx, float* dw, float* db,
+                  int M, int H, int V, int dtypes, void* stream);
 
 /* ---- K6: tf.nn.ctc_loss(ignore_longer_outputs_than_inputs=True) + mask_nans (ctc_loss.py:77-89)
  * logits fp32, element (b,t,v) at logits[b*stride_b + t*stride_t + v]; blank = V-1.
@@ -202,6 +257,9 @@ typedef struct os2s_opt_hparams {
   int lr_policy;
   float decay_rate;      /* exp_decay */
   int staircase;         /* exp_decay: use_staircase_decay */
+  float max_grad_norm;   /* > 0: tf.clip_by_global_norm on the unscaled, rank-averaged gradients
+                          * (optimizers.py:408-433); exclusive with LARC as in the reference (:161-164) */
+  int wb_f16;            /* working copies are written as fp16 (OS2S_HALF_F16) instead of bf16 */
 } os2s_opt_hparams;
 
 /* Tensor table (all device memory, owned by the caller):
@@ -229,6 +287,16 @@ int os2s_opt_step(void* const* w, void* const* g, void* const* m, void* const* w
  * regularizer), may be NULL. */
 int os2s_opt_step2(void* const* w, void* const* g, void* const* m, void* const* v, void* const* wb,
                    const float* reg, const long long* sizes, const int* chunk_tensor,
+                   const long long* chunk_offset, int n_tensors, int n_chunks, const os2s_opt_hparams* hp,
+                   float* norms,
+                   int* nonfinite, float* fstate, long long* istate, float* coef, float* ema,
+                   void* stream);
+
+/* Same step with `frozen`: device int32 [n_tensors], non-zero = the variable is not in var_list
+ * (freeze_variables_regex, models/model.py:502-507): no update, no weight decay, no momentum, not part of the
+ * global gradient norm.  May be NULL. */
+int os2s_opt_step3(void* const* w, void* const* g, void* const* m, void* const* v, void* const* wb,
+                   const float* reg, const int* frozen, const long long* sizes, const int* chunk_tensor,
                    const long long* chunk_offset, int n_tensors, int n_chunks, const os2s_opt_hparams* hp,
                    float* norms,
                    int* nonfinite, float* fstate, long long* istate, float* coef, float* ema,
@@ -266,6 +334,38 @@ int os2s_features_forward(const int16_t* wave, const long long* offsets, const i
                           int F, int T_pad, int max_samples, float dither, uint64_t seed, float preemph,
                           int psf_backend, int pad_to, int norm_per_feature, void* absmax_ws, float* raw_ws,
                           void* out_bf16, float* out_f32, int* out_lens, void* stream);
+
+/* ---- K1b: audio augmentation (speech_utils.py:225-268) and the remaining data-layer options ------------
+ * absmax[b] = max |wave_b| (uint32 [B]): the gain of normalize_signal (:216-222) is 1 / (absmax + 1e-5). */
+int os2s_wave_absmax(const int16_t* wave, const long long* offsets, const int* n_samples, int B, void* absmax,
+                     void* stream);
+/* out_b = resample(wave_b * gain_b, sr_orig -> sr_new[b]) + noise_amp[b] * N(0,1)   (fp32, normalised signal)
+ *   speed perturbation (:245-259): resampy.resample(filter='kaiser_best'), i.e. band-limited sinc interpolation
+ *   with the right half of the Kaiser-windowed sinc in interp_win (n_win = num_zeros * num_table + 1 entries,
+ *   num_table samples per zero crossing, linear interpolation between entries; the caller builds the table);
+ *   sr_new[b] = int(sr_orig * stretch) or 0 for "not resampled"; n_out[b] = int(n_samples[b] * sr_new / sr_orig).
+ *   noise (:262-266): noise_amp[b] = 10^(dB / 20) or 0.  sr_new / noise_amp / interp_win may be NULL.
+ *   gain > 0 replaces 1 / (absmax + 1e-5) (params['gain']); absmax may then be NULL. */
+int os2s_augment_signal(const int16_t* wave, const long long* offsets, const int* n_samples, int B,
+                        const void* absmax, float gain, const int* sr_new, int sr_orig, const float* interp_win,
+                        int n_win, int num_table, const float* noise_amp, uint64_t seed, float* out,
+                        const long long* out_offsets, const int* n_out, int max_out, void* stream);
+/* os2s_features_forward with the remaining options of get_speech_features_librosa (:322-441):
+ *   sig / sig_offsets : fp32 signal from os2s_augment_signal (replaces wave * gain; offsets / n_samples then
+ *                       describe sig); librosa backend only
+ *   gain              : > 0 = params['gain'] (fixed normalisation gain), 0 = 1 / (max|x| + 1e-5)
+ *   features_mean / features_std : fp32 [F] (params['features_mean'], ['features_std_dev']) or NULL = computed
+ *   masks             : int32 [B][n_masks][3] = (kind 0 = frequency / 1 = time, base, width): spec-augment
+ *                       (:419-433) zeros written into the normalised features; width 0 = no-op
+ *   dtypes & OS2S_HALF_F16 : out16 is fp16 instead of bf16 */
+int os2s_features_forward_p(const int16_t* wave, const float* sig, const long long* sig_offsets,
+                            const long long* offsets, const int* n_samples, int B,
+                            const float* mel, const int* mel_band, const float* window, int n_fft, int win, int hop,
+                            int F, int T_pad, int max_samples, float dither, uint64_t seed, float preemph,
+                            int psf_backend, int pad_to, int norm_per_feature, float gain,
+                            const float* features_mean, const float* features_std, const int* masks, int n_masks,
+                            void* absmax_ws, float* raw_ws, void* out16, float* out_f32, int* out_lens,
+                            int dtypes, void* stream);
 
 #ifdef __cplusplus
 }

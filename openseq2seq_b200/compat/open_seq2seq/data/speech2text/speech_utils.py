@@ -73,3 +73,16 @@ def read_wav(filename, expected_sr):
         signal = (np.clip(signal, -1.0, 1.0) * 32767).astype(np.int16) if signal.dtype.kind == "f" \
             else signal.astype(np.int16)
     return signal
+
+
+def kaiser_best_table():
+    """Interpolation table of resampy's 'kaiser_best' filter (the speed perturbation of
+    augment_audio_signal, speech_utils.py:245-259): the right half of a Kaiser-windowed sinc with 64 zero
+    crossings sampled 2**9 times per crossing, rolloff 0.9475937167399596, beta 14.769656459379492
+    (resampy.filters.sinc_window).  Returns (float64 [64 * 512 + 1], 512); os2s_augment_signal interpolates it."""
+    num_zeros, precision, rolloff, beta = 64, 9, 0.9475937167399596, 14.769656459379492
+    num_table = 2 ** precision
+    n = num_table * num_zeros
+    sinc_win = rolloff * np.sinc(rolloff * np.linspace(0, num_zeros, num=n + 1, endpoint=True))
+    taper = np.kaiser(2 * n + 1, beta)[n:]
+    return taper * sinc_win, num_table

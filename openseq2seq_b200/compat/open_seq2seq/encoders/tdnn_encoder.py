@@ -39,7 +39,9 @@ class TDNNEncoder(Encoder):
         apply_relu, clip = tf.resolve_activation(p["activation_fn"])
         if not apply_relu:
             raise NotImplementedError("TDNNEncoder: identity activation is not built")
-        return dict(convnet_layers=p["convnet_layers"], bn_momentum=p.get("bn_momentum", 0.90),
+        from open_seq2seq.utils.utils import resolve_initializer
+        init = resolve_initializer(p, self._model.params if self._model is not None else {}, "TDNNEncoder")
+        return dict(encoder_init=init, convnet_layers=p["convnet_layers"], bn_momentum=p.get("bn_momentum", 0.90),
                     bn_epsilon=p.get("bn_epsilon", 1e-3), use_conv_mask=p.get("use_conv_mask", False),
                     training=(self._mode == "train"), dropout_keep_default=p["dropout_keep_prob"],
                     relu_clip=clip)

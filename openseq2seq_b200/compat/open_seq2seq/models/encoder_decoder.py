@@ -51,9 +51,13 @@ class EncoderDecoderModel(Model):
         if share_with is not None:
             self.engine = share_with.engine
             self._shared = True
+            if hasattr(self._data_layer, "set_feature_dtype"):
+                self._data_layer.set_feature_dtype(self.engine.act_dtype)
             return
         self._shared = False
+        from open_seq2seq.utils.utils import resolve_initializer
         enc_kw = self._encoder.engine_kwargs()
+        enc_kw["decoder_init"] = resolve_initializer(self._decoder.params, self.params, type(self._decoder).__name__)
         dl = self._data_layer.params
         world = self._hvd.size() if self.on_horovod else 1
         opt_kw = {}
@@ -62,9 +66,17 @@ class EncoderDecoderModel(Model):
         self.engine = JasperEngine(num_features=dl["num_audio_features"],
                                    vocab_size=self._decoder.params["tgt_vocab_size"], opt=opt_kw,
                                    world_size=world, seed=self._seed, **enc_kw)
+        if hasattr(self._data_layer, "set_feature_dtype"):
+            self._data_layer.set_feature_dtype(self.engine.act_dtype)   # features arrive in the engine's 16-bit format
+        from open_seq2seq.utils import checkpoint as ckpt
         if checkpoint is not None:
-            from open_seq2seq.utils import checkpoint as ckpt
             ckpt.restore(self.engine, checkpoint)
+            self._restored_from = checkpoint
+        elif self.mode == "train" and self.params.get("load_model"):
+            # utils/funcs.py:117-144: no checkpoint in logdir -> initialise matching variables from load_model
+            n = ckpt.restore_partial(self.engine, self.params["load_model"])
+            from open_seq2seq.utils.utils import deco_print
+            deco_print("load_model: restored %d variables from %s" % (n, self.params["load_model"]))
         if self.on_horovod:
             self._hvd.broadcast_parameters(self.engine)
             if self.mode == "train":

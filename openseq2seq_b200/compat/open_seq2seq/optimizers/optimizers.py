@@ -55,6 +55,10 @@ def optimizer_engine_kwargs(params, last_step):
         kw["l2_regularizer_scale"] = float(rp.get("scale", 0.0))
     if params.get("max_grad_norm") is not None and params.get("larc_params") is not None:
         raise AttributeError("LARC and gradient norm clipping should not be used together")
+    if params.get("max_grad_norm") is not None:
+        kw["max_grad_norm"] = float(params["max_grad_norm"])      # optimizers.py:408-433, global-norm clipping
+    if params.get("freeze_variables_regex") is not None:
+        kw["freeze_variables_regex"] = params["freeze_variables_regex"]   # models/model.py:502-507
     larc = params.get("larc_params")
     if larc is not None:
         kw["larc_eta"] = larc["larc_eta"]

@@ -44,6 +44,32 @@ def save(engine, logdir, step, keep=5, extra=None, prefix="model.ckpt"):
     return path
 
 
+def restore_partial(engine, load_model_dir):
+    """`load_model` (utils/funcs.py:117-144): every variable of the latest checkpoint in load_model_dir whose name
+    and shape match a variable of this model is loaded (weights, BN moving statistics, optimizer slots);
+    global_step and the loss-scaler state are not.  Returns the number of restored tensors."""
+    path = load_model_dir if os.path.isfile(load_model_dir) else latest_checkpoint(load_model_dir)
+    if path is None:
+        raise IOError("load_model: there is no checkpoint in {}".format(load_model_dir))
+    state = torch.load(path, map_location="cpu")
+    n = 0
+    ok = {}
+    for name, v in state["params"].items():
+        if name in engine.by_name and tuple(engine.by_name[name]["shape"]) == tuple(v.shape):
+            ok[name] = v
+    engine.load_parameters(ok)
+    n += len(ok)
+    for name in ok:
+        m = state.get("momentum", {}).get(name)
+        if m is not None:
+            engine.param_view(name, engine.mom).copy_(m)
+    for k, v in state.get("moving", {}).items():
+        if k in engine.moving and tuple(engine.moving[k].shape) == tuple(v.shape):
+            engine.moving[k].copy_(v)
+            n += 1
+    return n
+
+
 def restore(engine, path):
     state = torch.load(path, map_location="cpu")
     engine.load_parameters(state["params"])

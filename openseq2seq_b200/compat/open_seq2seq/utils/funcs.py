@@ -60,7 +60,14 @@ def train(train_model, eval_model=None, debug_port=None, custom_hooks=None):
     total_time, total_objects = 0.0, 0.0
     deco_print("Starting training ({} steps)".format(last_step))
     t_print = time.time()
-    while step < last_step:
+    while True:
+        if step >= last_step:
+            # StopAtStepHook counts global_step, which a loss-scale overflow does not advance
+            # (mp_wrapper.py:115-120): the host counts attempts without synchronising and reconciles here
+            dev_step = int(train_model.engine.istate[2]) if hasattr(train_model.engine, "istate") else step
+            if dev_step >= last_step:
+                break
+            step = dev_step
         t0 = time.time()
         batch = next(it)
         loss, n_objects = train_model.train_step(batch)
@@ -107,6 +114,12 @@ def train(train_model, eval_model=None, debug_port=None, custom_hooks=None):
 
 
 def evaluate(model, checkpoint):
+    """utils/funcs.py:205-218: restore `checkpoint` (create_model already did when it compiled the model; a
+    model built elsewhere is restored here), then one pass over the evaluation set."""
+    if checkpoint is not None and getattr(model, "_restored_from", None) != checkpoint:
+        from . import checkpoint as ckpt
+        ckpt.restore(model.engine, checkpoint)
+        model._restored_from = checkpoint
     return evaluate_model(model)
 
 

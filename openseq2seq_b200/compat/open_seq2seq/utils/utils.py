@@ -192,6 +192,25 @@ def adjust_for_benchmark(train_config, args):
     deco_print("New benchmarking config: max_steps={} shuffle=False".format(args.bench_steps))
 
 
+def resolve_initializer(params, model_params, who):
+    """Plugin params -> the engine's initializer name.  The reference passes `initializer(**initializer_params)`
+    to tf.layers (encoder.py:60-72 / decoder.py: falls back to the model's `initializer`); without one tf.layers
+    uses glorot_uniform, which is xavier_initializer(uniform=True).  Anything that is not Xavier raises."""
+    import tensorflow as tf
+    init = params.get("initializer", model_params.get("initializer"))
+    ip = params.get("initializer_params", model_params.get("initializer_params")) or {}
+    if "initializer" not in params and "initializer" in model_params:
+        ip = model_params.get("initializer_params") or {}
+    if init is None:
+        return "xavier_uniform"
+    if init is tf.contrib.layers.xavier_initializer:
+        extra = set(ip) - {"uniform", "seed", "dtype"}
+        if extra:
+            raise NotImplementedError("%s: xavier_initializer arguments %r are not built" % (who, sorted(extra)))
+        return "xavier_uniform" if ip.get("uniform", True) else "xavier_truncnorm"
+    raise NotImplementedError("%s: initializer %r is not built (tf.contrib.layers.xavier_initializer is)" % (who, init))
+
+
 def create_model(args, base_config, config_module, base_model, hvd=None, checkpoint=None):
     """utils.py:791-882: merge mode-specific params, apply --benchmark rewrites, build + compile."""
     train_config = copy.deepcopy(base_config)
@@ -212,16 +231,17 @@ def create_model(args, base_config, config_module, base_model, hvd=None, checkpo
         args.mode = "train"
     if args.mode == "train_eval":
         train_model = base_model(params=train_config, mode="train", hvd=hvd)
-        train_model.compile()
+        train_model.compile(checkpoint=checkpoint)   # --continue_learning: resume from the found checkpoint
         eval_model = base_model(params=eval_config, mode="eval", hvd=hvd)
         eval_model.compile(force_var_reuse=True, share_with=train_model)
         return [train_model, eval_model]
     if args.mode == "train":
         model = base_model(params=train_config, mode="train", hvd=hvd)
-        model.compile(force_var_reuse=False)
+        model.compile(force_var_reuse=False, checkpoint=checkpoint)
     elif args.mode == "eval":
+        # funcs.evaluate restores the checkpoint check_logdir found before it runs (utils/funcs.py:205-218)
         model = base_model(params=eval_config, mode="eval", hvd=hvd)
-        model.compile(force_var_reuse=False)
+        model.compile(force_var_reuse=False, checkpoint=checkpoint)
     else:
         model = base_model(params=infer_config, mode=args.mode, hvd=hvd)
         model.compile(checkpoint=checkpoint)

@@ -42,7 +42,7 @@ constexpr int kABytes = kTileM * kChunkK * 2;
 constexpr int kNumThreads = 192;
 constexpr int kSmemBudget = 220 * 1024;
 
-enum OutMode : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ACC = 2, OUT_F16 = 3 };
+enum OutMode : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ACC = 2, OUT_F16 = 3, OUT_F16_GRAD = 4 };
 
 struct KMajorParams {
   int B, T_out, n_mtiles, n_ntiles, N_total;
@@ -54,8 +54,11 @@ struct KMajorParams {
   // epilogue accumulates that layer's BN-backward reductions into `stats` instead:
   //   stats[0][c] += sum_rows dz,  stats[1][c] += sum_rows dz * y,   dz = dA * [a != 0] * bwd_inv_keep
   const void* bwd_a;           // bf16 [B, T, N_total]: forward output of that layer (zeros = relu/dropout/mask)
-  const void* bwd_y;           // fp16 [B, T, N_total]: its conv output (the BN input)
+  const void* bwd_y;           // fp16 (fp32 when bwd_y_f32) [B, T, N_total]: its conv output (the BN input)
   float bwd_inv_keep;
+  int bwd_y_f32;
+  int a_bf16;                  // format of BOTH tensor-core operands: 1 = bf16, 0 = fp16 (tcgen05 kind::f16
+                               // rejects mixed operand formats: an illegal-instruction fault on sm_100a)
   int halo_rows, halo_off, sb_stages;  // halo variant: rows of the A halo tile, row offset of tap 0, B ring depth
   void* out;
   long long out_row_stride;    // elements
@@ -94,6 +97,16 @@ struct PipeState {
   }
 };
 
+// two fp32 accumulators -> one 32-bit word of the 2-byte output format
+__device__ __forceinline__ uint32_t pack16(int out_mode, float a, float b) {
+  return out_mode == OUT_BF16 ? pack_bf16(a, b) : out_mode == OUT_F16 ? pack_f16(a, b) : pack_f16_raw(a, b);
+}
+// the two values of a staged 32-bit word of the ROUNDED tile
+__device__ __forceinline__ float2 unpack16(int out_mode, uint32_t v) {
+  if (out_mode == OUT_BF16) return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+
 // One epilogue warp: 32 rows x ncur columns, TMEM -> registers -> staging rows -> coalesced global
 // stores (+ the BN statistics of the rounded outputs when do_stats).
 template <int BN>
@@ -113,34 +126,20 @@ __device__ __forceinline__ void epilogue_rows(const KMajorParams& p, uint8_t* st
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 v;
-        if (p.out_mode == OUT_BF16) {
-          v.x = pack_bf16(__uint_as_float(r0[q * 8 + 0]), __uint_as_float(r0[q * 8 + 1]));
-          v.y = pack_bf16(__uint_as_float(r0[q * 8 + 2]), __uint_as_float(r0[q * 8 + 3]));
-          v.z = pack_bf16(__uint_as_float(r0[q * 8 + 4]), __uint_as_float(r0[q * 8 + 5]));
-          v.w = pack_bf16(__uint_as_float(r0[q * 8 + 6]), __uint_as_float(r0[q * 8 + 7]));
-        } else {
-          v.x = pack_f16(__uint_as_float(r0[q * 8 + 0]), __uint_as_float(r0[q * 8 + 1]));
-          v.y = pack_f16(__uint_as_float(r0[q * 8 + 2]), __uint_as_float(r0[q * 8 + 3]));
-          v.z = pack_f16(__uint_as_float(r0[q * 8 + 4]), __uint_as_float(r0[q * 8 + 5]));
-          v.w = pack_f16(__uint_as_float(r0[q * 8 + 6]), __uint_as_float(r0[q * 8 + 7]));
-        }
+        v.x = pack16(p.out_mode, __uint_as_float(r0[q * 8 + 0]), __uint_as_float(r0[q * 8 + 1]));
+        v.y = pack16(p.out_mode, __uint_as_float(r0[q * 8 + 2]), __uint_as_float(r0[q * 8 + 3]));
+        v.z = pack16(p.out_mode, __uint_as_float(r0[q * 8 + 4]), __uint_as_float(r0[q * 8 + 5]));
+        v.w = pack16(p.out_mode, __uint_as_float(r0[q * 8 + 6]), __uint_as_float(r0[q * 8 + 7]));
         *reinterpret_cast<uint4*>(myrow + q * 16) = v;
       }
       if (wide) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 v;
-          if (p.out_mode == OUT_BF16) {
-            v.x = pack_bf16(__uint_as_float(r1[q * 8 + 0]), __uint_as_float(r1[q * 8 + 1]));
-            v.y = pack_bf16(__uint_as_float(r1[q * 8 + 2]), __uint_as_float(r1[q * 8 + 3]));
-            v.z = pack_bf16(__uint_as_float(r1[q * 8 + 4]), __uint_as_float(r1[q * 8 + 5]));
-            v.w = pack_bf16(__uint_as_float(r1[q * 8 + 6]), __uint_as_float(r1[q * 8 + 7]));
-          } else {
-            v.x = pack_f16(__uint_as_float(r1[q * 8 + 0]), __uint_as_float(r1[q * 8 + 1]));
-            v.y = pack_f16(__uint_as_float(r1[q * 8 + 2]), __uint_as_float(r1[q * 8 + 3]));
-            v.z = pack_f16(__uint_as_float(r1[q * 8 + 4]), __uint_as_float(r1[q * 8 + 5]));
-            v.w = pack_f16(__uint_as_float(r1[q * 8 + 6]), __uint_as_float(r1[q * 8 + 7]));
-          }
+          v.x = pack16(p.out_mode, __uint_as_float(r1[q * 8 + 0]), __uint_as_float(r1[q * 8 + 1]));
+          v.y = pack16(p.out_mode, __uint_as_float(r1[q * 8 + 2]), __uint_as_float(r1[q * 8 + 3]));
+          v.z = pack16(p.out_mode, __uint_as_float(r1[q * 8 + 4]), __uint_as_float(r1[q * 8 + 5]));
+          v.w = pack16(p.out_mode, __uint_as_float(r1[q * 8 + 6]), __uint_as_float(r1[q * 8 + 7]));
           *reinterpret_cast<uint4*>(myrow + 64 + q * 16) = v;
         }
       }
@@ -153,7 +152,31 @@ __device__ __forceinline__ void epilogue_rows(const KMajorParams& p, uint8_t* st
         const uint32_t* gy = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.bwd_y) + off + c) + lane;
         const long long rs2 = p.out_row_stride >> 1;   // row stride in 2-element words
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        {
+        if (p.bwd_y_f32) {
+          // fp32 conv outputs: two 16-row halves (32 + 16 + 16 registers of loads in flight)
+          const float2* gy4 = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p.bwd_y) + off + c) + lane;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t av[16];
+            float2 yv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = h * 16 + i;
+              const bool ok = r < nvalid;
+              av[i] = ok ? __ldg(ga + (long long)r * rs2) : 0u;
+              yv[i] = ok ? __ldg(gy4 + (long long)r * rs2) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(stage + (h * 16 + i) * kEpiRowBytes + lane * 4);
+              const float2 dv = unpack16(p.out_mode, v);
+              const float dz0 = (av[i] & 0x7FFFu) ? dv.x * p.bwd_inv_keep : 0.f;
+              const float dz1 = (av[i] & 0x7FFF0000u) ? dv.y * p.bwd_inv_keep : 0.f;
+              s0 += dz0; q0 += dz0 * yv[i].x;
+              s1 += dz1; q1 += dz1 * yv[i].y;
+            }
+          }
+        } else {
           // all 32 rows of the warp's slab at once: 64 independent 4-byte loads in flight per lane, one
           // memory round trip per 64-column chunk (the last tile's epilogue is not hidden by a main loop)
           uint32_t av[32], yv[32];
@@ -168,8 +191,9 @@ __device__ __forceinline__ void epilogue_rows(const KMajorParams& p, uint8_t* st
             const uint32_t v = *reinterpret_cast<const uint32_t*>(stage + i * kEpiRowBytes + lane * 4);
             const float2 yf = __half22float2(*reinterpret_cast<const __half2*>(&yv[i]));
             // rows >= nvalid have av == 0 -> dz == 0
-            const float dz0 = (av[i] & 0x7FFFu) ? __uint_as_float(v << 16) * p.bwd_inv_keep : 0.f;
-            const float dz1 = (av[i] & 0x7FFF0000u) ? __uint_as_float(v & 0xFFFF0000u) * p.bwd_inv_keep : 0.f;
+            const float2 dv = unpack16(p.out_mode, v);
+            const float dz0 = (av[i] & 0x7FFFu) ? dv.x * p.bwd_inv_keep : 0.f;
+            const float dz1 = (av[i] & 0x7FFF0000u) ? dv.y * p.bwd_inv_keep : 0.f;
             s0 += dz0; q0 += dz0 * yf.x;
             s1 += dz1; q1 += dz1 * yf.y;
           }
@@ -183,17 +207,9 @@ __device__ __forceinline__ void epilogue_rows(const KMajorParams& p, uint8_t* st
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
         for (int r = 0; r < nvalid; ++r) {
           const uint32_t v = *reinterpret_cast<const uint32_t*>(stage + r * kEpiRowBytes + lane * 4);
-          float x0, x1;
-          if (p.out_mode == OUT_BF16) {
-            x0 = __uint_as_float(v << 16);
-            x1 = __uint_as_float(v & 0xFFFF0000u);
-          } else {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
-            x0 = f.x;
-            x1 = f.y;
-          }
-          s0 += x0; q0 += x0 * x0;
-          s1 += x1; q1 += x1 * x1;
+          const float2 f = unpack16(p.out_mode, v);
+          s0 += f.x; q0 += f.x * f.x;
+          s1 += f.y; q1 += f.y * f.y;
         }
         sacc[c + 2 * lane] += s0;
         sacc[c + 2 * lane + 1] += s1;
@@ -236,6 +252,16 @@ __device__ __forceinline__ void epilogue_rows(const KMajorParams& p, uint8_t* st
       for (int q = 0; q < 8; ++q)
         *reinterpret_cast<uint4*>(myrow + q * 16) = make_uint4(r[q * 4 + 0], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
       __syncwarp();
+      if (do_stats) {
+        // fp32 conv outputs: lane owns column c + lane of the chunk
+        float s0 = 0.f, q0 = 0.f;
+        for (int rr = 0; rr < nvalid; ++rr) {
+          const float x = *reinterpret_cast<const float*>(stage + rr * kEpiRowBytes + lane * 4);
+          s0 += x; q0 += x * x;
+        }
+        sacc[c + lane] += s0;
+        sacc[BN + c + lane] += q0;
+      }
       // all eight read-modify-write loads are issued before the first use (one latency, not eight)
       float4 old[8];
       if (p.out_mode == OUT_F32_ACC) {
@@ -355,7 +381,7 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t ti = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
         const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
-        const uint32_t idesc = make_idesc(kTileM, ncur, 0, BMN ? 1 : 0);
+        const uint32_t idesc = make_idesc(kTileM, ncur, 0, BMN ? 1 : 0, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
@@ -387,8 +413,8 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int quad = warp & 3;
     uint8_t* stage = epi_stage + quad * kEpiWarpBytes;
     float* sacc = epi_stats + quad * 2 * BN;
-    const bool two_byte = (p.out_mode == OUT_BF16 || p.out_mode == OUT_F16);
-    const bool do_stats = (p.stats != nullptr) && two_byte;
+    const bool two_byte = (p.out_mode == OUT_BF16 || p.out_mode == OUT_F16 || p.out_mode == OUT_F16_GRAD);
+    const bool do_stats = (p.stats != nullptr) && (two_byte || p.out_mode == OUT_F32);
     if (do_stats)
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
     int cur_nt = -1;
@@ -538,7 +564,7 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint32_t ti = 0;
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
         const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
-        const uint32_t idesc = make_idesc(2 * kTileM, ncur, 0, BMN ? 1 : 0);
+        const uint32_t idesc = make_idesc(2 * kTileM, ncur, 0, BMN ? 1 : 0, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
@@ -566,8 +592,8 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int quad = warp & 3;
     uint8_t* stage = epi_stage + quad * kEpiWarpBytes;
     float* sacc = epi_stats + quad * 2 * BN;
-    const bool two_byte = (p.out_mode == OUT_BF16 || p.out_mode == OUT_F16);
-    const bool do_stats = (p.stats != nullptr) && two_byte;
+    const bool two_byte = (p.out_mode == OUT_BF16 || p.out_mode == OUT_F16 || p.out_mode == OUT_F16_GRAD);
+    const bool do_stats = (p.stats != nullptr) && (two_byte || p.out_mode == OUT_F32);
     if (do_stats)
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
     int cur_nt = -1;
@@ -725,7 +751,7 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
       uint32_t ti = 0;
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
         const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
-        const uint32_t idesc = make_idesc(2 * kTileM, ncur, 0, BMN ? 1 : 0);
+        const uint32_t idesc = make_idesc(2 * kTileM, ncur, 0, BMN ? 1 : 0, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
@@ -759,8 +785,8 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
     const int quad = warp & 3;
     uint8_t* stage = epi_stage + quad * kEpiWarpBytes;
     float* sacc = epi_stats + quad * 2 * BN;
-    const bool two_byte = (p.out_mode == OUT_BF16 || p.out_mode == OUT_F16);
-    const bool do_stats = (p.stats != nullptr) && two_byte;
+    const bool two_byte = (p.out_mode == OUT_BF16 || p.out_mode == OUT_F16 || p.out_mode == OUT_F16_GRAD);
+    const bool do_stats = (p.stats != nullptr) && (two_byte || p.out_mode == OUT_F32);
     if (do_stats)
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
     int cur_nt = -1;
@@ -815,6 +841,7 @@ struct MNMajorParams {
   float* dw;                   // [K][C_in][C_out] fp32; zeroed by the launcher, split units red.add into it
   int C_in, C_out;
   int m_off;                   // first C_in row of this launch
+  int a_bf16;                  // format of x AND dy: 1 = bf16, 0 = fp16
 };
 
 template <int BN>
@@ -918,7 +945,7 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         int unit, b_lo, b_hi, k_, mi_, ni_;
         next_segment(it, unit, b_lo, b_hi);
         decode(unit, k_, mi_, ni_);
-        const uint32_t idesc = make_idesc(kTileM, (ni_ == p.n_tiles - 1) ? p.n_tail : BN, 1, 1);
+        const uint32_t idesc = make_idesc(kTileM, (ni_ == p.n_tiles - 1) ? p.n_tail : BN, 1, 1, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
         const int n_iters = (b_hi - b_lo) * p.t_chunks;
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -1111,7 +1138,7 @@ tapgemm_mnmajor_pair(const __grid_constant__ CUtensorMap map_x, const __grid_con
         int unit, b_lo, b_hi, k_, mi_, ni_;
         next_segment(it, unit, b_lo, b_hi);
         decode(unit, k_, mi_, ni_);
-        const uint32_t idesc = make_idesc(2 * kTileM, (ni_ == p.n_tiles - 1) ? p.n_tail : BN, 1, 1);
+        const uint32_t idesc = make_idesc(2 * kTileM, (ni_ == p.n_tiles - 1) ? p.n_tail : BN, 1, 1, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
         const int n_iters = (b_hi - b_lo) * p.t_chunks;
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -1399,7 +1426,7 @@ static int pick_bn_mnmajor(int n) {
 //   out    : [B, T, N_total]  (bf16, or fp32 with optional accumulate)
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
                 int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st,
-                const void* bwd_a, const void* bwd_y, float bwd_inv_keep) {
+                const void* bwd_a, const void* bwd_y, float bwd_inv_keep, int act_f16, int bwd_y_f32) {
   if (C_red % 64 != 0) return fail(ERR_UNSUPPORTED, "conv_tc: reduction channels must be a multiple of 64");
   // pairs: 256-wide tiles whose last tile is 128 or 256 wide (each CTA stages half of it)
   // (N = 256 is one tile wide: 96 pair tiles over 74 SM pairs quantise worse than 128-wide single tiles)
@@ -1437,6 +1464,8 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
   p.bwd_a = bwd_a;
   p.bwd_y = bwd_y;
   p.bwd_inv_keep = bwd_inv_keep;
+  p.bwd_y_f32 = bwd_y_f32;
+  p.a_bf16 = act_f16 ? 0 : 1;
   p.out = out;
   p.out_row_stride = N_total;
   p.out_batch_stride = (long long)T * N_total;
@@ -1473,7 +1502,7 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
 // wgrad: dw[K][C_in][C_out] (fp32) += X^T * dY per tap. dw must be zeroed by the caller when
 // splits > 1 (the kernel reduces with red.global.add); with splits == 1 it is overwritten.
 int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out, int K,
-               int dil, int pad_left, int* splits_used, cudaStream_t st) {
+               int dil, int pad_left, int* splits_used, cudaStream_t st, int x_f16) {
   if (C_in % 128 != 0) return fail(ERR_UNSUPPORTED, "conv_wgrad: C_in must be a multiple of 128");
   const int BN = pick_bn_mnmajor(C_out);
   if (BN == 0) return fail(ERR_UNSUPPORTED, "conv_wgrad: C_out must be a multiple of 64");
@@ -1499,6 +1528,7 @@ int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in,
   p.C_in = C_in;
   p.C_out = C_out;
   p.m_off = 0;
+  p.a_bf16 = x_f16 ? 0 : 1;
   // stream-K: every CTA gets an equal share of (unit, utterance) items; tiles shared between CTAs are
   // reduced with red.add into the zeroed gradient (a plain store is used when a CTA owns a whole unit)
   if (splits_used) *splits_used = 0;

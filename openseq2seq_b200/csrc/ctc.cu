@@ -10,6 +10,7 @@
 #include "kernels.h"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 namespace os2s {
@@ -27,18 +28,24 @@ __device__ __forceinline__ float log_add(float a, float b) {
 // HBM-bound (49 MB of activations for 1.4 GFLOP): one 768-thread CTA per SM, a warp takes two rows at a
 // time, stages them in shared memory with 16-byte coalesced loads (all loads of a row pair in flight
 // before the first use), then lane l owns h = l, l+32, ... (row stride V = 29 floats: conflict-free).
+// layer outputs are bf16, or fp16 with OS2S_ACT_F16
+template <bool XF16>
+__device__ __forceinline__ float act_to_float(uint16_t v) {
+  if (XF16) return __half2float(__ushort_as_half(v));
+  return __uint_as_float((uint32_t)v << 16);
+}
 constexpr int kFcThreads = 768;
 constexpr int kFcWarps = kFcThreads / 32;
-template <int VMAX>
+template <int VMAX, bool XF16>
 __global__ void __launch_bounds__(kFcThreads)
-fc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+fc_fwd_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
               float* __restrict__ logits, int M, int H, int V) {
   extern __shared__ float wsh[];  // [H][V] fp32, then per warp 2 rows of x (bf16)
-  __nv_bfloat16* xsh = reinterpret_cast<__nv_bfloat16*>(wsh + (((size_t)H * V + 3) & ~(size_t)3));
+  uint16_t* xsh = reinterpret_cast<uint16_t*>(wsh + (((size_t)H * V + 3) & ~(size_t)3));
   for (int i = threadIdx.x; i < H * V; i += kFcThreads) wsh[i] = w[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __nv_bfloat16* xw = xsh + (size_t)warp * 2 * H;
+  uint16_t* xw = xsh + (size_t)warp * 2 * H;
   const int warp_global = blockIdx.x * kFcWarps + warp;
   const int n_warps = gridDim.x * kFcWarps;
   const int hv = H >> 3;  // 16-byte vectors per row
@@ -55,8 +62,8 @@ fc_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, 
 #pragma unroll
     for (int v = 0; v < VMAX; ++v) acc0[v] = acc1[v] = 0.f;
     for (int h = lane; h < H; h += 32) {
-      const float a0 = __bfloat162float(xw[h]);
-      const float a1 = __bfloat162float(xw[H + h]);
+      const float a0 = act_to_float<XF16>(xw[h]);
+      const float a1 = act_to_float<XF16>(xw[H + h]);
       const float* wr = &wsh[h * V];
 #pragma unroll
       for (int v = 0; v < VMAX; ++v) {
@@ -98,18 +105,20 @@ static size_t fc_smem_bytes(int H, int V) {
 }
 
 int fc_fwd(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V,
-           cudaStream_t st) {
+           cudaStream_t st, int x_f16) {
   if (V > 32 || V < 1) return fail(ERR_UNSUPPORTED, "fc_fwd: vocabulary > 32 not supported by the small-N kernel");
   if (H % 8 != 0) return fail(ERR_UNSUPPORTED, "fc_fwd: H must be a multiple of 8");
   const size_t smem = fc_smem_bytes(H, V);
   if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "fc_fwd: H*V too large for shared memory");
   static bool attr_done = false;
   if (!attr_done) {
-    OS2S_CUDA(cudaFuncSetAttribute(fc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(fc_fwd_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(fc_fwd_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_done = true;
   }
   const int grid = device_sm_count();
-  fc_fwd_kernel<32><<<grid, kFcThreads, smem, st>>>((const __nv_bfloat16*)x, w, bias, logits, M, H, V);
+  if (x_f16) fc_fwd_kernel<32, true><<<grid, kFcThreads, smem, st>>>((const uint16_t*)x, w, bias, logits, M, H, V);
+  else fc_fwd_kernel<32, false><<<grid, kFcThreads, smem, st>>>((const uint16_t*)x, w, bias, logits, M, H, V);
   return check_launch("fc_fwd");
 }
 
@@ -117,14 +126,14 @@ int fc_fwd(const void* x, const float* w, const float* bias, float* logits, int 
 // dx[m, h] = sum_v dl[m, v] * w[h, v]   (bf16 out);  one warp per row, lanes over h; the row is
 // assembled in shared memory and written with 16-byte coalesced stores.
 __global__ void __launch_bounds__(kFcThreads)
-fc_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w, __nv_bfloat16* __restrict__ dx,
-                int M, int H, int V) {
-  extern __shared__ float wsh[];  // [H][V], then per warp one output row (bf16)
-  __nv_bfloat16* xsh = reinterpret_cast<__nv_bfloat16*>(wsh + (((size_t)H * V + 3) & ~(size_t)3));
+fc_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w, uint16_t* __restrict__ dx,
+                int M, int H, int V, int f16) {
+  extern __shared__ float wsh[];  // [H][V], then per warp one output row (bf16 / fp16)
+  uint16_t* xsh = reinterpret_cast<uint16_t*>(wsh + (((size_t)H * V + 3) & ~(size_t)3));
   for (int i = threadIdx.x; i < H * V; i += kFcThreads) wsh[i] = w[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __nv_bfloat16* xw = xsh + (size_t)warp * 2 * H;
+  uint16_t* xw = xsh + (size_t)warp * 2 * H;
   const int warp_global = blockIdx.x * kFcWarps + warp;
   const int n_warps = gridDim.x * kFcWarps;
   const int hv = H >> 3;
@@ -139,7 +148,7 @@ fc_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w, __nv_
 #pragma unroll
       for (int v = 0; v < 32; ++v)
         if (v < V) acc += d[v] * wr[v];
-      xw[h] = __float2bfloat16(acc);
+      xw[h] = f16 ? __half_as_ushort(__float2half_rn(acc)) : __bfloat16_as_ushort(__float2bfloat16(acc));
     }
     __syncwarp();
     uint4* g = reinterpret_cast<uint4*>(dx + (size_t)m * H);
@@ -152,8 +161,9 @@ fc_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w, __nv_
 // h of a CTA keeps V partial sums over the CTA's row chunk (dl rows broadcast from shared memory),
 // then one atomicAdd per (h, v) -- chunks are sized for ~2 CTAs per SM so the atomics stay few.
 constexpr int kFcWgTile = 64;   // dl rows staged per pass
+template <bool XF16>
 __global__ void __launch_bounds__(256)
-fc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dl, float* __restrict__ dw,
+fc_wgrad_kernel(const uint16_t* __restrict__ x, const float* __restrict__ dl, float* __restrict__ dw,
                 float* __restrict__ db, int M, int H, int V, int rows_per_cta) {
   __shared__ float dsh[kFcWgTile][32];
   const int row0 = blockIdx.x * rows_per_cta;
@@ -172,10 +182,10 @@ fc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ d
     }
     __syncthreads();
     if (h < H) {
-      const __nv_bfloat16* xp = x + (size_t)r0 * H + h;
+      const uint16_t* xp = x + (size_t)r0 * H + h;
 #pragma unroll 8
       for (int r = 0; r < rows; ++r) {
-        const float a = __bfloat162float(xp[(size_t)r * H]);
+        const float a = act_to_float<XF16>(xp[(size_t)r * H]);
         const float4* drow = reinterpret_cast<const float4*>(dsh[r]);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -199,7 +209,7 @@ fc_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ d
 }
 
 int fc_bwd(const void* x, const float* dl, const float* w, void* dx, float* dw, float* db, int M, int H, int V,
-           cudaStream_t st) {
+           cudaStream_t st, int x_f16) {
   if (V > 32 || V < 1) return fail(ERR_UNSUPPORTED, "fc_bwd: vocabulary > 32 not supported");
   if (H % 8 != 0) return fail(ERR_UNSUPPORTED, "fc_bwd: H must be a multiple of 8");
   const size_t smem = fc_smem_bytes(H, V);
@@ -210,7 +220,7 @@ int fc_bwd(const void* x, const float* dl, const float* w, void* dx, float* dw, 
     attr_done = true;
   }
   if (dx) {
-    fc_dgrad_kernel<<<device_sm_count(), kFcThreads, smem, st>>>(dl, w, (__nv_bfloat16*)dx, M, H, V);
+    fc_dgrad_kernel<<<device_sm_count(), kFcThreads, smem, st>>>(dl, w, (uint16_t*)dx, M, H, V, x_f16);
     int s = check_launch("fc_dgrad");
     if (s) return s;
   }
@@ -222,7 +232,8 @@ int fc_bwd(const void* x, const float* dl, const float* w, void* dx, float* dw, 
     int rows_per_cta = (M + chunks - 1) / chunks;
     rows_per_cta = ((rows_per_cta + kFcWgTile - 1) / kFcWgTile) * kFcWgTile;
     chunks = (M + rows_per_cta - 1) / rows_per_cta;
-    fc_wgrad_kernel<<<dim3(chunks, hy), 256, 0, st>>>((const __nv_bfloat16*)x, dl, dw, db, M, H, V, rows_per_cta);
+    if (x_f16) fc_wgrad_kernel<true><<<dim3(chunks, hy), 256, 0, st>>>((const uint16_t*)x, dl, dw, db, M, H, V, rows_per_cta);
+    else fc_wgrad_kernel<false><<<dim3(chunks, hy), 256, 0, st>>>((const uint16_t*)x, dl, dw, db, M, H, V, rows_per_cta);
     return check_launch("fc_wgrad");
   }
   return OK;

@@ -9,8 +9,11 @@ namespace os2s {
 
 // ---------------------------------------------------------------- weight cast + transpose
 // w fp32 [K][R][C] -> w_bf16 [K][R][C] and wt_bf16 [K][C][R]; 32x32 smem tile, coalesced both ways.
-__global__ void weight_cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wb,
-                                             __nv_bfloat16* __restrict__ wt, int R, int C) {
+__device__ __forceinline__ uint16_t to_half16(float v, int f16) {
+  return f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16(v));
+}
+__global__ void weight_cast_transpose_kernel(const float* __restrict__ w, uint16_t* __restrict__ wb,
+                                             uint16_t* __restrict__ wt, int R, int C, int f16) {
   __shared__ float tile[32][33];
   const int k = blockIdx.z;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -20,7 +23,7 @@ __global__ void weight_cast_transpose_kernel(const float* __restrict__ w, __nv_b
     float v = 0.f;
     if (r < R && c < C) {
       v = src[(size_t)r * C + c];
-      if (wb) wb[(size_t)k * R * C + (size_t)r * C + c] = __float2bfloat16(v);
+      if (wb) wb[(size_t)k * R * C + (size_t)r * C + c] = to_half16(v, f16);
     }
     tile[i][threadIdx.x] = v;
   }
@@ -28,17 +31,16 @@ __global__ void weight_cast_transpose_kernel(const float* __restrict__ w, __nv_b
   if (wt) {
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
       const int c = c0 + i, r = r0 + threadIdx.x;
-      if (r < R && c < C) wt[(size_t)k * R * C + (size_t)c * R + r] = __float2bfloat16(tile[threadIdx.x][i]);
+      if (r < R && c < C) wt[(size_t)k * R * C + (size_t)c * R + r] = to_half16(tile[threadIdx.x][i], f16);
     }
   }
 }
 
 int weight_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int K, int C_in, int C_out,
-                          cudaStream_t st) {
+                          cudaStream_t st, int f16) {
   if (K <= 0 || C_in <= 0 || C_out <= 0) return fail(ERR_INVALID, "weight_cast_transpose: bad shape");
   dim3 grid((C_out + 31) / 32, (C_in + 31) / 32, K), block(32, 8);
-  weight_cast_transpose_kernel<<<grid, block, 0, st>>>(w, (__nv_bfloat16*)w_bf16, (__nv_bfloat16*)wt_bf16,
-                                                       C_in, C_out);
+  weight_cast_transpose_kernel<<<grid, block, 0, st>>>(w, (uint16_t*)w_bf16, (uint16_t*)wt_bf16, C_in, C_out, f16);
   return check_launch("weight_cast_transpose");
 }
 
@@ -66,6 +68,56 @@ __device__ __forceinline__ void f16x8_to_float(const uint4& v, float (&f)[8]) {
     const float2 t = __half22float2(h[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 float_to_f16x8(const float (&f)[8]) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+// One 8-channel vector of a conv output y: fp16 (16 bytes) or fp32 (32 bytes, OS2S_CONV_F32).
+template <bool YF32>
+struct YVec {
+  uint4 v[YF32 ? 2 : 1];
+};
+// vec = index of the 8-channel vector (row * (ld / 8) + column vector)
+template <bool YF32>
+__device__ __forceinline__ YVec<YF32> ld_yvec(const void* y, size_t vec) {
+  YVec<YF32> r;
+  if (YF32) {
+    const uint4* b = reinterpret_cast<const uint4*>(y) + vec * 2;
+    r.v[0] = __ldg(b);
+    r.v[YF32 ? 1 : 0] = __ldg(b + 1);
+  } else {
+    r.v[0] = __ldg(reinterpret_cast<const uint4*>(y) + vec);
+  }
+  return r;
+}
+template <bool YF32>
+__device__ __forceinline__ YVec<YF32> zero_yvec() {
+  YVec<YF32> r;
+  r.v[0] = make_uint4(0, 0, 0, 0);
+  r.v[YF32 ? 1 : 0] = make_uint4(0, 0, 0, 0);
+  return r;
+}
+template <bool YF32>
+__device__ __forceinline__ void yvec_to_float(const YVec<YF32>& y, float (&f)[8]) {
+  if (YF32) {
+    f[0] = __uint_as_float(y.v[0].x); f[1] = __uint_as_float(y.v[0].y);
+    f[2] = __uint_as_float(y.v[0].z); f[3] = __uint_as_float(y.v[0].w);
+    const uint4 w = y.v[YF32 ? 1 : 0];
+    f[4] = __uint_as_float(w.x); f[5] = __uint_as_float(w.y);
+    f[6] = __uint_as_float(w.z); f[7] = __uint_as_float(w.w);
+  } else {
+    const __half2* h = reinterpret_cast<const __half2*>(&y.v[0]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
   }
 }
 __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
@@ -262,8 +314,8 @@ __device__ __forceinline__ void bn_coef(const BnFwdParams& p, const BnBranchFwd&
   }
 }
 
-template <bool ONE>
-__global__ void __launch_bounds__(kEwMaxThreads, ONE ? 2 : 1)
+template <bool ONE, bool YF32, bool OF16>
+__global__ void __launch_bounds__(kEwMaxThreads, (ONE && !YF32) ? 2 : 1)
 bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
   const int C = p.C;
   const int M = p.B * p.T;
@@ -312,7 +364,7 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
     }
-    reinterpret_cast<uint4*>(p.out)[(size_t)ru * rs + t.cv] = float_to_bf16x8(o);
+    reinterpret_cast<uint4*>(p.out)[(size_t)ru * rs + t.cv] = OF16 ? float_to_f16x8(o) : float_to_bf16x8(o);
   };
   // (b, tt) of the thread's first row, advanced incrementally (no division in the loop)
   int row = t.row0 + t.r;
@@ -328,18 +380,17 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
       while (t2 >= p.T) { t2 -= p.T; ++bb; }
     }
     if (ONE) {
-      const uint4* yb = reinterpret_cast<const uint4*>(p.br[0].y) + t.cv;
       const size_t ys = (size_t)(p.br[0].ld >> 3);
-      uint4 v[kUnroll];
+      YVec<YF32> v[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
-        v[u] = live[u] ? __ldg(yb + (size_t)(row + u * t.RP) * ys) : make_uint4(0, 0, 0, 0);
+        v[u] = live[u] ? ld_yvec<YF32>(p.br[0].y, (size_t)(row + u * t.RP) * ys + t.cv) : zero_yvec<YF32>();
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const int ru = row + u * t.RP;
         if (ru >= t.row1) break;
         float f[8];
-        f16x8_to_float(v[u], f);
+        yvec_to_float<YF32>(v[u], f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = f[i] * sc0[i] + sf0[i];
         finish(f, ru, live[u]);
@@ -351,12 +402,11 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[u][i] = 0.f;
       for (int j = 0; j < p.n_branch; ++j) {
-        const uint4* yb = reinterpret_cast<const uint4*>(p.br[j].y) + t.cv;
         const size_t ys = (size_t)(p.br[j].ld >> 3);
-        uint4 v[kUnroll];
+        YVec<YF32> v[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
-          v[u] = live[u] ? __ldg(yb + (size_t)(row + u * t.RP) * ys) : make_uint4(0, 0, 0, 0);
+          v[u] = live[u] ? ld_yvec<YF32>(p.br[j].y, (size_t)(row + u * t.RP) * ys + t.cv) : zero_yvec<YF32>();
         float sc[8], sf[8];
         if (j == 0) {
 #pragma unroll
@@ -367,7 +417,7 @@ bn_apply_fwd_kernel(const BnFwdParams p, int rows_per_block) {
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           float f[8];
-          f16x8_to_float(v[u], f);
+          yvec_to_float<YF32>(v[u], f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[u][i] += f[i] * sc[i] + sf[i];
         }
@@ -393,10 +443,18 @@ int bn_apply_fwd(const BnFwdParams& p, cudaStream_t st) {
       return fail(ERR_INVALID, "bn_apply_fwd: bad leading dimension");
   const int M = p.B * p.T;
   const bool one = p.n_branch == 1;
-  const int rpb = rows_per_block_for(M, p.C, one ? 2 : 1);
+  const int rpb = rows_per_block_for(M, p.C, (one && !p.y_f32) ? 2 : 1);
   const int grid = (M + rpb - 1) / rpb;
-  if (one) bn_apply_fwd_kernel<true><<<grid, ew_threads(p.C), 0, st>>>(p, rpb);
-  else bn_apply_fwd_kernel<false><<<grid, ew_threads(p.C), 0, st>>>(p, rpb);
+  const int nt = ew_threads(p.C);
+#define OS2S_BN_FWD(ONE_, Y_, O_) bn_apply_fwd_kernel<ONE_, Y_, O_><<<grid, nt, 0, st>>>(p, rpb)
+  if (one) {
+    if (p.y_f32) { if (p.out_f16) OS2S_BN_FWD(true, true, true); else OS2S_BN_FWD(true, true, false); }
+    else { if (p.out_f16) OS2S_BN_FWD(true, false, true); else OS2S_BN_FWD(true, false, false); }
+  } else {
+    if (p.y_f32) { if (p.out_f16) OS2S_BN_FWD(false, true, true); else OS2S_BN_FWD(false, true, false); }
+    else { if (p.out_f16) OS2S_BN_FWD(false, false, true); else OS2S_BN_FWD(false, false, false); }
+  }
+#undef OS2S_BN_FWD
   return check_launch("bn_apply_fwd");
 }
 
@@ -414,24 +472,29 @@ __device__ __forceinline__ void load_dz_raw(const BnBwdParams& p, size_t vec_ind
     dz[0] = a0.x; dz[1] = a0.y; dz[2] = a0.z; dz[3] = a0.w;
     dz[4] = a1.x; dz[5] = a1.y; dz[6] = a1.z; dz[7] = a1.w;
   } else {
-    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.dA) + vec_index), dz);
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.dA) + vec_index);
+    if (p.h_f16) f16x8_to_float(raw, dz);
+    else bf16x8_to_float(raw, dz);
   }
   if (p.apply_relu) a_raw = __ldg(reinterpret_cast<const uint4*>(p.a) + vec_index);
 }
 __device__ __forceinline__ void gate_dz(const BnBwdParams& p, const uint4& a_raw, float (&dz)[8]) {
   if (p.apply_relu) {
-    float af[8];
-    bf16x8_to_float(a_raw, af);
+    // "a != 0" as a bit test: valid for bf16 and fp16 layer outputs alike (and immune to flush-to-zero)
+    const uint32_t w[4] = {a_raw.x, a_raw.y, a_raw.z, a_raw.w};
     const float inv_keep = 1.f / p.keep;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dz[i] = (af[i] != 0.f) ? dz[i] * inv_keep : 0.f;
+    for (int i = 0; i < 4; ++i) {
+      dz[2 * i] = (w[i] & 0x7FFFu) ? dz[2 * i] * inv_keep : 0.f;
+      dz[2 * i + 1] = (w[i] & 0x7FFF0000u) ? dz[2 * i + 1] * inv_keep : 0.f;
+    }
   }
 }
 
 // G = branches reduced per sweep over the rows: 1 for single-branch layers (64 registers, two CTAs
 // per SM), 4 for dense-residual layers.
-template <bool F32, int G>
-__global__ void __launch_bounds__(kEwMaxThreads, G == 1 ? 2 : 1)
+template <bool F32, int G, bool YF32>
+__global__ void __launch_bounds__(kEwMaxThreads, (G == 1 && !YF32) ? 2 : 1)
 bn_bwd_reduce_kernel(const BnBwdParams p, int rows_per_block) {
   extern __shared__ float sh[];  // [1 + n_branch][C]
   const int C = p.C;
@@ -454,17 +517,16 @@ bn_bwd_reduce_kernel(const BnBwdParams p, int rows_per_block) {
         const bool two = row + t.RP < t.row1;
         float dz0[8], dz1[8];
         uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
-        uint4 y0[G], y1[G];
+        YVec<YF32> y0[G], y1[G];
         const size_t v0 = (size_t)row * rs + t.cv, v1 = v0 + (size_t)t.RP * rs;
         load_dz_raw<F32>(p, v0, a0, dz0);
         if (two) load_dz_raw<F32>(p, v1, a1, dz1);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           if (g < nj) {
-            const uint4* yb = reinterpret_cast<const uint4*>(p.br[j0 + g].y) + t.cv;
             const size_t ys = (size_t)(p.br[j0 + g].ld >> 3);
-            y0[g] = __ldg(yb + (size_t)row * ys);
-            if (two) y1[g] = __ldg(yb + (size_t)(row + t.RP) * ys);
+            y0[g] = ld_yvec<YF32>(p.br[j0 + g].y, (size_t)row * ys + t.cv);
+            if (two) y1[g] = ld_yvec<YF32>(p.br[j0 + g].y, (size_t)(row + t.RP) * ys + t.cv);
           }
         }
         gate_dz(p, a0, dz0);
@@ -479,11 +541,11 @@ bn_bwd_reduce_kernel(const BnBwdParams p, int rows_per_block) {
         for (int g = 0; g < G; ++g) {
           if (g < nj) {
             float f[8];
-            f16x8_to_float(y0[g], f);
+            yvec_to_float<YF32>(y0[g], f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) S[g][i] += dz0[i] * f[i];
             if (two) {
-              f16x8_to_float(y1[g], f);
+              yvec_to_float<YF32>(y1[g], f);
 #pragma unroll
               for (int i = 0; i < 8; ++i) S[g][i] += dz1[i] * f[i];
             }
@@ -535,10 +597,10 @@ __device__ __forceinline__ void bn_bwd_coef(const BnBwdParams& p, int j, int c0,
   }
 }
 
-template <bool F32, bool ONE>
-__global__ void __launch_bounds__(kEwMaxThreads, ONE ? 2 : 1)
+template <bool F32, bool ONE, bool YF32>
+__global__ void __launch_bounds__(kEwMaxThreads, (ONE && !YF32) ? 2 : 1)
 bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
-  constexpr int U = ONE ? 2 : kUnroll;   // rows in flight per thread (3-4 loads each when ONE)
+  constexpr int U = (ONE || YF32) ? 2 : kUnroll;   // rows in flight per thread (3-4 loads each when ONE)
   const int C = p.C;
   const float inv_n = 1.f / (float)p.M;
   const RowTile t = make_row_tile(p.M, C, rows_per_block);
@@ -559,17 +621,16 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
     bool live[U];
     if (ONE) {
       // all loads of the U rows (dA, a, y) are issued before the first use
-      const uint4* yb = reinterpret_cast<const uint4*>(p.br[0].y) + t.cv;
       uint4* db = reinterpret_cast<uint4*>(p.br[0].dy) + t.cv;
       const size_t ys = (size_t)(p.br[0].ld >> 3);
-      uint4 v[U];
+      YVec<YF32> v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         live[u] = row + u * t.RP < t.row1;
         araw[u] = make_uint4(0, 0, 0, 0);
         if (live[u]) {
           load_dz_raw<F32>(p, (size_t)(row + u * t.RP) * rs + t.cv, araw[u], dz[u]);
-          v[u] = __ldg(yb + (size_t)(row + u * t.RP) * ys);
+          v[u] = ld_yvec<YF32>(p.br[0].y, (size_t)(row + u * t.RP) * ys + t.cv);
         }
       }
 #pragma unroll
@@ -577,10 +638,10 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
         if (live[u]) {
           gate_dz(p, araw[u], dz[u]);
           float f[8];
-          f16x8_to_float(v[u], f);
+          yvec_to_float<YF32>(v[u], f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = A0[i] * dz[u][i] + B0[i] * f[i] + C0[i];
-          db[(size_t)(row + u * t.RP) * ys] = float_to_bf16x8(f);
+          db[(size_t)(row + u * t.RP) * ys] = p.h_f16 ? float_to_f16x8(f) : float_to_bf16x8(f);
         }
       }
       continue;
@@ -595,13 +656,12 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
     for (int u = 0; u < U; ++u)
       if (live[u]) gate_dz(p, araw[u], dz[u]);
     for (int j = 0; j < p.n_branch; ++j) {
-      const uint4* yb = reinterpret_cast<const uint4*>(p.br[j].y) + t.cv;
       uint4* db = reinterpret_cast<uint4*>(p.br[j].dy) + t.cv;
       const size_t ys = (size_t)(p.br[j].ld >> 3);
-      uint4 v[U];
+      YVec<YF32> v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (live[u]) v[u] = __ldg(yb + (size_t)(row + u * t.RP) * ys);
+        if (live[u]) v[u] = ld_yvec<YF32>(p.br[j].y, (size_t)(row + u * t.RP) * ys + t.cv);
       float A[8], Bc[8], Cc[8];
       if (j == 0) {
 #pragma unroll
@@ -613,10 +673,10 @@ bn_bwd_apply_kernel(const BnBwdParams p, int rows_per_block) {
       for (int u = 0; u < U; ++u) {
         if (live[u]) {
           float f[8], o[8];
-          f16x8_to_float(v[u], f);
+          yvec_to_float<YF32>(v[u], f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = A[i] * dz[u][i] + Bc[i] * f[i] + Cc[i];
-          db[(size_t)(row + u * t.RP) * ys] = float_to_bf16x8(o);
+          db[(size_t)(row + u * t.RP) * ys] = p.h_f16 ? float_to_f16x8(o) : float_to_bf16x8(o);
         }
       }
     }
@@ -628,8 +688,10 @@ int bn_bwd(const BnBwdParams& p, cudaStream_t st, bool reduce) {
   if (p.C % 8 != 0 || p.C > 2048) return fail(ERR_UNSUPPORTED, "bn_bwd: C must be a multiple of 8, <= 2048");
   static bool attr_done = false;
   if (!attr_done) {
-    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<true, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    OS2S_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
   for (int j = 0; j < p.n_branch; ++j)
@@ -637,28 +699,34 @@ int bn_bwd(const BnBwdParams& p, cudaStream_t st, bool reduce) {
   const size_t smem_r = (size_t)(1 + p.n_branch) * p.C * sizeof(float);
   if (smem_r > 100 * 1024) return fail(ERR_UNSUPPORTED, "bn_bwd: too many branches x channels");
   const bool one = p.n_branch == 1;
-  const int rpb = rows_per_block_for(p.M, p.C, one ? 2 : 1);
+  const int rpb = rows_per_block_for(p.M, p.C, (one && !p.y_f32) ? 2 : 1);
   const int grid = (p.M + rpb - 1) / rpb;
   const int nt = ew_threads(p.C);
+#define OS2S_BN_RED(F_, G_) do { if (p.y_f32) bn_bwd_reduce_kernel<F_, (G_ == 4 ? 2 : G_), true><<<grid, nt, smem_r, st>>>(p, rpb); \
+                                 else bn_bwd_reduce_kernel<F_, G_, false><<<grid, nt, smem_r, st>>>(p, rpb); } while (0)
+#define OS2S_BN_APP(F_, ONE_) do { if (p.y_f32) bn_bwd_apply_kernel<F_, ONE_, true><<<grid, nt, 0, st>>>(p, rpb); \
+                                   else bn_bwd_apply_kernel<F_, ONE_, false><<<grid, nt, 0, st>>>(p, rpb); } while (0)
   if (!reduce) {
     // the reductions were accumulated by the data-gradient kernel that produced dA (single branch, bf16)
     if (!one || p.dA_is_f32) return fail(ERR_INVALID, "bn_bwd: apply-only needs one branch and a bf16 dA");
-    bn_bwd_apply_kernel<false, true><<<grid, nt, 0, st>>>(p, rpb);
+    OS2S_BN_APP(false, true);
   } else if (one) {
     if (p.dA_is_f32) {
-      bn_bwd_reduce_kernel<true, 1><<<grid, nt, smem_r, st>>>(p, rpb);
-      bn_bwd_apply_kernel<true, true><<<grid, nt, 0, st>>>(p, rpb);
+      OS2S_BN_RED(true, 1);
+      OS2S_BN_APP(true, true);
     } else {
-      bn_bwd_reduce_kernel<false, 1><<<grid, nt, smem_r, st>>>(p, rpb);
-      bn_bwd_apply_kernel<false, true><<<grid, nt, 0, st>>>(p, rpb);
+      OS2S_BN_RED(false, 1);
+      OS2S_BN_APP(false, true);
     }
   } else if (p.dA_is_f32) {
-    bn_bwd_reduce_kernel<true, 4><<<grid, nt, smem_r, st>>>(p, rpb);
-    bn_bwd_apply_kernel<true, false><<<grid, nt, 0, st>>>(p, rpb);
+    OS2S_BN_RED(true, 4);
+    OS2S_BN_APP(true, false);
   } else {
-    bn_bwd_reduce_kernel<false, 4><<<grid, nt, smem_r, st>>>(p, rpb);
-    bn_bwd_apply_kernel<false, false><<<grid, nt, 0, st>>>(p, rpb);
+    OS2S_BN_RED(false, 4);
+    OS2S_BN_APP(false, false);
   }
+#undef OS2S_BN_RED
+#undef OS2S_BN_APP
   return check_launch("bn_bwd");
 }
 

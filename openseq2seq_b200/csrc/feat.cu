@@ -15,6 +15,7 @@
 #include "kernels.h"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace os2s {
 
@@ -58,7 +59,31 @@ struct FeatOpts {
   int pad_to;         // psf: frames per utterance are a multiple of this
   int per_feature;    // normalisation: 1 = per feature over time, 0 = one mean/std per utterance
   float power_scale;  // multiplies |X|^2
+  int out_f16;        // the 16-bit output is fp16 instead of bf16 (OS2S_HALF_F16)
+  float fixed_gain;   // > 0: params['gain'] instead of 1 / (max|x| + 1e-5) (speech_utils.py:216-222)
+  // optional device arrays
+  const float* sig;          // augmented float signal (already normalised): replaces wave * gain
+  const long long* sig_off;  // [B] offsets into sig
+  const float* fixed_mean;   // [F] params['features_mean'] (speech_utils.py:411-417), per-feature norm only
+  const float* fixed_std;    // [F] params['features_std_dev']
+  const int* masks;          // [B][n_masks][3] = (kind 0 freq / 1 time, base, width): spec-augment (:419-433)
+  int n_masks;
 };
+// spec-augment: zeros written into the normalised features
+__device__ __forceinline__ bool feat_masked(const FeatOpts& o, int b, int t, int f) {
+  if (!o.masks) return false;
+  const int* m = o.masks + (size_t)b * o.n_masks * 3;
+  bool hit = false;
+  for (int i = 0; i < o.n_masks; ++i) {
+    const int kind = m[3 * i], base = m[3 * i + 1], width = m[3 * i + 2];
+    const int x = kind == 0 ? f : t;
+    hit |= (x >= base && x < base + width);
+  }
+  return hit;
+}
+__device__ __forceinline__ void store_act16(uint16_t* dst, size_t o, float v, int f16) {
+  dst[o] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16(v));
+}
 __device__ __forceinline__ int frames_of(const FeatOpts& o, int n, int hop, int win) {
   if (!o.psf) return 1 + n / hop;
   int len = 1 + (n - win + hop - 1) / hop;      // 1 + ceil((n - win) / hop) for n >= win
@@ -68,10 +93,10 @@ __device__ __forceinline__ int frames_of(const FeatOpts& o, int n, int hop, int 
 }
 
 // signal value at (reflect-resolved) sample index i: normalised, dithered, then pre-emphasised.
-__device__ __forceinline__ float sample_at(const short* w, int n, int i, float gain, float dither,
+__device__ __forceinline__ float sample_at(const short* w, const float* sig, int n, int i, float gain, float dither,
                                            unsigned long long seed, float preemph) {
   auto base = [&](int j) {
-    float v = (float)w[j] * gain;
+    float v = sig ? sig[j] : (float)w[j] * gain;
     if (dither > 0.f) v += dither * gauss_from_index(seed, (unsigned long long)j);
     return v;
   };
@@ -122,7 +147,8 @@ feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__
     n_padded = n + (n_frames - len0) * hop;
   }
   const short* w = wave + offsets[b];
-  const float gain = 1.f / ((float)absmax[b] + 1e-5f);
+  const float* sg = opts.sig ? opts.sig + opts.sig_off[b] : nullptr;
+  const float gain = opts.fixed_gain > 0.f ? opts.fixed_gain : 1.f / ((float)absmax[b] + 1e-5f);
   const unsigned long long useed = seed + (unsigned long long)b * 0x632BE59BD9B4E019ull;
   const int lpad = (NFFT - win) / 2;
   // bit-reversed load of the windowed frame (center=True: frame starts at frame*hop - NFFT/2)
@@ -139,7 +165,7 @@ feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__
         if (j < 0) j = -j;                      // np.pad(mode="reflect")
         if (j >= n) j = 2 * (n - 1) - j;
         j = min(max(j, 0), n - 1);
-        v = sample_at(w, n, j, gain, dither, useed, preemph) * window[wi];
+        v = sample_at(w, sg, n, j, gain, dither, useed, preemph) * window[wi];
       }
     }
     const int r = __brev((unsigned)i) >> (32 - LOG2N);
@@ -188,7 +214,7 @@ feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__
 
 // per (b, f): mean and population std over the utterance's frames, then normalise + pad.
 __global__ void feat_norm_kernel(const float* __restrict__ raw, const int* __restrict__ n_samples,
-                                 __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                                 uint16_t* __restrict__ out_bf16, float* __restrict__ out_f32,
                                  int* __restrict__ out_lens, int T_pad, int F, int hop, int win, const FeatOpts opts) {
   const int b = blockIdx.y;
   const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -200,7 +226,7 @@ __global__ void feat_norm_kernel(const float* __restrict__ raw, const int* __res
   for (int t = lane; t < n_frames; t += 32) s += src[(size_t)t * F];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)n_frames;
+  const float mean = opts.fixed_mean ? opts.fixed_mean[f] : s / (float)n_frames;
   float q = 0.f;
   for (int t = lane; t < n_frames; t += 32) {
     const float d = src[(size_t)t * F] - mean;
@@ -208,11 +234,12 @@ __global__ void feat_norm_kernel(const float* __restrict__ raw, const int* __res
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float inv_std = rsqrtf(q / (float)n_frames);
+  const float inv_std = opts.fixed_std ? 1.f / opts.fixed_std[f] : rsqrtf(q / (float)n_frames);
   for (int t = lane; t < T_pad; t += 32) {
-    const float v = (t < n_frames) ? (src[(size_t)t * F] - mean) * inv_std : 0.f;
+    float v = (t < n_frames) ? (src[(size_t)t * F] - mean) * inv_std : 0.f;
+    if (t < n_frames && feat_masked(opts, b, t, f)) v = 0.f;
     const size_t o = ((size_t)b * T_pad + t) * F + f;
-    if (out_bf16) out_bf16[o] = __float2bfloat16(v);
+    if (out_bf16) store_act16(out_bf16, o, v, opts.out_f16);
     if (out_f32) out_f32[o] = v;
   }
   if (f == 0 && lane == 0 && out_lens) out_lens[b] = n_frames;
@@ -222,7 +249,7 @@ __global__ void feat_norm_kernel(const float* __restrict__ raw, const int* __res
 // norm_per_feature = False): one CTA per utterance, three passes over its L2-resident [frames, F] slab.
 __global__ void __launch_bounds__(256)
 feat_norm_global_kernel(const float* __restrict__ raw, const int* __restrict__ n_samples,
-                        __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                        uint16_t* __restrict__ out_bf16, float* __restrict__ out_f32,
                         int* __restrict__ out_lens, int T_pad, int F, int hop, int win, const FeatOpts opts) {
   __shared__ float red[8];
   __shared__ float bc;
@@ -254,9 +281,10 @@ feat_norm_global_kernel(const float* __restrict__ raw, const int* __restrict__ n
   }
   const float inv_std = rsqrtf(block_sum(q) / (float)n);
   for (int i = threadIdx.x; i < T_pad * F; i += 256) {
-    const float v = (i < n) ? (src[i] - mean) * inv_std : 0.f;
+    float v = (i < n) ? (src[i] - mean) * inv_std : 0.f;
+    if (i < n && feat_masked(opts, b, i / F, i % F)) v = 0.f;
     const size_t o = (size_t)b * T_pad * F + i;
-    if (out_bf16) out_bf16[o] = __float2bfloat16(v);
+    if (out_bf16) store_act16(out_bf16, o, v, opts.out_f16);
     if (out_f32) out_f32[o] = v;
   }
   if (threadIdx.x == 0 && out_lens) out_lens[b] = n_frames;
@@ -266,7 +294,8 @@ int logmel_forward(const short* wave, const long long* offsets, const int* n_sam
                    const float* mel, const int* mel_band, const float* window, int n_fft, int win, int hop, int F, int T_pad,
                    int max_samples, float dither, unsigned long long seed, float preemph,
                    unsigned int* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
-                   cudaStream_t st, int psf_backend, int pad_to, int norm_per_feature) {
+                   cudaStream_t st, int psf_backend, int pad_to, int norm_per_feature, int out_f16,
+                   const FeatExtras* ex) {
   if (n_fft != 512) return fail(ERR_UNSUPPORTED, "logmel_forward: only n_fft = 512 is built");
   if (win > n_fft || F > 128) return fail(ERR_INVALID, "logmel_forward: bad window / feature count");
   FeatOpts opts;
@@ -274,8 +303,23 @@ int logmel_forward(const short* wave, const long long* offsets, const int* n_sam
   opts.pad_to = pad_to;
   opts.per_feature = norm_per_feature ? 1 : 0;
   opts.power_scale = psf_backend ? 1.f / (float)n_fft : 1.f;
-  OS2S_CUDA(cudaMemsetAsync(absmax_ws, 0, (size_t)B * sizeof(unsigned int), st));
-  feat_absmax_kernel<<<dim3(32, B), 256, 0, st>>>(wave, offsets, n_samples, absmax_ws);
+  opts.out_f16 = out_f16 ? 1 : 0;
+  opts.fixed_gain = ex ? ex->fixed_gain : 0.f;
+  opts.sig = ex ? ex->sig : nullptr;
+  opts.sig_off = ex ? ex->sig_off : nullptr;
+  opts.fixed_mean = ex ? ex->fixed_mean : nullptr;
+  opts.fixed_std = ex ? ex->fixed_std : nullptr;
+  opts.masks = ex ? ex->masks : nullptr;
+  opts.n_masks = ex ? ex->n_masks : 0;
+  if (opts.sig && psf_backend) return fail(ERR_UNSUPPORTED, "logmel_forward: augmented signals need the librosa backend");
+  if ((opts.fixed_mean || opts.fixed_std) && !norm_per_feature)
+    return fail(ERR_UNSUPPORTED, "logmel_forward: features_mean / features_std_dev need norm_per_feature");
+  if (opts.sig && !opts.sig_off) return fail(ERR_INVALID, "logmel_forward: sig needs sig_off");
+  if (!opts.sig && !(opts.fixed_gain > 0.f)) {
+    // (with an augmented signal the caller has run os2s_wave_absmax + os2s_augment_signal already)
+    OS2S_CUDA(cudaMemsetAsync(absmax_ws, 0, (size_t)B * sizeof(unsigned int), st));
+    feat_absmax_kernel<<<dim3(32, B), 256, 0, st>>>(wave, offsets, n_samples, absmax_ws);
+  }
   int max_frames = 1 + max_samples / hop;
   if (psf_backend) {
     max_frames = max_samples <= win ? 1 : 1 + (max_samples - win + hop - 1) / hop;
@@ -287,13 +331,20 @@ int logmel_forward(const short* wave, const long long* offsets, const int* n_sam
                                                            T_pad, F, hop, win, dither, seed, preemph, opts);
   if (norm_per_feature) {
     dim3 grid2((F + 7) / 8, B);
-    feat_norm_kernel<<<grid2, 256, 0, st>>>(raw_ws, n_samples, (__nv_bfloat16*)out_bf16, out_f32, out_lens, T_pad, F,
+    feat_norm_kernel<<<grid2, 256, 0, st>>>(raw_ws, n_samples, (uint16_t*)out_bf16, out_f32, out_lens, T_pad, F,
                                             hop, win, opts);
   } else {
-    feat_norm_global_kernel<<<B, 256, 0, st>>>(raw_ws, n_samples, (__nv_bfloat16*)out_bf16, out_f32, out_lens, T_pad,
+    feat_norm_global_kernel<<<B, 256, 0, st>>>(raw_ws, n_samples, (uint16_t*)out_bf16, out_f32, out_lens, T_pad,
                                                F, hop, win, opts);
   }
   return check_launch("logmel_forward");
+}
+
+int wave_absmax(const short* wave, const long long* offsets, const int* n_samples, int B, unsigned int* absmax,
+                cudaStream_t st) {
+  OS2S_CUDA(cudaMemsetAsync(absmax, 0, (size_t)B * sizeof(unsigned int), st));
+  feat_absmax_kernel<<<dim3(32, B), 256, 0, st>>>(wave, offsets, n_samples, absmax);
+  return check_launch("wave_absmax");
 }
 
 }  // namespace os2s

@@ -17,15 +17,16 @@ const char* last_error_cstr();
 int conv_tuning(int pair_mode, int halo_mode);
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
                 int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st,
-                const void* bwd_a = nullptr, const void* bwd_y = nullptr, float bwd_inv_keep = 1.f);
+                const void* bwd_a = nullptr, const void* bwd_y = nullptr, float bwd_inv_keep = 1.f,
+                int act_f16 = 0, int bwd_y_f32 = 0);
 int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out, int K,
-               int dil, int pad_left, int* splits_used, cudaStream_t st);
+               int dil, int pad_left, int* splits_used, cudaStream_t st, int x_f16 = 0);
 
 // elementwise.cu
 int weight_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int K, int C_in, int C_out,
-                          cudaStream_t st);
+                          cudaStream_t st, int f16 = 0);
 struct BnBranchFwd {
-  const __half* y;        // conv output, fp16
+  const void* y;        // conv output, fp16 (fp32 when BnFwdParams::y_f32)
   const float* stats;   // [2][C] sums
   const float* gamma;
   const float* beta;
@@ -37,7 +38,8 @@ struct BnBranchFwd {
 struct BnFwdParams {
   BnBranchFwd br[kMaxBranches];
   int n_branch;
-  __nv_bfloat16* out;
+  void* out;            // bf16 (fp16 when out_f16)
+  int y_f32, out_f16;
   const int* lens;      // [B] valid rows per utterance (nullptr = no mask)
   int B, T, C;
   float eps, momentum;  // momentum as in TF: moving = moving*momentum + batch*(1-momentum)
@@ -49,12 +51,12 @@ struct BnFwdParams {
   const long long* step_ctr;  // optional device counter mixed into the dropout seed (CUDA-graph replays)
 };
 struct BnBranchBwd {
-  const __half* y;          // conv output, fp16
+  const void* y;            // conv output, fp16 (fp32 when BnBwdParams::y_f32)
   const float* mean_invstd;  // [2][C]
   const float* gamma;
   float* dgamma;             // [C] gradient outputs (scaled by loss scale like dA)
   float* dbeta;              // [C]
-  __nv_bfloat16* dy;         // [M, C]
+  void* dy;                  // [M, C] bf16 (fp16 when BnBwdParams::h_f16)
   int ld;                    // row stride of y AND dy in elements
 };
 struct BnBwdParams {
@@ -62,7 +64,9 @@ struct BnBwdParams {
   int n_branch;
   const void* dA;            // bf16 or fp32 [M, C]
   int dA_is_f32;
-  const __nv_bfloat16* a;    // forward output of this layer (post relu/dropout/mask)
+  int y_f32;
+  int h_f16;                 // dA (when 16-bit) and every dy are fp16 instead of bf16
+  const void* a;             // forward output of this layer (post relu/dropout/mask), bf16 or fp16: only its zeros matter
   float* red;                // [1 + n_branch][C] fp32 scratch, pre-zeroed: dbeta, dgamma_j
   int M, C;
   float keep;
@@ -84,9 +88,10 @@ int bn_bwd(const BnBwdParams& p, cudaStream_t st, bool reduce = true);
 
 
 // ctc.cu
-int fc_fwd(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V, cudaStream_t st);
+int fc_fwd(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V, cudaStream_t st,
+           int x_f16 = 0);
 int fc_bwd(const void* x, const float* dl, const float* w, void* dx, float* dw, float* db, int M, int H, int V,
-           cudaStream_t st);
+           cudaStream_t st, int x_f16 = 0);
 size_t ctc_workspace_bytes(int B, int T, int L_max);
 int ctc_loss_fwd_bwd(const float* logits, const int* labels, const int* label_lens, const int* input_lens,
                      float* grad, float* loss, float* workspace, size_t workspace_bytes, const float* loss_scale,
@@ -103,6 +108,7 @@ struct OptTable {
   void* const* wb;
   void* const* v;   // Adam second moments (nullptr otherwise)
   const float* reg; // per-tensor L2-regulariser scale (nullptr = none)
+  const int* frozen; // per-tensor flag: excluded from the update and from the global norm (nullptr = none)
   const long long* sizes;
   const int* chunk_tensor;
   const long long* chunk_offset;
@@ -121,12 +127,28 @@ int opt_step(const OptTable& tab, const OptHParams& hp, float* norms, int* nonfi
 int opt_chunk_elems();
 int multi_transpose(const TransposeTable& tab, long long total_tiles, cudaStream_t st);
 
-// feat.cu
+// feat.cu / augment.cu
+struct FeatExtras {
+  float fixed_gain;
+  const float* sig;
+  const long long* sig_off;
+  const float* fixed_mean;
+  const float* fixed_std;
+  const int* masks;
+  int n_masks;
+};
+int wave_absmax(const short* wave, const long long* offsets, const int* n_samples, int B, unsigned int* absmax,
+                cudaStream_t st);
+int augment_signal(const short* wave, const long long* offsets, const int* n_in, int B, const unsigned int* absmax,
+                   float fixed_gain, const int* sr_new, int sr_orig, const float* win, int nwin, int num_table,
+                   const float* noise_amp, unsigned long long seed, float* out, const long long* out_offsets,
+                   const int* n_out, int max_out, cudaStream_t st);
 int logmel_forward(const short* wave, const long long* offsets, const int* n_samples, int B,
                    const float* mel, const int* mel_band, const float* window, int n_fft, int win, int hop, int F, int T_pad,
                    int max_samples, float dither, unsigned long long seed, float preemph,
                    unsigned int* absmax_ws, float* raw_ws, void* out_bf16, float* out_f32, int* out_lens,
                    cudaStream_t st,
-                   int psf_backend = 0, int pad_to = 0, int norm_per_feature = 1);
+                   int psf_backend = 0, int pad_to = 0, int norm_per_feature = 1, int out_f16 = 0,
+                   const FeatExtras* ex = nullptr);
 
 }  // namespace os2s

@@ -149,11 +149,30 @@ __global__ void opt_prepare_kernel(const OptTable tab, const OptHParams hp, floa
   __syncthreads();
   const float unscale = 1.f / (s_scale_used * (float)hp.world_size);  // mp_wrapper.py:94, hvd mean
   const float lr = s_lr;
+  // global gradient norm over the trainable variables (summary, optimizers.py:292-296, and
+  // tf.clip_by_global_norm when max_grad_norm is set, optimizers.py:408-433)
   float total = 0.f;
+  for (int t = threadIdx.x; t < tab.n_tensors; t += blockDim.x)
+    if (!(tab.frozen && tab.frozen[t])) total += norms[2 * t] * unscale * unscale;
+  __shared__ float red[32];
+  __shared__ float s_clip;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    const float gn = sqrtf(s);
+    fstate[2] = gn;
+    s_clip = (hp.max_grad_norm > 0.f) ? hp.max_grad_norm / fmaxf(gn, hp.max_grad_norm) : 1.f;
+    *nonfinite = 0;
+  }
+  __syncthreads();
+  const float clip = s_clip;
   for (int t = threadIdx.x; t < tab.n_tensors; t += blockDim.x) {
-    const float g_norm = sqrtf(norms[2 * t]) * unscale;
+    const float g_norm = sqrtf(norms[2 * t]) * unscale * clip;
     const float w_norm = sqrtf(norms[2 * t + 1]);
-    total += g_norm * g_norm;
     float r = 1.f;
     if (hp.larc_eta > 0.f) {  // optimizers.py:349-369
       if (hp.larc_mode == 0) {
@@ -163,30 +182,19 @@ __global__ void opt_prepare_kernel(const OptTable tab, const OptHParams hp, floa
         r = fmaxf(hp.larc_eta * w_norm / (g_norm + hp.larc_eps), hp.larc_min_update);
       }
     }
-    float c = unscale * r;
+    float c = unscale * clip * r;
+    if (tab.frozen && tab.frozen[t]) c = 0.f;
     if (hp.algo == 0) {  // NovoGrad (novograd.py:108-115)
       const float g2 = (r * g_norm) * (r * g_norm);
       const float prev = ema[t];
       const float v = (prev == 0.f) ? g2 : prev * hp.beta2 + g2 * (1.f - hp.beta2);
-      if (hp.ema_persist && !s_skip) ema[t] = v;
+      if (hp.ema_persist && !s_skip && !(tab.frozen && tab.frozen[t])) ema[t] = v;
       c *= rsqrtf(v + hp.epsilon);
       if (hp.grad_averaging) c *= (1.f - hp.beta1);
     }
     coef[t] = c;
     norms[2 * t] = 0.f;
     norms[2 * t + 1] = 0.f;
-  }
-  // global gradient norm (summary only, optimizers.py:292-296)
-  __shared__ float red[32];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = total;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
-    fstate[2] = sqrtf(s);
-    *nonfinite = 0;
   }
 }
 
@@ -197,13 +205,17 @@ opt_update_kernel(const OptTable tab, const OptHParams hp, const float* __restri
                   const long long* __restrict__ istate, const float* __restrict__ coef) {
   if (istate[3] != 0) return;  // overflow: skip the whole step
   const int tid = tab.chunk_tensor[blockIdx.x];
+  if (tab.frozen && tab.frozen[tid]) return;  // freeze_variables_regex: not in var_list (model.py:502-507)
   const long long off = tab.chunk_offset[blockIdx.x];
   const long long n = tab.sizes[tid];
   const int len = (int)min((long long)kOptChunk, n - off);
   const float* g = reinterpret_cast<const float*>(tab.g[tid]) + off;
   float* w = reinterpret_cast<float*>(tab.w[tid]) + off;
   float* m = reinterpret_cast<float*>(tab.m[tid]) + off;
-  __nv_bfloat16* wb = tab.wb[tid] ? reinterpret_cast<__nv_bfloat16*>(tab.wb[tid]) + off : nullptr;
+  uint16_t* wb = tab.wb[tid] ? reinterpret_cast<uint16_t*>(tab.wb[tid]) + off : nullptr;
+  auto half16 = [&](float v) -> uint16_t {
+    return hp.wb_f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16(v));
+  };
   const float c = coef[tid];
   const float lr = fstate[1];
   const float kreg = tab.reg ? tab.reg[tid] * fstate[4] * (float)hp.world_size : 0.f;
@@ -221,7 +233,7 @@ opt_update_kernel(const OptTable tab, const OptHParams hp, const float* __restri
       m[i] = mv;
       v[i] = vv;
       w[i] = nw;
-      if (wb) wb[i] = __float2bfloat16(nw);
+      if (wb) wb[i] = half16(nw);
     }
     return;
   }
@@ -232,7 +244,7 @@ opt_update_kernel(const OptTable tab, const OptHParams hp, const float* __restri
     const float nw = wv - lr * mv;
     m[i] = mv;
     w[i] = nw;
-    if (wb) wb[i] = __float2bfloat16(nw);
+    if (wb) wb[i] = half16(nw);
   }
 }
 

@@ -212,12 +212,14 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
   d |= 2ull << 61;
   return d;
 }
-// Instruction descriptor for kind::f16, BF16 x BF16 -> FP32.
-//   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1 (BF16)
+// Instruction descriptor for kind::f16, {F16|BF16} x {F16|BF16} -> FP32 (the two operand formats are
+// independent fields: fp16 activations multiply bf16 weights / gradients at the same rate).
+//   [4,6) c_format=1 (F32)  [7,10) a_format (0 = F16, 1 = BF16)  [10,13) b_format (0 = F16, 1 = BF16)
 //   [15] a_major (0 = K, 1 = MN)  [16] b_major  [17,23) N>>3  [24,29) M>>4
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, uint32_t a_mn_major,
-                                                  uint32_t b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
+                                                  uint32_t b_mn_major, uint32_t a_bf16 = 1,
+                                                  uint32_t b_bf16 = 1) {
+  return (1u << 4) | (a_bf16 << 7) | (b_bf16 << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
          ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
@@ -230,6 +232,12 @@ __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
   // saturate instead of producing inf: |x| > 65504 only happens in an already-diverged network
   a = fminf(fmaxf(a, -65504.f), 65504.f);
   b = fminf(fmaxf(b, -65504.f), 65504.f);
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// gradients: no saturation -- an overflow must become inf so that the loss scaler sees it and backs off
+__device__ __forceinline__ uint32_t pack_f16_raw(float a, float b) {
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }

@@ -17,6 +17,7 @@ All launches of a step are pre-bound once per (batch, time) shape into a flat "p
 (function, argument-list) pairs, so the per-step Python cost is one loop over ctypes calls and
 the step never synchronises with the host.
 """
+import collections
 import ctypes
 import math
 import os
@@ -44,6 +45,7 @@ class OptHParams(ctypes.Structure):
         ("use_loss_scaler", _c_int), ("scale_min", _c_float), ("scale_max", _c_float),
         ("step_factor", _c_float), ("step_window", _c_ll), ("world_size", _c_int),
         ("lr_policy", _c_int), ("decay_rate", _c_float), ("staircase", _c_int),
+        ("max_grad_norm", _c_float), ("wb_f16", _c_int),
     ]
 
 
@@ -78,8 +80,29 @@ class ConvLayer(object):
 class JasperEngine(object):
     def __init__(self, convnet_layers, num_features, vocab_size, device="cuda", bn_momentum=0.9,
                  bn_epsilon=1e-3, use_conv_mask=True, training=True, dropout_keep_default=1.0,
-                 opt=None, world_size=1, seed=0, relu_clip=0.0):
+                 opt=None, world_size=1, seed=0, relu_clip=0.0, act_dtype=None, conv_dtype=None,
+                 encoder_init="xavier_truncnorm", decoder_init="xavier_uniform"):
+        """act_dtype: format of every 16-bit tensor of the path (layer inputs / outputs, weight working
+        copies, activation gradients): "bf16" (default) or "fp16" (the reference's "mixed" mode; one switch
+        because tcgen05 kind::f16 needs both MMA operands in the same format); conv_dtype: storage format of
+        the conv outputs (the BN inputs), "fp16" (default) or "fp32".  Environment defaults: OS2S_ACT_DTYPE,
+        OS2S_CONV_DTYPE."""
         self.lib = L.load()
+        for k in (encoder_init, decoder_init):
+            if k not in ("xavier_truncnorm", "xavier_uniform"):
+                raise ValueError("JasperEngine: initializer %r is not built (xavier_truncnorm | xavier_uniform)" % (k,))
+        self.encoder_init, self.decoder_init = encoder_init, decoder_init
+        act_dtype = act_dtype or os.environ.get("OS2S_ACT_DTYPE", "bf16")
+        conv_dtype = conv_dtype or os.environ.get("OS2S_CONV_DTYPE", "fp16")
+        if act_dtype not in ("bf16", "fp16") or conv_dtype not in ("fp16", "fp32"):
+            raise ValueError("JasperEngine: act_dtype is 'bf16' | 'fp16', conv_dtype is 'fp16' | 'fp32'")
+        self.act_dtype, self.conv_dtype = act_dtype, conv_dtype
+        self.act_torch = torch.float16 if act_dtype == "fp16" else torch.bfloat16
+        self.conv_torch = torch.float32 if conv_dtype == "fp32" else torch.float16
+        # OS2S_HALF_F16 | OS2S_CONV_F32 (include/os2s.h)
+        self.dtypes = (1 if act_dtype == "fp16" else 0) | (2 if conv_dtype == "fp32" else 0)
+        self.conv_out_mode = 1 if conv_dtype == "fp32" else 3
+        self.grad_out_mode = 4 if act_dtype == "fp16" else 0   # OS2S_OUT_F16_GRAD | OS2S_OUT_BF16
         self.device = torch.device(device)
         self.F = num_features
         self.V = vocab_size
@@ -91,7 +114,7 @@ class JasperEngine(object):
         self.seed = seed
         self.relu_clip = float(relu_clip)
         self.step_count = 0
-        self._ws = {}
+        self._ws = collections.OrderedDict()
         self._profile = None
         self._suppress_comm = False
         # replay the whole step as one CUDA graph after 2 eager steps (OS2S_CUDA_GRAPH=0 disables)
@@ -176,6 +199,14 @@ class JasperEngine(object):
                 self.res_col[(li, n)] = (j, col)
 
     @staticmethod
+    def var_scope_name(name):
+        """The reference's full variable name of a parameter: encoder variables live
+        under ForwardPass/w2l_encoder/, the decoder's dense layer under ForwardPass/fully_connected_ctc_decoder/."""
+        if name.startswith("fc/"):
+            return "ForwardPass/fully_connected_ctc_decoder/fully_connected/" + name[3:]
+        return "ForwardPass/w2l_encoder/" + name
+
+    @staticmethod
     def res_name(lyr, n):
         return (lyr.name + "/res_%d" % n) if lyr.dense else (lyr.name + "/res")
 
@@ -243,10 +274,10 @@ class JasperEngine(object):
         self.mom = torch.zeros(total, dtype=torch.float32, device=dev)
         # one bf16 working copy in the natural TF layout [K][Cin][Cout]: it is dgrad's K-major B operand
         # (reduction over C_out) and forward's MN-major B operand (reduction over C_in) at the same time
-        self.wb = torch.zeros(self._half_total, dtype=torch.bfloat16, device=dev)
+        self.wb = torch.zeros(self._half_total, dtype=self.act_torch, device=dev)
         # per residual source: bf16 kernels of all consumers side by side [C_j, Ntot_j] (gathered from wb
         # at the start of every forward) and the fp32 weight gradient of the merged GEMM (scattered back)
-        self.wcat = [torch.zeros(g["cj"], g["ntot"], dtype=torch.bfloat16, device=dev) for g in self.res_groups]
+        self.wcat = [torch.zeros(g["cj"], g["ntot"], dtype=self.act_torch, device=dev) for g in self.res_groups]
         self.dwcat = [torch.zeros(g["cj"], g["ntot"], dtype=torch.float32, device=dev) for g in self.res_groups]
         # BN moving statistics [2][C] per BN instance (moving_mean = 0, moving_variance = 1)
         self.moving = {}
@@ -310,26 +341,33 @@ class JasperEngine(object):
         return [(s["name"], self.param_view(s["name"])) for s in self.specs]
 
     def init_parameters(self, seed=0):
-        """tf.contrib.layers.xavier_initializer as the Jasper config uses it:
-        encoder kernels truncated-normal (uniform=False), decoder uniform, BN gamma=1/beta=0, bias=0."""
+        """tf.contrib.layers.xavier_initializer, n = (fan_in + fan_out) / 2: "xavier_truncnorm"
+        (uniform=False: truncated normal, std sqrt(1.3 / n)) or "xavier_uniform" (uniform=True, also what
+        tf.layers uses when no initializer is given: limit sqrt(3 / n)).  The Jasper config initialises the
+        encoder kernels truncated-normal and the decoder uniform.  BN gamma = 1 / beta = 0, bias = 0."""
         gen = torch.Generator().manual_seed(seed)
+
+        def xavier(shape, fan_in, fan_out, kind):
+            n = (fan_in + fan_out) / 2.0
+            if kind == "xavier_uniform":
+                lim = math.sqrt(3.0 / n)
+                return (torch.rand(shape, generator=gen) * 2 - 1) * lim
+            std = math.sqrt(1.3 / n)
+            t = torch.empty(shape)
+            torch.nn.init.trunc_normal_(t, 0.0, std, -2 * std, 2 * std, generator=gen)
+            return t
+
         for s in self.specs:
             v = self.param_view(s["name"])
             if s["kind"] == "conv":
                 K, ci, co = s["shape"]
-                n = (K * ci + K * co) / 2.0
-                std = math.sqrt(1.3 / n)
-                t = torch.empty(s["shape"])
-                torch.nn.init.trunc_normal_(t, 0.0, std, -2 * std, 2 * std, generator=gen)
-                v.copy_(t)
+                v.copy_(xavier(s["shape"], K * ci, K * co, self.encoder_init))
             elif s["kind"] == "gamma":
                 v.fill_(1.0)
             elif s["kind"] in ("beta", "fc_b"):
                 v.zero_()
             elif s["kind"] == "fc_w":
-                n = (s["shape"][0] + s["shape"][1]) / 2.0
-                lim = math.sqrt(3.0 / n)
-                v.copy_((torch.rand(s["shape"], generator=gen) * 2 - 1) * lim)
+                v.copy_(xavier(s["shape"], s["shape"][0], s["shape"][1], self.decoder_init))
         self.sync_half_copies()
 
     def load_parameters(self, params):
@@ -347,9 +385,9 @@ class JasperEngine(object):
             if s["kind"] != "conv":
                 continue
             K, R, C = self._kernel_geom(s)
-            L.check(self.lib.os2s_weight_cast_transpose(
+            L.check(self.lib.os2s_weight_cast_transpose_p(
                 _vp(self.master.data_ptr() + 4 * s["offset"]), _vp(self.wb.data_ptr() + 2 * s["half_offset"]),
-                _vp(0), K, R, C, st), "weight_cast_transpose")
+                _vp(0), K, R, C, self.dtypes, st), "weight_cast_transpose")
 
     def _kernel_geom(self, s):
         lyr = s["layer"]
@@ -364,12 +402,14 @@ class JasperEngine(object):
                       decay_steps=0, begin_decay_at=0, warmup_steps=0, loss_scaling=True, scale_min=1.0,
                       scale_max=2.0 ** 14, step_factor=2.0, step_window=2000, initial_scale=None,
                       lr_policy="poly_decay", decay_rate=1.0, use_staircase_decay=False, iter_size=1,
-                      l2_regularizer_scale=0.0):
+                      l2_regularizer_scale=0.0, max_grad_norm=0.0, freeze_variables_regex=None):
         """algo: "novograd" | "momentum" | "adam"; lr_policy: "poly_decay" | "cosine_decay" | "exp_decay" |
         "fixed_lr" (lr_policies.py); l2_regularizer_scale: tf.contrib.layers.l2_regularizer(scale) on the
         variables the reference builds with it (conv / dense kernels and BN gammas, conv_blocks.py:203,219;
         fc_decoders.py:138); iter_size > 1 accumulates g / iter_size over that many calls of
-        train_step and updates on the last one (optimizers.py:212-259)."""
+        train_step and updates on the last one (optimizers.py:212-259); max_grad_norm > 0: global-norm
+        clipping (optimizers.py:408-433, exclusive with LARC :161-164); freeze_variables_regex: variables whose
+        name matches (re.match on the reference's variable name, models/model.py:502-507) are not updated."""
         hp = OptHParams()
         if algo not in ("novograd", "momentum", "adam"):
             raise ValueError("JasperEngine: optimizer %r has no fused step (novograd / momentum / adam)" % (algo,))
@@ -393,6 +433,10 @@ class JasperEngine(object):
         hp.scale_min, hp.scale_max, hp.step_factor = scale_min, scale_max, step_factor
         hp.step_window = int(step_window)
         hp.world_size = self.world_size
+        if max_grad_norm and larc_eta > 0:
+            raise AttributeError("LARC and gradient norm clipping should not be used together")
+        hp.max_grad_norm = float(max_grad_norm or 0.0)
+        hp.wb_f16 = 1 if self.act_dtype == "fp16" else 0
         self.hp = hp
         dev = self.device
         n = len(self.specs)
@@ -413,8 +457,19 @@ class JasperEngine(object):
         self.mom2 = torch.zeros(self._total, dtype=torch.float32, device=dev) if algo == "adam" else None
         self.grad_acc = torch.zeros(self._total, dtype=torch.float32, device=dev) if self.iter_size > 1 else None
         v = [ptr(self.mom2, s, 4) for s in self.specs] if algo == "adam" else [0] * n
-        reg = [float(l2_regularizer_scale) if s["kind"] in ("conv", "gamma", "fc_w") else 0.0 for s in self.specs]
+        # the reference builds the 1x1 residual kernels WITHOUT a regularizer (conv_blocks.py:80-86)
+        reg = [float(l2_regularizer_scale) if (s["kind"] in ("conv", "gamma", "fc_w") and "/res_" not in s["name"]
+                                                and not s["name"].endswith("/res/kernel")) else 0.0 for s in self.specs]
         self._reg = torch.tensor(reg, dtype=torch.float32, device=dev) if l2_regularizer_scale else None
+        self._frozen = None
+        self.frozen_names = []
+        if freeze_variables_regex:
+            import re
+            pat = re.compile(freeze_variables_regex)
+            flags = [1 if pat.match(self.var_scope_name(s["name"])) else 0 for s in self.specs]
+            self.frozen_names = [s["name"] for s, f in zip(self.specs, flags) if f]
+            if any(flags):
+                self._frozen = torch.tensor(flags, dtype=torch.int32, device=dev)
         self._opt = {
             "w": i64(w), "g": i64(g), "m": i64(m), "v": i64(v), "wb": i64(wb), "sizes": i64(sizes),
             "ct": torch.tensor(ct, dtype=torch.int32, device=dev), "co": i64(co),
@@ -429,23 +484,48 @@ class JasperEngine(object):
         self.fstate[0] = scale0
         self.istate = torch.zeros(8, dtype=torch.int64, device=dev)
         self.istate[1] = -1
-        self._ws = {}
+        self._ws = collections.OrderedDict()
 
     # ----------------------------------------------------------------- workspace
     def _workspace(self, B, T):
+        """Per-shape workspaces (activations, launch plan, captured graph) are cached least-recently-used
+        under a byte budget (OS2S_WS_BUDGET_GB, default 60% of the device memory): with real variable-length
+        data T takes ~100 values, and a B = 32 x 15 s workspace alone is 4.5 GB."""
         key = (B, T, self.training)
-        ws = self._ws.get(key)
+        ws = self._ws.pop(key, None)
         if ws is None:
+            budget = self._ws_budget_bytes()
+            need = _Workspace.estimate_bytes(self, B, T)
+            while self._ws and sum(w.nbytes for w in self._ws.values()) + need > budget:
+                old_key = next(iter(self._ws))
+                old = self._ws.pop(old_key)
+                if getattr(self, "_last_ws", None) is old:
+                    self._last_ws = None
+                old.release()
             ws = _Workspace(self, B, T)
-            self._ws[key] = ws
+        self._ws[key] = ws          # (re)insert as most recently used
         return ws
+
+    def clear_workspaces(self):
+        """Forget every cached per-shape workspace (after changing dropout / topology options by hand)."""
+        for w in self._ws.values():
+            w.release()
+        self._ws = collections.OrderedDict()
+        self._last_ws = None
+
+    def _ws_budget_bytes(self):
+        b = os.environ.get("OS2S_WS_BUDGET_GB")
+        if b:
+            return int(float(b) * (1 << 30))
+        if self.device.type == "cuda":
+            return int(0.6 * torch.cuda.get_device_properties(self.device).total_memory)
+        return 1 << 62
 
     # ---------------------------------------------------------------- public API
     def forward_encoder(self, feats, feat_lens):
         """TDNNEncoder._encode: feats bf16 [B,T,F] (zero padded), lens int32 [B] -> (bf16 [B,T',H], lens)."""
         B, T, F = feats.shape
-        if F != self.F or feats.dtype != torch.bfloat16 or not feats.is_contiguous():
-            raise ValueError("JasperEngine: features must be contiguous bf16 [B,T,%d]" % self.F)
+        self._check_feats(feats)
         ws = self._workspace(B, T)
         ws.run_forward(feats, feat_lens)
         return ws.A[-1], ws.lens_out
@@ -472,7 +552,7 @@ class JasperEngine(object):
             self.bucket_bytes = int(bucket_bytes)
         if self.comm is not None and self._side is None:
             self._side = torch.cuda.Stream()
-        self._ws = {}
+        self._ws = collections.OrderedDict()
 
     def set_training(self, flag):
         """train mode: batch statistics + dropout; eval mode: moving statistics, no dropout
@@ -503,9 +583,10 @@ class JasperEngine(object):
     def _launch_optimizer(self):
         o = self._opt
         st = L.stream_ptr()
-        L.check(self.lib.os2s_opt_step2(
+        L.check(self.lib.os2s_opt_step3(
             L.ptr(o["w"]), L.ptr(o["g"]), L.ptr(o["m"]), L.ptr(o["v"]) if self.mom2 is not None else _vp(0),
-            L.ptr(o["wb"]), L.ptr(self._reg) if self._reg is not None else _vp(0), L.ptr(o["sizes"]), L.ptr(o["ct"]),
+            L.ptr(o["wb"]), L.ptr(self._reg) if self._reg is not None else _vp(0),
+            L.ptr(self._frozen) if self._frozen is not None else _vp(0), L.ptr(o["sizes"]), L.ptr(o["ct"]),
             L.ptr(o["co"]), o["n"], o["n_chunks"], ctypes.byref(self.hp), L.ptr(o["norms"]),
             L.ptr(o["nonfinite"]), L.ptr(self.fstate), L.ptr(self.istate), L.ptr(o["coef"]), L.ptr(o["ema"]),
             st), "os2s_opt_step")
@@ -516,9 +597,16 @@ class JasperEngine(object):
         optimizer -- one call, replayed as a CUDA graph in steady state.  Returns the per-utterance
         loss tensor (device, static buffer)."""
         B, T, F = feats.shape
-        if F != self.F or feats.dtype != torch.bfloat16 or not feats.is_contiguous():
-            raise ValueError("JasperEngine: features must be contiguous bf16 [B,T,%d]" % self.F)
+        self._check_feats(feats)
         return self._workspace(B, T).run_train_step(feats, feat_lens, labels, label_lens)
+
+    def _check_feats(self, feats):
+        """Features arrive in the activation storage format; a bf16 / fp16 / fp32 tensor of the other kind is
+        converted here (one small elementwise kernel), anything else is an error."""
+        if feats.dim() != 3 or feats.shape[2] != self.F or not feats.is_contiguous():
+            raise ValueError("JasperEngine: features must be contiguous [B,T,%d]" % self.F)
+        if feats.dtype not in (torch.bfloat16, torch.float16, torch.float32):
+            raise ValueError("JasperEngine: features must be bf16 / fp16 / fp32")
 
     def greedy_decode(self):
         """tf.nn.ctc_greedy_decoder on the last forward's logits -> (tokens [B,T'], lens [B])."""
@@ -539,7 +627,7 @@ class JasperEngine(object):
         n += 1  # fc fwd
         for entry in (ws._bwd_plan or []):
             name = entry[0].__name__
-            n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd": 2, "os2s_bn_bwd": 2, "os2s_bn_bwd_ld": 2, "os2s_bn_bwd_apply": 1, "zero_slices": 0,
+            n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd_p": 2, "os2s_bn_bwd_p": 2, "os2s_bn_bwd_apply_p": 1, "zero_slices": 0,
                   "bucket_allreduce": 0, "stream_record": 0, "stream_wait": 0}.get(name, 1)
         return n + 3 + 3
 
@@ -643,6 +731,27 @@ class _BucketAllReduce(object):
 class _Workspace(object):
     """Per-(B,T) activations, gradients and the pre-bound launch plan."""
 
+    @staticmethod
+    def estimate_bytes(eng, B, T):
+        T2 = T // 2 if eng.layers[0].fold else T
+        csz = 4 if eng.conv_dtype == "fp32" else 2
+        rows = B * T2
+        n = sum(l.c_out for l in eng.layers) * (csz + 2)
+        n += sum(g["ntot"] for g in eng.res_groups) * (csz + 2)
+        n += sum(c for (c, _) in eng.block_inputs) * 4
+        n += 3 * max(l.c_out for l in eng.layers) * 2
+        return rows * n + B * T * eng.F * 2 + (64 << 20)
+
+    def release(self):
+        """Drop the captured graph and every tensor so the caching allocator can reuse the memory."""
+        self.graph = None
+        self._fwd_plan = self._bwd_plan = None
+        self._keep = []
+        for k in ("Y", "A", "YRcat", "dYRcat", "dA", "dY2", "dY", "dres", "red", "stats_all", "stats", "stats_cat",
+                  "mean_invstd", "red_all", "fused_red", "logits", "dlogits", "feats", "_ctc_ws", "tokens"):
+            if hasattr(self, k):
+                setattr(self, k, None)
+
     def __init__(self, eng, B, T):
         self.eng = eng
         self.B, self.T = B, T
@@ -662,14 +771,16 @@ class _Workspace(object):
         self.T2 = T2
         M = B * T2
         self.M = M
-        bf = lambda *shape: torch.empty(*shape, dtype=torch.bfloat16, device=dev)
+        bf = lambda *shape: torch.empty(*shape, dtype=eng.act_torch, device=dev)   # gradients: the 16-bit format
         f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
         layers = eng.layers
         nl = len(layers)
-        f16 = lambda *shape: torch.empty(*shape, dtype=torch.float16, device=dev)
-        # conv outputs (BN inputs) are fp16: never a tensor-core operand, 3 more mantissa bits than bf16
+        # conv outputs (BN inputs) are fp16 (never a tensor-core operand, 3 more mantissa bits than bf16) or
+        # fp32 (conv_dtype); layer outputs are bf16 or fp16 (act_dtype)
+        f16 = lambda *shape: torch.empty(*shape, dtype=eng.conv_torch, device=dev)
+        act = lambda *shape: torch.empty(*shape, dtype=eng.act_torch, device=dev)
         self.Y = [f16(B, T2, l.c_out) for l in layers]
-        self.A = [bf(B, T2, l.c_out) for l in layers]
+        self.A = [act(B, T2, l.c_out) for l in layers]
         # residual-branch conv outputs / their gradients, one matrix per SOURCE: [B, T2, sum_b C_b]
         # (consumer b's branch is the column slice starting at its first column)
         self.YRcat = [f16(B, T2, g["ntot"]) for g in eng.res_groups]
@@ -715,7 +826,7 @@ class _Workspace(object):
         self.tokens = torch.zeros(B, T2, dtype=torch.int32, device=dev)
         self.tok_lens = torch.zeros(B, dtype=torch.int32, device=dev)
         self.neg_sum = f32(B)
-        self.feats = torch.zeros(B, T, eng.F, dtype=torch.bfloat16, device=dev)  # static input buffer
+        self.feats = torch.zeros(B, T, eng.F, dtype=eng.act_torch, device=dev)  # static input buffer
         self.graph = None
         self.graph_L = -1
         self._eager_steps = 0
@@ -724,6 +835,7 @@ class _Workspace(object):
         self._build_forward_plan(st)
         self._bwd_plan = None
         self._bwd_L = -1
+        self.nbytes = _Workspace.estimate_bytes(eng, B, T)
 
     # -- helpers
     def _p(self, t, off_elems=0, esz=None):
@@ -773,16 +885,18 @@ class _Workspace(object):
             for j, g in enumerate(eng.res_groups):
                 if g["first_layer"] == li:
                     stats_ptr = self._p(self.stats_cat[j]) if eng.training else _vp(0)
-                    plan.append([lib.os2s_conv1d_fwd, [x_ptr, self._p(eng.wcat[j]), self._p(self.YRcat[j]), B, T2,
-                                                       g["cj"], g["ntot"], 1, 1, 0, 3, stats_ptr, st],
+                    plan.append([lib.os2s_conv1d_fwd_p, [x_ptr, self._p(eng.wcat[j]), self._p(self.YRcat[j]), B, T2,
+                                                         g["cj"], g["ntot"], 1, 1, 0, eng.conv_out_mode, stats_ptr,
+                                                         eng.dtypes, st],
                                  ("fwd", 2.0 * B * T2 * g["cj"] * g["ntot"])])
             flops = 2.0 * B * T2 * l.K * l.c_in * l.c_out  # algorithmic (un-folded) FLOPs
             slot_main = bn_idx
             bn_idx += 1
             # training: the conv epilogue accumulates the BN statistics of its (rounded) output
             stats_ptr = self._p(self.stats[li]) if eng.training else _vp(0)
-            call = [lib.os2s_conv1d_fwd, [x_ptr, self._half_ptr(eng.wb, l.name + "/kernel"), self._p(self.Y[li]),
-                                          B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, 3, stats_ptr, st],
+            call = [lib.os2s_conv1d_fwd_p, [x_ptr, self._half_ptr(eng.wb, l.name + "/kernel"), self._p(self.Y[li]),
+                                            B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, eng.conv_out_mode, stats_ptr,
+                                            eng.dtypes, st],
                     ("fwd", flops)]
             plan.append(call)
             ys, lds = [self._p(self.Y[li])], [l.c_out]
@@ -812,12 +926,12 @@ class _Workspace(object):
             args = [nb, y_h, ld_h, st_h, stld_h, g_h, b_h, mi_h, mv_h, self._p(self.A[li]), lens_ptr, B, T2, l.c_out,
                     _c_float(eng.bn_eps), _c_float(eng.bn_momentum), _c_float(l.keep if eng.training else 1.0),
                     _c_u64((eng.seed * 1000003 + 4099 * li + 17) & 0xFFFFFFFFFFFFFFFF), 1, _c_float(eng.relu_clip),
-                    0 if eng.training else 1, _vp(eng.istate.data_ptr() + 5 * 8), st]
+                    0 if eng.training else 1, _vp(eng.istate.data_ptr() + 5 * 8), eng.dtypes, st]
             self._keep.append(stld_h)
-            plan.append([lib.os2s_bn_apply_fwd_ld, args])
-        self._fc_call = [lib.os2s_fc_fwd, [self._p(self.A[-1]), self._param_ptr(eng.master, "fc/kernel"),
-                                           self._param_ptr(eng.master, "fc/bias"), self._p(self.logits), M, eng.H,
-                                           eng.V, st]]
+            plan.append([lib.os2s_bn_apply_fwd_p, args])
+        self._fc_call = [lib.os2s_fc_fwd_p, [self._p(self.A[-1]), self._param_ptr(eng.master, "fc/kernel"),
+                                             self._param_ptr(eng.master, "fc/bias"), self._p(self.logits), M, eng.H,
+                                             eng.V, eng.dtypes, st]]
         self._fwd_plan = plan
         self.n_launch_fwd = len(plan) + 2
 
@@ -896,7 +1010,7 @@ class _Workspace(object):
     def run_decoder(self):
         self._st.value = torch.cuda.current_stream().cuda_stream
         fn, args = self._fc_call[0], self._fc_call[1]
-        L.check(fn(*args), "os2s_fc_fwd")
+        L.check(fn(*args), "os2s_fc_fwd_p")
 
     def _build_backward_plan(self, L_max):
         eng, lib = self.eng, self.eng.lib
@@ -912,10 +1026,10 @@ class _Workspace(object):
                      [self._p(self.logits), self._p(self.labels), self._p(self.label_lens), self._p(self.lens_out),
                       self._p(self.dlogits), self._p(self.loss), self._p(self._ctc_ws), _c_size_t(int(need)),
                       self._p(eng.fstate), B, T2, eng.V, L_max, _c_ll(T2 * eng.V), _c_ll(eng.V), st]])
-        plan.append([lib.os2s_fc_bwd, [self._p(self.A[-1]), self._p(self.dlogits),
-                                       self._param_ptr(eng.master, "fc/kernel"), self._p(self.dA),
-                                       self._param_ptr(eng.grad, "fc/kernel"), self._param_ptr(eng.grad, "fc/bias"),
-                                       M, eng.H, eng.V, st]])
+        plan.append([lib.os2s_fc_bwd_p, [self._p(self.A[-1]), self._p(self.dlogits),
+                                         self._param_ptr(eng.master, "fc/kernel"), self._p(self.dA),
+                                         self._param_ptr(eng.grad, "fc/kernel"), self._param_ptr(eng.grad, "fc/bias"),
+                                         M, eng.H, eng.V, eng.dtypes, st]])
         nl = len(eng.layers)
         if self.fused_red:
             plan.append([_ZeroMain(self.red_all), []])
@@ -950,16 +1064,16 @@ class _Workspace(object):
             if li in self.fused_red:
                 # the two reductions were accumulated by dgrad(li + 1) below (enqueued earlier)
                 nm = names[0]
-                plan.append([lib.os2s_bn_bwd_apply, [self._p(self.Y[li]), self._p(self.mean_invstd[slots[0]]),
-                                                     self._param_ptr(eng.master, nm + "/gamma"),
-                                                     self._param_ptr(eng.grad, nm + "/gamma"),
-                                                     self._param_ptr(eng.grad, nm + "/beta"), self._p(dY), dA_ptr,
-                                                     self._p(self.A[li]), self._p(self.fused_red[li]), M, l.c_out,
-                                                     _c_float(l.keep), st]])
+                plan.append([lib.os2s_bn_bwd_apply_p, [self._p(self.Y[li]), self._p(self.mean_invstd[slots[0]]),
+                                                       self._param_ptr(eng.master, nm + "/gamma"),
+                                                       self._param_ptr(eng.grad, nm + "/gamma"),
+                                                       self._param_ptr(eng.grad, nm + "/beta"), self._p(dY), dA_ptr,
+                                                       self._p(self.A[li]), self._p(self.fused_red[li]), M, l.c_out,
+                                                       _c_float(l.keep), eng.dtypes, st]])
             else:
-                plan.append([lib.os2s_bn_bwd_ld, [nb, y_h, ld_h, mi_h, g_h, dg_h, db_h, dy_h, dA_ptr, dA_f32,
-                                                  self._p(self.A[li]), self._p(self.red), M, l.c_out, _c_float(l.keep),
-                                                  1, st]])
+                plan.append([lib.os2s_bn_bwd_p, [nb, y_h, ld_h, mi_h, g_h, dg_h, db_h, dy_h, dA_ptr, dA_f32,
+                                                 self._p(self.A[li]), self._p(self.red), M, l.c_out, _c_float(l.keep),
+                                                 1, eng.dtypes, st]])
             self._keep += [dg_h, db_h, dy_h]
             plan.append([_StreamRecord(self, "main", ev_bn[li]), []])
             # the input of this layer is residual source j: every consumer block has written its slice of
@@ -971,32 +1085,33 @@ class _Workspace(object):
                 g = eng.res_groups[src_j]
                 # all residual branches that read source j: ONE GEMM, reduction over sum_b C_b (first writer
                 # of the fp32 accumulator; the main-path gradient below adds to it)
-                plan.append([lib.os2s_conv1d_dgrad, [self._p(self.dYRcat[src_j]), self._p(eng.wcat[src_j]),
-                                                     self._p(self.dres[src_j]), B, T2, g["cj"], g["ntot"], 1, 1, 0, 1,
-                                                     st], ("dgrad", 2.0 * B * T2 * g["cj"] * g["ntot"])])
+                plan.append([lib.os2s_conv1d_dgrad_p, [self._p(self.dYRcat[src_j]), self._p(eng.wcat[src_j]),
+                                                       self._p(self.dres[src_j]), B, T2, g["cj"], g["ntot"], 1, 1, 0, 1,
+                                                       eng.dtypes, st], ("dgrad", 2.0 * B * T2 * g["cj"] * g["ntot"])])
             if li > 0:
                 if src_j is not None:
                     mode, out_ptr = 2, self._p(self.dres[src_j])
                 else:
-                    mode, out_ptr = 0, self._p(self.dA)
+                    mode, out_ptr = eng.grad_out_mode, self._p(self.dA)
                 if (li - 1) in self.fused_red:
                     # dA of the plain layer below + its BN-backward sums in the same kernel
                     lp = eng.layers[li - 1]
-                    plan.append([lib.os2s_conv1d_dgrad_bnred,
+                    plan.append([lib.os2s_conv1d_dgrad_bnred_p,
                                  [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"), out_ptr, B, T2, l.kC_in,
                                   l.c_out, l.kK, l.dil, l.kpad, self._p(self.A[li - 1]), self._p(self.Y[li - 1]),
-                                  _c_float(lp.keep), self._p(self.fused_red[li - 1]), st],
+                                  _c_float(lp.keep), self._p(self.fused_red[li - 1]), eng.dtypes, st],
                                  ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
                 else:
-                    plan.append([lib.os2s_conv1d_dgrad, [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"),
-                                                         out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
-                                                         st], ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
+                    plan.append([lib.os2s_conv1d_dgrad_p, [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"),
+                                                           out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
+                                                           eng.dtypes, st],
+                                 ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
             # ---- aux stream: weight gradients of this layer (enqueued after the critical-path kernels)
             plan.append([_StreamWait(self, "aux", ev_bn[li]), []])
             # main conv wgrad (stored layout == kernel layout, also for the folded stride-2 layer)
             x_ptr = self._p(self.A[li - 1]) if li > 0 else self._p(self.feats)
-            plan.append([lib.os2s_conv1d_wgrad, [x_ptr, self._p(dY), self._param_ptr(eng.grad, l.name + "/kernel"),
-                                                 B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, sa],
+            plan.append([lib.os2s_conv1d_wgrad_p, [x_ptr, self._p(dY), self._param_ptr(eng.grad, l.name + "/kernel"),
+                                                   B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, eng.dtypes, sa],
                          ("wgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
             if l.fold:
                 # structurally-zero taps of the folded stride-2 kernel get no gradient
@@ -1013,8 +1128,8 @@ class _Workspace(object):
                 # weight gradients of all 1x1 kernels that read source j: one GEMM into [C_j, Ntot_j], then
                 # scattered to the per-variable gradient buffers (which live in this layer's region)
                 g = eng.res_groups[src_j]
-                plan.append([lib.os2s_conv1d_wgrad, [x_ptr, self._p(self.dYRcat[src_j]), self._p(eng.dwcat[src_j]),
-                                                     B, T2, g["cj"], g["ntot"], 1, 1, 0, sa],
+                plan.append([lib.os2s_conv1d_wgrad_p, [x_ptr, self._p(self.dYRcat[src_j]), self._p(eng.dwcat[src_j]),
+                                                       B, T2, g["cj"], g["ntot"], 1, 1, 0, eng.dtypes, sa],
                              ("wgrad", 2.0 * B * T2 * g["cj"] * g["ntot"])])
                 src, dst, rows, rbytes, sp, dp = [], [], [], [], [], []
                 for (lc, n, cb, col) in g["consumers"]:

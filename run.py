@@ -40,10 +40,7 @@ def main():
     if args.mode == "train_eval":
         train(model[0], eval_model=model[1])
     elif args.mode == "train":
-        if checkpoint is not None:
-            from open_seq2seq.utils import checkpoint as ckpt
-            ckpt.restore(model.engine, checkpoint)
-        train(model)
+        train(model)   # create_model restored `checkpoint` (--continue_learning) before the first step
     elif args.mode == "eval":
         evaluate(model, checkpoint)
     elif args.mode == "infer":

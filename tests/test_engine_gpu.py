@@ -52,7 +52,7 @@ def _setup(B=3, T=96, F=64, V=29, seed=0, fuse_min_channels=None):
         # the production threshold (384 channels) is above this toy net's widths: lower it so that the
         # dgrad kernels that also accumulate the BN-backward reductions are the ones under test
         eng.fuse_bn_min_channels = fuse_min_channels
-    eng._ws = {}
+    eng.clear_workspaces()
     eng.load_parameters(params)
     L = 12
     gl = torch.Generator().manual_seed(5)
@@ -271,7 +271,7 @@ def test_full_jasper10x5_logits_vs_oracle_small_batch():
     eng = JasperEngine(layers, F, V, training=True, dropout_keep_default=1.0, opt=dict(loss_scaling=False))
     for l in eng.layers:
         l.keep = 1.0
-    eng._ws = {}
+    eng.clear_workspaces()
     assert sum(s["size"] for s in eng.specs) == 332632349  # SURVEY.md Appendix B parameter count
     assert len(eng.layers) == 53 and sum(len(l.res_sources) for l in eng.layers) == 55
     eng.load_parameters(params)

@@ -582,3 +582,148 @@ def test_featurizer_psf_backend_and_global_normalisation_vs_oracle(mode):
         assert np.all(got[b, n:] == 0)
         # the reference's own pin for this backend (speech_utils_test.py:72-73): mean 0, std 1
         assert abs(float(got[b, :n].mean())) < 1e-4 and abs(float(got[b, :n].std()) - 1.0) < 1e-4
+
+
+def test_speed_perturbation_and_noise_vs_oracle(golden_dir):
+    """os2s_augment_signal (speech_utils.py:245-266): resampy 'kaiser_best' band-limited interpolation at the
+    ratios of the Jasper recipe (0.9, 1.0, 1.1) on a real toy-speech wav vs the oracle's restatement, and the
+    additive noise at the drawn level (statistics)."""
+    import scipy.io.wavfile as wavfile
+    from oracle import augment as AU
+    from open_seq2seq.data.speech2text import speech_utils as SU
+    L, lib = _lib()
+    sr, sig = wavfile.read(os.path.join(golden_dir, "toy_speech_data", "wav_files", "46gc040q.wav"))
+    sig = sig.astype(np.int16)[:40000]
+    sigs = [sig, sig[:30001], sig[5000:33333]]
+    sr_new = np.array([14400, 0, 17600], dtype=np.int32)
+    n_out = np.array([AU.resample_out_len(len(s), sr, r) if r else len(s) for s, r in zip(sigs, sr_new)], dtype=np.int32)
+    B = len(sigs)
+    dev = "cuda"
+    wave = torch.tensor(np.concatenate(sigs), dtype=torch.int16, device=dev)
+    offs = torch.tensor(np.cumsum([0] + [len(s) for s in sigs[:-1]]), dtype=torch.int64, device=dev)
+    ns = torch.tensor([len(s) for s in sigs], dtype=torch.int32, device=dev)
+    ooffs = torch.tensor(np.cumsum([0] + list(n_out[:-1])), dtype=torch.int64, device=dev)
+    tab, num_table = SU.kaiser_best_table()
+    assert np.array_equal(tab, AU.kaiser_best_table()[0])   # product table == oracle table
+    tabd = torch.tensor(tab, dtype=torch.float32, device=dev)
+    absmax = torch.zeros(B, dtype=torch.int32, device=dev)
+    out = torch.full((int(n_out.sum()),), float("nan"), device=dev)
+    st = L.stream_ptr()
+    L.check(lib.os2s_wave_absmax(L.ptr(wave), L.ptr(offs), L.ptr(ns), B, L.ptr(absmax), st), "absmax")
+    L.check(lib.os2s_augment_signal(L.ptr(wave), L.ptr(offs), L.ptr(ns), B, L.ptr(absmax), _f(0.0),
+                                    L.ptr(torch.tensor(sr_new, device=dev)), sr, L.ptr(tabd), tabd.numel(), num_table,
+                                    None, ctypes.c_uint64(1), L.ptr(out), L.ptr(ooffs),
+                                    L.ptr(torch.tensor(n_out, device=dev)), int(n_out.max()), st), "augment")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert absmax.cpu().tolist() == [int(np.abs(s.astype(np.int32)).max()) for s in sigs]
+    o = 0
+    for b, s in enumerate(sigs):
+        x = s.astype(np.float32) * (1.0 / (np.abs(s.astype(np.float32)).max() + 1e-5))
+        ref = AU.resample(x, sr, int(sr_new[b])) if sr_new[b] else x.astype(np.float64)
+        assert len(ref) == n_out[b]
+        err = np.abs(got[o:o + n_out[b]] - ref).max()
+        assert err < 2e-5, (b, err)      # fp32 accumulation of ~130 taps of an O(1) signal
+        o += n_out[b]
+    # noise: out - clean has the drawn amplitude, zero mean, unit-variance Gaussian shape
+    amp = torch.tensor([0.01, 0.0, 0.002], device=dev)
+    noisy = torch.empty_like(out)
+    L.check(lib.os2s_augment_signal(L.ptr(wave), L.ptr(offs), L.ptr(ns), B, L.ptr(absmax), _f(0.0),
+                                    L.ptr(torch.tensor(sr_new, device=dev)), sr, L.ptr(tabd), tabd.numel(), num_table,
+                                    L.ptr(amp), ctypes.c_uint64(7), L.ptr(noisy), L.ptr(ooffs),
+                                    L.ptr(torch.tensor(n_out, device=dev)), int(n_out.max()), st), "augment+noise")
+    torch.cuda.synchronize()
+    d = (noisy - out).cpu().numpy()
+    o = 0
+    for b in range(B):
+        seg = d[o:o + n_out[b]]
+        if float(amp[b]) == 0:
+            assert np.all(seg == 0)
+        else:
+            z = seg / float(amp[b])
+            assert abs(z.mean()) < 0.03 and abs(z.std() - 1.0) < 0.03
+            assert abs(np.mean(z ** 4) - 3.0) < 0.3      # Gaussian kurtosis
+        o += n_out[b]
+
+
+def test_featurizer_on_augmented_signal_with_spec_masks_gain_and_fixed_normalisation():
+    """os2s_features_forward_p: (a) features of the speed-perturbed float signal + spec-augment masks vs the
+    oracle (speech_utils.py:354-433); (b) params['gain'] with features_mean / features_std_dev instead of
+    the computed statistics; (c) fp16 output format."""
+    from oracle import augment as AU
+    from oracle import featurizer as FZ
+    L, lib = _lib()
+    rng = np.random.default_rng(5)
+    sigs = [np.clip(3000 * rng.standard_normal(n), -32768, 32767).astype(np.int16) for n in (24000, 17777)]
+    sigs = [np.clip(np.convolve(s.astype(np.float64), np.ones(8) / 8, mode="same"), -32768, 32767).astype(np.int16)
+            for s in sigs]
+    sr, F, hop = 16000, 64, 160
+    sr_new = [17600, 14400]
+    xs = [s.astype(np.float32) * (1.0 / (np.abs(s.astype(np.float32)).max() + 1e-5)) for s in sigs]
+    aug_sig = [AU.resample(x, sr, r) for x, r in zip(xs, sr_new)]
+    r = np.random.RandomState(11)
+    augp = {"n_freq_mask": 2, "n_time_mask": 2, "width_freq_mask": 6, "width_time_mask": 6}
+    masks_l = [AU.draw_spec_masks(1 + len(a) // hop, F, augp, r) for a in aug_sig]
+    # the normalised features do not depend on the signal's scale: the oracle featurizer may renormalise
+    ref = [AU.apply_spec_masks(FZ.logfbank_features(a, dither=0.0)[0], m) for a, m in zip(aug_sig, masks_l)]
+    B = 2
+    ref_lens = [f.shape[0] for f in ref]
+    T_pad = -(-max(ref_lens) // 16) * 16
+    dev = "cuda"
+    n_out = np.array([len(a) for a in aug_sig], dtype=np.int32)
+    sig = torch.tensor(np.concatenate(aug_sig), dtype=torch.float32, device=dev)
+    soff = torch.tensor([0, n_out[0]], dtype=torch.int64, device=dev)
+    nsd = torch.tensor(n_out, device=dev)
+    melnp = FZ.mel_filterbank()
+    mel = torch.tensor(melnp, dtype=torch.float32, device=dev)
+    band = torch.tensor([[int(np.nonzero(q)[0].min()), int(np.nonzero(q)[0].max()) + 1] for q in melnp],
+                        dtype=torch.int32, device=dev)
+    win = torch.tensor(np.hanning(320), dtype=torch.float32, device=dev)
+    nm = 4
+    mk = np.zeros((B, nm, 3), dtype=np.int32)
+    for b, ml in enumerate(masks_l):
+        for i, m in enumerate(ml):
+            mk[b, i] = m
+    mkd = torch.tensor(mk, device=dev)
+    absmax = torch.zeros(B, dtype=torch.int32, device=dev)
+    raw = torch.zeros(B * T_pad * F, device=dev)
+    out = torch.full((B, T_pad, F), float("nan"), device=dev)
+    out16 = torch.zeros(B, T_pad, F, dtype=torch.float16, device=dev)
+    lens = torch.zeros(B, dtype=torch.int32, device=dev)
+    L.check(lib.os2s_features_forward_p(None, L.ptr(sig), L.ptr(soff), L.ptr(soff), L.ptr(nsd), B, L.ptr(mel), L.ptr(band),
+                                        L.ptr(win), 512, 320, hop, F, T_pad, int(n_out.max()), _f(0.0), ctypes.c_uint64(0),
+                                        _f(0.97), 0, 16, 1, _f(0.0), None, None, L.ptr(mkd), nm, L.ptr(absmax), L.ptr(raw),
+                                        L.ptr(out16), L.ptr(out), L.ptr(lens), 1, L.stream_ptr()), "features_p")
+    torch.cuda.synchronize()
+    assert lens.cpu().tolist() == ref_lens
+    got = out.cpu().numpy()
+    for b in range(B):
+        n = ref_lens[b]
+        assert np.abs(got[b, :n] - ref[b]).max() < 2e-2, (b, np.abs(got[b, :n] - ref[b]).max())
+        assert np.all(got[b, n:] == 0)
+        for kind, base, width in masks_l[b]:     # the bands are exact zeros
+            blk = got[b, :n, base:base + width] if kind == 0 else got[b, base:base + width, :]
+            assert np.all(blk == 0)
+    assert np.abs(out16.float().cpu().numpy() - got).max() < 4e-3      # fp16 rounding of O(1) values
+    # (b) fixed gain + given mean / std: (log-mel - mean) / std of the un-normalised features
+    gain = 1.0 / 20000.0
+    s0 = sigs[0]
+    wave = torch.tensor(s0, dtype=torch.int16, device=dev)
+    off0 = torch.zeros(1, dtype=torch.int64, device=dev)
+    n0 = torch.tensor([len(s0)], dtype=torch.int32, device=dev)
+    x = FZ.preemphasis(s0.astype(np.float32) * np.float32(gain))
+    logmel = np.log(melnp @ FZ.stft_power(x) + 1e-20).T
+    fm = rng.standard_normal(F).astype(np.float32)
+    fs = (1.0 + rng.random(F)).astype(np.float32)
+    want = (logmel - fm) / fs
+    T1 = -(-logmel.shape[0] // 16) * 16
+    out1 = torch.full((1, T1, F), float("nan"), device=dev)
+    raw1 = torch.zeros(T1 * F, device=dev)
+    L.check(lib.os2s_features_forward_p(L.ptr(wave), None, None, L.ptr(off0), L.ptr(n0), 1, L.ptr(mel), L.ptr(band), L.ptr(win),
+                                        512, 320, hop, F, T1, len(s0), _f(0.0), ctypes.c_uint64(0), _f(0.97), 0, 16, 1,
+                                        _f(gain), L.ptr(torch.tensor(fm, device=dev)), L.ptr(torch.tensor(fs, device=dev)),
+                                        None, 0, L.ptr(absmax), L.ptr(raw1), None, L.ptr(out1), L.ptr(lens), 0,
+                                        L.stream_ptr()), "features_p fixed")
+    torch.cuda.synchronize()
+    g1 = out1.cpu().numpy()[0, :logmel.shape[0]]
+    assert np.abs(g1 - want).max() < 2e-2 * max(1.0, np.abs(want).max() / 10)

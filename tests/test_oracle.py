@@ -219,3 +219,70 @@ def test_psf_backend_shape_and_normalisation_pins(golden_dir):
     assert np.all(np.diff(peaks) >= 0)
     inner = fb[:, peaks[0]:peaks[-1] + 1].sum(0)
     assert np.allclose(inner, 1.0, atol=1e-12)
+
+
+def test_augmentation_length_bounds_pin(golden_dir):
+    """The reference's own test of augment_audio_signal (speech_utils_test.py:20-43): 100 draws with
+    speed_perturbation_ratio 0.2 / 0.5 (+ noise) keep the length within [1 - r, 1 + r] x the input length."""
+    import scipy.io.wavfile as wave
+    from oracle import augment as AU
+    sr, signal = wave.read(os.path.join(golden_dir, "toy_speech_data", "wav_files", "46gc040q.wav"))
+    signal = signal.astype(np.float32)[:16000]     # 1 s of it: the bound is length-independent
+    rng = np.random.RandomState(0)
+    for r in (0.2, 0.5):
+        aug = {"speed_perturbation_ratio": r, "noise_level_min": -90, "noise_level_max": -46}
+        for _ in range(100 if r == 0.2 else 20):
+            sr_new, amp = AU.draw_augmentation(len(signal), sr, aug, rng)
+            n_out = AU.resample_out_len(len(signal), sr, sr_new)
+            assert signal.shape[0] * (1 - r) <= n_out <= signal.shape[0] * (1 + r)
+            assert 10 ** (-90 / 20.0) <= amp < 10 ** (-46 / 20.0)
+        out = AU.augment_audio_signal(signal, sr, aug, rng)
+        assert signal.shape[0] * (1 - r) <= out.shape[0] <= signal.shape[0] * (1 + r)
+    # a list of ratios is a uniform choice among them (speech_utils.py:247-248)
+    aug = {"speed_perturbation_ratio": [0.9, 1.0, 1.1]}
+    seen = {AU.draw_augmentation(16000, 16000, aug, rng)[0] for _ in range(60)}
+    assert seen == {14400, 16000, 17600}
+
+
+def test_resampler_restatement_against_an_independent_polyphase_resampler():
+    """resampy is not installed: the restated 'kaiser_best' band-limited interpolation must agree with
+    scipy.signal.resample_poly (an independent Kaiser-windowed polyphase resampler) on a band-limited signal,
+    and with the closed form of a resampled sinusoid."""
+    import scipy.signal as ss
+    from oracle import augment as AU
+    sr, n = 16000, 8000
+    t = np.arange(n) / sr
+    x = np.sin(2 * np.pi * 440 * t) + 0.5 * np.sin(2 * np.pi * 3000 * t + 1) + 0.25 * np.sin(2 * np.pi * 6500 * t)
+    for sr_new, up, down in ((17600, 11, 10), (14400, 9, 10)):
+        y = AU.resample(x, sr, sr_new)
+        assert len(y) == AU.resample_out_len(n, sr, sr_new) == n * up // down
+        tt = np.arange(len(y)) / sr_new
+        # 6.5 kHz survives both rates' Nyquist (7.2 kHz at 14.4 kHz) but sits in the filter's transition band
+        exact = np.sin(2 * np.pi * 440 * tt) + 0.5 * np.sin(2 * np.pi * 3000 * tt + 1)
+        ref = ss.resample_poly(x - 0.25 * np.sin(2 * np.pi * 6500 * t), up, down)
+        y2 = AU.resample(x - 0.25 * np.sin(2 * np.pi * 6500 * t), sr, sr_new)
+        core = slice(300, len(y2) - 300)
+        assert np.abs(y2[core] - exact[core]).max() < 5e-3
+        assert np.abs(y2[core] - ref[core]).max() < 5e-3
+
+
+def test_spec_augment_masks_restatement():
+    """speech_utils.py:419-433: n_freq_mask bands of width <= width_freq_mask over the features, n_time_mask
+    bands of width <= width_time_mask over the frames, zeros written into the normalised features."""
+    from oracle import augment as AU
+    rng = np.random.RandomState(3)
+    aug = {"n_freq_mask": 2, "n_time_mask": 2, "width_freq_mask": 6, "width_time_mask": 6}
+    f = np.ones((120, 64))
+    masks = AU.draw_spec_masks(120, 64, aug, rng)
+    assert len(masks) == 4 and [m[0] for m in masks] == [0, 0, 1, 1]
+    out = AU.apply_spec_masks(f, masks)
+    for kind, base, width in masks:
+        assert 0 <= width <= 6
+        if kind == 0:
+            assert (out[:, base:base + width] == 0).all() and base + width <= 64
+        else:
+            assert (out[base:base + width] == 0).all() and base + width <= 120
+    assert out.sum() >= 120 * 64 - 2 * 6 * 120 - 2 * 6 * 64
+    # a time band that does not fit is dropped (features.shape[0] - time_band > 0 guard)
+    assert all(m[0] == 0 for m in AU.draw_spec_masks(3, 64, dict(aug, width_time_mask=50), np.random.RandomState(0))
+               if m[2] >= 3)
