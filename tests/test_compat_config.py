@@ -171,3 +171,48 @@ def test_benchmark_flag_rewrites_the_train_config_like_the_reference():
     assert train_cfg["bench_start"] == 10 and train_cfg["save_checkpoint_steps"] is None
     assert train_cfg["data_layer_params"]["shuffle"] is False
     check_params(train_cfg, Speech2Text.get_required_params(), Speech2Text.get_optional_params())
+
+
+def test_nothing_in_the_headline_config_is_silently_ignored():
+    """The reference's jasper10x5_LibriSpeech_nvgrad.py trains with speed perturbation (train_params
+    augmentation :199-201); accepted-but-unimplemented options must raise, implemented ones must reach the
+    engine / data layer."""
+    import numpy as np
+    from open_seq2seq.data import Speech2TextDataLayer
+    from open_seq2seq.optimizers.optimizers import optimizer_engine_kwargs
+    from open_seq2seq.utils.utils import resolve_initializer
+    import tensorflow as tf
+    _, cfg, _, mod = get_base_config(["--config_file=" + OWN_CFG])
+    aug = mod["train_params"]["data_layer_params"]["augmentation"]
+    assert aug == {"speed_perturbation_ratio": [0.9, 1.0, 1.1]}
+    if os.path.exists(REF_CFG):
+        _, _, _, ref_mod = get_base_config(["--config_file=" + REF_CFG])
+        assert ref_mod["train_params"]["data_layer_params"]["augmentation"] == aug
+    base = dict(cfg["data_layer_params"], mode="train", batch_size=2, dataset_files=["synthetic:4:1.0"])
+    dl = Speech2TextDataLayer(dict(base, augmentation=dict(aug, noise_level_min=-90, noise_level_max=-46)), None, 1, 0)
+    rs = np.random.RandomState(0)
+    sr_new, noise, n_out = dl._draw_augmentation([16000] * 64, rs)
+    assert set(sr_new.tolist()) == {14400, 16000, 17600}
+    assert all(int(n) == int(16000 * (s / 16000.0)) for n, s in zip(n_out, sr_new))
+    assert (noise >= 10 ** (-90 / 20.0)).all() and (noise < 10 ** (-46 / 20.0)).all()
+    eval_dl = Speech2TextDataLayer(dict(base, mode="eval", augmentation=aug, shuffle=False), None, 1, 0)
+    assert eval_dl._aug is None                       # training-time transform only
+    with pytest.raises(ValueError):
+        Speech2TextDataLayer(dict(base, augmentation={"pitch_shift": 2}), None, 1, 0)
+    with pytest.raises(NotImplementedError):
+        Speech2TextDataLayer(dict(base, backend="psf", augmentation=aug), None, 1, 0)
+    with pytest.raises(NotImplementedError):
+        Speech2TextDataLayer(dict(base, backend="psf", gain=0.5), None, 1, 0)
+    # optimizer options that used to be dropped
+    p = dict(cfg, max_grad_norm=5.0, freeze_variables_regex="ForwardPass/w2l_encoder/conv1.*")
+    p.pop("larc_params")
+    kw = optimizer_engine_kwargs(p, 1000)
+    assert kw["max_grad_norm"] == 5.0 and kw["freeze_variables_regex"].startswith("ForwardPass")
+    with pytest.raises(AttributeError):
+        optimizer_engine_kwargs(dict(cfg, max_grad_norm=5.0), 1000)     # LARC + clipping (optimizers.py:161-164)
+    # initializers: Xavier in both flavours is built, anything else raises
+    assert resolve_initializer(cfg["encoder_params"], cfg, "enc") == "xavier_truncnorm"
+    assert resolve_initializer(cfg["decoder_params"], cfg, "dec") == "xavier_uniform"
+    assert resolve_initializer({}, {}, "x") == "xavier_uniform"
+    with pytest.raises(NotImplementedError):
+        resolve_initializer({"initializer": lambda **kw: None}, {}, "x")

@@ -129,3 +129,44 @@ def test_train_loop_checkpoints_evaluates_and_keeps_best_models(tmp_path):
     params2 = dict(params, logdir=str(tmp_path / "log2"), eval_steps=None)
     train(_Model(params2, eng2))
     assert int(eng2.istate[2]) == 10 and float(eng2.w["a/kernel"][0]) == 10.0
+
+
+def test_evaluate_restores_the_checkpoint_and_skipped_steps_do_not_count(tmp_path):
+    """(a) funcs.evaluate(model, checkpoint) runs on the restored weights (utils/funcs.py:205-218) -- not on a
+    freshly initialised engine; (b) the loop stops on the DEVICE global step, which an overflow-skipped step
+    does not advance (mp_wrapper.py:115-120); (c) load_model restores name- and shape-matching variables only
+    and leaves the step counters alone (utils/funcs.py:117-144)."""
+    from open_seq2seq.utils.funcs import evaluate
+    logdir = str(tmp_path / "log")
+    eng = _Engine()
+    eng.w["a/kernel"] += 7.0
+    eng.istate[2] = 3
+    path = ckpt.save(eng, logdir, 3)
+    fresh = _Engine()
+    em = _EvalModel({"max_steps": 1}, fresh, losses=[1.0])
+    out = evaluate(em, path)
+    assert float(fresh.w["a/kernel"][0]) == 7.0 and em.evals == 1 and out["Eval loss"] == 1.0
+
+    class _Skippy(_Model):
+        def train_step(self, batch):
+            self.attempts = getattr(self, "attempts", 0) + 1
+            if self.attempts % 3 != 0:          # every third attempt overflows: global_step stays
+                self.engine.istate[2] += 1
+            return torch.tensor(1.0), 100.0
+    e2 = _Engine()
+    m = _Skippy({"max_steps": 6, "print_loss_steps": None, "print_samples_steps": None, "save_checkpoint_steps": None,
+                 "eval_steps": None, "logdir": None, "bench_start": 0}, e2)
+    train(m)
+    assert int(e2.istate[2]) == 6 and m.attempts == 8       # 6 applied + 2 skipped attempts
+
+    class _E3(_Engine):
+        def __init__(self):
+            _Engine.__init__(self)
+            self.w["b/kernel"] = torch.zeros(5)              # not in the checkpoint
+            self.w["a/bn/gamma"] = torch.ones(3)             # shape differs from the checkpoint's
+            self.mom = {k: torch.zeros_like(v) for k, v in self.w.items()}
+            self.by_name = {k: {"shape": tuple(v.shape)} for k, v in self.w.items()}
+    e3 = _E3()
+    n = ckpt.restore_partial(e3, logdir)
+    assert float(e3.w["a/kernel"][0]) == 7.0 and float(e3.w["a/bn/gamma"][0]) == 1.0 and int(e3.istate[2]) == 0
+    assert n == 2    # a/kernel + the BN moving statistics
