@@ -81,13 +81,15 @@ class ClockSampler(object):
 
 
 def _host_threads():
-    """Threads the CPU arm uses: the cores this process may run on (cgroup / affinity aware), capped at
-    32 -- beyond that the many small convolutions of a 4 s sample slow down from oversubscription."""
+    """Threads of the CPU arm: every core this process may run on (cgroup / affinity aware), as BASELINE.md
+    section 3 asks (`torch.set_num_threads(os.cpu_count())`).  OS2S_CPU_THREADS overrides."""
+    if os.environ.get("OS2S_CPU_THREADS"):
+        return max(1, int(os.environ["OS2S_CPU_THREADS"]))
     try:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
         n = os.cpu_count() or 1
-    return max(1, min(n, 32))
+    return max(1, n)
 
 
 def synth_waveforms(rank, n_utts, seconds):
@@ -109,64 +111,97 @@ def synth_labels(rank, n_utts):
 
 
 # --------------------------------------------------------------------------- reference arm
+def _own_config(batch, world, augmentation=True):
+    """`config` of the JSON line: the SAME dict for the own arm and the reference arm (the reference arm
+    times bounded samples of this workload, described in its cpu_baseline.sample)."""
+    return {"workload": WORKLOAD,
+            "batch_per_gpu": batch, "global_batch": batch * world, "audio_seconds_per_utt": AUDIO_SECONDS,
+            "parallelism": "dp%d" % world,
+            "augmentation": ("speed_perturbation_ratio [0.9, 1.0, 1.1] (train_params of the headline config), on: the "
+                             "padded batch is 16.5 s long, audio-seconds count the resampled signals"
+                             if augmentation else "off (--no_augmentation A/B run)"),
+            "l2_policy": "working set per step (activations ~6 GB, params/grads ~5 GB) >> 126 MB L2; no flush needed",
+            "train_gflop_per_audio_s": TRAIN_GFLOP_PER_AUDIO_S}
+
+
+class _CpuPort(object):
+    """The reference's CPU path restated (oracle/torch_twin.py + oracle/featurizer.py + oracle/augment.py): fp32
+    PyTorch-CPU port of the identical graph -- featurizer (with the recipe's speed perturbation), Jasper 10x5
+    DR forward, CTC, backward, LARC + NovoGrad.  TF1 / librosa / resampy are not installable offline."""
+
+    def __init__(self, n_utts, secs, cores):
+        import numpy as np
+        import torch
+        from oracle import torch_twin as TT
+        import openseq2seq_b200.compat as compat
+        compat.install()
+        from open_seq2seq.utils.utils import get_base_config
+        _, cfg, _, _ = get_base_config(["--config_file=" + os.path.join(ROOT, "configs", "jasper10x5_dr.py")])
+        self.layers = cfg["encoder_params"]["convnet_layers"]
+        torch.set_num_threads(cores)
+        self.params = TT.init_params(self.layers, 64, 29, seed=0)
+        for v in self.params.values():
+            v.requires_grad_(True)
+        self.mom = {}
+        self.waves = synth_waveforms(0, n_utts, secs)
+        # the same label generator as the own arm (synth_labels), scaled to the sample's duration
+        g = np.random.default_rng(4321)
+        lens = g.integers(int(12 * secs), int(17.3 * secs) + 1, size=n_utts)
+        y = np.zeros((n_utts, int(lens.max())), dtype=np.int64)
+        for i, L in enumerate(lens):
+            y[i, :L] = g.integers(0, 28, size=L)
+        self.y, self.ylen = torch.tensor(y), torch.tensor(lens, dtype=torch.long)
+        self.rng = np.random.RandomState(1)
+        self.n_utts, self.secs = n_utts, secs
+
+    def step(self):
+        import numpy as np
+        import torch
+        from oracle import augment as AU
+        from oracle import featurizer as FZ
+        from oracle import torch_twin as TT
+        aug = {"speed_perturbation_ratio": [0.9, 1.0, 1.1]}
+        sigs = []
+        for w in self.waves:
+            x = FZ.normalize_signal(w.astype(np.float32))
+            sigs.append(AU.augment_audio_signal(x, SR, aug, self.rng))
+        feats, lens = FZ.batch_features(sigs, pad_to=16)
+        x = torch.tensor(feats, dtype=torch.float32)
+        loss, _, _ = TT.forward_loss(self.params, self.layers, x, torch.tensor(lens, dtype=torch.long), self.y, self.ylen)
+        grads = torch.autograd.grad(loss, list(self.params.values()))
+        TT.larc_novograd_step(self.params, dict(zip(self.params.keys(), grads)), self.mom, lr=0.02)
+        return float(loss.detach())
+
+
 def run_reference(args):
-    """The reference's CPU path: TF1 is not installable here (no wheel for py3.12, no network), so
-    this times the oracle's PyTorch-CPU fp32 port of the identical graph (oracle/torch_twin.py) on
-    all host cores, each step a bounded sample (1 utterance x 4 s) of the same workload."""
-    import torch
+    """`--impl reference`: the reference's CPU path (restated port, see _CpuPort) on all host cores, same metric /
+    unit / config as the own arm; each of the K steps is a bounded sample of that workload -- BASELINE.md
+    section 3's batch of 2 utterances, shortened to 4 s each so that K + W steps end within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import featurizer as FZ
-    from oracle import torch_twin as TT
-    import openseq2seq_b200.compat as compat
-    compat.install()
-    from open_seq2seq.utils.utils import get_base_config
-    _, cfg, _, _ = get_base_config(["--config_file=" + os.path.join(ROOT, "configs", "jasper10x5_dr.py")])
-    layers = cfg["encoder_params"]["convnet_layers"]
     cores = _host_threads()
-    torch.set_num_threads(cores)
-    secs, B = 4.0, 1
-    params = TT.init_params(layers, 64, 29, seed=0)
-    for v in params.values():
-        v.requires_grad_(True)
-    mom = {}
-    waves = synth_waveforms(0, B, secs)
-    y, ylen = synth_labels(0, B)
-    y = torch.tensor(y[:, :40], dtype=torch.long)
-    ylen = torch.tensor([40] * B, dtype=torch.long)
-
-    def step():
-        feats, lens = FZ.batch_features(waves, pad_to=16)
-        x = torch.tensor(feats, dtype=torch.float32)
-        loss, _, _ = TT.forward_loss(params, layers, x, torch.tensor(lens, dtype=torch.long), y, ylen)
-        grads = torch.autograd.grad(loss, list(params.values()))
-        TT.larc_novograd_step(params, dict(zip(params.keys(), grads)), mom, lr=0.02)
-        return float(loss)
-
+    secs, B = 4.0, 2
+    port = _CpuPort(B, secs, cores)
     for _ in range(max(1, min(args.warmup, 1))):
-        step()
+        port.step()
     t0 = time.time()
     n = 0
-    budget = 150.0
+    budget = 200.0
     for _ in range(args.steps):
-        step()
+        port.step()
         n += 1
         if time.time() - t0 > budget:
             break
     dt = time.time() - t0
     val = n * B * secs / dt
-    sample = "%d steps of %d utterance x %.0f s (fp32, torch CPU port of the reference graph)" % (n, B, secs)
-    # same metric / unit / workload as the own arm; each step is a bounded sample of that workload (the
-    # reference's CPU path computes in fp32)
+    sample = ("%d training steps of %d utterances x %.0f s each (fp32 torch-CPU port of the reference graph incl. the "
+              "speed-perturbation resampler; TF1 not installable offline)" % (n, B, secs))
     out = {"impl": "reference", "metric": METRIC, "value": round(val, 4),
            "unit": "audio-s/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
            "ms_per_step": round(1000 * dt / n, 2), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B,
-                      "audio_seconds_per_utt": secs, "parallelism": "cpu",
-                      "sample": "bounded sample of the workload: " + sample,
-                      "train_gflop_per_audio_s": TRAIN_GFLOP_PER_AUDIO_S},
+           "config": _own_config(args.batch, max(1, args.gpus)),
            "cpu_baseline": {"value": round(val, 4), "unit": "audio-s/s", "cores": cores, "kind": "port",
                             "sample": sample},
            "e2e": {"value": round(val, 4), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -174,43 +209,25 @@ def run_reference(args):
 
 
 def cpu_baseline_quick():
-    """Bounded CPU sample timed inside the default run (rank 0, N = 1)."""
-    import torch
-    from oracle import featurizer as FZ
-    from oracle import torch_twin as TT
-    import openseq2seq_b200.compat as compat
-    compat.install()
-    from open_seq2seq.utils.utils import get_base_config
-    _, cfg, _, _ = get_base_config(["--config_file=" + os.path.join(ROOT, "configs", "jasper10x5_dr.py")])
-    layers = cfg["encoder_params"]["convnet_layers"]
+    """BASELINE.md section 3 protocol, timed inside the default run (rank 0, N = 1): B = 2 utterances x 15 s of
+    the same synthetic waveforms, 1 warm-up + 3 timed training steps (featurizer + fwd + bwd + optimizer), all
+    host cores, fp32.  If the warm-up step shows that 3 more steps would take over ~2 minutes, fewer steps are
+    timed and the line says so."""
     cores = _host_threads()
-    torch.set_num_threads(cores)
-    secs = 4.0
-    params = TT.init_params(layers, 64, 29, seed=0)
-    for v in params.values():
-        v.requires_grad_(True)
-    mom = {}
-    waves = synth_waveforms(0, 1, secs)
-    y = torch.randint(0, 28, (1, 40))
-    ylen = torch.tensor([40])
-
-    def step():
-        feats, lens = FZ.batch_features(waves, pad_to=16)
-        x = torch.tensor(feats, dtype=torch.float32)
-        loss, _, _ = TT.forward_loss(params, layers, x, torch.tensor(lens, dtype=torch.long), y, ylen)
-        grads = torch.autograd.grad(loss, list(params.values()))
-        TT.larc_novograd_step(params, dict(zip(params.keys(), grads)), mom, lr=0.02)
-
-    step()
+    B, secs = 2, AUDIO_SECONDS
+    port = _CpuPort(B, secs, cores)
     t0 = time.time()
-    n = 0
-    while n < 8 and (time.time() - t0) < 20.0:
-        step()
-        n += 1
+    port.step()
+    warm = time.time() - t0
+    n_timed = 3 if warm * 3 <= 130.0 else (2 if warm * 2 <= 130.0 else 1)
+    t0 = time.time()
+    for _ in range(n_timed):
+        port.step()
     dt = time.time() - t0
-    return {"value": round(n * secs / dt, 4), "unit": "audio-s/s", "cores": cores, "kind": "port",
-            "sample": "%d training steps of 1 utterance x 4 s, fp32 torch-CPU port of the reference graph "
-                      "(oracle/torch_twin.py); TF1 not installable offline" % n}
+    return {"value": round(n_timed * B * secs / dt, 4), "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "sample": "BASELINE.md section 3: 1 warm-up + %d timed training steps of 2 utterances x 15 s, all %d host "
+                      "cores, fp32 torch-CPU port of the reference graph (oracle/); TF1 not installable offline"
+                      % (n_timed, cores)}
 
 
 # --------------------------------------------------------------------------- CUDA arm
@@ -241,6 +258,8 @@ def run_own(args):
     cfg.pop("num_epochs", None)
     cfg["max_steps"] = 100000  # lr schedule horizon; the bench runs K + W steps of it
     cfg["batch_size_per_gpu"] = args.batch
+    if args.no_augmentation:
+        cfg["data_layer_params"].pop("augmentation", None)   # A/B only: the headline recipe trains with it
     model = model_cls(params=cfg, mode="train", hvd=hvd if world > 1 else None)
     model.compile()
     eng = model.engine
@@ -327,11 +346,10 @@ def run_own(args):
         "value": round(value, 2), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "batch_per_gpu": args.batch, "global_batch": args.batch * world, "audio_seconds_per_utt": AUDIO_SECONDS,
-                   "parallelism": "dp%d" % world,
-                   "l2_policy": "working set per step (activations ~6 GB, params/grads ~5 GB) >> 126 MB L2; no flush needed",
-                   "train_gflop_per_audio_s": TRAIN_GFLOP_PER_AUDIO_S},
+        "config": _own_config(args.batch, world, not args.no_augmentation),
+        "storage": {"half": eng.act_dtype, "conv_out": eng.conv_dtype,
+                    "note": "format of the 16-bit tensors (activations, weight copies, gradients) / of the conv outputs; "
+                            "fp32 masters and fp32 accumulation in every mode"},
         "e2e": {"value": round(e2e, 2), "unit": "audio-s/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": int(host.numel() * 2 + y_host.numel() * 4 + ylen_host.numel() * 4 + args.batch * 12),
                 "d2h_bytes_per_step": 4},
@@ -368,6 +386,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_augmentation", action="store_true",
+                    help="A/B measurement without the recipe's speed perturbation (fixed 15 s utterances)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

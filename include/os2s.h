@@ -62,6 +62,11 @@ int os2s_version(void);
  *              tile (default), -1 = leave unchanged
  * Initial values come from the environment (OS2S_CONV_PAIR, OS2S_CONV_HALO). */
 int os2s_conv_tuning(int pair_mode, int halo_mode);
+/* Grid size of the conv kernels in units of one CTA (or CTA pair) per SM: 1 = one persistent wave with a
+ * static round-robin over the tiles (default), m > 1 = m x as many CTAs with 1/m of the tiles each, handed
+ * out by the hardware block scheduler as CTAs retire (bounds the tail when the all-reduce's CTAs hold SMs).
+ * Initial value: environment OS2S_CONV_WAVES. */
+int os2s_conv_grid_waves(int waves);
 
 /* ---- K2: tf.layers.conv1d(use_bias=False, padding=SAME), stride 1 -----------------------------
  * reference: open_seq2seq/parts/cnns/conv_blocks.py:195-206 (main), :79-85 (1x1 residual).
@@ -334,6 +339,29 @@ int os2s_features_forward(const int16_t* wave, const long long* offsets, const i
                           int F, int T_pad, int max_samples, float dither, uint64_t seed, float preemph,
                           int psf_backend, int pad_to, int norm_per_feature, void* absmax_ws, float* raw_ws,
                           void* out_bf16, float* out_f32, int* out_lens, void* stream);
+
+/* ---- K2b: tf.layers.separable_conv1d(use_bias=False, padding=SAME) of the sep_conv1d layers -----------
+ * reference: open_seq2seq/parts/cnns/conv_blocks.py:27-40,180-193 (main conv), :79-85 (the residual branch of a
+ * sep_conv1d block is a separable conv with kernel_size 1).  depthwise_kernel D fp32 [K][C_in] (TF shape
+ * [K, C_in, 1]), pointwise_kernel P fp32 [C_in][C_out] (TF shape [1, C_in, C_out]).
+ *
+ * Depthwise stage of a wide stride-1 layer (the pointwise stage is os2s_conv1d_* with K = 1):
+ *   out[b,t,c] = sum_k taps[k,c] * x[b, t + t_off0 + k*t_step, c]      (zero outside [0,T))
+ *   forward: t_off0 = -pad_left, t_step = dilation;  data gradient: t_off0 = +pad_left, t_step = -dilation.
+ *   x: 16-bit [B,T,C]; out_mode: OS2S_OUT_BF16 / OS2S_OUT_F16_GRAD (the 16-bit format that `dtypes` selects),
+ *   OS2S_OUT_F32 or OS2S_OUT_F32_ACC (gradient of a residual source).  C % 64 == 0. */
+int os2s_depthwise_conv1d(const void* x, const float* taps, void* out, int B, int T, int C, int K, int t_off0,
+                          int t_step, int out_mode, int dtypes, void* stream);
+/* d_taps[k,c] = sum_{b,t} x[b, t - pad_left + k*dil, c] * dz[b,t,c]   (fp32 [K][C], overwritten; K <= 96) */
+int os2s_depthwise_conv1d_wgrad(const void* x, const void* dz, float* d_taps, int B, int T, int C, int K, int dil,
+                                int pad_left, int dtypes, void* stream);
+/* Composed form (K = 1 residual branches, the stride-2 first layer): w_half[k,c,o] = D[k,c] * P[c,o], the
+ * 16-bit working copy of the equivalent dense kernel, and the fold-back of its dense weight gradient:
+ *   d_depthwise[k,c] = sum_o dw_dense[k,c,o] * P[c,o],   d_pointwise[c,o] = sum_k dw_dense[k,c,o] * D[k,c]. */
+int os2s_sepconv_compose(const float* depthwise, const float* pointwise, void* w_half, int K, int C_in, int C_out,
+                         int dtypes, void* stream);
+int os2s_sepconv_decompose_grad(const float* dw_dense, const float* depthwise, const float* pointwise,
+                                float* d_depthwise, float* d_pointwise, int K, int C_in, int C_out, void* stream);
 
 /* ---- K1b: audio augmentation (speech_utils.py:225-268) and the remaining data-layer options ------------
  * absmax[b] = max |wave_b| (uint32 [B]): the gain of normalize_signal (:216-222) is 1 / (absmax + 1e-5). */

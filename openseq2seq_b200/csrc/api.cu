@@ -11,6 +11,7 @@ extern "C" {
 const char* os2s_last_error(void) { return last_error_cstr(); }
 int os2s_version(void) { return 101; }
 int os2s_conv_tuning(int pair_mode, int halo_mode) { return conv_tuning(pair_mode, halo_mode); }
+int os2s_conv_grid_waves(int waves) { return conv_grid_waves_set(waves); }
 
 int os2s_conv1d_fwd_p(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
                       int K, int dil, int pad_left, int out_mode, float* bn_stats, int dtypes, void* stream) {
@@ -356,6 +357,40 @@ int os2s_features_forward(const int16_t* wave, const long long* offsets, const i
   return logmel_forward(wave, offsets, n_samples, B, mel, mel_band, window, n_fft, win, hop, F, T_pad, max_samples, dither,
                         seed, preemph, (unsigned int*)absmax_ws, raw_ws, out_bf16, out_f32, out_lens,
                         (cudaStream_t)stream, psf_backend, pad_to, norm_per_feature);
+}
+
+int os2s_sepconv_compose(const float* depthwise, const float* pointwise, void* w_half, int K, int C_in, int C_out,
+                         int dtypes, void* stream) {
+  if (!depthwise || !pointwise || !w_half) return fail(ERR_INVALID, "os2s_sepconv_compose: null pointer");
+  return sepconv_compose(depthwise, pointwise, w_half, K, C_in, C_out, (dtypes & OS2S_HALF_F16) ? 1 : 0,
+                         (cudaStream_t)stream);
+}
+
+int os2s_sepconv_decompose_grad(const float* dw_dense, const float* depthwise, const float* pointwise,
+                                float* d_depthwise, float* d_pointwise, int K, int C_in, int C_out, void* stream) {
+  if (!dw_dense || !depthwise || !pointwise || !d_depthwise || !d_pointwise)
+    return fail(ERR_INVALID, "os2s_sepconv_decompose_grad: null pointer");
+  return sepconv_decompose_grad(dw_dense, depthwise, pointwise, d_depthwise, d_pointwise, K, C_in, C_out,
+                                (cudaStream_t)stream);
+}
+
+int os2s_depthwise_conv1d(const void* x, const float* taps, void* out, int B, int T, int C, int K, int t_off0,
+                          int t_step, int out_mode, int dtypes, void* stream) {
+  if (!x || !taps || !out) return fail(ERR_INVALID, "os2s_depthwise_conv1d: null pointer");
+  int mode;
+  if (out_mode == OS2S_OUT_F32) mode = 1;
+  else if (out_mode == OS2S_OUT_F32_ACC) mode = 2;
+  else if (out_mode == OS2S_OUT_BF16 || out_mode == OS2S_OUT_F16_GRAD) mode = 0;
+  else return fail(ERR_INVALID, "os2s_depthwise_conv1d: out_mode is the 16-bit format of the mode, F32 or F32_ACC");
+  return depthwise_conv1d(x, taps, out, B, T, C, K, t_off0, t_step, mode, (dtypes & OS2S_HALF_F16) ? 1 : 0,
+                          (cudaStream_t)stream);
+}
+
+int os2s_depthwise_conv1d_wgrad(const void* x, const void* dz, float* d_taps, int B, int T, int C, int K, int dil,
+                                int pad_left, int dtypes, void* stream) {
+  if (!x || !dz || !d_taps) return fail(ERR_INVALID, "os2s_depthwise_conv1d_wgrad: null pointer");
+  return depthwise_conv1d_wgrad(x, dz, d_taps, B, T, C, K, dil, pad_left, (dtypes & OS2S_HALF_F16) ? 1 : 0,
+                                (cudaStream_t)stream);
 }
 
 int os2s_wave_absmax(const int16_t* wave, const long long* offsets, const int* n_samples, int B, void* absmax,

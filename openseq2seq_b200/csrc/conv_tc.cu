@@ -515,9 +515,13 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // pair tiles: 256 rows; n_mtiles here counts pair tiles per utterance
-  const int n_ptiles = (p.T_out + 2 * kTileM - 1) / (2 * kTileM);
-  const int tiles_per_n = p.B * n_ptiles;
+  // The two 128-row halves of a pair tile are independent row blocks (each CTA loads its own A rows): the
+  // 128-row blocks of the whole batch are enumerated utterance by utterance and paired two by two, so a
+  // pair may straddle two utterances and T only quantises to 128 rows (T = 832: 7 blocks per utterance,
+  // not 4 x 256).  An odd block count pads the last pair (its second CTA recomputes the last block, no store).
+  const int n_blk = (p.T_out + kTileM - 1) / kTileM;
+  const int n_blocks = p.B * n_blk;
+  const int tiles_per_n = (n_blocks + 1) >> 1;
   const int n_tiles = tiles_per_n * p.n_ntiles;
   const int n_iters = p.K_taps * p.c_chunks;
   const int cluster_id = blockIdx.x >> 1;
@@ -529,8 +533,9 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
         const int nt = tile / tiles_per_n;
         const int rem = tile - nt * tiles_per_n;
-        const int b = rem / n_ptiles;
-        const int t0 = (rem - b * n_ptiles) * 2 * kTileM + (int)rank * kTileM;
+        const int blk = min(2 * rem + (int)rank, n_blocks - 1);
+        const int b = blk / n_blk;
+        const int t0 = (blk - b * n_blk) * kTileM;
         const int n0 = nt * BN;
         const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
         const int hcur = ncur / 2;                   // columns of B each CTA provides
@@ -613,8 +618,10 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
       const int nt = tile / tiles_per_n;
       const int rem = tile - nt * tiles_per_n;
-      const int b = rem / n_ptiles;
-      const int t0w = (rem - b * n_ptiles) * 2 * kTileM + (int)rank * kTileM + quad * 32;
+      const int blk = 2 * rem + (int)rank;
+      const bool blk_ok = blk < n_blocks;
+      const int b = min(blk, n_blocks - 1) / n_blk;
+      const int t0w = (min(blk, n_blocks - 1) - b * n_blk) * kTileM + quad * 32;
       const int n0 = nt * BN;
       const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
       if (do_stats && cur_nt >= 0 && nt != cur_nt) flush_stats(cur_nt);
@@ -623,8 +630,9 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      const int nvalid = min(32, max(0, p.T_out - t0w));
+      const int nvalid = blk_ok ? min(32, max(0, p.T_out - t0w)) : 0;
       const long long off = (long long)b * p.out_batch_stride + (long long)t0w * p.out_row_stride + n0;
+      // (a padding block still drains its accumulator: nvalid = 0 stores nothing and adds nothing to the sums)
       epilogue_rows<BN>(p, stage, sacc, do_stats, two_byte, taddr, nvalid, off, ncur, lane);
       tc_fence_before();
       if (leader) mbar_arrive(&tempty_bar[as]);
@@ -701,8 +709,9 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int n_ptiles = (p.T_out + 2 * kTileM - 1) / (2 * kTileM);
-  const int tiles_per_n = p.B * n_ptiles;
+  const int n_blk = (p.T_out + kTileM - 1) / kTileM;     // see tapgemm_kmajor_pair: pairs of 128-row blocks
+  const int n_blocks = p.B * n_blk;
+  const int tiles_per_n = (n_blocks + 1) >> 1;
   const int n_tiles = tiles_per_n * p.n_ntiles;
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
@@ -713,8 +722,9 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
         const int nt = tile / tiles_per_n;
         const int rem = tile - nt * tiles_per_n;
-        const int b = rem / n_ptiles;
-        const int t0 = (rem - b * n_ptiles) * 2 * kTileM + (int)rank * kTileM;
+        const int blk = min(2 * rem + (int)rank, n_blocks - 1);
+        const int b = blk / n_blk;
+        const int t0 = (blk - b * n_blk) * kTileM;
         const int n0 = nt * BN;
         const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
         const int hcur = ncur / 2;
@@ -806,8 +816,10 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
     for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
       const int nt = tile / tiles_per_n;
       const int rem = tile - nt * tiles_per_n;
-      const int b = rem / n_ptiles;
-      const int t0w = (rem - b * n_ptiles) * 2 * kTileM + (int)rank * kTileM + quad * 32;
+      const int blk = 2 * rem + (int)rank;
+      const bool blk_ok = blk < n_blocks;
+      const int b = min(blk, n_blocks - 1) / n_blk;
+      const int t0w = (min(blk, n_blocks - 1) - b * n_blk) * kTileM + quad * 32;
       const int n0 = nt * BN;
       const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
       if (do_stats && cur_nt >= 0 && nt != cur_nt) flush_stats(cur_nt);
@@ -816,8 +828,9 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      const int nvalid = min(32, max(0, p.T_out - t0w));
+      const int nvalid = blk_ok ? min(32, max(0, p.T_out - t0w)) : 0;
       const long long off = (long long)b * p.out_batch_stride + (long long)t0w * p.out_row_stride + n0;
+      // (a padding block still drains its accumulator: nvalid = 0 stores nothing and adds nothing to the sums)
       epilogue_rows<BN>(p, stage, sacc, do_stats, two_byte, taddr, nvalid, off, ncur, lane);
       tc_fence_before();
       if (leader) mbar_arrive(&tempty_bar[as]);
@@ -1213,6 +1226,26 @@ tapgemm_mnmajor_pair(const __grid_constant__ CUtensorMap map_x, const __grid_con
 }
 
 // ------------------------------------------------------------------ launchers
+// Grid size in units of "one CTA (or CTA pair) per SM".  1 = one persistent wave with a static round-robin
+// over the tiles.  m > 1 launches m times as many CTAs with 1/m of the tiles each: the hardware block
+// scheduler then hands out work dynamically as CTAs retire, which bounds the tail when other kernels (NCCL's
+// CTAs during the gradient all-reduce) hold SMs -- a static schedule makes the tiles of every CTA that cannot
+// be resident wait for a whole second wave.  OS2S_CONV_WAVES / os2s_conv_grid_waves(); default 1.
+static int g_grid_waves = -1;
+static int conv_grid_waves() {
+  if (g_grid_waves < 0) {
+    const char* e = getenv("OS2S_CONV_WAVES");
+    g_grid_waves = e ? atoi(e) : 1;
+    if (g_grid_waves < 1) g_grid_waves = 1;
+  }
+  return g_grid_waves;
+}
+int conv_grid_waves_set(int waves) {
+  if (waves < 1 || waves > 16) return fail(ERR_INVALID, "conv_grid_waves: 1..16");
+  g_grid_waves = waves;
+  return 0;
+}
+
 template <int BN>
 static size_t smem_bytes() {
   return (size_t)num_stages<BN>() * (kABytes + BN * kChunkK * 2) + (2 * num_stages<BN>() + 4) * 8 + 16 +
@@ -1229,7 +1262,8 @@ static int launch_kmajor(const CUtensorMap* ma, const CUtensorMap* mb, const KMa
     attr_done = true;
   }
   const int tiles = p.B * p.n_mtiles * p.n_ntiles;
-  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  const int cap = device_sm_count() * conv_grid_waves();
+  const int grid = tiles < cap ? tiles : cap;
   tapgemm_kmajor<BN, BMN><<<grid, kNumThreads, smem, st>>>(*ma, *mb, p);
   return check_launch("tapgemm_kmajor");
 }
@@ -1247,8 +1281,8 @@ static int launch_kmajor_pair(const CUtensorMap* ma, const CUtensorMap* mb, cons
                                    (int)smem));
     attr_done = true;
   }
-  const int ptiles = p.B * ((p.T_out + 2 * kTileM - 1) / (2 * kTileM)) * p.n_ntiles;
-  const int pairs = device_sm_count() / 2;
+  const int ptiles = ((p.B * ((p.T_out + kTileM - 1) / kTileM) + 1) / 2) * p.n_ntiles;
+  const int pairs = (device_sm_count() / 2) * conv_grid_waves();
   const int clusters = ptiles < pairs ? ptiles : pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
@@ -1282,8 +1316,8 @@ static int launch_kmajor_pair_halo(const CUtensorMap* ma, const CUtensorMap* mb,
                                    (int)(kSmemBudget + 4096)));
     attr_done = true;
   }
-  const int ptiles = p.B * ((p.T_out + 2 * kTileM - 1) / (2 * kTileM)) * p.n_ntiles;
-  const int pairs = device_sm_count() / 2;
+  const int ptiles = ((p.B * ((p.T_out + kTileM - 1) / kTileM) + 1) / 2) * p.n_ntiles;
+  const int pairs = (device_sm_count() / 2) * conv_grid_waves();
   const int clusters = ptiles < pairs ? ptiles : pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
@@ -1336,7 +1370,8 @@ static int launch_mnmajor(const CUtensorMap* mx, const CUtensorMap* mdy, const M
     attr_done = true;
   }
   const long long items = (long long)p.K_taps * p.m_tiles * p.n_tiles * p.B;
-  const int grid = items < device_sm_count() ? (int)items : device_sm_count();
+  const int cap = device_sm_count() * conv_grid_waves();
+  const int grid = items < cap ? (int)items : cap;
   tapgemm_mnmajor<BN><<<grid, kNumThreads, smem, st>>>(*mx, *mdy, p);
   return check_launch("tapgemm_mnmajor");
 }
@@ -1353,7 +1388,7 @@ static int launch_mnmajor_pair(const CUtensorMap* mx, const CUtensorMap* mdy, co
     attr_done = true;
   }
   const long long items = (long long)((p.K_taps * p.m_tiles + 1) / 2) * p.n_tiles * p.B;
-  const int pairs = device_sm_count() / 2;
+  const int pairs = (device_sm_count() / 2) * conv_grid_waves();
   const int clusters = items < pairs ? (int)items : pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);

@@ -15,6 +15,7 @@ const char* last_error_cstr();
 
 // conv_tc.cu
 int conv_tuning(int pair_mode, int halo_mode);
+int conv_grid_waves_set(int waves);
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
                 int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st,
                 const void* bwd_a = nullptr, const void* bwd_y = nullptr, float bwd_inv_keep = 1.f,
@@ -86,6 +87,15 @@ int bn_stats(const void* y, float* stats, int M, int C, cudaStream_t st);
 int bn_apply_fwd(const BnFwdParams& p, cudaStream_t st);
 int bn_bwd(const BnBwdParams& p, cudaStream_t st, bool reduce = true);
 
+
+// sepconv.cu
+int sepconv_compose(const float* D, const float* P, void* w, int K, int C, int Co, int f16, cudaStream_t st);
+int sepconv_decompose_grad(const float* dW, const float* D, const float* P, float* dD, float* dP, int K, int C, int Co,
+                           cudaStream_t st);
+int depthwise_conv1d(const void* x, const float* taps, void* out, int B, int T, int C, int K, int off0, int step,
+                     int out_mode, int f16, cudaStream_t st);
+int depthwise_conv1d_wgrad(const void* x, const void* dz, float* dtaps, int B, int T, int C, int K, int dil, int pad,
+                           int f16, cudaStream_t st);
 
 // ctc.cu
 int fc_fwd(const void* x, const float* w, const float* bias, float* logits, int M, int H, int V, cudaStream_t st,

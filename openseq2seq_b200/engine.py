@@ -75,6 +75,17 @@ class ConvLayer(object):
         self.kC_in = c_in
         self.kpad = 0
         self.lead_taps = 0
+        # sep_conv1d (QuartzNet / Jasper-Mini): "split" = depthwise kernel on the CUDA cores + 1x1 tcgen05 GEMM,
+        # "compose" = equivalent dense kernel D[k,c] * P[c,o] formed on the fly (K = 1, stride 2, narrow inputs)
+        self.sep = False
+        self.sep_mode = None
+
+    @property
+    def wname(self):
+        """Name of the 16-bit kernel the MAIN conv of this layer multiplies with."""
+        if not self.sep:
+            return self.name + "/kernel"
+        return self.name + ("/kernel@composed" if self.sep_mode == "compose" else "/pointwise_kernel")
 
 
 class JasperEngine(object):
@@ -144,8 +155,9 @@ class JasperEngine(object):
         c_in = self.F
         res_list = []
         for bi, lc in enumerate(cfg):
-            if lc.get("type", "conv1d") != "conv1d":
-                raise ValueError("JasperEngine: only 'conv1d' layers are built (got %r)" % lc.get("type"))
+            ltype = lc.get("type", "conv1d")
+            if ltype not in ("conv1d", "sep_conv1d"):
+                raise ValueError("JasperEngine: 'conv1d' and 'sep_conv1d' layers are built (got %r)" % (ltype,))
             if lc.get("padding", "SAME") != "SAME":
                 raise ValueError("JasperEngine: only SAME padding is built")
             K = lc["kernel_size"][0]
@@ -168,8 +180,12 @@ class JasperEngine(object):
                 raise ValueError("JasperEngine: stride > 1 is only built for the first layer")
             for ri in range(lc["repeat"]):
                 end = residual and ri == lc["repeat"] - 1
-                layers.append(ConvLayer("conv%d%d" % (bi + 1, ri + 1), K, stride, dil, c_in, c_out, keep, bi, ri,
-                                        end, sources if end else [], dense))
+                lyr = ConvLayer("conv%d%d" % (bi + 1, ri + 1), K, stride, dil, c_in, c_out, keep, bi, ri,
+                                end, sources if end else [], dense)
+                if ltype == "sep_conv1d":
+                    lyr.sep = True
+                    lyr.sep_mode = "compose" if (K == 1 or stride > 1 or c_in % 128 != 0 or K > 96) else "split"
+                layers.append(lyr)
                 c_in = c_out
         self.layers = layers
         self.H = c_in
@@ -211,6 +227,12 @@ class JasperEngine(object):
         return (lyr.name + "/res_%d" % n) if lyr.dense else (lyr.name + "/res")
 
     @staticmethod
+    def res_wname(lyr, n):
+        """16-bit 1x1 kernel of residual branch n: a sep_conv1d block builds its residual convs with
+        tf.layers.separable_conv1d(kernel_size=1) too (conv_blocks.py:79-85) -> composed per-channel scale x 1x1."""
+        return JasperEngine.res_name(lyr, n) + ("/kernel@composed" if lyr.sep else "/kernel")
+
+    @staticmethod
     def res_bn_name(lyr, n):
         return (lyr.name + "/res_bn_%d" % n) if lyr.dense else (lyr.name + "/res_bn")
 
@@ -231,7 +253,17 @@ class JasperEngine(object):
                 lyr.fold = True
             else:
                 lyr.fold = False
-            add(lyr.name + "/kernel", (lyr.K, lyr.c_in, lyr.c_out), "conv", lyr)
+            if not lyr.sep:
+                add(lyr.name + "/kernel", (lyr.K, lyr.c_in, lyr.c_out), "conv", lyr)
+            else:
+                # tf.layers.separable_conv1d variables: depthwise_kernel [K, C_in, 1], pointwise_kernel [1, C_in, C_out]
+                add(lyr.name + "/depthwise_kernel", (lyr.K, lyr.c_in, 1), "dw", lyr)
+                if lyr.sep_mode == "split":
+                    add(lyr.name + "/pointwise_kernel", (1, lyr.c_in, lyr.c_out), "conv", lyr)
+                else:
+                    add(lyr.name + "/pointwise_kernel", (1, lyr.c_in, lyr.c_out), "pw", lyr)
+                    # the composed dense kernel: a frozen pseudo-variable (16-bit slot + dense-gradient slot)
+                    add(lyr.name + "/kernel@composed", (lyr.K, lyr.c_in, lyr.c_out), "conv", lyr)
             add(lyr.name + "/bn/gamma", (lyr.c_out,), "gamma", lyr)
             add(lyr.name + "/bn/beta", (lyr.c_out,), "beta", lyr)
             for n, j in enumerate(lyr.res_sources):
@@ -247,7 +279,13 @@ class JasperEngine(object):
                     continue
                 for (lc, n, cb, col) in g["consumers"]:
                     cons = self.layers[lc]
-                    add(self.res_name(cons, n) + "/kernel", (1, g["cj"], cb), "conv", cons)
+                    rn = self.res_name(cons, n)
+                    if cons.sep:
+                        add(rn + "/depthwise_kernel", (1, g["cj"], 1), "dw", cons)
+                        add(rn + "/pointwise_kernel", (1, g["cj"], cb), "pw", cons)
+                        add(rn + "/kernel@composed", (1, g["cj"], cb), "conv", cons)
+                    else:
+                        add(rn + "/kernel", (1, g["cj"], cb), "conv", cons)
         add("fc/kernel", (self.H, self.V), "fc_w")
         add("fc/bias", (self.V,), "fc_b")
         off = 0
@@ -296,7 +334,7 @@ class JasperEngine(object):
         hoff = 0
         for s in self.specs:
             lyr = s["layer"]
-            if s["kind"] == "conv" and lyr is not None and lyr.fold and s["name"] == lyr.name + "/kernel":
+            if s["kind"] == "conv" and lyr is not None and lyr.fold and s["name"] == lyr.wname:
                 K, pl_info = lyr.K, None
                 # pad_left depends on T parity; pad_to guarantees even T (asserted at run time)
                 pl = max((lyr.K - 1) * lyr.dil + 1 - lyr.stride, 0) // 2  # SAME pad_left for even T_in
@@ -310,7 +348,7 @@ class JasperEngine(object):
                 lyr.orig_pad_left = pl
                 s["store_size"] = 2 * lyr.kK * lyr.c_in * lyr.c_out
                 s["store_shape"] = (2 * lyr.kK, lyr.c_in, lyr.c_out)
-            elif s["kind"] == "conv" and lyr is not None and s["name"] == lyr.name + "/kernel":
+            elif lyr is not None and s["name"] in (lyr.wname, lyr.name + "/depthwise_kernel") and not lyr.fold:
                 lyr.kK, lyr.kC_in = lyr.K, lyr.c_in
                 _, lyr.kpad, _ = same_padding(1 << 20, lyr.K, 1, lyr.dil)
                 lyr.lead_taps = 0
@@ -325,7 +363,7 @@ class JasperEngine(object):
     def _valid_slice(self, s):
         """(start, size) of the trainable part inside the stored tensor."""
         lyr = s["layer"]
-        if s["kind"] == "conv" and lyr is not None and lyr.fold and s["name"] == lyr.name + "/kernel":
+        if s["kind"] == "conv" and lyr is not None and lyr.fold and s["name"] == lyr.wname:
             per_tap = lyr.c_in * lyr.c_out
             return lyr.lead_taps * per_tap, s["size"]
         return 0, s["size"]
@@ -338,7 +376,8 @@ class JasperEngine(object):
         return buf[s["offset"] + st:s["offset"] + st + n].view(*s["shape"])
 
     def named_parameters(self):
-        return [(s["name"], self.param_view(s["name"])) for s in self.specs]
+        """The model's variables (the composed pseudo-kernels of sep_conv1d layers are derived, not variables)."""
+        return [(s["name"], self.param_view(s["name"])) for s in self.specs if not s["name"].endswith("@composed")]
 
     def init_parameters(self, seed=0):
         """tf.contrib.layers.xavier_initializer, n = (fan_in + fan_out) / 2: "xavier_truncnorm"
@@ -359,7 +398,9 @@ class JasperEngine(object):
 
         for s in self.specs:
             v = self.param_view(s["name"])
-            if s["kind"] == "conv":
+            if s["name"].endswith("@composed"):
+                v.zero_()
+            elif s["kind"] in ("conv", "dw", "pw"):
                 K, ci, co = s["shape"]
                 v.copy_(xavier(s["shape"], K * ci, K * co, self.encoder_init))
             elif s["kind"] == "gamma":
@@ -384,14 +425,51 @@ class JasperEngine(object):
         for s in self.specs:
             if s["kind"] != "conv":
                 continue
+            if s["name"].endswith("@composed"):
+                self._compose_call(s["name"])()
+                continue
             K, R, C = self._kernel_geom(s)
             L.check(self.lib.os2s_weight_cast_transpose_p(
                 _vp(self.master.data_ptr() + 4 * s["offset"]), _vp(self.wb.data_ptr() + 2 * s["half_offset"]),
                 _vp(0), K, R, C, self.dtypes, st), "weight_cast_transpose")
 
+    def _compose_call(self, cname, stream_handle=None):
+        """Bound launch of os2s_sepconv_compose for one composed pseudo-kernel: D[k,c] * P[c,o] -> its 16-bit slot."""
+        base = cname[:-len("/kernel@composed")]
+        s = self.by_name[cname]
+        sd, sp = self.by_name[base + "/depthwise_kernel"], self.by_name[base + "/pointwise_kernel"]
+        K, ci, co = s["shape"]
+        st0, _ = self._valid_slice(s)
+        args = [_vp(self.master.data_ptr() + 4 * sd["offset"]), _vp(self.master.data_ptr() + 4 * sp["offset"]),
+                _vp(self.wb.data_ptr() + 2 * (s["half_offset"] + st0)), K, ci, co, self.dtypes]
+        fn = self.lib.os2s_sepconv_compose
+
+        def call():
+            st = stream_handle if stream_handle is not None else L.stream_ptr()
+            return L.check(fn(*(args + [st])), "os2s_sepconv_compose")
+        call.fn, call.args = fn, args
+        return call
+
+    def layer_first_offset(self, li):
+        """Offset (elements) of the first variable of layer li in the flat parameter / gradient buffers."""
+        l = self.layers[li]
+        return self.by_name[(l.name + "/depthwise_kernel") if l.sep else (l.name + "/kernel")]["offset"]
+
+    def _decompose_args(self, cname):
+        """Arguments of os2s_sepconv_decompose_grad (without the stream) for one composed pseudo-kernel."""
+        base = cname[:-len("/kernel@composed")]
+        s = self.by_name[cname]
+        sd, sp = self.by_name[base + "/depthwise_kernel"], self.by_name[base + "/pointwise_kernel"]
+        K, ci, co = s["shape"]
+        st0, _ = self._valid_slice(s)
+        g = self.grad.data_ptr()
+        m = self.master.data_ptr()
+        return [_vp(g + 4 * (s["offset"] + st0)), _vp(m + 4 * sd["offset"]), _vp(m + 4 * sp["offset"]),
+                _vp(g + 4 * sd["offset"]), _vp(g + 4 * sp["offset"]), K, ci, co]
+
     def _kernel_geom(self, s):
         lyr = s["layer"]
-        if lyr is not None and s["name"] == lyr.name + "/kernel":
+        if lyr is not None and s["name"] == lyr.wname:
             return lyr.kK, lyr.kC_in, lyr.c_out
         return s["shape"]
 
@@ -445,7 +523,8 @@ class JasperEngine(object):
         w = [ptr(self.master, s, 4) for s in self.specs]
         g = [ptr(self.grad, s, 4) for s in self.specs]
         m = [ptr(self.mom, s, 4) for s in self.specs]
-        wb = [(self.wb.data_ptr() + 2 * s["half_offset"]) if s["kind"] == "conv" else 0 for s in self.specs]
+        wb = [(self.wb.data_ptr() + 2 * s["half_offset"]) if (s["kind"] == "conv" and not s["name"].endswith("@composed"))
+              else 0 for s in self.specs]
         sizes = [s["store_size"] for s in self.specs]
         ct, co = [], []
         for i, sz in enumerate(sizes):
@@ -458,18 +537,26 @@ class JasperEngine(object):
         self.grad_acc = torch.zeros(self._total, dtype=torch.float32, device=dev) if self.iter_size > 1 else None
         v = [ptr(self.mom2, s, 4) for s in self.specs] if algo == "adam" else [0] * n
         # the reference builds the 1x1 residual kernels WITHOUT a regularizer (conv_blocks.py:80-86)
-        reg = [float(l2_regularizer_scale) if (s["kind"] in ("conv", "gamma", "fc_w") and "/res_" not in s["name"]
-                                                and not s["name"].endswith("/res/kernel")) else 0.0 for s in self.specs]
+        def regularized(s):
+            n = s["name"]
+            if n.endswith("@composed") or s["kind"] not in ("conv", "dw", "pw", "gamma", "fc_w"):
+                return False
+            # residual convs are built without a regularizer (their BN gammas have one)
+            return not (s["kind"] in ("conv", "dw", "pw") and ("/res_" in n or "/res/" in n))
+        reg = [float(l2_regularizer_scale) if regularized(s) else 0.0 for s in self.specs]
         self._reg = torch.tensor(reg, dtype=torch.float32, device=dev) if l2_regularizer_scale else None
         self._frozen = None
         self.frozen_names = []
+        flags = [1 if s["name"].endswith("@composed") else 0 for s in self.specs]   # derived, never updated
         if freeze_variables_regex:
             import re
             pat = re.compile(freeze_variables_regex)
-            flags = [1 if pat.match(self.var_scope_name(s["name"])) else 0 for s in self.specs]
-            self.frozen_names = [s["name"] for s, f in zip(self.specs, flags) if f]
-            if any(flags):
-                self._frozen = torch.tensor(flags, dtype=torch.int32, device=dev)
+            for i, s in enumerate(self.specs):
+                if not s["name"].endswith("@composed") and pat.match(self.var_scope_name(s["name"])):
+                    flags[i] = 1
+                    self.frozen_names.append(s["name"])
+        if any(flags):
+            self._frozen = torch.tensor(flags, dtype=torch.int32, device=dev)
         self._opt = {
             "w": i64(w), "g": i64(g), "m": i64(m), "v": i64(v), "wb": i64(wb), "sizes": i64(sizes),
             "ct": torch.tensor(ct, dtype=torch.int32, device=dev), "co": i64(co),
@@ -583,6 +670,9 @@ class JasperEngine(object):
     def _launch_optimizer(self):
         o = self._opt
         st = L.stream_ptr()
+        if self._profile is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         L.check(self.lib.os2s_opt_step3(
             L.ptr(o["w"]), L.ptr(o["g"]), L.ptr(o["m"]), L.ptr(o["v"]) if self.mom2 is not None else _vp(0),
             L.ptr(o["wb"]), L.ptr(self._reg) if self._reg is not None else _vp(0),
@@ -590,6 +680,11 @@ class JasperEngine(object):
             L.ptr(o["co"]), o["n"], o["n_chunks"], ctypes.byref(self.hp), L.ptr(o["norms"]),
             L.ptr(o["nonfinite"]), L.ptr(self.fstate), L.ptr(self.istate), L.ptr(o["coef"]), L.ptr(o["ema"]),
             st), "os2s_opt_step")
+        if self._profile is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            # per parameter: g, w read twice (norms + update), m read + written, w written, 2-byte copy of conv kernels
+            self._profile.append(("hbm:optimizer", float(self._total) * 28.0 + float(self._half_total) * 2.0, e0, e1))
         self.step_count += 1
 
     def train_step(self, feats, feat_lens, labels, label_lens):
@@ -628,6 +723,7 @@ class JasperEngine(object):
         for entry in (ws._bwd_plan or []):
             name = entry[0].__name__
             n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd_p": 2, "os2s_bn_bwd_p": 2, "os2s_bn_bwd_apply_p": 1, "zero_slices": 0,
+                  "os2s_sepconv_decompose_grad": 2,
                   "bucket_allreduce": 0, "stream_record": 0, "stream_wait": 0}.get(name, 1)
         return n + 3 + 3
 
@@ -642,19 +738,27 @@ class JasperEngine(object):
             rec = self._profile
         finally:
             self._profile = None
-        by = {}
-        for kind, flops, e0, e1 in rec:
-            d = by.setdefault(kind, [0.0, 0.0, 0])
-            d[0] += flops
+        by, hb = {}, {}
+        for kind, work, e0, e1 in rec:
+            tgt = hb if kind.startswith("hbm:") else by
+            d = tgt.setdefault(kind, [0.0, 0.0, 0])
+            d[0] += work
             d[1] += e0.elapsed_time(e1)
             d[2] += 1
         tot_f = sum(d[0] for d in by.values())
         tot_ms = sum(d[1] for d in by.values())
+        tot_b = sum(d[0] for d in hb.values())
+        tot_bms = sum(d[1] for d in hb.values())
         return {"tflops": round(tot_f / tot_ms / 1e9, 1) if tot_ms > 0 else 0.0,
                 "ms": round(tot_ms / steps, 3), "tflop": round(tot_f / steps / 1e12, 3),
                 "launches": int(sum(d[2] for d in by.values()) / steps),
                 "by_kind": {k: {"tflops": round(d[0] / d[1] / 1e9, 1), "ms_per_step": round(d[1] / steps, 3),
-                                "launches_per_step": d[2] // steps} for k, d in by.items()}}
+                                "launches_per_step": d[2] // steps} for k, d in by.items()},
+                # HBM-bound family (BN forward / backward, optimizer): algorithmic bytes / CUDA-event time
+                "hbm": {"gbs": round(tot_b / tot_bms / 1e6, 1) if tot_bms > 0 else 0.0,
+                        "ms": round(tot_bms / steps, 3), "gbytes": round(tot_b / steps / 1e9, 3),
+                        "by_kind": {k[4:]: {"gbs": round(d[0] / d[1] / 1e6, 1), "ms_per_step": round(d[1] / steps, 3),
+                                            "launches_per_step": d[2] // steps} for k, d in hb.items()}}}
 
 
 class _ZeroSlices(object):
@@ -792,6 +896,10 @@ class _Workspace(object):
         # read dY of layer l while bn_bwd(l-1) already writes the other buffer
         self.dY2 = [bf(B, T2, cmax), bf(B, T2, cmax)]
         self.dY = self.dY2[0]
+        # split sep_conv1d layers: depthwise outputs (saved for the pointwise weight gradient) and their gradients
+        self.Z = {li: act(B, T2, l.c_in) for li, l in enumerate(layers) if l.sep and l.sep_mode == "split"}
+        cin_max = max([l.c_in for l in layers if l.sep and l.sep_mode == "split"] + [0])
+        self.dZ2 = [bf(B, T2, cin_max), bf(B, T2, cin_max)] if cin_max else None
         self._st_aux = _vp(0)
         self.dres = [f32(B, T2, c) for (c, _) in eng.block_inputs]
         self.red = f32((2 + nres_max) * cmax)
@@ -814,6 +922,9 @@ class _Workspace(object):
         offs, o = {}, 0
         for li, l in enumerate(layers):
             plain = (not l.res_sources) and (li not in eng.src_of_layer_output) and li + 1 < len(layers)
+            # (the fused sums ride in the tcgen05 data-gradient kernel of the NEXT layer: not when that is a
+            # depthwise + pointwise pair, whose dA comes out of the CUDA-core depthwise kernel)
+            plain = plain and not (li + 1 < len(layers) and layers[li + 1].sep and layers[li + 1].sep_mode == "split")
             if eng.fuse_bn_reduce and plain and l.c_out >= eng.fuse_bn_min_channels and l.c_out % 64 == 0:
                 offs[li] = o
                 o += 2 * l.c_out
@@ -861,11 +972,16 @@ class _Workspace(object):
         vparr = lambda ptrs: (ctypes.c_void_p * len(ptrs))(*[p.value if isinstance(p, _vp) else p for p in ptrs])
         iarr = lambda xs: (ctypes.c_int * len(xs))(*xs)
         llarr = lambda xs: (ctypes.c_longlong * len(xs))(*xs)
+        # (0) sep_conv1d: form the composed dense kernels D[k,c] * P[c,o] from the fp32 masters
+        for sp_ in eng.specs:
+            if sp_["name"].endswith("@composed"):
+                cc = eng._compose_call(sp_["name"])
+                plan.append([cc.fn, cc.args + [st]])
         # (1) lay the 1x1 residual kernels of every source side by side (bf16, from the working copy)
         src, dst, rows, rbytes, sp, dp = [], [], [], [], [], []
         for j, g in enumerate(eng.res_groups):
             for (lc, n, cb, col) in g["consumers"]:
-                rn = eng.res_name(eng.layers[lc], n) + "/kernel"
+                rn = eng.res_wname(eng.layers[lc], n)
                 src.append(self._half_ptr(eng.wb, rn))
                 dst.append(self._p(eng.wcat[j], col))
                 rows.append(g["cj"])
@@ -894,10 +1010,21 @@ class _Workspace(object):
             bn_idx += 1
             # training: the conv epilogue accumulates the BN statistics of its (rounded) output
             stats_ptr = self._p(self.stats[li]) if eng.training else _vp(0)
-            call = [lib.os2s_conv1d_fwd_p, [x_ptr, self._half_ptr(eng.wb, l.name + "/kernel"), self._p(self.Y[li]),
-                                            B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, eng.conv_out_mode, stats_ptr,
-                                            eng.dtypes, st],
-                    ("fwd", flops)]
+            if l.sep and l.sep_mode == "split":
+                # depthwise K-tap stage on the CUDA cores, then the pointwise stage as a 1x1 tcgen05 GEMM
+                plan.append([lib.os2s_depthwise_conv1d,
+                             [x_ptr, self._param_ptr(eng.master, l.name + "/depthwise_kernel"), self._p(self.Z[li]), B, T2,
+                              l.c_in, l.K, -l.kpad, l.dil, eng.grad_out_mode, eng.dtypes, st],
+                             ("hbm:depthwise", float(M) * l.c_in * 4)])
+                call = [lib.os2s_conv1d_fwd_p, [self._p(self.Z[li]), self._half_ptr(eng.wb, l.wname), self._p(self.Y[li]),
+                                                B, T2, l.c_in, l.c_out, 1, 1, 0, eng.conv_out_mode, stats_ptr,
+                                                eng.dtypes, st],
+                        ("fwd", 2.0 * B * T2 * l.c_in * l.c_out)]
+            else:
+                call = [lib.os2s_conv1d_fwd_p, [x_ptr, self._half_ptr(eng.wb, l.wname), self._p(self.Y[li]),
+                                                B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, eng.conv_out_mode, stats_ptr,
+                                                eng.dtypes, st],
+                        ("fwd", flops)]
             plan.append(call)
             ys, lds = [self._p(self.Y[li])], [l.c_out]
             sts, st_lds = [self._p(self.stats[li])], [l.c_out]
@@ -928,7 +1055,8 @@ class _Workspace(object):
                     _c_u64((eng.seed * 1000003 + 4099 * li + 17) & 0xFFFFFFFFFFFFFFFF), 1, _c_float(eng.relu_clip),
                     0 if eng.training else 1, _vp(eng.istate.data_ptr() + 5 * 8), eng.dtypes, st]
             self._keep.append(stld_h)
-            plan.append([lib.os2s_bn_apply_fwd_p, args])
+            ysz = 4 if eng.conv_dtype == "fp32" else 2
+            plan.append([lib.os2s_bn_apply_fwd_p, args, ("hbm:bn_fwd", float(M) * l.c_out * (nb * ysz + 2))])
         self._fc_call = [lib.os2s_fc_fwd_p, [self._p(self.A[-1]), self._param_ptr(eng.master, "fc/kernel"),
                                              self._param_ptr(eng.master, "fc/bias"), self._p(self.logits), M, eng.H,
                                              eng.V, eng.dtypes, st]]
@@ -1069,11 +1197,16 @@ class _Workspace(object):
                                                        self._param_ptr(eng.grad, nm + "/gamma"),
                                                        self._param_ptr(eng.grad, nm + "/beta"), self._p(dY), dA_ptr,
                                                        self._p(self.A[li]), self._p(self.fused_red[li]), M, l.c_out,
-                                                       _c_float(l.keep), eng.dtypes, st]])
+                                                       _c_float(l.keep), eng.dtypes, st],
+                             # apply pass only: dA + a + y in, dy out
+                             ("hbm:bn_bwd", float(M) * l.c_out * (2 + 2 + (4 if eng.conv_dtype == "fp32" else 2) + 2))])
             else:
                 plan.append([lib.os2s_bn_bwd_p, [nb, y_h, ld_h, mi_h, g_h, dg_h, db_h, dy_h, dA_ptr, dA_f32,
                                                  self._p(self.A[li]), self._p(self.red), M, l.c_out, _c_float(l.keep),
-                                                 1, eng.dtypes, st]])
+                                                 1, eng.dtypes, st],
+                             # reduce pass (dA, a, y_j) + apply pass (dA, a, y_j in, dy_j out)
+                             ("hbm:bn_bwd", float(M) * l.c_out * (2 * ((4 if dA_f32 else 2) + 2)
+                                                                  + nb * (2 * (4 if eng.conv_dtype == "fp32" else 2) + 2)))])
             self._keep += [dg_h, db_h, dy_h]
             plan.append([_StreamRecord(self, "main", ev_bn[li]), []])
             # the input of this layer is residual source j: every consumer block has written its slice of
@@ -1088,7 +1221,26 @@ class _Workspace(object):
                 plan.append([lib.os2s_conv1d_dgrad_p, [self._p(self.dYRcat[src_j]), self._p(eng.wcat[src_j]),
                                                        self._p(self.dres[src_j]), B, T2, g["cj"], g["ntot"], 1, 1, 0, 1,
                                                        eng.dtypes, st], ("dgrad", 2.0 * B * T2 * g["cj"] * g["ntot"])])
-            if li > 0:
+            split = l.sep and l.sep_mode == "split"
+            dZ = self.dZ2[par] if split else None
+            ev_dz = None
+            if split:
+                # pointwise data gradient dZ = dY . P^T (tcgen05), then the depthwise data gradient (flipped taps)
+                plan.append([lib.os2s_conv1d_dgrad_p, [self._p(dY), self._half_ptr(eng.wb, l.wname), self._p(dZ), B, T2,
+                                                       l.c_in, l.c_out, 1, 1, 0, eng.grad_out_mode, eng.dtypes, st],
+                             ("dgrad", 2.0 * B * T2 * l.c_in * l.c_out)])
+                ev_dz = torch.cuda.Event()
+                plan.append([_StreamRecord(self, "main", ev_dz), []])   # the depthwise weight gradient (aux) reads dZ
+                if li > 0:
+                    if src_j is not None:
+                        mode, out_ptr = 2, self._p(self.dres[src_j])
+                    else:
+                        mode, out_ptr = eng.grad_out_mode, self._p(self.dA)
+                    plan.append([lib.os2s_depthwise_conv1d,
+                                 [self._p(dZ), self._param_ptr(eng.master, l.name + "/depthwise_kernel"), out_ptr, B, T2,
+                                  l.c_in, l.K, l.kpad, -l.dil, mode, eng.dtypes, st],
+                                 ("hbm:depthwise", float(M) * l.c_in * (2 + (8 if mode == 2 else 2)))])
+            elif li > 0:
                 if src_j is not None:
                     mode, out_ptr = 2, self._p(self.dres[src_j])
                 else:
@@ -1097,12 +1249,12 @@ class _Workspace(object):
                     # dA of the plain layer below + its BN-backward sums in the same kernel
                     lp = eng.layers[li - 1]
                     plan.append([lib.os2s_conv1d_dgrad_bnred_p,
-                                 [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"), out_ptr, B, T2, l.kC_in,
+                                 [self._p(dY), self._half_ptr(eng.wb, l.wname), out_ptr, B, T2, l.kC_in,
                                   l.c_out, l.kK, l.dil, l.kpad, self._p(self.A[li - 1]), self._p(self.Y[li - 1]),
                                   _c_float(lp.keep), self._p(self.fused_red[li - 1]), eng.dtypes, st],
                                  ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
                 else:
-                    plan.append([lib.os2s_conv1d_dgrad_p, [self._p(dY), self._half_ptr(eng.wb, l.name + "/kernel"),
+                    plan.append([lib.os2s_conv1d_dgrad_p, [self._p(dY), self._half_ptr(eng.wb, l.wname),
                                                            out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
                                                            eng.dtypes, st],
                                  ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
@@ -1110,12 +1262,21 @@ class _Workspace(object):
             plan.append([_StreamWait(self, "aux", ev_bn[li]), []])
             # main conv wgrad (stored layout == kernel layout, also for the folded stride-2 layer)
             x_ptr = self._p(self.A[li - 1]) if li > 0 else self._p(self.feats)
-            plan.append([lib.os2s_conv1d_wgrad_p, [x_ptr, self._p(dY), self._param_ptr(eng.grad, l.name + "/kernel"),
-                                                   B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, eng.dtypes, sa],
-                         ("wgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
+            if split:
+                plan.append([lib.os2s_conv1d_wgrad_p, [self._p(self.Z[li]), self._p(dY), self._param_ptr(eng.grad, l.wname),
+                                                       B, T2, l.c_in, l.c_out, 1, 1, 0, eng.dtypes, sa],
+                             ("wgrad", 2.0 * B * T2 * l.c_in * l.c_out)])
+                plan.append([_StreamWait(self, "aux", ev_dz), []])
+                plan.append([lib.os2s_depthwise_conv1d_wgrad,
+                             [x_ptr, self._p(dZ), self._param_ptr(eng.grad, l.name + "/depthwise_kernel"), B, T2,
+                              l.c_in, l.K, l.dil, l.kpad, eng.dtypes, sa]])
+            else:
+                plan.append([lib.os2s_conv1d_wgrad_p, [x_ptr, self._p(dY), self._param_ptr(eng.grad, l.wname),
+                                                       B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, eng.dtypes, sa],
+                             ("wgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
             if l.fold:
                 # structurally-zero taps of the folded stride-2 kernel get no gradient
-                s_ = eng.by_name[l.name + "/kernel"]
+                s_ = eng.by_name[l.wname]
                 st0, n_ = eng._valid_slice(s_)
                 zs = []
                 if st0 > 0:
@@ -1124,6 +1285,9 @@ class _Workspace(object):
                     zs.append(eng.grad[s_["offset"] + st0 + n_:s_["offset"] + s_["store_size"]])
                 if zs:
                     plan.append([_ZeroSlices(self, zs), []])
+            if l.sep and l.sep_mode == "compose":
+                # fold the dense weight gradient back onto the depthwise / pointwise variables
+                plan.append([lib.os2s_sepconv_decompose_grad, eng._decompose_args(l.wname) + [sa]])
             if src_j is not None:
                 # weight gradients of all 1x1 kernels that read source j: one GEMM into [C_j, Ntot_j], then
                 # scattered to the per-variable gradient buffers (which live in this layer's region)
@@ -1133,7 +1297,7 @@ class _Workspace(object):
                              ("wgrad", 2.0 * B * T2 * g["cj"] * g["ntot"])])
                 src, dst, rows, rbytes, sp, dp = [], [], [], [], [], []
                 for (lc, n, cb, col) in g["consumers"]:
-                    rn = eng.res_name(eng.layers[lc], n) + "/kernel"
+                    rn = eng.res_wname(eng.layers[lc], n)
                     src.append(self._p(eng.dwcat[src_j], col))
                     dst.append(self._param_ptr(eng.grad, rn))
                     rows.append(g["cj"])
@@ -1145,9 +1309,13 @@ class _Workspace(object):
                     a = (vparr(src[sl]), vparr(dst[sl]), iarr(rows[sl]), iarr(rbytes[sl]), llarr(sp[sl]), llarr(dp[sl]))
                     self._keep.append(a)
                     plan.append([lib.os2s_multi_copy_2d, [len(src[sl])] + list(a) + [sa]])
+                for (lc, n, cb, col) in g["consumers"]:
+                    if eng.layers[lc].sep:
+                        plan.append([lib.os2s_sepconv_decompose_grad,
+                                     eng._decompose_args(eng.res_wname(eng.layers[lc], n)) + [sa]])
             plan.append([_StreamRecord(self, "aux", ev_wg[li]), []])
             if eng.comm is not None:
-                start = eng.by_name[l.name + "/kernel"]["offset"]
+                start = eng.layer_first_offset(li)
                 if (bucket_end - start) * 4 >= eng.bucket_bytes or li == 0:
                     # the bucket also holds weight gradients produced on the aux stream
                     plan.append([_StreamWait(self, "main", ev_wg[li]), []])

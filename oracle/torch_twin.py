@@ -29,6 +29,26 @@ def conv1d_same(x, w, stride=1, dilation=1):
     return y.transpose(1, 2)
 
 
+def sep_conv1d_same(x, depthwise, pointwise, stride=1, dilation=1):
+    """tf.layers.separable_conv1d(use_bias=False, padding='SAME', depth_multiplier=1) as conv_blocks.py:27-40 calls
+    it: x [B,T,C], depthwise_kernel [K,C,1], pointwise_kernel [1,C,Cout] -> [B,T_out,Cout].  The depthwise stage
+    is a grouped cross-correlation with SAME padding computed from (K, stride, dilation) like conv1d."""
+    B, T, C = x.shape
+    K = depthwise.shape[0]
+    _, pl, pr = same_padding(T, K, stride, dilation)
+    xin = F.pad(x.transpose(1, 2), (pl, pr))
+    z = F.conv1d(xin, depthwise.permute(1, 2, 0), stride=stride, dilation=dilation, groups=C)   # [B,C,T_out]
+    return z.transpose(1, 2) @ pointwise[0]
+
+
+def layer_conv(x, params, name, layer, stride, dilation):
+    """Main / residual convolution of a block: conv1d or sep_conv1d by the layer's type (the residual convs of
+    a sep_conv1d block are separable too, conv_blocks.py:66,79-85)."""
+    if layer.get("type", "conv1d") == "sep_conv1d":
+        return sep_conv1d_same(x, params[name + "/depthwise_kernel"], params[name + "/pointwise_kernel"], stride, dilation)
+    return conv1d_same(x, params[name + "/kernel"], stride, dilation)
+
+
 def batch_norm_train(x, gamma, beta, eps=1e-3):
     mean = x.mean(dim=(0, 1))
     var = x.var(dim=(0, 1), unbiased=False)
@@ -82,7 +102,7 @@ def tdnn_encode(x, src_len, layers, params, training=True, bn_eps=1e-3, use_conv
                 feats = feats * mask
             if use_conv_mask and stride > 1:
                 mask = sequence_mask(src_len, max_len, x.dtype)
-            conv = rc_(conv1d_same(feats, params[name + "/kernel"], stride, dil))
+            conv = rc_(layer_conv(feats, params, name, layer, stride, dil))
             if collect is not None:
                 collect[name + "/conv"] = conv
             bn, mean, var = batch_norm_train(conv, params[name + "/bn/gamma"], params[name + "/bn/beta"], bn_eps)
@@ -92,7 +112,7 @@ def tdnn_encode(x, src_len, layers, params, training=True, bn_eps=1e-3, use_conv
                 for j, res in enumerate(layer_res):
                     rname = (name + "/res_%d" % j) if dense else (name + "/res")
                     bname = (name + "/res_bn_%d" % j) if dense else (name + "/res_bn")
-                    rc = rc_(conv1d_same(res, params[rname + "/kernel"], 1, 1))
+                    rc = rc_(layer_conv(res, params, rname, layer, 1, 1))
                     rb, mean, var = batch_norm_train(rc, params[bname + "/gamma"], params[bname + "/beta"], bn_eps)
                     if stats is not None:
                         stats[bname] = (mean.detach(), var.detach(), rc.shape[0] * rc.shape[1])
@@ -162,14 +182,23 @@ def init_params(layers, num_features, vocab, seed=0):
                 res_ch = [c_in]
         for ri in range(layer["repeat"]):
             name = "conv%d%d" % (bi + 1, ri + 1)
-            p[name + "/kernel"] = xavier_init((K, c_in, c_out), False, gen)
+            sep = layer.get("type", "conv1d") == "sep_conv1d"
+            if sep:
+                p[name + "/depthwise_kernel"] = xavier_init((K, c_in, 1), False, gen)
+                p[name + "/pointwise_kernel"] = xavier_init((1, c_in, c_out), False, gen)
+            else:
+                p[name + "/kernel"] = xavier_init((K, c_in, c_out), False, gen)
             p[name + "/bn/gamma"] = torch.ones(c_out)
             p[name + "/bn/beta"] = torch.zeros(c_out)
             if residual and ri == layer["repeat"] - 1:
                 for j, rc in enumerate(res_ch):
                     rname = (name + "/res_%d" % j) if dense else (name + "/res")
                     bname = (name + "/res_bn_%d" % j) if dense else (name + "/res_bn")
-                    p[rname + "/kernel"] = xavier_init((1, rc, c_out), False, gen)
+                    if sep:
+                        p[rname + "/depthwise_kernel"] = xavier_init((1, rc, 1), False, gen)
+                        p[rname + "/pointwise_kernel"] = xavier_init((1, rc, c_out), False, gen)
+                    else:
+                        p[rname + "/kernel"] = xavier_init((1, rc, c_out), False, gen)
                     p[bname + "/gamma"] = torch.ones(c_out)
                     p[bname + "/beta"] = torch.zeros(c_out)
             c_in = c_out
@@ -243,7 +272,8 @@ def backward_with_saved_forward(params, layers, feats, feat_len, saved_conv, sav
             m = sequence_mask(src_len, max_len, torch.float64) if (use_conv_mask and not last) else None
             end = residual and ri == layer["repeat"] - 1
             plan.append({"name": name, "in": prev, "K": layer["kernel_size"][0], "stride": stride,
-                         "dil": layer["dilation"][0], "mask": m, "res": layer_res if end else [], "dense": dense})
+                         "dil": layer["dilation"][0], "mask": m, "res": layer_res if end else [], "dense": dense,
+                         "layer": layer})
             prev = name
     # ---- FC
     enc = saved_out[plan[-1]["name"]].detach().double().requires_grad_(True)
@@ -280,17 +310,21 @@ def backward_with_saved_forward(params, layers, feats, feat_len, saved_conv, sav
         # main conv
         x_src = feats if node["in"] is None else saved_out[node["in"]]
         x = x_src.detach().double().requires_grad_(node["in"] is not None)
-        w = p[name + "/kernel"].clone().requires_grad_(True)
-        conv1d_same(x, w, node["stride"], node["dil"]).backward(ys[0].grad)
-        grads[name + "/kernel"] = w.grad
+        wnames = [k for k in (name + "/kernel", name + "/depthwise_kernel", name + "/pointwise_kernel") if k in p]
+        wl = {k: p[k].clone().requires_grad_(True) for k in wnames}
+        layer_conv(x, wl, name, node["layer"], node["stride"], node["dil"]).backward(ys[0].grad)
+        for k in wnames:
+            grads[k] = wl[k].grad
         if node["in"] is not None:
             dA[node["in"]] = dA.get(node["in"], 0) + x.grad
         # residual 1x1 convs
         for n, src in enumerate(node["res"]):
             cn = (name + "/res_%d" % n) if node["dense"] else (name + "/res")
             xr = saved_out[src].detach().double().requires_grad_(True)
-            wr = p[cn + "/kernel"].clone().requires_grad_(True)
-            conv1d_same(xr, wr, 1, 1).backward(ys[1 + n].grad)
-            grads[cn + "/kernel"] = wr.grad
+            rnames = [k for k in (cn + "/kernel", cn + "/depthwise_kernel", cn + "/pointwise_kernel") if k in p]
+            wr = {k: p[k].clone().requires_grad_(True) for k in rnames}
+            layer_conv(xr, wr, cn, node["layer"], 1, 1).backward(ys[1 + n].grad)
+            for k in rnames:
+                grads[k] = wr[k].grad
             dA[src] = dA.get(src, 0) + xr.grad
     return grads

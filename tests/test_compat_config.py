@@ -216,3 +216,23 @@ def test_nothing_in_the_headline_config_is_silently_ignored():
     assert resolve_initializer({}, {}, "x") == "xavier_uniform"
     with pytest.raises(NotImplementedError):
         resolve_initializer({"initializer": lambda **kw: None}, {}, "x")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference checkout not present (GPU box)")
+def test_quartznet_config_matches_the_reference_and_sep_conv_topology_builds_on_paper():
+    """configs/quartznet15x5.py == example_configs/speech2text/quartznet15x5_LibriSpeech.py (layers, optimizer,
+    lr policy, spec-augment); sep_conv1d layers map to variables with tf.layers.separable_conv1d's names."""
+    ref_path = "/root/reference/example_configs/speech2text/quartznet15x5_LibriSpeech.py"
+    _, ref, _, rmod = get_base_config(["--config_file=" + ref_path, "--mode=train"])
+    _, own, _, omod = get_base_config(["--config_file=" + os.path.join(ROOT, "configs", "quartznet15x5.py"), "--mode=train"])
+    assert ref["encoder_params"]["convnet_layers"] == own["encoder_params"]["convnet_layers"]
+    for key in ("optimizer_params", "lr_policy_params", "dtype", "batch_size_per_gpu", "num_epochs"):
+        assert ref[key] == own[key], key
+    assert ref["lr_policy"].__name__ == own["lr_policy"].__name__ == "cosine_decay"
+    assert rmod["train_params"]["data_layer_params"]["augmentation"] == omod["train_params"]["data_layer_params"]["augmentation"]
+    # the oracle's variable set for this topology: separable main convs AND separable residual convs
+    from oracle import torch_twin as TT
+    p = TT.init_params(own["encoder_params"]["convnet_layers"][:3], 64, 29, seed=0)
+    assert p["conv11/depthwise_kernel"].shape == (33, 64, 1) and p["conv11/pointwise_kernel"].shape == (1, 64, 256)
+    assert p["conv25/res/depthwise_kernel"].shape == (1, 256, 1) and p["conv25/res/pointwise_kernel"].shape == (1, 256, 256)
+    assert "conv25/res_bn/gamma" in p and "conv21/kernel" not in p

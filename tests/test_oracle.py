@@ -286,3 +286,26 @@ def test_spec_augment_masks_restatement():
     # a time band that does not fit is dropped (features.shape[0] - time_band > 0 guard)
     assert all(m[0] == 0 for m in AU.draw_spec_masks(3, 64, dict(aug, width_time_mask=50), np.random.RandomState(0))
                if m[2] >= 3)
+
+
+def test_separable_conv_restatement():
+    """tf.layers.separable_conv1d(depth_multiplier=1, use_bias=False, SAME) restated in torch_twin.sep_conv1d_same:
+    equal to the dense convolution with W[k,c,o] = D[k,c] P[c,o] (the definition of a separable kernel) for the
+    stride / dilation combinations of the QuartzNet config, and to an explicit per-channel loop."""
+    torch.manual_seed(0)
+    x = torch.randn(2, 37, 8, dtype=torch.float64)
+    D = torch.randn(5, 8, 1, dtype=torch.float64)
+    P = torch.randn(1, 8, 6, dtype=torch.float64)
+    for stride, dil in ((1, 1), (2, 1), (1, 2)):
+        a = TT.sep_conv1d_same(x, D, P, stride, dil)
+        b = TT.conv1d_same(x, D * P, stride, dil)
+        assert float((a - b).abs().max()) < 1e-12
+    # explicit loops, stride 1: z[t,c] = sum_k D[k,c] x[t - pad + k, c]
+    K, pad = 5, 2
+    z = torch.zeros(2, 37, 8, dtype=torch.float64)
+    for t in range(37):
+        for k in range(K):
+            s = t - pad + k
+            if 0 <= s < 37:
+                z[:, t] += D[k, :, 0] * x[:, s]
+    assert float((z @ P[0] - TT.sep_conv1d_same(x, D, P, 1, 1)).abs().max()) < 1e-12
