@@ -334,13 +334,18 @@ def run_own(args):
     if rank != 0:
         return
     peak_tf, peak_hbm, peak_src = _peaks()
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_conv_summary.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    # roofline.traffic: DRAM bytes per launch of the dominant conv kernel from the committed `ncu --set full`
+    # capture (a profiler run of an earlier build of the same kernel, not this run: say so in the line)
+    traffic, traffic_src = None, None
+    for name in ("r02_ncu_conv_halo_summary.json", "ncu_conv_summary.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic_src = "profiles/" + name + " (ncu --set full capture of this kernel, committed; not measured in this run)"
+                break
+            except Exception:
+                traffic = None
     out = {
         "metric": METRIC,
         "value": round(value, 2), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
@@ -359,7 +364,7 @@ def run_own(args):
                      "kernel": "tapgemm_kmajor_pair_halo / tapgemm_mnmajor_pair (+ single-CTA variants on the narrow layers): "
                                "tcgen05 cta_group::2 implicit-GEMM conv fwd + dgrad + wgrad",
                      "achieved": roof["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": round(roof["tflops"] / peak_tf, 4), "traffic": traffic,
+                     "frac": round(roof["tflops"] / peak_tf, 4), "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src,
                      # the measured peak is cuBLAS bf16 run back to back under the same 1000 W cap; a frac
                      # above 1 means these kernels sustain more than cuBLAS does, not more than the silicon
@@ -370,6 +375,10 @@ def run_own(args):
                      "algorithmic_tflop_per_step": roof["tflop"],
                      "how": "CUDA events around every conv launch of 2 instrumented steps after the timed region",
                      "by_kind": roof["by_kind"],
+                     # the HBM-bound family (BN forward / backward, optimizer, depthwise): algorithmic bytes / CUDA-event
+                     # time of the same instrumented steps, against the measured copy bandwidth
+                     "hbm_family": dict(roof["hbm"], peak=peak_hbm, unit="GB/s",
+                                        frac=round(roof["hbm"]["gbs"] / peak_hbm, 4)),
                      "step_frac_of_peak": round(value / world * TRAIN_GFLOP_PER_AUDIO_S / 1000.0 / peak_tf, 4)},
         "loss": last_loss, "skipped_steps": skipped,
     }

@@ -11,8 +11,13 @@
  *   - no hidden allocation, no hidden synchronisation; work is enqueued on `stream`
  *     (a cudaStream_t passed as void*; NULL = legacy default stream)
  *   - return value: 0 = OK, negative = error; os2s_last_error() gives the message (thread local)
- *   - activations are NWC bf16 [B, T, C] with C contiguous; parameters/gradients are fp32 masters
- *     with bf16 working copies written by the optimizer step
+ *   - activations are NWC 16-bit [B, T, C] with C contiguous (bf16, or fp16 with OS2S_HALF_F16);
+ *     parameters/gradients are fp32 masters with 16-bit working copies written by the optimizer step
+ *   - collectives are NOT part of this ABI: the gradient all-reduce (hvd.allreduce, optimizers/optimizers.py:
+ *     77-104) and the initial broadcast (utils/hooks.py:15-55) run on the caller's flat fp32 gradient /
+ *     parameter buffers through NCCL (torch.distributed, openseq2seq_b200/dist.py); the kernels here only
+ *     require that `g` holds the rank-summed gradients when os2s_opt_step* runs (os2s_opt_hparams.world_size
+ *     folds the 1/N of the mean into the unscale factor)
  */
 #ifndef OS2S_H_
 #define OS2S_H_
@@ -28,7 +33,6 @@ extern "C" {
 #define OS2S_ERR_INVALID (-1)
 #define OS2S_ERR_CUDA (-2)
 #define OS2S_ERR_UNSUPPORTED (-3)
-#define OS2S_ERR_NCCL (-4)
 
 /* Output modes of the conv epilogue. */
 #define OS2S_OUT_BF16 0

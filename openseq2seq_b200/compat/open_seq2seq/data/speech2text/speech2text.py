@@ -588,6 +588,20 @@ class Speech2TextDataLayer(DataLayer):
         stop = threading.Event()
         side = torch.cuda.Stream()
         device = torch.cuda.current_device()
+        # released[k]: event on the CONSUMER's stream after everything it enqueued for batch k.  The output ring
+        # has prefetch + 2 slots and the queue holds at most `prefetch` batches, so when the producer starts
+        # batch n the consumer has already come back for batch n - (prefetch + 1), i.e. released[n - ring] exists;
+        # the side stream waits on it before the slot is overwritten (the consumer's GPU work may lag far behind
+        # its host thread).
+        released = []
+        ring = self.prefetch + 2
+        n_made = [0]
+
+        def guard_slot():
+            k = n_made[0] - ring
+            if k >= 0:
+                side.wait_event(released[k])
+            n_made[0] += 1
 
         def produce():
             try:
@@ -610,6 +624,7 @@ class Speech2TextDataLayer(DataLayer):
                                 batch.append((sig, ids, idx, draw))
                                 if len(batch) == B:
                                     with torch.cuda.stream(side):
+                                        guard_slot()
                                         out = self._collate(batch, epoch, aug_rng)
                                         ev = torch.cuda.Event()
                                         ev.record(side)
@@ -617,6 +632,7 @@ class Speech2TextDataLayer(DataLayer):
                                     batch = []
                         if batch and p["mode"] != "train":
                             with torch.cuda.stream(side):
+                                guard_slot()
                                 out = self._collate(batch, epoch, aug_rng)
                                 ev = torch.cuda.Event()
                                 ev.record(side)
@@ -635,9 +651,15 @@ class Speech2TextDataLayer(DataLayer):
                     return
                 if isinstance(out, BaseException):
                     raise out
-                torch.cuda.current_stream().wait_event(ev)
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ev)
+                for t in out.get("target_tensors", []):
+                    t.record_stream(cur)      # allocated on the side stream, consumed on this one
                 self._input_tensors = out
                 yield out
+                rel = torch.cuda.Event()
+                rel.record(torch.cuda.current_stream())
+                released.append(rel)
         finally:
             stop.set()
 

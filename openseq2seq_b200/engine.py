@@ -150,9 +150,16 @@ class JasperEngine(object):
 
     # ------------------------------------------------------------------ topology
     def _build_layers(self, cfg, keep_default):
+        # Channel counts are padded to multiples of 128 (the tcgen05 tiles need C % 64 == 0, the weight
+        # gradient C_in % 128 == 0): a layer's c_in / c_out are the PHYSICAL widths every kernel sees, lc_in /
+        # lc_out the reference's.  Pad channels are exact zeros everywhere (zero kernel rows / columns, gamma =
+        # beta = 0), so norms, gradients and statistics of the real channels are untouched.
+        pad128 = lambda c: -(-c // 128) * 128
         layers = []
-        self.block_inputs = []  # channel count of every residual source, in order of creation
-        c_in = self.F
+        self.block_inputs = []  # (physical channels, first consumer layer, logical channels) of every residual source
+        first_stride = cfg[0]["stride"][0] if cfg else 1
+        self.Fp = (-(-self.F // 64) * 64) if first_stride > 1 else pad128(self.F)
+        c_in, lc_in = self.Fp, self.F
         res_list = []
         for bi, lc in enumerate(cfg):
             ltype = lc.get("type", "conv1d")
@@ -163,13 +170,14 @@ class JasperEngine(object):
             K = lc["kernel_size"][0]
             stride = lc["stride"][0]
             dil = lc["dilation"][0]
-            c_out = lc["num_channels"]
+            lc_out = lc["num_channels"]
+            c_out = pad128(lc_out)
             keep = lc.get("dropout_keep_prob", keep_default) if self.training else 1.0
             residual = lc.get("residual", False)
             dense = lc.get("residual_dense", False)
             sources = []
             if residual:
-                self.block_inputs.append((c_in, len(layers)))
+                self.block_inputs.append((c_in, len(layers), lc_in))
                 idx = len(self.block_inputs) - 1
                 if dense:
                     res_list.append(idx)
@@ -185,13 +193,14 @@ class JasperEngine(object):
                 if ltype == "sep_conv1d":
                     lyr.sep = True
                     lyr.sep_mode = "compose" if (K == 1 or stride > 1 or c_in % 128 != 0 or K > 96) else "split"
+                lyr.lc_in, lyr.lc_out = lc_in, lc_out
                 layers.append(lyr)
-                c_in = c_out
+                c_in, lc_in = c_out, lc_out
         self.layers = layers
-        self.H = c_in
+        self.H, self.Hl = c_in, lc_in
         # which layers' OUTPUT is a residual source (needs an fp32 gradient accumulator)
         self.src_of_layer_output = {}
-        for idx, (c, first_layer) in enumerate(self.block_inputs):
+        for idx, (c, first_layer, _lc) in enumerate(self.block_inputs):
             if first_layer == 0:
                 raise ValueError("JasperEngine: a residual block cannot be the first layer")
             self.src_of_layer_output[first_layer - 1] = idx
@@ -201,14 +210,14 @@ class JasperEngine(object):
         # data-gradient GEMM with K = sum_b C_b and one weight-gradient GEMM per source).
         # res_groups[j] = {"cj", "ntot", "consumers": [(layer index, branch position, C_b, first column)]}
         self.res_groups = []
-        for j, (cj, first_layer) in enumerate(self.block_inputs):
+        for j, (cj, first_layer, lcj) in enumerate(self.block_inputs):
             cons, col = [], 0
             for li, l in enumerate(layers):
                 for n, jj in enumerate(l.res_sources):
                     if jj == j:
                         cons.append((li, n, l.c_out, col))
                         col += l.c_out
-            self.res_groups.append({"cj": cj, "ntot": col, "consumers": cons, "first_layer": first_layer})
+            self.res_groups.append({"cj": cj, "lcj": lcj, "ntot": col, "consumers": cons, "first_layer": first_layer})
         self.res_col = {}  # (layer index, branch position) -> (source, first column)
         for j, g in enumerate(self.res_groups):
             for (li, n, cb, col) in g["consumers"]:
@@ -242,6 +251,7 @@ class JasperEngine(object):
         specs = []  # (name, shape, kind, layer)
 
         def add(name, shape, kind, layer=None, store_shape=None):
+            """shape: the reference's (logical) shape; store_shape: the zero-padded physical one."""
             specs.append({"name": name, "shape": tuple(shape), "kind": kind, "layer": layer,
                           "store_shape": tuple(store_shape or shape)})
 
@@ -253,23 +263,24 @@ class JasperEngine(object):
                 lyr.fold = True
             else:
                 lyr.fold = False
+            ci, co, pci, pco = lyr.lc_in, lyr.lc_out, lyr.c_in, lyr.c_out
             if not lyr.sep:
-                add(lyr.name + "/kernel", (lyr.K, lyr.c_in, lyr.c_out), "conv", lyr)
+                add(lyr.name + "/kernel", (lyr.K, ci, co), "conv", lyr, (lyr.K, pci, pco))
             else:
                 # tf.layers.separable_conv1d variables: depthwise_kernel [K, C_in, 1], pointwise_kernel [1, C_in, C_out]
-                add(lyr.name + "/depthwise_kernel", (lyr.K, lyr.c_in, 1), "dw", lyr)
+                add(lyr.name + "/depthwise_kernel", (lyr.K, ci, 1), "dw", lyr, (lyr.K, pci, 1))
                 if lyr.sep_mode == "split":
-                    add(lyr.name + "/pointwise_kernel", (1, lyr.c_in, lyr.c_out), "conv", lyr)
+                    add(lyr.name + "/pointwise_kernel", (1, ci, co), "conv", lyr, (1, pci, pco))
                 else:
-                    add(lyr.name + "/pointwise_kernel", (1, lyr.c_in, lyr.c_out), "pw", lyr)
+                    add(lyr.name + "/pointwise_kernel", (1, ci, co), "pw", lyr, (1, pci, pco))
                     # the composed dense kernel: a frozen pseudo-variable (16-bit slot + dense-gradient slot)
-                    add(lyr.name + "/kernel@composed", (lyr.K, lyr.c_in, lyr.c_out), "conv", lyr)
-            add(lyr.name + "/bn/gamma", (lyr.c_out,), "gamma", lyr)
-            add(lyr.name + "/bn/beta", (lyr.c_out,), "beta", lyr)
+                    add(lyr.name + "/kernel@composed", (lyr.K, ci, co), "conv", lyr, (lyr.K, pci, pco))
+            add(lyr.name + "/bn/gamma", (co,), "gamma", lyr, (pco,))
+            add(lyr.name + "/bn/beta", (co,), "beta", lyr, (pco,))
             for n, j in enumerate(lyr.res_sources):
                 bn = (lyr.name + "/res_bn_%d" % n) if lyr.dense else (lyr.name + "/res_bn")
-                add(bn + "/gamma", (lyr.c_out,), "gamma", lyr)
-                add(bn + "/beta", (lyr.c_out,), "beta", lyr)
+                add(bn + "/gamma", (co,), "gamma", lyr, (pco,))
+                add(bn + "/beta", (co,), "beta", lyr, (pco,))
             # the 1x1 residual kernels of every consumer of the source that feeds THIS layer: their
             # (merged) weight gradient is produced when backward reaches this layer, so they sit in its
             # region of the flat buffers (gradient buckets are cut by layer, last layer first)
@@ -280,13 +291,14 @@ class JasperEngine(object):
                 for (lc, n, cb, col) in g["consumers"]:
                     cons = self.layers[lc]
                     rn = self.res_name(cons, n)
+                    lcj, lcb = g["lcj"], cons.lc_out
                     if cons.sep:
-                        add(rn + "/depthwise_kernel", (1, g["cj"], 1), "dw", cons)
-                        add(rn + "/pointwise_kernel", (1, g["cj"], cb), "pw", cons)
-                        add(rn + "/kernel@composed", (1, g["cj"], cb), "conv", cons)
+                        add(rn + "/depthwise_kernel", (1, lcj, 1), "dw", cons, (1, g["cj"], 1))
+                        add(rn + "/pointwise_kernel", (1, lcj, lcb), "pw", cons, (1, g["cj"], cb))
+                        add(rn + "/kernel@composed", (1, lcj, lcb), "conv", cons, (1, g["cj"], cb))
                     else:
-                        add(rn + "/kernel", (1, g["cj"], cb), "conv", cons)
-        add("fc/kernel", (self.H, self.V), "fc_w")
+                        add(rn + "/kernel", (1, lcj, lcb), "conv", cons, (1, g["cj"], cb))
+        add("fc/kernel", (self.Hl, self.V), "fc_w", None, (self.H, self.V))
         add("fc/bias", (self.V,), "fc_b")
         off = 0
         hoff = 0
@@ -295,7 +307,12 @@ class JasperEngine(object):
             for d in s["shape"]:
                 n *= d
             s["size"] = n
+            n = 1
+            for d in s["store_shape"]:
+                n *= d
             s["store_size"] = n
+            s["phys"] = s["store_shape"]          # (K, C_in, C_out) the kernels see (the folded layer keeps K here)
+            s["view"] = tuple(slice(0, d) for d in s["shape"])
             s["offset"] = off
             if s["kind"] == "conv":
                 s["half_offset"] = hoff
@@ -321,7 +338,7 @@ class JasperEngine(object):
         self.moving = {}
         for s in specs:
             if s["kind"] == "gamma":
-                C = s["shape"][0]
+                C = s["store_shape"][0]
                 mv = torch.zeros(2, C, dtype=torch.float32, device=dev)
                 mv[1].fill_(1.0)
                 self.moving[s["name"][:-len("/gamma")]] = mv
@@ -348,6 +365,7 @@ class JasperEngine(object):
                 lyr.orig_pad_left = pl
                 s["store_size"] = 2 * lyr.kK * lyr.c_in * lyr.c_out
                 s["store_shape"] = (2 * lyr.kK, lyr.c_in, lyr.c_out)
+                s["view"] = (slice(lyr.lead_taps, lyr.lead_taps + K), slice(0, lyr.lc_in), slice(0, lyr.lc_out))
             elif lyr is not None and s["name"] in (lyr.wname, lyr.name + "/depthwise_kernel") and not lyr.fold:
                 lyr.kK, lyr.kC_in = lyr.K, lyr.c_in
                 _, lyr.kpad, _ = same_padding(1 << 20, lyr.K, 1, lyr.dil)
@@ -365,15 +383,15 @@ class JasperEngine(object):
         lyr = s["layer"]
         if s["kind"] == "conv" and lyr is not None and lyr.fold and s["name"] == lyr.wname:
             per_tap = lyr.c_in * lyr.c_out
-            return lyr.lead_taps * per_tap, s["size"]
-        return 0, s["size"]
+            return lyr.lead_taps * per_tap, lyr.K * per_tap
+        return 0, s["store_size"]
 
     def param_view(self, name, buf=None):
         """fp32 view (logical shape) of a parameter inside the flat master (or grad / mom) buffer."""
         s = self.by_name[name]
         buf = self.master if buf is None else buf
-        st, n = self._valid_slice(s)
-        return buf[s["offset"] + st:s["offset"] + st + n].view(*s["shape"])
+        full = buf[s["offset"]:s["offset"] + s["store_size"]].view(*s["store_shape"])
+        return full[s["view"]]
 
     def named_parameters(self):
         """The model's variables (the composed pseudo-kernels of sep_conv1d layers are derived, not variables)."""
@@ -438,7 +456,7 @@ class JasperEngine(object):
         base = cname[:-len("/kernel@composed")]
         s = self.by_name[cname]
         sd, sp = self.by_name[base + "/depthwise_kernel"], self.by_name[base + "/pointwise_kernel"]
-        K, ci, co = s["shape"]
+        K, (_, ci, co) = s["shape"][0], s["phys"]
         st0, _ = self._valid_slice(s)
         args = [_vp(self.master.data_ptr() + 4 * sd["offset"]), _vp(self.master.data_ptr() + 4 * sp["offset"]),
                 _vp(self.wb.data_ptr() + 2 * (s["half_offset"] + st0)), K, ci, co, self.dtypes]
@@ -460,7 +478,7 @@ class JasperEngine(object):
         base = cname[:-len("/kernel@composed")]
         s = self.by_name[cname]
         sd, sp = self.by_name[base + "/depthwise_kernel"], self.by_name[base + "/pointwise_kernel"]
-        K, ci, co = s["shape"]
+        K, (_, ci, co) = s["shape"][0], s["phys"]
         st0, _ = self._valid_slice(s)
         g = self.grad.data_ptr()
         m = self.master.data_ptr()
@@ -471,7 +489,7 @@ class JasperEngine(object):
         lyr = s["layer"]
         if lyr is not None and s["name"] == lyr.wname:
             return lyr.kK, lyr.kC_in, lyr.c_out
-        return s["shape"]
+        return s["phys"]
 
     # ----------------------------------------------------------------- optimizer
     def set_optimizer(self, algo="novograd", beta1=0.95, beta2=0.98, epsilon=1e-8, weight_decay=0.0,
@@ -698,7 +716,7 @@ class JasperEngine(object):
     def _check_feats(self, feats):
         """Features arrive in the activation storage format; a bf16 / fp16 / fp32 tensor of the other kind is
         converted here (one small elementwise kernel), anything else is an error."""
-        if feats.dim() != 3 or feats.shape[2] != self.F or not feats.is_contiguous():
+        if feats.dim() != 3 or feats.shape[2] != self.F or not feats.is_contiguous():  # F: the reference's feature count
             raise ValueError("JasperEngine: features must be contiguous [B,T,%d]" % self.F)
         if feats.dtype not in (torch.bfloat16, torch.float16, torch.float32):
             raise ValueError("JasperEngine: features must be bf16 / fp16 / fp32")
@@ -842,9 +860,9 @@ class _Workspace(object):
         rows = B * T2
         n = sum(l.c_out for l in eng.layers) * (csz + 2)
         n += sum(g["ntot"] for g in eng.res_groups) * (csz + 2)
-        n += sum(c for (c, _) in eng.block_inputs) * 4
+        n += sum(b[0] for b in eng.block_inputs) * 4
         n += 3 * max(l.c_out for l in eng.layers) * 2
-        return rows * n + B * T * eng.F * 2 + (64 << 20)
+        return rows * n + B * T * eng.Fp * 2 + (64 << 20)
 
     def release(self):
         """Drop the captured graph and every tensor so the caching allocator can reuse the memory."""
@@ -901,7 +919,7 @@ class _Workspace(object):
         cin_max = max([l.c_in for l in layers if l.sep and l.sep_mode == "split"] + [0])
         self.dZ2 = [bf(B, T2, cin_max), bf(B, T2, cin_max)] if cin_max else None
         self._st_aux = _vp(0)
-        self.dres = [f32(B, T2, c) for (c, _) in eng.block_inputs]
+        self.dres = [f32(B, T2, b[0]) for b in eng.block_inputs]
         self.red = f32((2 + nres_max) * cmax)
         self.lens_in = torch.zeros(B, dtype=torch.int32, device=dev)
         self.lens_out = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -937,7 +955,8 @@ class _Workspace(object):
         self.tokens = torch.zeros(B, T2, dtype=torch.int32, device=dev)
         self.tok_lens = torch.zeros(B, dtype=torch.int32, device=dev)
         self.neg_sum = f32(B)
-        self.feats = torch.zeros(B, T, eng.F, dtype=eng.act_torch, device=dev)  # static input buffer
+        # static input buffer, Fp >= F channels wide (pad channels stay zero)
+        self.feats = torch.zeros(B, T, eng.Fp, dtype=eng.act_torch, device=dev)
         self.graph = None
         self.graph_L = -1
         self._eager_steps = 0
@@ -1066,7 +1085,10 @@ class _Workspace(object):
     def set_inputs(self, feats, feat_lens):
         """Copy one batch into the static input buffers (the plans / graphs read only these)."""
         if feats.data_ptr() != self.feats.data_ptr():
-            self.feats.copy_(feats, non_blocking=True)
+            if self.eng.Fp == self.eng.F:
+                self.feats.copy_(feats, non_blocking=True)
+            else:
+                self.feats[:, :, :self.eng.F].copy_(feats, non_blocking=True)
         self.lens_in.copy_(feat_lens.to(torch.int32), non_blocking=True)
 
     def set_targets(self, labels, label_lens):

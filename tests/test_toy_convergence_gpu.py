@@ -4,7 +4,9 @@ plugin API (`create`-style config dicts -> Speech2Text -> train()/evaluate()), t
 thresholds of open_seq2seq/models/speech2text_w2l_test.py:23-24: train loss < 5, eval loss < 30,
 WER < 0.1.  The layer widths are the tensor-core-aligned analogue of test_speech_configs/
 w2l_test_config.py (200/400 channels there, 256/384 here; stride-2 first layer so that the 64 log-mel
-features fold to 128 channels); optimizer, LARC, lr policy and activation follow that config."""
+features fold to 128 channels); optimizer, LARC, lr policy and activation follow that config.  The third
+case ("w2l_exact") is that config's own layer table and data layer -- 40 features, 3 x (K = 7, 200 channels),
+1 x (K = 1, 400 channels), stride 1, no conv mask -- run through the engine's zero-padded channels."""
 import copy
 import os
 
@@ -40,10 +42,11 @@ def _config(tmpdir, backend="librosa"):
         }
     else:
         # exactly the data-layer section of test_speech_configs/w2l_test_config.py:80-90 (default backend =
-        # python_speech_features, default pad_to = 8, one mean/std per utterance), 64 features instead of 40
+        # python_speech_features, default pad_to = 8, one mean/std per utterance); 64 features instead of 40
+        # unless the exact config is asked for
         dl = {
-            "num_audio_features": 64, "input_type": "logfbank", "vocab_file": os.path.join(TOY, "vocab.txt"),
-            "dataset_files": [csv_path],
+            "num_audio_features": 40 if backend == "w2l_exact" else 64, "input_type": "logfbank",
+            "vocab_file": os.path.join(TOY, "vocab.txt"), "dataset_files": [csv_path],
         }
     base = {
         "use_horovod": False, "num_epochs": 500, "num_gpus": 1, "batch_size_per_gpu": 10,
@@ -73,6 +76,17 @@ def _config(tmpdir, backend="librosa"):
         "loss": CTCLoss, "loss_params": {},
         "data_layer": Speech2TextDataLayer,
     }
+    if backend == "w2l_exact":
+        # test_speech_configs/w2l_test_config.py:44-71: the reference's own widths (not multiples of 64)
+        base["encoder_params"]["convnet_layers"] = [
+            {"type": "conv1d", "repeat": 3, "kernel_size": [7], "stride": [1], "num_channels": 200,
+             "padding": "SAME", "dilation": [1]},
+            {"type": "conv1d", "repeat": 1, "kernel_size": [1], "stride": [1], "num_channels": 400,
+             "padding": "SAME", "dilation": [1]},
+        ]
+        base["encoder_params"]["use_conv_mask"] = False
+        base["dtype"] = tf.float32
+        base.pop("loss_scaling")
     train_cfg = copy.deepcopy(base)
     train_cfg["data_layer_params"] = dict(dl, shuffle=True)
     eval_cfg = copy.deepcopy(base)
@@ -80,7 +94,7 @@ def _config(tmpdir, backend="librosa"):
     return Speech2Text, train_cfg, eval_cfg
 
 
-@pytest.mark.parametrize("backend", ["librosa", "psf"])
+@pytest.mark.parametrize("backend", ["librosa", "psf", "w2l_exact"])
 def test_w2l_style_model_converges_on_reference_toy_speech(tmp_path, backend):
     model_cls, train_cfg, eval_cfg = _config(tmp_path, backend)  # installs the compat import surface
     from open_seq2seq.utils.funcs import train, evaluate_model
