@@ -389,6 +389,11 @@ int os2s_augment_signal(const int16_t* wave, const long long* offsets, const int
  *   features_mean / features_std : fp32 [F] (params['features_mean'], ['features_std_dev']) or NULL = computed
  *   masks             : int32 [B][n_masks][3] = (kind 0 = frequency / 1 = time, base, width): spec-augment
  *                       (:419-433) zeros written into the normalised features; width 0 = no-op
+ *   feature_type      : 0 = logfbank; the psf backend's other input types (:490-512): 1 = spectrogram (Hann
+ *                       frames, |DFT|^2 / win with NFFT = win, 10 log10, lowest F bins; pass window = hanning(win)),
+ *                       2 = mfcc (psf.mfcc: `mel` has n_filt = 2 F rows, mfcc_matrix fp32 [F][n_filt] = sinusoidal
+ *                       lifter x orthonormal DCT-II rows, applied to the log filterbank energies)
+ *   offsets           : always a valid int64 [B] array (the wave offsets; unused values when sig is given)
  *   dtypes & OS2S_HALF_F16 : out16 is fp16 instead of bf16 */
 int os2s_features_forward_p(const int16_t* wave, const float* sig, const long long* sig_offsets,
                             const long long* offsets, const int* n_samples, int B,
@@ -396,6 +401,7 @@ int os2s_features_forward_p(const int16_t* wave, const float* sig, const long lo
                             int F, int T_pad, int max_samples, float dither, uint64_t seed, float preemph,
                             int psf_backend, int pad_to, int norm_per_feature, float gain,
                             const float* features_mean, const float* features_std, const int* masks, int n_masks,
+                            int feature_type, const float* mfcc_matrix, int n_filt,
                             void* absmax_ws, float* raw_ws, void* out16, float* out_f32, int* out_lens,
                             int dtypes, void* stream);
 

@@ -175,20 +175,29 @@ class Speech2TextDataLayer(DataLayer):
     # ---------------------------------------------------------------- featurizer
     def _setup_device_tables(self):
         p = self.params
-        if p["input_type"] != "logfbank":
-            raise NotImplementedError("Speech2TextDataLayer: the GPU featurizer implements input_type='logfbank' "
-                                      "(both backends); 'spectrogram' / 'mfcc' are not built")
+        self._ftype = {"logfbank": 0, "spectrogram": 1, "mfcc": 2}[p["input_type"]]
+        if self._ftype != 0 and not self._psf:
+            raise NotImplementedError("Speech2TextDataLayer: input_type %r is built for the python_speech_features "
+                                      "backend (the default); the librosa backend has 'logfbank'" % p["input_type"])
         # psf normalises with one mean / std per utterance; librosa per feature unless norm_per_feature=False
         self._per_feature = (not self._psf) and bool(p.get("norm_per_feature", False))
         sr = p["sample_freq"]
         self.n_win = int(sr * p["window_size"])
         self.n_hop = int(sr * p["window_stride"])
         F = p["num_audio_features"]
+        self._post, self._n_filt = None, 0
         if self._psf:
-            # psf.logfbank(nfft=512, winfunc = rectangular) (speech_utils.py:514-522)
+            # psf.logfbank(nfft=512, winfunc = rectangular) (speech_utils.py:514-522); psf.mfcc(nfilt = 2 F, ceplifter =
+            # 2 F) (:504-512); spectrogram: Hann frames, NFFT = window length (:490-502)
             self.n_fft = 512
-            mel = speech_utils.psf_filterbank(F, self.n_fft, sr, 0.0, sr / 2.0)
-            win = np.ones(self.n_win)
+            n_filt = 2 * F if self._ftype == 2 else F
+            mel = speech_utils.psf_filterbank(n_filt, self.n_fft, sr, 0.0, sr / 2.0)
+            win = np.hanning(self.n_win) if self._ftype == 1 else np.ones(self.n_win)
+            if self._ftype == 1 and F > self.n_win // 2 + 1:
+                raise AssertionError("num_features for spectrogram should be <= (sample_freq * window_size // 2 + 1)")
+            if self._ftype == 2:
+                self._n_filt = n_filt
+                self._post_np = speech_utils.psf_mfcc_matrix(F, n_filt, 2 * F)
         else:
             self.n_fft = p.get("num_fft") or speech_utils.num_fft_for(p["window_size"], sr)
             mel = speech_utils.mel_filterbank(sr, self.n_fft, F, 0.0, int(sr / 2))
@@ -200,6 +209,8 @@ class Speech2TextDataLayer(DataLayer):
         band = [[int(np.nonzero(r)[0].min()), int(np.nonzero(r)[0].max()) + 1] if np.any(r) else [0, 0] for r in mel]
         self._band = torch.tensor(band, dtype=torch.int32, device=dev)
         self._win = torch.tensor(win, dtype=torch.float32, device=dev)
+        if self._ftype == 2:
+            self._post = torch.tensor(self._post_np, dtype=torch.float32, device=dev)
         self._fixed_mean = self._fixed_std = None
         if p.get("features_mean") is not None or p.get("features_std_dev") is not None:
             if not self._per_feature:
@@ -406,8 +417,8 @@ class Speech2TextDataLayer(DataLayer):
             p_wave, sig_ptr, sigoff_ptr, p_off, n_ptr, B, L.ptr(self._mel), L.ptr(self._band), L.ptr(self._win),
             self.n_fft, self.n_win, self.n_hop, F, T, max_n, ctypes.c_float(dither), ctypes.c_uint64(seed),
             ctypes.c_float(0.97), int(self._psf), int(pad_to), int(self._per_feature), ctypes.c_float(self._gain),
-            L.ptr(self._fixed_mean), L.ptr(self._fixed_std), p_masks, nm, L.ptr(absmax), L.ptr(raw), L.ptr(out), None,
-            L.ptr(out_lens), dt, st), "os2s_features_forward_p")
+            L.ptr(self._fixed_mean), L.ptr(self._fixed_std), p_masks, nm, self._ftype, L.ptr(self._post), self._n_filt,
+            L.ptr(absmax), L.ptr(raw), L.ptr(out), None, L.ptr(out_lens), dt, st), "os2s_features_forward_p")
         self.h2d_bytes = wave_bytes + meta_bytes
         self._last = dict(B=B, T=T, max_n=max_n, dither=dither, aug=aug, nm=nm, n_out_sum=int(n_out.sum()),
                           ptrs=(p_wave, p_off, p_ooff, p_n, p_nout, p_srn, p_noise, p_masks), keep=dwave)
@@ -452,8 +463,9 @@ class Speech2TextDataLayer(DataLayer):
             p_wave, sig_ptr, sigoff_ptr, p_off, n_ptr, B, L.ptr(self._mel), L.ptr(self._band), L.ptr(self._win),
             self.n_fft, self.n_win, self.n_hop, F, T, max_n, ctypes.c_float(s["dither"]), ctypes.c_uint64(seed),
             ctypes.c_float(0.97), int(self._psf), int(p.get("pad_to", 8)), int(self._per_feature),
-            ctypes.c_float(self._gain), L.ptr(self._fixed_mean), L.ptr(self._fixed_std), p_masks, s["nm"], L.ptr(absmax),
-            L.ptr(raw), L.ptr(out), None, L.ptr(out_lens), dt, st), "os2s_features_forward_p")
+            ctypes.c_float(self._gain), L.ptr(self._fixed_mean), L.ptr(self._fixed_std), p_masks, s["nm"], self._ftype,
+            L.ptr(self._post), self._n_filt, L.ptr(absmax), L.ptr(raw), L.ptr(out), None, L.ptr(out_lens), dt, st),
+            "os2s_features_forward_p")
         return out, out_lens
 
     # ------------------------------------------------------------------ batching

@@ -86,3 +86,16 @@ def kaiser_best_table():
     sinc_win = rolloff * np.sinc(rolloff * np.linspace(0, num_zeros, num=n + 1, endpoint=True))
     taper = np.kaiser(2 * n + 1, beta)[n:]
     return taper * sinc_win, num_table
+
+
+def psf_mfcc_matrix(numcep, nfilt, ceplifter):
+    """python_speech_features.base.mfcc after the log filterbank (get_speech_features_psf, speech_utils.py:504-512):
+    scipy.fftpack.dct(type=2, norm='ortho') over the nfilt log energies, the first numcep coefficients, the
+    sinusoidal lifter 1 + (L/2) sin(pi n / L) -> one [numcep, nfilt] matrix (appendEnergy=False)."""
+    n = np.arange(nfilt)
+    dct = np.cos(np.pi * (n[None, :] + 0.5) * np.arange(nfilt)[:, None] / nfilt)
+    scale = np.full(nfilt, math.sqrt(2.0 / nfilt))
+    scale[0] = math.sqrt(1.0 / nfilt)
+    m = (dct * scale[:, None])[:numcep]
+    lift = 1.0 + (ceplifter / 2.0) * np.sin(np.pi * np.arange(numcep) / ceplifter) if ceplifter > 0 else np.ones(numcep)
+    return m * lift[:, None]

@@ -28,7 +28,11 @@ class FullyConnectedTimeDecoder(Decoder):
         logits = logits_btv.transpose(0, 1)  # time-major view, no copy
         outputs = [logits]
         f = self.params.get("logits_to_outputs_func")
-        if f is not None:
+        if self._mode == "infer" and self.params.get("infer_logits_to_pickle"):
+            # fc_decoders.py:146-147 + models/speech2text.py:214-217: the logits themselves, batch-major, are
+            # the model outputs (dumped by Speech2Text.finalize_inference for scripts/decode.py)
+            outputs = [logits_btv]
+        elif f is not None:
             outputs = f(logits, input_dict)
         return {"outputs": outputs, "logits": logits, "src_length": enc["src_length"]}
 

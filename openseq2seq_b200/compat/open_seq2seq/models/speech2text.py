@@ -77,6 +77,10 @@ class Speech2Text(EncoderDecoderModel):
         return {"Eval WER": wer}
 
     def infer(self, input_values, output_values):
+        if self.dump_outputs:
+            # models/speech2text.py:300-304: one [T, V] logits array per utterance
+            lg = output_values.float().cpu().numpy()
+            return [lg[b] for b in range(lg.shape[0])], input_values["source_ids"]
         toks, tl = output_values
         return self._decode_batch(toks, tl), input_values["source_ids"]
 
@@ -88,5 +92,18 @@ class Speech2Text(EncoderDecoderModel):
             ids += list(np.asarray(i[0]).reshape(-1))
         order = np.argsort(ids)
         files = [self.get_data_layer()._files[ids[k]][0] for k in order]
+        if self.dump_outputs:
+            # models/speech2text.py:325-343: {"logits": {wav: [T, V]}, "step_size": stride product x window_stride,
+            # "vocab": idx2char}, the input of scripts/decode.py
+            import pickle
+            scale = 1
+            for c in self.encoder.params.get("convnet_layers") or []:
+                scale *= c["stride"][0]
+            dump_out = {"logits": {f: preds[k] for f, k in zip(files, order)},
+                        "step_size": scale * self.get_data_layer().params["window_stride"],
+                        "vocab": self.get_data_layer().params["idx2char"]}
+            with open(output_file, "wb") as f:
+                pickle.dump(dump_out, f, protocol=pickle.HIGHEST_PROTOCOL)
+            return
         pd.DataFrame({"wav_filename": files, "predicted_transcript": [preds[k] for k in order]},
                      columns=["wav_filename", "predicted_transcript"]).to_csv(output_file, index=False)

@@ -416,6 +416,7 @@ int os2s_features_forward_p(const int16_t* wave, const float* sig, const long lo
                             int F, int T_pad, int max_samples, float dither, uint64_t seed, float preemph,
                             int psf_backend, int pad_to, int norm_per_feature, float gain,
                             const float* features_mean, const float* features_std, const int* masks, int n_masks,
+                            int feature_type, const float* mfcc_matrix, int n_filt,
                             void* absmax_ws, float* raw_ws, void* out16, float* out_f32, int* out_lens,
                             int dtypes, void* stream) {
   if ((!wave && !sig) || !offsets || !n_samples || !mel || !window || !absmax_ws || !raw_ws)
@@ -423,7 +424,7 @@ int os2s_features_forward_p(const int16_t* wave, const float* sig, const long lo
   if (!out16 && !out_f32) return fail(ERR_INVALID, "os2s_features_forward: no output buffer");
   if (psf_backend && dither != 0.f) return fail(ERR_INVALID, "os2s_features_forward: the psf backend has no dither");
   if (pad_to < 0 || n_masks < 0 || (n_masks > 0 && !masks)) return fail(ERR_INVALID, "os2s_features_forward: bad argument");
-  FeatExtras ex{gain, sig, sig_offsets, features_mean, features_std, masks, n_masks};
+  FeatExtras ex{gain, sig, sig_offsets, features_mean, features_std, masks, n_masks, feature_type, mfcc_matrix, n_filt};
   return logmel_forward(wave, offsets, n_samples, B, mel, mel_band, window, n_fft, win, hop, F, T_pad, max_samples, dither,
                         seed, preemph, (unsigned int*)absmax_ws, raw_ws, out16, out_f32, out_lens,
                         (cudaStream_t)stream, psf_backend, pad_to, norm_per_feature, (dtypes & OS2S_HALF_F16) ? 1 : 0,

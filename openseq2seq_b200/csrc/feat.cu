@@ -68,6 +68,10 @@ struct FeatOpts {
   const float* fixed_std;    // [F] params['features_std_dev']
   const int* masks;          // [B][n_masks][3] = (kind 0 freq / 1 time, base, width): spec-augment (:419-433)
   int n_masks;
+  // psf feature types other than logfbank (speech_utils.py:490-512)
+  int feature_type;          // 0 = logfbank, 1 = spectrogram (NFFT = window length DFT), 2 = mfcc
+  const float* post;         // mfcc: [F][n_filt] = lifter * orthonormal DCT-II rows applied to the log energies
+  int n_filt;                // mfcc: rows of `mel` (= 2 F)
 };
 // spec-augment: zeros written into the normalised features
 __device__ __forceinline__ bool feat_masked(const FeatOpts& o, int b, int t, int f) {
@@ -197,8 +201,9 @@ feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__
     re[warp][i] = a * a + c * c;
   }
   __syncwarp();
-  // mel mat-vec: feature f = lane, lane+32; mel is [F][NB] row-major (dense)
-  for (int f = lane; f < F; f += 32) {
+  // mel mat-vec: filter f = lane, lane+32; mel is [n_filt][NB] row-major (dense)
+  const int n_filt = opts.feature_type == 2 ? opts.n_filt : F;
+  for (int f = lane; f < n_filt; f += 32) {
     const float* mrow = mel + (size_t)f * NB;
     // triangular filters are zero outside [lo, hi): only the support is visited when bands are given
     const int lo = mel_band ? mel_band[2 * f] : 0;
@@ -207,8 +212,67 @@ feat_logmel_kernel(const short* __restrict__ wave, const long long* __restrict__
     for (int k = lo; k < hi; ++k) acc += mrow[k] * re[warp][k];
     acc *= opts.power_scale;
     // librosa path: log(S + 1e-20) (speech_utils.py:406); psf: zeros -> float eps, then log (base.fbank)
-    raw[((size_t)b * T_pad + frame) * F + f] = opts.psf ? logf(acc == 0.f ? 2.220446049250313e-16f : acc)
-                                                        : logf(acc + 1e-20f);
+    const float lg = opts.psf ? logf(acc == 0.f ? 2.220446049250313e-16f : acc) : logf(acc + 1e-20f);
+    if (opts.feature_type == 2) im[warp][f] = lg;       // mfcc: keep the log energies for the DCT
+    else raw[((size_t)b * T_pad + frame) * F + f] = lg;
+  }
+  if (opts.feature_type == 2) {
+    // psf.mfcc (speech_utils.py:504-512): cepstrum c = lifter * DCT-II_ortho(log energies), first F coefficients
+    __syncwarp();
+    for (int f = lane; f < F; f += 32) {
+      const float* prow = opts.post + (size_t)f * n_filt;
+      float acc = 0.f;
+      for (int j = 0; j < n_filt; ++j) acc += prow[j] * im[warp][j];
+      raw[((size_t)b * T_pad + frame) * F + f] = acc;
+    }
+  }
+}
+
+// psf spectrogram (speech_utils.py:490-502): frame f = samples [f*hop, f*hop + win) of the re-quantised, zero-padded
+// signal times the window, |DFT_win|^2 / win with NFFT = the window length (320: not a power of two, so a direct
+// DFT from a twiddle table), 10 log10(max(., 1e-30)), the lowest F bins.  (logpowspec's "minus the maximum" is a
+// constant that the global mean / std normalisation removes.)  One warp per frame, lane = bins j, j + 32, ...
+__global__ void __launch_bounds__(kFeatWarps * 32)
+feat_spectrogram_kernel(const short* __restrict__ wave, const long long* __restrict__ offsets,
+                        const int* __restrict__ n_samples, const unsigned int* __restrict__ absmax,
+                        const float* __restrict__ window, float* __restrict__ raw, int T_pad, int F, int hop, int win,
+                        const FeatOpts opts) {
+  extern __shared__ float sh[];              // [2*win] twiddles, then per warp [win] samples
+  float* tc = sh;
+  float* ts = sh + win;
+  float* xs = sh + 2 * win + (threadIdx.x >> 5) * win;
+  for (int m = threadIdx.x; m < win; m += kFeatWarps * 32) {
+    float sn, cs;
+    sincospif(-2.f * (float)m / (float)win, &sn, &cs);
+    tc[m] = cs;
+    ts[m] = sn;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, b = blockIdx.y;
+  const int frame = blockIdx.x * kFeatWarps + (threadIdx.x >> 5);
+  const int n = n_samples[b];
+  const int n_frames = frames_of(opts, n, hop, win);
+  if (frame >= n_frames) return;
+  const int len0 = (n <= win) ? 1 : 1 + (n - win + hop - 1) / hop;
+  const int n_padded = n + (n_frames - len0) * hop;
+  const short* w = wave + offsets[b];
+  const float gain = 1.f / ((float)absmax[b] + 1e-5f);
+  for (int i = lane; i < win; i += 32)   // no pre-emphasis for the spectrogram (sigproc.framesig on the raw signal)
+    xs[i] = sample_at_psf(w, n, n_padded, frame * hop + i, gain, 0.f) * window[i];
+  __syncwarp();
+  for (int j = lane; j < F; j += 32) {
+    float ar = 0.f, ai = 0.f;
+    int idx = 0;
+    for (int i = 0; i < win; ++i) {
+      const float x = xs[i];
+      ar += x * tc[idx];
+      ai += x * ts[idx];
+      idx += j;
+      if (idx >= win) idx -= win;
+    }
+    float p = (ar * ar + ai * ai) / (float)win;
+    p = fmaxf(p, 1e-30f);
+    raw[((size_t)b * T_pad + frame) * F + j] = 10.f * log10f(p);
   }
 }
 
@@ -297,7 +361,7 @@ int logmel_forward(const short* wave, const long long* offsets, const int* n_sam
                    cudaStream_t st, int psf_backend, int pad_to, int norm_per_feature, int out_f16,
                    const FeatExtras* ex) {
   if (n_fft != 512) return fail(ERR_UNSUPPORTED, "logmel_forward: only n_fft = 512 is built");
-  if (win > n_fft || F > 128) return fail(ERR_INVALID, "logmel_forward: bad window / feature count");
+  if (win > n_fft || F > 256) return fail(ERR_INVALID, "logmel_forward: bad window / feature count");
   FeatOpts opts;
   opts.psf = psf_backend ? 1 : 0;
   opts.pad_to = pad_to;
@@ -311,6 +375,17 @@ int logmel_forward(const short* wave, const long long* offsets, const int* n_sam
   opts.fixed_std = ex ? ex->fixed_std : nullptr;
   opts.masks = ex ? ex->masks : nullptr;
   opts.n_masks = ex ? ex->n_masks : 0;
+  opts.feature_type = ex ? ex->feature_type : 0;
+  opts.post = ex ? ex->post : nullptr;
+  opts.n_filt = ex ? ex->n_filt : 0;
+  if (opts.feature_type != 0) {
+    if (!psf_backend) return fail(ERR_UNSUPPORTED, "logmel_forward: spectrogram / mfcc are built for the psf backend");
+    if (opts.feature_type == 2 && (!opts.post || opts.n_filt < F || opts.n_filt > kNfftMax))
+      return fail(ERR_INVALID, "logmel_forward: mfcc needs the [F][n_filt] DCT matrix");
+    if (opts.feature_type == 1 && F > win / 2 + 1)
+      return fail(ERR_INVALID, "logmel_forward: num_features for spectrogram should be <= window / 2 + 1");
+    if (opts.feature_type < 0 || opts.feature_type > 2) return fail(ERR_INVALID, "logmel_forward: unknown feature type");
+  }
   if (opts.sig && psf_backend) return fail(ERR_UNSUPPORTED, "logmel_forward: augmented signals need the librosa backend");
   if ((opts.fixed_mean || opts.fixed_std) && !norm_per_feature)
     return fail(ERR_UNSUPPORTED, "logmel_forward: features_mean / features_std_dev need norm_per_feature");
@@ -327,8 +402,14 @@ int logmel_forward(const short* wave, const long long* offsets, const int* n_sam
   }
   if (max_frames > T_pad) return fail(ERR_INVALID, "logmel_forward: T_pad smaller than the frame count");
   dim3 grid((max_frames + kFeatWarps - 1) / kFeatWarps, B);
-  feat_logmel_kernel<512><<<grid, kFeatWarps * 32, 0, st>>>(wave, offsets, n_samples, absmax_ws, mel, mel_band, window, raw_ws,
-                                                           T_pad, F, hop, win, dither, seed, preemph, opts);
+  if (opts.feature_type == 1) {
+    const size_t smem = (size_t)(2 + kFeatWarps) * win * sizeof(float);
+    feat_spectrogram_kernel<<<grid, kFeatWarps * 32, smem, st>>>(wave, offsets, n_samples, absmax_ws, window, raw_ws, T_pad, F,
+                                                               hop, win, opts);
+  } else {
+    feat_logmel_kernel<512><<<grid, kFeatWarps * 32, 0, st>>>(wave, offsets, n_samples, absmax_ws, mel, mel_band, window,
+                                                             raw_ws, T_pad, F, hop, win, dither, seed, preemph, opts);
+  }
   if (norm_per_feature) {
     dim3 grid2((F + 7) / 8, B);
     feat_norm_kernel<<<grid2, 256, 0, st>>>(raw_ws, n_samples, (uint16_t*)out_bf16, out_f32, out_lens, T_pad, F,

@@ -146,6 +146,9 @@ struct FeatExtras {
   const float* fixed_std;
   const int* masks;
   int n_masks;
+  int feature_type;          // 0 = logfbank, 1 = psf spectrogram, 2 = psf mfcc
+  const float* post;         // mfcc: [F][n_filt]
+  int n_filt;
 };
 int wave_absmax(const short* wave, const long long* offsets, const int* n_samples, int B, unsigned int* absmax,
                 cudaStream_t st);

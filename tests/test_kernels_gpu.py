@@ -692,7 +692,7 @@ def test_featurizer_on_augmented_signal_with_spec_masks_gain_and_fixed_normalisa
     lens = torch.zeros(B, dtype=torch.int32, device=dev)
     L.check(lib.os2s_features_forward_p(None, L.ptr(sig), L.ptr(soff), L.ptr(soff), L.ptr(nsd), B, L.ptr(mel), L.ptr(band),
                                         L.ptr(win), 512, 320, hop, F, T_pad, int(n_out.max()), _f(0.0), ctypes.c_uint64(0),
-                                        _f(0.97), 0, 16, 1, _f(0.0), None, None, L.ptr(mkd), nm, L.ptr(absmax), L.ptr(raw),
+                                        _f(0.97), 0, 16, 1, _f(0.0), None, None, L.ptr(mkd), nm, 0, None, 0, L.ptr(absmax), L.ptr(raw),
                                         L.ptr(out16), L.ptr(out), L.ptr(lens), 1, L.stream_ptr()), "features_p")
     torch.cuda.synchronize()
     assert lens.cpu().tolist() == ref_lens
@@ -722,8 +722,60 @@ def test_featurizer_on_augmented_signal_with_spec_masks_gain_and_fixed_normalisa
     L.check(lib.os2s_features_forward_p(L.ptr(wave), None, None, L.ptr(off0), L.ptr(n0), 1, L.ptr(mel), L.ptr(band), L.ptr(win),
                                         512, 320, hop, F, T1, len(s0), _f(0.0), ctypes.c_uint64(0), _f(0.97), 0, 16, 1,
                                         _f(gain), L.ptr(torch.tensor(fm, device=dev)), L.ptr(torch.tensor(fs, device=dev)),
-                                        None, 0, L.ptr(absmax), L.ptr(raw1), None, L.ptr(out1), L.ptr(lens), 0,
+                                        None, 0, 0, None, 0, L.ptr(absmax), L.ptr(raw1), None, L.ptr(out1), L.ptr(lens), 0,
                                         L.stream_ptr()), "features_p fixed")
     torch.cuda.synchronize()
     g1 = out1.cpu().numpy()[0, :logmel.shape[0]]
     assert np.abs(g1 - want).max() < 2e-2 * max(1.0, np.abs(want).max() / 10)
+
+
+@pytest.mark.parametrize("ftype", ["spectrogram", "mfcc"])
+def test_psf_spectrogram_and_mfcc_feature_types_vs_oracle(ftype):
+    """get_speech_features_psf(features_type='spectrogram' | 'mfcc') (speech_utils.py:490-512) on the GPU vs the
+    oracle restatement (pinned on the reference's shape / mean 0 / std 1 test in tests/test_oracle.py)."""
+    from oracle import featurizer as FZ
+    from open_seq2seq.data.speech2text import speech_utils as SU
+    L, lib = _lib()
+    rng = np.random.default_rng(7)
+    sigs = [np.clip(3000 * rng.standard_normal(n), -32768, 32767).astype(np.int16) for n in (16000, 9999, 4001)]
+    sigs = [np.clip(np.convolve(s.astype(np.float64), np.ones(8) / 8, mode="same"), -32768, 32767).astype(np.int16)
+            for s in sigs]
+    if ftype == "spectrogram":
+        F, code = 161, 1
+        feats = [FZ.psf_spectrogram_features(s, num_features=F, pad_to=8)[0] for s in sigs]
+        melnp, win, post, n_filt = np.zeros((1, 257)), np.hanning(320), None, 0
+    else:
+        F, code = 40, 2
+        feats = [FZ.psf_mfcc_features(s, num_features=F, pad_to=8)[0] for s in sigs]
+        melnp, win = FZ.psf_mel_filterbank(2 * F, 512, 16000, 0.0, 8000.0), np.ones(320)
+        post, n_filt = SU.psf_mfcc_matrix(F, 2 * F, 2 * F), 2 * F
+    ref_lens = [f.shape[0] for f in feats]
+    B, T_pad = len(sigs), -(-max(ref_lens) // 8) * 8
+    dev = "cuda"
+    wave = torch.tensor(np.concatenate(sigs), dtype=torch.int16, device=dev)
+    offs = torch.tensor(np.cumsum([0] + [len(s) for s in sigs[:-1]]), dtype=torch.int64, device=dev)
+    ns = torch.tensor([len(s) for s in sigs], dtype=torch.int32, device=dev)
+    mel = torch.tensor(melnp, dtype=torch.float32, device=dev)
+    band = None
+    if ftype == "mfcc":
+        band = torch.tensor([[int(np.nonzero(r)[0].min()), int(np.nonzero(r)[0].max()) + 1] if np.any(r) else [0, 0]
+                             for r in melnp], dtype=torch.int32, device=dev)
+    wint = torch.tensor(win, dtype=torch.float32, device=dev)
+    postd = torch.tensor(post, dtype=torch.float32, device=dev) if post is not None else None
+    absmax = torch.zeros(B, dtype=torch.int32, device=dev)
+    raw = torch.zeros(B * T_pad * F, device=dev)
+    out = torch.full((B, T_pad, F), float("nan"), device=dev)
+    lens = torch.zeros(B, dtype=torch.int32, device=dev)
+    L.check(lib.os2s_features_forward_p(L.ptr(wave), None, None, L.ptr(offs), L.ptr(ns), B, L.ptr(mel), L.ptr(band), L.ptr(wint),
+                                        512, 320, 160, F, T_pad, max(len(s) for s in sigs), _f(0.0), ctypes.c_uint64(0),
+                                        _f(0.97), 1, 8, 0, _f(0.0), None, None, None, 0, code, L.ptr(postd), n_filt,
+                                        L.ptr(absmax), L.ptr(raw), None, L.ptr(out), L.ptr(lens), 0, L.stream_ptr()), ftype)
+    torch.cuda.synchronize()
+    assert lens.cpu().tolist() == ref_lens
+    got = out.cpu().numpy()
+    for b in range(B):
+        n = ref_lens[b]
+        err = np.abs(got[b, :n] - feats[b]).max()
+        assert err < 3e-2, (ftype, b, err)
+        assert np.all(got[b, n:] == 0)
+        assert abs(float(got[b, :n].mean())) < 1e-3 and abs(float(got[b, :n].std()) - 1.0) < 1e-3
