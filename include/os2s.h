@@ -85,9 +85,17 @@ int os2s_conv_grid_waves(int waves);
 int os2s_conv1d_fwd(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
                     int K, int dil, int pad_left, int out_mode, float* bn_stats, void* stream);
 /* dtypes & OS2S_HALF_F16: x and w are fp16.  bn_stats may be combined with OS2S_OUT_F32 (statistics of the fp32
- * outputs) as well as with the 2-byte modes. */
+ * outputs) as well as with the 2-byte modes.
+ * row_lens (int32 [B] on the device, may be NULL) -- length-aware tile skipping, all four *_p conv entry points:
+ * the caller guarantees that rows t >= row_lens[b] of the ACTIVATION the call reads (x here and in wgrad; for the
+ * data gradients: of the layer input whose gradient is produced) are zero / masked, as the conv mask of
+ * tdnn_encoder.py:185-186,204-205 and the zero padding of the batch make them.  Output tiles that then are exactly
+ * zero (forward: t0 >= row_lens[b] + pad_left), are never read ungated (data gradient: t0 >= row_lens[b]) or add
+ * nothing (weight gradient: 64-row chunks past row_lens[b] + pad_left) are not computed; a skipped forward tile
+ * leaves y untouched (the BN kernels never read those rows unmasked, the fused statistics miss only zeros). */
 int os2s_conv1d_fwd_p(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
-                      int K, int dil, int pad_left, int out_mode, float* bn_stats, int dtypes, void* stream);
+                      int K, int dil, int pad_left, int out_mode, float* bn_stats, const int* row_lens, int dtypes,
+                      void* stream);
 
 /* Same convolution with the weights given transposed, wt : bf16 [K][C_out][C_in] (K-major B
  * operand).  Kept for A/B measurements of the two operand layouts (tools/gpu_conv_check.py). */
@@ -100,7 +108,7 @@ int os2s_conv1d_dgrad(const void* dy, const void* w, void* dx, int B, int T, int
                       int K, int dil, int pad_left, int out_mode, void* stream);
 /* dtypes & OS2S_HALF_F16: dy and w are fp16; pass out_mode = OS2S_OUT_F16_GRAD for an fp16 dx. */
 int os2s_conv1d_dgrad_p(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
-                        int K, int dil, int pad_left, int out_mode, int dtypes, void* stream);
+                        int K, int dil, int pad_left, int out_mode, const int* row_lens, int dtypes, void* stream);
 
 /* Data gradient whose output dx is the gradient dA of a single-branch BN + ReLU + dropout layer
  * (conv_blocks.py:208-227 followed by tdnn_encoder.py:255): dx is written as bf16 and the epilogue
@@ -115,7 +123,7 @@ int os2s_conv1d_dgrad_bnred(const void* dy, const void* w, void* dx, int B, int 
  * zero bits, so either format is accepted). */
 int os2s_conv1d_dgrad_bnred_p(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
                               int K, int dil, int pad_left, const void* a, const void* y, float keep, float* red,
-                              int dtypes, void* stream);
+                              const int* row_lens, int dtypes, void* stream);
 /* Second half of os2s_bn_bwd for one branch when `red` already holds the two sums (see above). */
 int os2s_bn_bwd_apply(const void* y, const float* mean_invstd, const float* gamma, float* dgamma, float* dbeta,
                       void* dy, const void* dA, const void* a, const float* red, int M, int C, float keep,
@@ -129,7 +137,7 @@ int os2s_bn_bwd_apply_p(const void* y, const float* mean_invstd, const float* ga
 int os2s_conv1d_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out,
                       int K, int dil, int pad_left, void* stream);
 int os2s_conv1d_wgrad_p(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out,
-                        int K, int dil, int pad_left, int dtypes, void* stream);
+                        int K, int dil, int pad_left, const int* row_lens, int dtypes, void* stream);
 
 /* W fp32 [K][C_in][C_out] -> w bf16 (same layout) and wt bf16 [K][C_out][C_in]. Either output may
  * be NULL.  Replaces the fp32->fp16 assign of mp_wrapper.py:104-109 when used standalone. */

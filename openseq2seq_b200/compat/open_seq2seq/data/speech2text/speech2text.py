@@ -545,6 +545,10 @@ class Speech2TextDataLayer(DataLayer):
                 yield self._collate(batch, epoch, aug_rng)
 
     def _collate(self, batch, epoch, aug_rng=None):
+        if self.params["mode"] == "train":
+            # longest first (the order inside a batch carries no meaning): utterances of similar length sit next
+            # to each other, so the tail tiles of the short ones pair up and are skipped by the conv kernels
+            batch = sorted(batch, key=lambda b: -(b[3][2] if len(b) > 3 else len(b[0])))
         sigs = [b[0] for b in batch]
         Lmax = max(1, max(len(b[1]) for b in batch))
         y = np.zeros((len(batch), Lmax), dtype=np.int32)

@@ -14,18 +14,19 @@ int os2s_conv_tuning(int pair_mode, int halo_mode) { return conv_tuning(pair_mod
 int os2s_conv_grid_waves(int waves) { return conv_grid_waves_set(waves); }
 
 int os2s_conv1d_fwd_p(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
-                      int K, int dil, int pad_left, int out_mode, float* bn_stats, int dtypes, void* stream) {
+                      int K, int dil, int pad_left, int out_mode, float* bn_stats, const int* row_lens, int dtypes,
+                      void* stream) {
   if (!x || !w || !y) return fail(ERR_INVALID, "os2s_conv1d_fwd: null pointer");
   if (bn_stats && out_mode == OS2S_OUT_F32_ACC)
     return fail(ERR_INVALID, "os2s_conv1d_fwd: fused BN statistics need an overwriting output mode");
   if (dtypes & ~(OS2S_HALF_F16 | OS2S_CONV_F32)) return fail(ERR_INVALID, "os2s_conv1d_fwd: unknown dtype flag");
   // B operand MN-major straight from the natural [K][C_in][C_out] layout
   return conv_kmajor(x, w, y, B, T, C_in, C_out, K, -pad_left, dil, out_mode, 1, bn_stats, (cudaStream_t)stream,
-                     nullptr, nullptr, 1.f, (dtypes & OS2S_HALF_F16) ? 1 : 0, 0);
+                     nullptr, nullptr, 1.f, (dtypes & OS2S_HALF_F16) ? 1 : 0, 0, row_lens, pad_left);
 }
 int os2s_conv1d_fwd(const void* x, const void* w, void* y, int B, int T, int C_in, int C_out,
                     int K, int dil, int pad_left, int out_mode, float* bn_stats, void* stream) {
-  return os2s_conv1d_fwd_p(x, w, y, B, T, C_in, C_out, K, dil, pad_left, out_mode, bn_stats, 0, stream);
+  return os2s_conv1d_fwd_p(x, w, y, B, T, C_in, C_out, K, dil, pad_left, out_mode, bn_stats, nullptr, 0, stream);
 }
 
 int os2s_conv1d_fwd_wt(const void* x, const void* wt, void* y, int B, int T, int C_in, int C_out,
@@ -35,42 +36,42 @@ int os2s_conv1d_fwd_wt(const void* x, const void* wt, void* y, int B, int T, int
 }
 
 int os2s_conv1d_dgrad_p(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
-                        int K, int dil, int pad_left, int out_mode, int dtypes, void* stream) {
+                        int K, int dil, int pad_left, int out_mode, const int* row_lens, int dtypes, void* stream) {
   if (!dy || !w || !dx) return fail(ERR_INVALID, "os2s_conv1d_dgrad: null pointer");
   return conv_kmajor(dy, w, dx, B, T, C_out, C_in, K, pad_left, -dil, out_mode, 0, nullptr, (cudaStream_t)stream,
-                     nullptr, nullptr, 1.f, (dtypes & OS2S_HALF_F16) ? 1 : 0, 0);
+                     nullptr, nullptr, 1.f, (dtypes & OS2S_HALF_F16) ? 1 : 0, 0, row_lens, 0);
 }
 int os2s_conv1d_dgrad(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
                       int K, int dil, int pad_left, int out_mode, void* stream) {
-  return os2s_conv1d_dgrad_p(dy, w, dx, B, T, C_in, C_out, K, dil, pad_left, out_mode, 0, stream);
+  return os2s_conv1d_dgrad_p(dy, w, dx, B, T, C_in, C_out, K, dil, pad_left, out_mode, nullptr, 0, stream);
 }
 
 int os2s_conv1d_dgrad_bnred_p(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
                               int K, int dil, int pad_left, const void* a, const void* y, float keep, float* red,
-                              int dtypes, void* stream) {
+                              const int* row_lens, int dtypes, void* stream) {
   if (!dy || !w || !dx || !a || !y || !red) return fail(ERR_INVALID, "os2s_conv1d_dgrad_bnred: null pointer");
   if (!(keep > 0.f && keep <= 1.f)) return fail(ERR_INVALID, "os2s_conv1d_dgrad_bnred: keep must be in (0,1]");
   // dx is written in the 16-bit format of the mode (fp16 gradients are NOT saturated: overflow -> inf -> the
   // loss scaler backs off); a is only tested for zero bits
   const int f16 = (dtypes & OS2S_HALF_F16) ? 1 : 0;
   return conv_kmajor(dy, w, dx, B, T, C_out, C_in, K, pad_left, -dil, f16 ? OS2S_OUT_F16_GRAD : OS2S_OUT_BF16, 0, red,
-                     (cudaStream_t)stream, a, y, 1.f / keep, f16, (dtypes & OS2S_CONV_F32) ? 1 : 0);
+                     (cudaStream_t)stream, a, y, 1.f / keep, f16, (dtypes & OS2S_CONV_F32) ? 1 : 0, row_lens, 0);
 }
 int os2s_conv1d_dgrad_bnred(const void* dy, const void* w, void* dx, int B, int T, int C_in, int C_out,
                             int K, int dil, int pad_left, const void* a, const void* y, float keep, float* red,
                             void* stream) {
-  return os2s_conv1d_dgrad_bnred_p(dy, w, dx, B, T, C_in, C_out, K, dil, pad_left, a, y, keep, red, 0, stream);
+  return os2s_conv1d_dgrad_bnred_p(dy, w, dx, B, T, C_in, C_out, K, dil, pad_left, a, y, keep, red, nullptr, 0, stream);
 }
 
 int os2s_conv1d_wgrad_p(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out,
-                        int K, int dil, int pad_left, int dtypes, void* stream) {
+                        int K, int dil, int pad_left, const int* row_lens, int dtypes, void* stream) {
   if (!x || !dy || !dw) return fail(ERR_INVALID, "os2s_conv1d_wgrad: null pointer");
   return conv_wgrad(x, dy, dw, B, T, C_in, C_out, K, dil, pad_left, nullptr, (cudaStream_t)stream,
-                    (dtypes & OS2S_HALF_F16) ? 1 : 0);
+                    (dtypes & OS2S_HALF_F16) ? 1 : 0, row_lens);
 }
 int os2s_conv1d_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out,
                       int K, int dil, int pad_left, void* stream) {
-  return os2s_conv1d_wgrad_p(x, dy, dw, B, T, C_in, C_out, K, dil, pad_left, 0, stream);
+  return os2s_conv1d_wgrad_p(x, dy, dw, B, T, C_in, C_out, K, dil, pad_left, nullptr, 0, stream);
 }
 
 int os2s_weight_cast_transpose_p(const float* w_master, void* w_half, void* wt_half, int K, int C_in,

@@ -59,6 +59,12 @@ struct KMajorParams {
   int bwd_y_f32;
   int a_bf16;                  // format of BOTH tensor-core operands: 1 = bf16, 0 = fp16 (tcgen05 kind::f16
                                // rejects mixed operand formats: an illegal-instruction fault on sm_100a)
+  // Length-aware tile skipping: rows t >= row_lens[b] of the activation operand are zero (the conv mask of
+  // tdnn_encoder.py:185-186,204-205 / the zero padding of the batch), so an output tile that starts at
+  // t0 >= row_lens[b] + skip_margin is exactly zero (forward: margin = pad_left) or is never read ungated
+  // (data gradient: margin = 0) and is not computed.  nullptr = compute every tile.
+  const int* row_lens;
+  int skip_margin;
   int halo_rows, halo_off, sb_stages;  // halo variant: rows of the A halo tile, row offset of tap 0, B ring depth
   void* out;
   long long out_row_stride;    // elements
@@ -347,6 +353,7 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int rem = tile - nt * tiles_per_n;
         const int b = rem / p.n_mtiles;
         const int t0 = (rem - b * p.n_mtiles) * kTileM;
+        if (p.row_lens && t0 >= __ldg(p.row_lens + b) + p.skip_margin) continue;   // all three roles skip alike
         const int n0 = nt * BN;
         const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
         // chunk-major, taps inner: consecutive stages read overlapping activation rows (L2 hits) and
@@ -379,7 +386,12 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (elect_one()) {
       PipeState ps;
       uint32_t ti = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (p.row_lens) {
+          const int rem = tile % tiles_per_n;
+          const int b = rem / p.n_mtiles;
+          if ((rem - b * p.n_mtiles) * kTileM >= __ldg(p.row_lens + b) + p.skip_margin) continue;
+        }
         const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
         const uint32_t idesc = make_idesc(kTileM, ncur, 0, BMN ? 1 : 0, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
@@ -403,6 +415,7 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (it == n_iters - 1) umma_commit(&tfull_bar[as]);
           ps.advance<S>();
         }
+        ++ti;
       }
     }
   } else {
@@ -432,10 +445,11 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
     };
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int nt = tile / tiles_per_n;
       const int rem = tile - nt * tiles_per_n;
       const int b = rem / p.n_mtiles;
+      if (p.row_lens && (rem - b * p.n_mtiles) * kTileM >= __ldg(p.row_lens + b) + p.skip_margin) continue;
       const int t0w = (rem - b * p.n_mtiles) * kTileM + quad * 32;  // first row of this warp
       const int n0 = nt * BN;
       const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
@@ -450,6 +464,7 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       epilogue_rows<BN>(p, stage, sacc, do_stats, two_byte, taddr, nvalid, off, ncur, lane);
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
+      ++ti;
     }
     if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
   }
@@ -460,6 +475,31 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ forward / dgrad, CTA pairs
+// Block enumeration of the pair kernels: the 128-row blocks of the batch are numbered TIME-major
+// (blk = t_index * B + b) and paired two by two, so the two halves of a pair tile are the same time block of
+// two neighbouring utterances: T only quantises to 128 rows (T = 832: 7 blocks per utterance, not 4 x 256), and
+// the tail blocks of short utterances pair up with each other (the data layer sorts a batch by length), which is
+// what lets whole pair tiles be skipped.
+__device__ __forceinline__ void pair_block(const KMajorParams& p, int blk, int n_blocks, int& b, int& t0) {
+  blk = min(blk, n_blocks - 1);
+  const int tix = blk / p.B;
+  b = blk - tix * p.B;
+  t0 = tix * kTileM;
+}
+// true when neither half of pair `rem` has anything to compute (see KMajorParams::row_lens)
+__device__ __forceinline__ bool pair_skip(const KMajorParams& p, int rem, int n_blocks) {
+  if (p.row_lens == nullptr) return false;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int blk = 2 * rem + h;
+    if (blk < n_blocks) {
+      int b, t0;
+      pair_block(p, blk, n_blocks, b, t0);
+      if (t0 < __ldg(p.row_lens + b) + p.skip_margin) return false;
+    }
+  }
+  return true;
+}
 // Same computation as tapgemm_kmajor on a cluster of two CTAs (cta_group::2): the pair owns a
 // 256-row x BN output tile, each CTA stages ITS 128 activation rows and only HALF of the weight
 // tile; one tcgen05.mma.cta_group::2 (M = 256) issued by the leader reads A from both CTAs and the
@@ -515,10 +555,8 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // The two 128-row halves of a pair tile are independent row blocks (each CTA loads its own A rows): the
-  // 128-row blocks of the whole batch are enumerated utterance by utterance and paired two by two, so a
-  // pair may straddle two utterances and T only quantises to 128 rows (T = 832: 7 blocks per utterance,
-  // not 4 x 256).  An odd block count pads the last pair (its second CTA recomputes the last block, no store).
+  // The two 128-row halves of a pair tile are independent row blocks (each CTA loads its own A rows), see
+  // pair_block().  An odd block count pads the last pair (its second CTA recomputes the last block, no store).
   const int n_blk = (p.T_out + kTileM - 1) / kTileM;
   const int n_blocks = p.B * n_blk;
   const int tiles_per_n = (n_blocks + 1) >> 1;
@@ -533,9 +571,9 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
         const int nt = tile / tiles_per_n;
         const int rem = tile - nt * tiles_per_n;
-        const int blk = min(2 * rem + (int)rank, n_blocks - 1);
-        const int b = blk / n_blk;
-        const int t0 = (blk - b * n_blk) * kTileM;
+        if (pair_skip(p, rem, n_blocks)) continue;     // all roles of both CTAs skip alike
+        int b, t0;
+        pair_block(p, 2 * rem + (int)rank, n_blocks, b, t0);
         const int n0 = nt * BN;
         const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
         const int hcur = ncur / 2;                   // columns of B each CTA provides
@@ -567,7 +605,8 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (leader && elect_one()) {
       PipeState ps;
       uint32_t ti = 0;
-      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        if (pair_skip(p, tile % tiles_per_n, n_blocks)) continue;
         const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
         const uint32_t idesc = make_idesc(2 * kTileM, ncur, 0, BMN ? 1 : 0, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
@@ -590,6 +629,7 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (it == n_iters - 1) umma2_commit(&tfull_bar[as]);
           ps.advance<S>();
         }
+        ++ti;
       }
     }
   } else {
@@ -615,13 +655,15 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
     };
     uint32_t ti = 0;
-    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
       const int nt = tile / tiles_per_n;
       const int rem = tile - nt * tiles_per_n;
+      if (pair_skip(p, rem, n_blocks)) continue;
       const int blk = 2 * rem + (int)rank;
       const bool blk_ok = blk < n_blocks;
-      const int b = min(blk, n_blocks - 1) / n_blk;
-      const int t0w = (min(blk, n_blocks - 1) - b * n_blk) * kTileM + quad * 32;
+      int b, t0w;
+      pair_block(p, blk, n_blocks, b, t0w);
+      t0w += quad * 32;
       const int n0 = nt * BN;
       const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
       if (do_stats && cur_nt >= 0 && nt != cur_nt) flush_stats(cur_nt);
@@ -637,6 +679,7 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tc_fence_before();
       if (leader) mbar_arrive(&tempty_bar[as]);
       else mbar_arrive_cluster(&tempty_bar[as], 0);
+      ++ti;
     }
     if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
   }
@@ -722,9 +765,9 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
       for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
         const int nt = tile / tiles_per_n;
         const int rem = tile - nt * tiles_per_n;
-        const int blk = min(2 * rem + (int)rank, n_blocks - 1);
-        const int b = blk / n_blk;
-        const int t0 = (blk - b * n_blk) * kTileM;
+        if (pair_skip(p, rem, n_blocks)) continue;     // all roles of both CTAs skip alike
+        int b, t0;
+        pair_block(p, 2 * rem + (int)rank, n_blocks, b, t0);
         const int n0 = nt * BN;
         const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
         const int hcur = ncur / 2;
@@ -759,7 +802,8 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
     if (leader && elect_one()) {
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
       uint32_t ti = 0;
-      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        if (pair_skip(p, tile % tiles_per_n, n_blocks)) continue;
         const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
         const uint32_t idesc = make_idesc(2 * kTileM, ncur, 0, BMN ? 1 : 0, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
@@ -789,6 +833,7 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
           if (++sa == SA) { sa = 0; pha ^= 1; }
         }
         umma2_commit(&tfull_bar[as]);
+        ++ti;
       }
     }
   } else {
@@ -813,13 +858,15 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
     };
     uint32_t ti = 0;
-    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++ti) {
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
       const int nt = tile / tiles_per_n;
       const int rem = tile - nt * tiles_per_n;
+      if (pair_skip(p, rem, n_blocks)) continue;
       const int blk = 2 * rem + (int)rank;
       const bool blk_ok = blk < n_blocks;
-      const int b = min(blk, n_blocks - 1) / n_blk;
-      const int t0w = (min(blk, n_blocks - 1) - b * n_blk) * kTileM + quad * 32;
+      int b, t0w;
+      pair_block(p, blk, n_blocks, b, t0w);
+      t0w += quad * 32;
       const int n0 = nt * BN;
       const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
       if (do_stats && cur_nt >= 0 && nt != cur_nt) flush_stats(cur_nt);
@@ -835,6 +882,7 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
       tc_fence_before();
       if (leader) mbar_arrive(&tempty_bar[as]);
       else mbar_arrive_cluster(&tempty_bar[as], 0);
+      ++ti;
     }
     if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
   }
@@ -855,7 +903,16 @@ struct MNMajorParams {
   int C_in, C_out;
   int m_off;                   // first C_in row of this launch
   int a_bf16;                  // format of x AND dy: 1 = bf16, 0 = fp16
+  const int* row_lens;         // rows t >= row_lens[b] of x are zero: 64-row chunks past row_lens[b] + pad_left add nothing
 };
+
+// 64-row time chunks of utterance b that can contribute to the weight gradient: x[t - pad + k*dil] is zero for
+// every tap once t >= row_lens[b] + pad_left (at least one chunk, so every segment issues an MMA)
+__device__ __forceinline__ int wgrad_chunks(const MNMajorParams& p, int b) {
+  if (p.row_lens == nullptr) return p.t_chunks;
+  const int rows = __ldg(p.row_lens + b) + p.pad_left;
+  return max(1, min(p.t_chunks, (rows + 63) >> 6));
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -932,7 +989,8 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const int tsh = k * p.dil - p.pad_left;
         const int ncur = (ni == p.n_tiles - 1) ? p.n_tail : BN;
         for (int b = b_lo; b < b_hi; ++b) {
-          for (int tc = 0; tc < p.t_chunks; ++tc) {
+          const int tcn = wgrad_chunks(p, b);
+          for (int tc = 0; tc < tcn; ++tc) {
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
             mbar_expect_tx(&full_bar[ps.stage], kABytes + ncur * kChunkK * 2);
             uint8_t* sa = smem_a + ps.stage * kABytes;
@@ -959,12 +1017,13 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         next_segment(it, unit, b_lo, b_hi);
         decode(unit, k_, mi_, ni_);
         const uint32_t idesc = make_idesc(kTileM, (ni_ == p.n_tiles - 1) ? p.n_tail : BN, 1, 1, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
-        const int n_iters = (b_hi - b_lo) * p.t_chunks;
+        int n_iters = 0;
+        for (int b = b_lo; b < b_hi; ++b) n_iters += wgrad_chunks(p, b);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        int tc = 0;
+        int tc = 0, bcur = b_lo, tcn = wgrad_chunks(p, b_lo);
         for (int i = 0; i < n_iters; ++i) {
           mbar_wait(&full_bar[ps.stage], ps.phase);
           tc_fence_after();
@@ -973,7 +1032,10 @@ tapgemm_mnmajor(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           // the last time chunk of an utterance holds T - 64*tc real rows (dY beyond T is zero-filled):
           // 16-row MMA steps that are all padding are skipped (T = 752: 3 of 4 steps, -2 % MMA work)
           const int kk_n = (tc == p.t_chunks - 1) ? (p.T - tc * 64 + 15) >> 4 : 4;
-          if (++tc == p.t_chunks) tc = 0;
+          if (++tc == tcn) {
+            tc = 0;
+            if (++bcur < b_hi) tcn = wgrad_chunks(p, bcur);
+          }
 #pragma unroll
           for (int kk = 0; kk < 64 / 16; ++kk) {
             if (kk >= kk_n) break;
@@ -1125,7 +1187,8 @@ tapgemm_mnmajor_pair(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int n0 = ni * BN + (int)rank * hcur;
         const uint32_t my_bytes = kABytes + hcur * kChunkK * 2;
         for (int b = b_lo; b < b_hi; ++b) {
-          for (int tc = 0; tc < p.t_chunks; ++tc) {
+          const int tcn = wgrad_chunks(p, b);
+          for (int tc = 0; tc < tcn; ++tc) {
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
             if (leader) mbar_expect_tx(&full_bar[ps.stage], 2 * my_bytes);
             uint8_t* sa = smem_a + ps.stage * kABytes;
@@ -1152,19 +1215,23 @@ tapgemm_mnmajor_pair(const __grid_constant__ CUtensorMap map_x, const __grid_con
         next_segment(it, unit, b_lo, b_hi);
         decode(unit, k_, mi_, ni_);
         const uint32_t idesc = make_idesc(2 * kTileM, (ni_ == p.n_tiles - 1) ? p.n_tail : BN, 1, 1, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
-        const int n_iters = (b_hi - b_lo) * p.t_chunks;
+        int n_iters = 0;
+        for (int b = b_lo; b < b_hi; ++b) n_iters += wgrad_chunks(p, b);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        int tc = 0;
+        int tc = 0, bcur = b_lo, tcn = wgrad_chunks(p, b_lo);
         for (int i = 0; i < n_iters; ++i) {
           mbar_wait(&full_bar[ps.stage], ps.phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + ps.stage * kABytes);
           const uint32_t b_addr = smem_u32(smem_b + ps.stage * kBHalf);
           const int kk_n = (tc == p.t_chunks - 1) ? (p.T - tc * 64 + 15) >> 4 : 4;  // skip all-padding steps
-          if (++tc == p.t_chunks) tc = 0;
+          if (++tc == tcn) {
+            tc = 0;
+            if (++bcur < b_hi) tcn = wgrad_chunks(p, bcur);
+          }
 #pragma unroll
           for (int kk = 0; kk < 64 / 16; ++kk) {
             if (kk >= kk_n) break;
@@ -1461,7 +1528,8 @@ static int pick_bn_mnmajor(int n) {
 //   out    : [B, T, N_total]  (bf16, or fp32 with optional accumulate)
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
                 int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st,
-                const void* bwd_a, const void* bwd_y, float bwd_inv_keep, int act_f16, int bwd_y_f32) {
+                const void* bwd_a, const void* bwd_y, float bwd_inv_keep, int act_f16, int bwd_y_f32,
+                const int* row_lens, int skip_margin) {
   if (C_red % 64 != 0) return fail(ERR_UNSUPPORTED, "conv_tc: reduction channels must be a multiple of 64");
   // pairs: 256-wide tiles whose last tile is 128 or 256 wide (each CTA stages half of it)
   // (N = 256 is one tile wide: 96 pair tiles over 74 SM pairs quantise worse than 128-wide single tiles)
@@ -1501,6 +1569,8 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
   p.bwd_inv_keep = bwd_inv_keep;
   p.bwd_y_f32 = bwd_y_f32;
   p.a_bf16 = act_f16 ? 0 : 1;
+  p.row_lens = row_lens;
+  p.skip_margin = skip_margin;
   p.out = out;
   p.out_row_stride = N_total;
   p.out_batch_stride = (long long)T * N_total;
@@ -1537,7 +1607,7 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
 // wgrad: dw[K][C_in][C_out] (fp32) += X^T * dY per tap. dw must be zeroed by the caller when
 // splits > 1 (the kernel reduces with red.global.add); with splits == 1 it is overwritten.
 int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out, int K,
-               int dil, int pad_left, int* splits_used, cudaStream_t st, int x_f16) {
+               int dil, int pad_left, int* splits_used, cudaStream_t st, int x_f16, const int* row_lens) {
   if (C_in % 128 != 0) return fail(ERR_UNSUPPORTED, "conv_wgrad: C_in must be a multiple of 128");
   const int BN = pick_bn_mnmajor(C_out);
   if (BN == 0) return fail(ERR_UNSUPPORTED, "conv_wgrad: C_out must be a multiple of 64");
@@ -1564,6 +1634,7 @@ int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in,
   p.C_out = C_out;
   p.m_off = 0;
   p.a_bf16 = x_f16 ? 0 : 1;
+  p.row_lens = row_lens;
   // stream-K: every CTA gets an equal share of (unit, utterance) items; tiles shared between CTAs are
   // reduced with red.add into the zeroed gradient (a plain store is used when a CTA owns a whole unit)
   if (splits_used) *splits_used = 0;

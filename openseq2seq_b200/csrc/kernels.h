@@ -19,9 +19,9 @@ int conv_grid_waves_set(int waves);
 int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int C_red, int N_total,
                 int K, int t_off0, int t_step, int out_mode, int b_mn_major, float* stats, cudaStream_t st,
                 const void* bwd_a = nullptr, const void* bwd_y = nullptr, float bwd_inv_keep = 1.f,
-                int act_f16 = 0, int bwd_y_f32 = 0);
+                int act_f16 = 0, int bwd_y_f32 = 0, const int* row_lens = nullptr, int skip_margin = 0);
 int conv_wgrad(const void* x, const void* dy, float* dw, int B, int T, int C_in, int C_out, int K,
-               int dil, int pad_left, int* splits_used, cudaStream_t st, int x_f16 = 0);
+               int dil, int pad_left, int* splits_used, cudaStream_t st, int x_f16 = 0, const int* row_lens = nullptr);
 
 // elementwise.cu
 int weight_cast_transpose(const float* w, void* w_bf16, void* wt_bf16, int K, int C_in, int C_out,

@@ -487,9 +487,9 @@ class JasperEngine(object):
 
     def _kernel_geom(self, s):
         lyr = s["layer"]
-        if lyr is not None and s["name"] == lyr.wname:
-            return lyr.kK, lyr.kC_in, lyr.c_out
-        return s["phys"]
+        if lyr is not None and s["name"] == lyr.wname and not (lyr.sep and lyr.sep_mode == "split"):
+            return lyr.kK, lyr.kC_in, lyr.c_out      # (the folded stride-2 layer: K' taps over 2 C_in channels)
+        return s["phys"]                             # pointwise / residual kernels: K = 1
 
     # ----------------------------------------------------------------- optimizer
     def set_optimizer(self, algo="novograd", beta1=0.95, beta2=0.98, epsilon=1e-8, weight_decay=0.0,
@@ -899,7 +899,9 @@ class _Workspace(object):
         nl = len(layers)
         # conv outputs (BN inputs) are fp16 (never a tensor-core operand, 3 more mantissa bits than bf16) or
         # fp32 (conv_dtype); layer outputs are bf16 or fp16 (act_dtype)
-        f16 = lambda *shape: torch.empty(*shape, dtype=eng.conv_torch, device=dev)
+        # (zeros: a skipped forward tile leaves its rows untouched, and the BN-backward sums multiply those rows by
+        # exact zeros -- they must never hold the NaN bit patterns of uninitialised memory)
+        f16 = lambda *shape: torch.zeros(*shape, dtype=eng.conv_torch, device=dev)
         act = lambda *shape: torch.empty(*shape, dtype=eng.act_torch, device=dev)
         self.Y = [f16(B, T2, l.c_out) for l in layers]
         self.A = [act(B, T2, l.c_out) for l in layers]
@@ -991,6 +993,11 @@ class _Workspace(object):
         vparr = lambda ptrs: (ctypes.c_void_p * len(ptrs))(*[p.value if isinstance(p, _vp) else p for p in ptrs])
         iarr = lambda xs: (ctypes.c_int * len(xs))(*xs)
         llarr = lambda xs: (ctypes.c_longlong * len(xs))(*xs)
+        # length-aware tile skipping (include/os2s.h, os2s_conv1d_fwd_p): only with the conv mask, which is what
+        # makes every layer input zero past the utterance's length (OS2S_SKIP_TILES=0 computes every tile)
+        self.skip_tiles = eng.use_conv_mask and os.environ.get("OS2S_SKIP_TILES", "1") != "0"
+        rl = self._p(self.lens_out) if self.skip_tiles else _vp(0)
+        nl_ = len(eng.layers)
         # (0) sep_conv1d: form the composed dense kernels D[k,c] * P[c,o] from the fp32 masters
         for sp_ in eng.specs:
             if sp_["name"].endswith("@composed"):
@@ -1022,7 +1029,7 @@ class _Workspace(object):
                     stats_ptr = self._p(self.stats_cat[j]) if eng.training else _vp(0)
                     plan.append([lib.os2s_conv1d_fwd_p, [x_ptr, self._p(eng.wcat[j]), self._p(self.YRcat[j]), B, T2,
                                                          g["cj"], g["ntot"], 1, 1, 0, eng.conv_out_mode, stats_ptr,
-                                                         eng.dtypes, st],
+                                                         rl, eng.dtypes, st],
                                  ("fwd", 2.0 * B * T2 * g["cj"] * g["ntot"])])
             flops = 2.0 * B * T2 * l.K * l.c_in * l.c_out  # algorithmic (un-folded) FLOPs
             slot_main = bn_idx
@@ -1037,12 +1044,13 @@ class _Workspace(object):
                              ("hbm:depthwise", float(M) * l.c_in * 4)])
                 call = [lib.os2s_conv1d_fwd_p, [self._p(self.Z[li]), self._half_ptr(eng.wb, l.wname), self._p(self.Y[li]),
                                                 B, T2, l.c_in, l.c_out, 1, 1, 0, eng.conv_out_mode, stats_ptr,
-                                                eng.dtypes, st],
+                                                _vp(0), eng.dtypes, st],
                         ("fwd", 2.0 * B * T2 * l.c_in * l.c_out)]
             else:
                 call = [lib.os2s_conv1d_fwd_p, [x_ptr, self._half_ptr(eng.wb, l.wname), self._p(self.Y[li]),
                                                 B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, eng.conv_out_mode, stats_ptr,
-                                                eng.dtypes, st],
+                                                # the last layer's output is not masked: every row of it is defined
+                                                rl if li < nl_ - 1 else _vp(0), eng.dtypes, st],
                         ("fwd", flops)]
             plan.append(call)
             ys, lds = [self._p(self.Y[li])], [l.c_out]
@@ -1094,10 +1102,14 @@ class _Workspace(object):
     def set_targets(self, labels, label_lens):
         L_max = int(labels.shape[1])
         L_cap = max(32, -(-L_max // 32) * 32)  # bucket label capacity so plans / graphs are reused
-        if self._bwd_plan is None or self._bwd_L != L_cap:
+        if self._bwd_plan is None or L_cap > self._bwd_L:
+            # the capacity only grows (label_lens carries the real lengths): batches whose longest transcript
+            # differs do not rebuild the plan / re-capture the graph
             self._build_backward_plan(L_cap)
             self.graph = None
             self._eager_steps = 0
+        elif L_max < self._bwd_L:
+            self.labels[:, L_max:].zero_()
         self.labels[:, :L_max].copy_(labels.to(torch.int32), non_blocking=True)
         self.label_lens.copy_(label_lens.to(torch.int32), non_blocking=True)
 
@@ -1181,6 +1193,7 @@ class _Workspace(object):
                                          self._param_ptr(eng.grad, "fc/kernel"), self._param_ptr(eng.grad, "fc/bias"),
                                          M, eng.H, eng.V, eng.dtypes, st]])
         nl = len(eng.layers)
+        rl = self._p(self.lens_out) if self.skip_tiles else _vp(0)
         if self.fused_red:
             plan.append([_ZeroMain(self.red_all), []])
         bucket_end = eng._total          # gradients in [bucket_start, bucket_end) are final once enqueued
@@ -1242,14 +1255,14 @@ class _Workspace(object):
                 # of the fp32 accumulator; the main-path gradient below adds to it)
                 plan.append([lib.os2s_conv1d_dgrad_p, [self._p(self.dYRcat[src_j]), self._p(eng.wcat[src_j]),
                                                        self._p(self.dres[src_j]), B, T2, g["cj"], g["ntot"], 1, 1, 0, 1,
-                                                       eng.dtypes, st], ("dgrad", 2.0 * B * T2 * g["cj"] * g["ntot"])])
+                                                       rl, eng.dtypes, st], ("dgrad", 2.0 * B * T2 * g["cj"] * g["ntot"])])
             split = l.sep and l.sep_mode == "split"
             dZ = self.dZ2[par] if split else None
             ev_dz = None
             if split:
                 # pointwise data gradient dZ = dY . P^T (tcgen05), then the depthwise data gradient (flipped taps)
                 plan.append([lib.os2s_conv1d_dgrad_p, [self._p(dY), self._half_ptr(eng.wb, l.wname), self._p(dZ), B, T2,
-                                                       l.c_in, l.c_out, 1, 1, 0, eng.grad_out_mode, eng.dtypes, st],
+                                                       l.c_in, l.c_out, 1, 1, 0, eng.grad_out_mode, _vp(0), eng.dtypes, st],
                              ("dgrad", 2.0 * B * T2 * l.c_in * l.c_out)])
                 ev_dz = torch.cuda.Event()
                 plan.append([_StreamRecord(self, "main", ev_dz), []])   # the depthwise weight gradient (aux) reads dZ
@@ -1273,12 +1286,12 @@ class _Workspace(object):
                     plan.append([lib.os2s_conv1d_dgrad_bnred_p,
                                  [self._p(dY), self._half_ptr(eng.wb, l.wname), out_ptr, B, T2, l.kC_in,
                                   l.c_out, l.kK, l.dil, l.kpad, self._p(self.A[li - 1]), self._p(self.Y[li - 1]),
-                                  _c_float(lp.keep), self._p(self.fused_red[li - 1]), eng.dtypes, st],
+                                  _c_float(lp.keep), self._p(self.fused_red[li - 1]), rl, eng.dtypes, st],
                                  ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
                 else:
                     plan.append([lib.os2s_conv1d_dgrad_p, [self._p(dY), self._half_ptr(eng.wb, l.wname),
                                                            out_ptr, B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, mode,
-                                                           eng.dtypes, st],
+                                                           rl, eng.dtypes, st],
                                  ("dgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
             # ---- aux stream: weight gradients of this layer (enqueued after the critical-path kernels)
             plan.append([_StreamWait(self, "aux", ev_bn[li]), []])
@@ -1286,7 +1299,7 @@ class _Workspace(object):
             x_ptr = self._p(self.A[li - 1]) if li > 0 else self._p(self.feats)
             if split:
                 plan.append([lib.os2s_conv1d_wgrad_p, [self._p(self.Z[li]), self._p(dY), self._param_ptr(eng.grad, l.wname),
-                                                       B, T2, l.c_in, l.c_out, 1, 1, 0, eng.dtypes, sa],
+                                                       B, T2, l.c_in, l.c_out, 1, 1, 0, _vp(0), eng.dtypes, sa],
                              ("wgrad", 2.0 * B * T2 * l.c_in * l.c_out)])
                 plan.append([_StreamWait(self, "aux", ev_dz), []])
                 plan.append([lib.os2s_depthwise_conv1d_wgrad,
@@ -1294,7 +1307,7 @@ class _Workspace(object):
                               l.c_in, l.K, l.dil, l.kpad, eng.dtypes, sa]])
             else:
                 plan.append([lib.os2s_conv1d_wgrad_p, [x_ptr, self._p(dY), self._param_ptr(eng.grad, l.wname),
-                                                       B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, eng.dtypes, sa],
+                                                       B, T2, l.kC_in, l.c_out, l.kK, l.dil, l.kpad, rl, eng.dtypes, sa],
                              ("wgrad", 2.0 * B * T2 * l.K * l.c_in * l.c_out)])
             if l.fold:
                 # structurally-zero taps of the folded stride-2 kernel get no gradient
@@ -1315,7 +1328,7 @@ class _Workspace(object):
                 # scattered to the per-variable gradient buffers (which live in this layer's region)
                 g = eng.res_groups[src_j]
                 plan.append([lib.os2s_conv1d_wgrad_p, [x_ptr, self._p(self.dYRcat[src_j]), self._p(eng.dwcat[src_j]),
-                                                       B, T2, g["cj"], g["ntot"], 1, 1, 0, eng.dtypes, sa],
+                                                       B, T2, g["cj"], g["ntot"], 1, 1, 0, rl, eng.dtypes, sa],
                              ("wgrad", 2.0 * B * T2 * g["cj"] * g["ntot"])])
                 src, dst, rows, rbytes, sp, dp = [], [], [], [], [], []
                 for (lc, n, cb, col) in g["consumers"]:
@@ -1386,7 +1399,9 @@ class _Workspace(object):
             if self._eager_steps >= 2:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # thread_local: the data layer's producer thread keeps allocating / synchronising events on its
+                # side stream while this thread captures (the default "global" mode would invalidate the capture)
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self._step_body()
                 self.graph = g
                 g.replay()
