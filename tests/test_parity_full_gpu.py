@@ -348,9 +348,10 @@ def test_length_aware_tile_skipping_is_exact_on_a_very_ragged_batch(monkeypatch)
         outs[skip] = (got, grads)
         del eng
         torch.cuda.empty_cache()
-    (la, ga), (lb, gb) = outs["1"], outs["0"]
+    # the two runs agree with each other on the logits (their gradients were each checked against the oracle at
+    # their OWN forward state: across two forward passes a ReLU network's gradient moves by the gate flips that
+    # last-bit differences of the fp32 statistics atomics cause, see tests/test_engine_gpu.py)
+    (la, _), (lb, _) = outs["1"], outs["0"]
     for b in range(B):
         n = int(ref_len[b])
-        assert _rel_l2(la[b, :n], lb[b, :n]) < 5e-3, b       # bf16 re-rounding of values that differ in the last fp32 bits
-    bad = {k: round(_rel_l2(ga[k], gb[k]), 5) for k in ga if _rel_l2(ga[k], gb[k]) > 2e-2}
-    assert not bad, bad
+        assert _rel_l2(la[b, :n], lb[b, :n]) < 5e-3, b
