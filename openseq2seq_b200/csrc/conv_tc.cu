@@ -31,7 +31,9 @@
 //   warps 2-5 : epilogue, TMEM -> registers -> global; the accumulator is double buffered in TMEM so
 //   the epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.h"
+#include <algorithm>
 #include <cstdlib>
+#include <vector>
 #include "ptx.cuh"
 
 namespace os2s {
@@ -65,6 +67,13 @@ struct KMajorParams {
   // (data gradient: margin = 0) and is not computed.  nullptr = compute every tile.
   const int* row_lens;
   int skip_margin;
+  // Tile schedule: sched[row * sched_stride + i] = (M unit, first column n0, width ncur, -) of the i-th tile of
+  // CTA (or CTA pair) `row`, x < 0 terminates.  Built on the host (build_schedule): longest-processing-time
+  // assignment of the tiles to the persistent CTAs, with 256-wide tiles split into 128-wide halves where that
+  // shortens the makespan -- a static round robin leaves SMs idle for up to a whole tile (T = 832: tensor pipe
+  // 52 % .. 93 % across the SMs, profiles/r02_ncu_conv_halo_summary.json).
+  const int4* sched;
+  int sched_stride;
   int halo_rows, halo_off, sb_stages;  // halo variant: rows of the A halo tile, row offset of tap 0, B ring depth
   void* out;
   long long out_row_stride;    // elements
@@ -341,21 +350,19 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int tiles_per_n = p.B * p.n_mtiles;
-  const int n_tiles = tiles_per_n * p.n_ntiles;
   const int n_iters = p.K_taps * p.c_chunks;
+  const int4* sched = p.sched + (size_t)blockIdx.x * p.sched_stride;
 
   if (warp == 0) {
     if (elect_one()) {
       PipeState ps;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int nt = tile / tiles_per_n;
-        const int rem = tile - nt * tiles_per_n;
+      for (int si = 0;; ++si) {
+        const int4 se = __ldg(sched + si);
+        if (se.x < 0) break;
+        const int rem = se.x, n0 = se.y, ncur = se.z;
         const int b = rem / p.n_mtiles;
         const int t0 = (rem - b * p.n_mtiles) * kTileM;
         if (p.row_lens && t0 >= __ldg(p.row_lens + b) + p.skip_margin) continue;   // all three roles skip alike
-        const int n0 = nt * BN;
-        const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
         // chunk-major, taps inner: consecutive stages read overlapping activation rows (L2 hits) and
         // every variant of the kernel accumulates in the same order (bitwise-identical outputs)
         for (int c = 0; c < p.c_chunks; ++c) {
@@ -386,13 +393,15 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (elect_one()) {
       PipeState ps;
       uint32_t ti = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int si = 0;; ++si) {
+        const int4 se = __ldg(sched + si);
+        if (se.x < 0) break;
+        const int ncur = se.z;
         if (p.row_lens) {
-          const int rem = tile % tiles_per_n;
+          const int rem = se.x;
           const int b = rem / p.n_mtiles;
           if ((rem - b * p.n_mtiles) * kTileM >= __ldg(p.row_lens + b) + p.skip_margin) continue;
         }
-        const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
         const uint32_t idesc = make_idesc(kTileM, ncur, 0, BMN ? 1 : 0, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -430,31 +439,30 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool do_stats = (p.stats != nullptr) && (two_byte || p.out_mode == OUT_F32);
     if (do_stats)
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
-    int cur_nt = -1;
-    auto flush_stats = [&](int nt) {
+    int cur_n0 = -1, cur_w = 0;
+    auto flush_stats = [&](int n0f, int width) {
       // all four epilogue warps reach this point for the same tile sequence
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int tid = threadIdx.x - 64;  // 0..127
-      const int width = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
       for (int i = tid; i < 2 * BN; i += 128) {
         const float v = epi_stats[i] + epi_stats[2 * BN + i] + epi_stats[4 * BN + i] + epi_stats[6 * BN + i];
         const int which = i / BN, col = i - which * BN;
-        if (col < width) atomicAdd(&p.stats[(size_t)which * p.N_total + nt * BN + col], v);
+        if (col < width) atomicAdd(&p.stats[(size_t)which * p.N_total + n0f + col], v);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
     };
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int nt = tile / tiles_per_n;
-      const int rem = tile - nt * tiles_per_n;
+    for (int si = 0;; ++si) {
+      const int4 se = __ldg(sched + si);
+      if (se.x < 0) break;
+      const int rem = se.x, n0 = se.y, ncur = se.z;
       const int b = rem / p.n_mtiles;
       if (p.row_lens && (rem - b * p.n_mtiles) * kTileM >= __ldg(p.row_lens + b) + p.skip_margin) continue;
       const int t0w = (rem - b * p.n_mtiles) * kTileM + quad * 32;  // first row of this warp
-      const int n0 = nt * BN;
-      const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
-      if (do_stats && cur_nt >= 0 && nt != cur_nt) flush_stats(cur_nt);
-      cur_nt = nt;
+      if (do_stats && cur_n0 >= 0 && (n0 != cur_n0 || ncur != cur_w)) flush_stats(cur_n0, cur_w);
+      cur_n0 = n0;
+      cur_w = ncur;
       const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -466,7 +474,7 @@ tapgemm_kmajor(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_arrive(&tempty_bar[as]);
       ++ti;
     }
-    if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
+    if (do_stats && cur_n0 >= 0) flush_stats(cur_n0, cur_w);
   }
 
   tc_fence_before();
@@ -559,23 +567,20 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   // pair_block().  An odd block count pads the last pair (its second CTA recomputes the last block, no store).
   const int n_blk = (p.T_out + kTileM - 1) / kTileM;
   const int n_blocks = p.B * n_blk;
-  const int tiles_per_n = (n_blocks + 1) >> 1;
-  const int n_tiles = tiles_per_n * p.n_ntiles;
   const int n_iters = p.K_taps * p.c_chunks;
   const int cluster_id = blockIdx.x >> 1;
-  const int n_clusters = gridDim.x >> 1;
+  const int4* sched = p.sched + (size_t)cluster_id * p.sched_stride;
 
   if (warp == 0) {
     if (elect_one()) {
       PipeState ps;
-      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-        const int nt = tile / tiles_per_n;
-        const int rem = tile - nt * tiles_per_n;
+      for (int si = 0;; ++si) {
+        const int4 se = __ldg(sched + si);
+        if (se.x < 0) break;
+        const int rem = se.x, n0 = se.y, ncur = se.z;
         if (pair_skip(p, rem, n_blocks)) continue;     // all roles of both CTAs skip alike
         int b, t0;
         pair_block(p, 2 * rem + (int)rank, n_blocks, b, t0);
-        const int n0 = nt * BN;
-        const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
         const int hcur = ncur / 2;                   // columns of B each CTA provides
         for (int c = 0; c < p.c_chunks; ++c) {
           for (int k = 0; k < p.K_taps; ++k) {
@@ -605,9 +610,11 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (leader && elect_one()) {
       PipeState ps;
       uint32_t ti = 0;
-      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-        if (pair_skip(p, tile % tiles_per_n, n_blocks)) continue;
-        const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
+      for (int si = 0;; ++si) {
+        const int4 se = __ldg(sched + si);
+        if (se.x < 0) break;
+        if (pair_skip(p, se.x, n_blocks)) continue;
+        const int ncur = se.z;
         const uint32_t idesc = make_idesc(2 * kTileM, ncur, 0, BMN ? 1 : 0, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -641,33 +648,32 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const bool do_stats = (p.stats != nullptr) && (two_byte || p.out_mode == OUT_F32);
     if (do_stats)
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
-    int cur_nt = -1;
-    auto flush_stats = [&](int nt) {
+    int cur_n0 = -1, cur_w = 0;
+    auto flush_stats = [&](int n0f, int width) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int tid = threadIdx.x - 64;
-      const int width = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
       for (int i = tid; i < 2 * BN; i += 128) {
         const float v = epi_stats[i] + epi_stats[2 * BN + i] + epi_stats[4 * BN + i] + epi_stats[6 * BN + i];
         const int which = i / BN, col = i - which * BN;
-        if (col < width) atomicAdd(&p.stats[(size_t)which * p.N_total + nt * BN + col], v);
+        if (col < width) atomicAdd(&p.stats[(size_t)which * p.N_total + n0f + col], v);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
     };
     uint32_t ti = 0;
-    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-      const int nt = tile / tiles_per_n;
-      const int rem = tile - nt * tiles_per_n;
+    for (int si = 0;; ++si) {
+      const int4 se = __ldg(sched + si);
+      if (se.x < 0) break;
+      const int rem = se.x, n0 = se.y, ncur = se.z;
       if (pair_skip(p, rem, n_blocks)) continue;
       const int blk = 2 * rem + (int)rank;
       const bool blk_ok = blk < n_blocks;
       int b, t0w;
       pair_block(p, blk, n_blocks, b, t0w);
       t0w += quad * 32;
-      const int n0 = nt * BN;
-      const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
-      if (do_stats && cur_nt >= 0 && nt != cur_nt) flush_stats(cur_nt);
-      cur_nt = nt;
+      if (do_stats && cur_n0 >= 0 && (n0 != cur_n0 || ncur != cur_w)) flush_stats(cur_n0, cur_w);
+      cur_n0 = n0;
+      cur_w = ncur;
       const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -681,7 +687,7 @@ tapgemm_kmajor_pair(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       else mbar_arrive_cluster(&tempty_bar[as], 0);
       ++ti;
     }
-    if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
+    if (do_stats && cur_n0 >= 0) flush_stats(cur_n0, cur_w);
   }
 
   tc_fence_before();
@@ -754,22 +760,19 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
 
   const int n_blk = (p.T_out + kTileM - 1) / kTileM;     // see tapgemm_kmajor_pair: pairs of 128-row blocks
   const int n_blocks = p.B * n_blk;
-  const int tiles_per_n = (n_blocks + 1) >> 1;
-  const int n_tiles = tiles_per_n * p.n_ntiles;
   const int cluster_id = blockIdx.x >> 1;
-  const int n_clusters = gridDim.x >> 1;
+  const int4* sched = p.sched + (size_t)cluster_id * p.sched_stride;
 
   if (warp == 0) {
     if (elect_one()) {
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
-      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-        const int nt = tile / tiles_per_n;
-        const int rem = tile - nt * tiles_per_n;
+      for (int si = 0;; ++si) {
+        const int4 se = __ldg(sched + si);
+        if (se.x < 0) break;
+        const int rem = se.x, n0 = se.y, ncur = se.z;
         if (pair_skip(p, rem, n_blocks)) continue;     // all roles of both CTAs skip alike
         int b, t0;
         pair_block(p, 2 * rem + (int)rank, n_blocks, b, t0);
-        const int n0 = nt * BN;
-        const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
         const int hcur = ncur / 2;
         const uint32_t b_bytes = BMN ? hcur * kChunkK * 2 : kBHalf;
         for (int c = 0; c < p.c_chunks; ++c) {
@@ -802,9 +805,11 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
     if (leader && elect_one()) {
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
       uint32_t ti = 0;
-      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-        if (pair_skip(p, tile % tiles_per_n, n_blocks)) continue;
-        const int ncur = (tile / tiles_per_n == p.n_ntiles - 1) ? p.n_tail : BN;
+      for (int si = 0;; ++si) {
+        const int4 se = __ldg(sched + si);
+        if (se.x < 0) break;
+        if (pair_skip(p, se.x, n_blocks)) continue;
+        const int ncur = se.z;
         const uint32_t idesc = make_idesc(2 * kTileM, ncur, 0, BMN ? 1 : 0, (uint32_t)p.a_bf16, (uint32_t)p.a_bf16);
         const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -844,33 +849,32 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
     const bool do_stats = (p.stats != nullptr) && (two_byte || p.out_mode == OUT_F32);
     if (do_stats)
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
-    int cur_nt = -1;
-    auto flush_stats = [&](int nt) {
+    int cur_n0 = -1, cur_w = 0;
+    auto flush_stats = [&](int n0f, int width) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int tid = threadIdx.x - 64;
-      const int width = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
       for (int i = tid; i < 2 * BN; i += 128) {
         const float v = epi_stats[i] + epi_stats[2 * BN + i] + epi_stats[4 * BN + i] + epi_stats[6 * BN + i];
         const int which = i / BN, col = i - which * BN;
-        if (col < width) atomicAdd(&p.stats[(size_t)which * p.N_total + nt * BN + col], v);
+        if (col < width) atomicAdd(&p.stats[(size_t)which * p.N_total + n0f + col], v);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int i = lane; i < 2 * BN; i += 32) sacc[i] = 0.f;
     };
     uint32_t ti = 0;
-    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-      const int nt = tile / tiles_per_n;
-      const int rem = tile - nt * tiles_per_n;
+    for (int si = 0;; ++si) {
+      const int4 se = __ldg(sched + si);
+      if (se.x < 0) break;
+      const int rem = se.x, n0 = se.y, ncur = se.z;
       if (pair_skip(p, rem, n_blocks)) continue;
       const int blk = 2 * rem + (int)rank;
       const bool blk_ok = blk < n_blocks;
       int b, t0w;
       pair_block(p, blk, n_blocks, b, t0w);
       t0w += quad * 32;
-      const int n0 = nt * BN;
-      const int ncur = (nt == p.n_ntiles - 1) ? p.n_tail : BN;
-      if (do_stats && cur_nt >= 0 && nt != cur_nt) flush_stats(cur_nt);
-      cur_nt = nt;
+      if (do_stats && cur_n0 >= 0 && (n0 != cur_n0 || ncur != cur_w)) flush_stats(cur_n0, cur_w);
+      cur_n0 = n0;
+      cur_w = ncur;
       const uint32_t as = ti & 1, aphase = (ti >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -884,7 +888,7 @@ tapgemm_kmajor_pair_halo(const __grid_constant__ CUtensorMap map_a, const __grid
       else mbar_arrive_cluster(&tempty_bar[as], 0);
       ++ti;
     }
-    if (do_stats && cur_nt >= 0) flush_stats(cur_nt);
+    if (do_stats && cur_n0 >= 0) flush_stats(cur_n0, cur_w);
   }
 
   tc_fence_before();
@@ -1328,9 +1332,7 @@ static int launch_kmajor(const CUtensorMap* ma, const CUtensorMap* mb, const KMa
     OS2S_CUDA(cudaFuncSetAttribute(tapgemm_kmajor<BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int tiles = p.B * p.n_mtiles * p.n_ntiles;
-  const int cap = device_sm_count() * conv_grid_waves();
-  const int grid = tiles < cap ? tiles : cap;
+  const int grid = p.n_ntiles;   // rows of the tile schedule (set by conv_kmajor)
   tapgemm_kmajor<BN, BMN><<<grid, kNumThreads, smem, st>>>(*ma, *mb, p);
   return check_launch("tapgemm_kmajor");
 }
@@ -1348,9 +1350,7 @@ static int launch_kmajor_pair(const CUtensorMap* ma, const CUtensorMap* mb, cons
                                    (int)smem));
     attr_done = true;
   }
-  const int ptiles = ((p.B * ((p.T_out + kTileM - 1) / kTileM) + 1) / 2) * p.n_ntiles;
-  const int pairs = (device_sm_count() / 2) * conv_grid_waves();
-  const int clusters = ptiles < pairs ? ptiles : pairs;
+  const int clusters = p.n_ntiles;   // rows of the tile schedule (set by conv_kmajor)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kNumThreads);
@@ -1383,9 +1383,7 @@ static int launch_kmajor_pair_halo(const CUtensorMap* ma, const CUtensorMap* mb,
                                    (int)(kSmemBudget + 4096)));
     attr_done = true;
   }
-  const int ptiles = ((p.B * ((p.T_out + kTileM - 1) / kTileM) + 1) / 2) * p.n_ntiles;
-  const int pairs = (device_sm_count() / 2) * conv_grid_waves();
-  const int clusters = ptiles < pairs ? ptiles : pairs;
+  const int clusters = p.n_ntiles;   // rows of the tile schedule (set by conv_kmajor)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kNumThreads);
@@ -1522,6 +1520,106 @@ static int pick_bn_mnmajor(int n) {
   return n >= 256 ? 256 : n >= 192 ? 192 : n >= 128 ? 128 : 64;
 }
 
+// ------------------------------------------------------------------ tile schedule (forward / dgrad)
+// Tiles = (M unit, n0, width); M unit = a 128-row block (single-CTA kernels) or a pair of blocks (pair kernels).
+// Every unit starts from the N tiling [BN, ..., BN, tail]; for the pair kernels a fraction of the units may have
+// their 256-wide tiles split into 128-wide halves.  Tiles are assigned to the G persistent CTAs (pairs) by
+// longest-processing-time-first, cost = width / width_eff(width); the split fraction with the smallest makespan
+// wins.  Rows are then ordered by (n0, unit) so that concurrent CTAs share weight tiles in L2 and the fused
+// BN-statistics flush stays rare.  Schedules are cached per shape (device memory, built outside graph capture).
+struct SchedEntry {
+  int kind, units, N, BN, G, gran;
+  int4* dev;
+  int stride, rows;
+};
+static const SchedEntry* get_schedule(int kind, int units, int N_total, int BN, int G_max, int gran) {
+  static SchedEntry cache[256];
+  static int n_cache = 0;
+  for (int i = 0; i < n_cache; ++i) {
+    const SchedEntry& e = cache[i];
+    if (e.kind == kind && e.units == units && e.N == N_total && e.BN == BN && e.G == G_max && e.gran == gran) return &e;
+  }
+  if (n_cache >= 256) {
+    fail(ERR_UNSUPPORTED, "conv_tc: schedule cache full");
+    return nullptr;
+  }
+  struct Tile { int unit, n0, w; float cost; };
+  const int nt = (N_total + BN - 1) / BN;
+  const int tail = N_total - (nt - 1) * BN;
+  auto cost_of = [](int w) { return (float)w / 256.f / width_eff(w); };
+  std::vector<Tile> best_tiles;
+  std::vector<int> best_owner;
+  int best_G = 0;
+  float best_span = 1e30f;
+  const int n_frac = (kind == 1 && BN == 256 && gran <= 128) ? 7 : 1;
+  const float fracs[7] = {0.f, 0.125f, 0.25f, 0.375f, 0.5f, 0.75f, 1.f};
+  for (int fi = 0; fi < n_frac; ++fi) {
+    const int n_split = (int)(fracs[fi] * units + 0.5f);
+    std::vector<Tile> tiles;
+    for (int u = 0; u < units; ++u) {
+      // split units are spread evenly over the unit range
+      const bool split = n_split > 0 && ((long long)u * n_split / units) != ((long long)(u + 1) * n_split / units);
+      for (int n = 0; n < nt; ++n) {
+        const int w = (n == nt - 1) ? tail : BN;
+        if (split && w == 256) {
+          tiles.push_back({u, n * BN, 128, cost_of(128)});
+          tiles.push_back({u, n * BN + 128, 128, cost_of(128)});
+        } else {
+          tiles.push_back({u, n * BN, w, cost_of(w)});
+        }
+      }
+    }
+    const int G = (int)tiles.size() < G_max ? (int)tiles.size() : G_max;
+    std::vector<int> order(tiles.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tiles[a].cost > tiles[b].cost; });
+    std::vector<float> load(G, 0.f);
+    std::vector<int> owner(tiles.size());
+    for (int idx : order) {
+      int g = 0;
+      for (int j = 1; j < G; ++j)
+        if (load[j] < load[g] - 1e-6f) g = j;
+      owner[idx] = g;
+      load[g] += tiles[idx].cost;
+    }
+    float span = 0.f;
+    for (float l : load) span = l > span ? l : span;
+    if (span < best_span * 0.99f) {   // prefer fewer splits on (near) ties
+      best_span = span;
+      best_tiles = tiles;
+      best_owner = owner;
+      best_G = G;
+    }
+  }
+  std::vector<std::vector<int>> rows(best_G);
+  for (size_t i = 0; i < best_tiles.size(); ++i) rows[best_owner[i]].push_back((int)i);
+  size_t longest = 0;
+  for (auto& r : rows) {
+    std::sort(r.begin(), r.end(), [&](int a, int b) {
+      const Tile &x = best_tiles[a], &y = best_tiles[b];
+      if (x.n0 != y.n0) return x.n0 < y.n0;
+      if (x.w != y.w) return x.w > y.w;
+      return x.unit < y.unit;
+    });
+    longest = r.size() > longest ? r.size() : longest;
+  }
+  const int stride = (int)longest + 1;
+  std::vector<int4> host((size_t)best_G * stride, make_int4(-1, 0, 0, 0));
+  for (int g = 0; g < best_G; ++g)
+    for (size_t i = 0; i < rows[g].size(); ++i) {
+      const Tile& t = best_tiles[rows[g][i]];
+      host[(size_t)g * stride + i] = make_int4(t.unit, t.n0, t.w, 0);
+    }
+  int4* dev = nullptr;
+  if (cudaMalloc(&dev, host.size() * sizeof(int4)) != cudaSuccess ||
+      cudaMemcpy(dev, host.data(), host.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) {
+    fail(ERR_CUDA, "conv_tc: cannot upload the tile schedule");
+    return nullptr;
+  }
+  cache[n_cache] = SchedEntry{kind, units, N_total, BN, G_max, gran, dev, stride, best_G};
+  return &cache[n_cache++];
+}
+
 // Shared driver for forward / dgrad.
 //   act    : [B, T, C_red] bf16   (conv input for forward, dY for dgrad)
 //   wmat   : [K][N_total][C_red] bf16 (C_red contiguous)
@@ -1556,8 +1654,16 @@ int conv_kmajor(const void* act, const void* wmat, void* out, int B, int T, int 
   p.B = B;
   p.T_out = T;
   p.n_mtiles = (T + kTileM - 1) / kTileM;
-  p.n_ntiles = (N_total + BN - 1) / BN;
-  p.n_tail = N_total - (p.n_ntiles - 1) * BN;
+  // tile schedule: M units = 128-row blocks (single CTA) or pairs of blocks (pair kernels)
+  const int n_blk_all = B * ((T + kTileM - 1) / kTileM);
+  const int units = pair ? (n_blk_all + 1) / 2 : n_blk_all;
+  const int G_max = (pair ? device_sm_count() / 2 : device_sm_count()) * conv_grid_waves();
+  const SchedEntry* sch = get_schedule(pair ? 1 : 0, units, N_total, BN, G_max, b_mn_major ? 64 : 16);
+  if (!sch) return ERR_CUDA;
+  p.sched = sch->dev;
+  p.sched_stride = sch->stride;
+  p.n_ntiles = sch->rows;            // grid size in CTAs (single) / clusters (pair)
+  p.n_tail = 0;
   p.N_total = N_total;
   p.K_taps = K;
   p.c_chunks = C_red / 64;
