@@ -127,7 +127,8 @@ class JasperEngine(object):
         self.step_count = 0
         self._ws = collections.OrderedDict()
         self._profile = None
-        self._suppress_comm = False
+        # OS2S_NO_COMM=1: timing diagnosis only -- the gradient all-reduce is not issued (ranks diverge)
+        self._suppress_comm = os.environ.get("OS2S_NO_COMM", "0") == "1"
         # replay the whole step as one CUDA graph after 2 eager steps (OS2S_CUDA_GRAPH=0 disables)
         self.use_cuda_graph = os.environ.get("OS2S_CUDA_GRAPH", "1") != "0"
         # with a communicator attached (N > 1) the step runs from the eager launch plan unless
@@ -142,7 +143,7 @@ class JasperEngine(object):
         self.fuse_bn_min_channels = 384
         self._aux = None
         self.comm = None            # object with allreduce_(tensor) (openseq2seq_b200.dist.TorchDistHvd)
-        self.bucket_bytes = 128 << 20
+        self.bucket_bytes = int(float(os.environ.get("OS2S_BUCKET_MB", "128")) * (1 << 20))
         self._side = None
         self._build_layers(convnet_layers, dropout_keep_default)
         self._alloc_params()
