@@ -391,6 +391,9 @@ def run_own(args):
                      "step_frac_of_peak": round(value / world * TRAIN_GFLOP_PER_AUDIO_S / 1000.0 / peak_tf, 4)},
         "loss": last_loss, "skipped_steps": skipped,
     }
+    if world > 1:
+        out["grad_exchange"] = ("peer memory: copy engines over NVLink + slice-sum kernel (csrc/peer.cu)"
+                                if getattr(eng, "peer", None) is not None else "nccl all_reduce")
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_quick()
     print(json.dumps(out), flush=True)

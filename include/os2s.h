@@ -13,11 +13,11 @@
  *   - return value: 0 = OK, negative = error; os2s_last_error() gives the message (thread local)
  *   - activations are NWC 16-bit [B, T, C] with C contiguous (bf16, or fp16 with OS2S_HALF_F16);
  *     parameters/gradients are fp32 masters with 16-bit working copies written by the optimizer step
- *   - collectives are NOT part of this ABI: the gradient all-reduce (hvd.allreduce, optimizers/optimizers.py:
- *     77-104) and the initial broadcast (utils/hooks.py:15-55) run on the caller's flat fp32 gradient /
- *     parameter buffers through NCCL (torch.distributed, openseq2seq_b200/dist.py); the kernels here only
- *     require that `g` holds the rank-summed gradients when os2s_opt_step* runs (os2s_opt_hparams.world_size
- *     folds the 1/N of the mean into the unscale factor)
+ *   - rendezvous and the initial broadcast (utils/hooks.py:15-55) are the caller's business (torch.distributed,
+ *     openseq2seq_b200/dist.py).  The gradient sum (hvd.allreduce, optimizers/optimizers.py:77-104) is either
+ *     the caller's NCCL all-reduce or os2s_peer_* below (CUDA IPC + copy engines over NVLink, one node); the
+ *     optimizer only requires that `g` holds the rank-summed gradients when os2s_opt_step* runs
+ *     (os2s_opt_hparams.world_size folds the 1/N of the mean into the unscale factor)
  */
 #ifndef OS2S_H_
 #define OS2S_H_
@@ -412,6 +412,34 @@ int os2s_features_forward_p(const int16_t* wave, const float* sig, const long lo
                             int feature_type, const float* mfcc_matrix, int n_filt,
                             void* absmax_ws, float* raw_ws, void* out16, float* out_f32, int* out_lens,
                             int dtypes, void* stream);
+
+/* ---- C1: gradient sum across the ranks of one node over NVLink peer memory ----------------------------
+ * Replaces hvd.allreduce(grad) per variable (optimizers/optimizers.py:77-104, reduce_gradients).  Every rank
+ * exports its flat fp32 gradient buffer and one zero-filled staging buffer (os2s_peer_stage_bytes) with
+ * os2s_ipc_export, the 64-byte handles + offsets travel through the caller's rendezvous, and every rank maps
+ * the others' buffers with os2s_ipc_open (base pointer of the exporter's allocation; add the offset).
+ * os2s_peer_exchange_bucket(ctx, b, stream) sums bucket b = [bucket_start[b], bucket_end[b]) (floats, starts
+ * 16-byte aligned, the same list on every rank) over all ranks IN PLACE in every rank's gradient buffer:
+ *   contribution to slice p -> staging slot on rank p (copy engine), flag; rank r adds the N-1 staged slices
+ *   onto its slice r (one narrow kernel); summed slice -> every other rank's gradient buffer (copy engine), flag.
+ * os2s_peer_finish enqueues the wait for the last phase of ALL buckets: after it, `g` holds the sum on this
+ * rank.  Each bucket must be exchanged exactly once between two os2s_peer_finish calls, in the same order on
+ * every rank.  All work is stream-ordered (graph-capturable); waits that exceed timeout_s raise a device flag
+ * (os2s_peer_timed_out, synchronising) instead of spinning forever.  Every rank ends with identical bits. */
+long long os2s_peer_stage_bytes(int world, int n_buckets, const long long* bucket_start_host,
+                                const long long* bucket_end_host);
+int os2s_ipc_export(const void* ptr, unsigned char* handle64_host, long long* offset_host);
+int os2s_ipc_open(const unsigned char* handle64_host, void** base_host);
+int os2s_ipc_close(void* base);
+/* grad_host / stage_host: `world` device pointers each (entry [rank] = the local buffers) */
+int os2s_peer_create(int rank, int world, void* const* grad_host, void* const* stage_host, int n_buckets,
+                     const long long* bucket_start_host, const long long* bucket_end_host, double timeout_s,
+                     void** ctx_host);
+int os2s_peer_destroy(void* ctx);
+int os2s_peer_set_timeout(void* ctx, double timeout_s); /* applies to waits enqueued afterwards */
+int os2s_peer_exchange_bucket(void* ctx, int bucket, void* stream);
+int os2s_peer_finish(void* ctx, void* stream);
+int os2s_peer_timed_out(void* ctx, int* flag_host);
 
 #ifdef __cplusplus
 }

@@ -432,4 +432,52 @@ int os2s_features_forward_p(const int16_t* wave, const float* sig, const long lo
                         &ex);
 }
 
+// ---- gradient exchange over NVLink peer memory (peer.cu) ----
+long long os2s_peer_stage_bytes(int world, int n_buckets, const long long* bucket_start_host,
+                                const long long* bucket_end_host) {
+  if (world < 2 || n_buckets < 1 || !bucket_start_host || !bucket_end_host) return -1;
+  return peer_stage_bytes(world, n_buckets, bucket_start_host, bucket_end_host);
+}
+
+int os2s_ipc_export(const void* ptr, unsigned char* handle64_host, long long* offset_host) {
+  if (!ptr || !handle64_host || !offset_host) return fail(ERR_INVALID, "os2s_ipc_export: null pointer");
+  return ipc_export(ptr, handle64_host, offset_host);
+}
+
+int os2s_ipc_open(const unsigned char* handle64_host, void** base_host) {
+  if (!handle64_host || !base_host) return fail(ERR_INVALID, "os2s_ipc_open: null pointer");
+  return ipc_open(handle64_host, base_host);
+}
+
+int os2s_ipc_close(void* base) {
+  if (!base) return fail(ERR_INVALID, "os2s_ipc_close: null pointer");
+  return ipc_close(base);
+}
+
+int os2s_peer_create(int rank, int world, void* const* grad_host, void* const* stage_host, int n_buckets,
+                     const long long* bucket_start_host, const long long* bucket_end_host, double timeout_s,
+                     void** ctx_host) {
+  if (!grad_host || !stage_host || !bucket_start_host || !bucket_end_host || !ctx_host)
+    return fail(ERR_INVALID, "os2s_peer_create: null pointer");
+  PeerExchange* px = nullptr;
+  int s = peer_create(rank, world, grad_host, stage_host, n_buckets, bucket_start_host, bucket_end_host, timeout_s, &px);
+  *ctx_host = px;
+  return s;
+}
+
+int os2s_peer_destroy(void* ctx) {
+  peer_destroy((PeerExchange*)ctx);
+  return OK;
+}
+
+int os2s_peer_set_timeout(void* ctx, double timeout_s) { return peer_set_timeout((PeerExchange*)ctx, timeout_s); }
+
+int os2s_peer_exchange_bucket(void* ctx, int bucket, void* stream) {
+  return peer_exchange_bucket((PeerExchange*)ctx, bucket, (cudaStream_t)stream);
+}
+
+int os2s_peer_finish(void* ctx, void* stream) { return peer_finish((PeerExchange*)ctx, (cudaStream_t)stream); }
+
+int os2s_peer_timed_out(void* ctx, int* flag_host) { return peer_timed_out((PeerExchange*)ctx, flag_host); }
+
 }  // extern "C"

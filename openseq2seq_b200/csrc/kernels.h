@@ -164,4 +164,18 @@ int logmel_forward(const short* wave, const long long* offsets, const int* n_sam
                    int psf_backend = 0, int pad_to = 0, int norm_per_feature = 1, int out_f16 = 0,
                    const FeatExtras* ex = nullptr);
 
+// ---- peer.cu: gradient sum over NVLink peer memory (CUDA IPC + copy engines) ----
+struct PeerExchange;
+long long peer_stage_bytes(int world, int n_buckets, const long long* start, const long long* end);
+int ipc_export(const void* ptr, unsigned char* handle, long long* offset);
+int ipc_open(const unsigned char* handle, void** base);
+int ipc_close(void* base);
+int peer_create(int rank, int world, void* const* grad, void* const* stage, int n_buckets, const long long* start,
+                const long long* end, double timeout_s, PeerExchange** out);
+void peer_destroy(PeerExchange* px);
+int peer_set_timeout(PeerExchange* px, double timeout_s);
+int peer_exchange_bucket(PeerExchange* px, int b, cudaStream_t st);
+int peer_finish(PeerExchange* px, cudaStream_t st);
+int peer_timed_out(PeerExchange* px, int* flag);
+
 }  // namespace os2s

@@ -144,7 +144,9 @@ class JasperEngine(object):
         self._aux = None
         self.comm = None            # object with allreduce_(tensor) (openseq2seq_b200.dist.TorchDistHvd)
         self.bucket_bytes = int(float(os.environ.get("OS2S_BUCKET_MB", "128")) * (1 << 20))
+        self.tail_bucket_bytes = int(float(os.environ.get("OS2S_TAIL_BUCKET_MB", "16")) * (1 << 20))
         self._side = None
+        self.peer = None
         self._build_layers(convnet_layers, dropout_keep_default)
         self._alloc_params()
         self.set_optimizer(**(opt or {}))
@@ -658,7 +660,28 @@ class JasperEngine(object):
             self.bucket_bytes = int(bucket_bytes)
         if self.comm is not None and self._side is None:
             self._side = torch.cuda.Stream()
+        # one node, NCCL backend: the buckets are summed over NVLink peer memory by the copy engines
+        # (csrc/peer.cu) instead of NCCL's SM-resident ring; None = NCCL all-reduce
+        self.peer = None
+        if self.comm is not None and hasattr(self.comm, "make_peer_exchange"):
+            self.peer = self.comm.make_peer_exchange(self.grad, self.grad_buckets())
         self._ws = collections.OrderedDict()
+
+    def grad_buckets(self):
+        """[(start, end)] (elements of the flat gradient buffer) in the order backward completes them: cut at
+        layer boundaries, last layer first, as soon as a bucket holds bucket_bytes."""
+        out = []
+        end = self._total
+        tail_cut = False
+        for li in range(len(self.layers) - 1, -1, -1):
+            start = self.layer_first_offset(li)
+            # the exchange of the LAST bucket is not hidden by any backward work: keep it short
+            taper = not tail_cut and 0 < start * 4 <= self.tail_bucket_bytes and end > start
+            if (end - start) * 4 >= self.bucket_bytes or li == 0 or taper:
+                out.append((start, end))
+                end = start
+                tail_cut = tail_cut or taper
+        return out
 
     def set_training(self, flag):
         """train mode: batch statistics + dropout; eval mode: moving statistics, no dropout
@@ -836,8 +859,8 @@ class _BucketAllReduce(object):
     enqueued so far on the compute stream has finished."""
     __name__ = "bucket_allreduce"
 
-    def __init__(self, eng, flat_slice):
-        self.eng, self.slice = eng, flat_slice
+    def __init__(self, eng, index, flat_slice):
+        self.eng, self.index, self.slice = eng, index, flat_slice
         self.event = torch.cuda.Event()
 
     def __call__(self):
@@ -845,6 +868,10 @@ class _BucketAllReduce(object):
         if eng._suppress_comm:
             return 0
         self.event.record()
+        if eng.peer is not None:
+            eng._side.wait_event(self.event)
+            eng.peer.exchange_bucket(self.index, eng._side)
+            return 0
         with torch.cuda.stream(eng._side):
             eng._side.wait_event(self.event)
             eng.comm.allreduce_(self.slice)
@@ -1139,6 +1166,8 @@ class _Workspace(object):
         self._st_aux.value = self.aux_stream().cuda_stream
         self._exec(plan)
         if eng.comm is not None:
+            if eng.peer is not None and not eng._suppress_comm:
+                eng.peer.finish(eng._side)
             torch.cuda.current_stream().wait_stream(eng._side)
 
     def run_forward(self, feats, feat_lens):
@@ -1197,7 +1226,8 @@ class _Workspace(object):
         rl = self._p(self.lens_out) if self.skip_tiles else _vp(0)
         if self.fused_red:
             plan.append([_ZeroMain(self.red_all), []])
-        bucket_end = eng._total          # gradients in [bucket_start, bucket_end) are final once enqueued
+        buckets = eng.grad_buckets() if eng.comm is not None else []   # final once their first layer is enqueued
+        n_bucket = 0
         sa = self._st_aux                # aux-stream handle (== main stream when overlap is off / profiling)
         ev_bn = [torch.cuda.Event() for _ in range(nl)]
         ev_wg = [torch.cuda.Event() for _ in range(nl)]
@@ -1350,13 +1380,12 @@ class _Workspace(object):
                         plan.append([lib.os2s_sepconv_decompose_grad,
                                      eng._decompose_args(eng.res_wname(eng.layers[lc], n)) + [sa]])
             plan.append([_StreamRecord(self, "aux", ev_wg[li]), []])
-            if eng.comm is not None:
-                start = eng.layer_first_offset(li)
-                if (bucket_end - start) * 4 >= eng.bucket_bytes or li == 0:
-                    # the bucket also holds weight gradients produced on the aux stream
-                    plan.append([_StreamWait(self, "main", ev_wg[li]), []])
-                    plan.append([_BucketAllReduce(eng, eng.grad[start:bucket_end]), []])
-                    bucket_end = start
+            if n_bucket < len(buckets) and buckets[n_bucket][0] == eng.layer_first_offset(li):
+                # the bucket also holds weight gradients produced on the aux stream
+                b0, b1 = buckets[n_bucket]
+                plan.append([_StreamWait(self, "main", ev_wg[li]), []])
+                plan.append([_BucketAllReduce(eng, n_bucket, eng.grad[b0:b1]), []])
+                n_bucket += 1
         # join: the optimizer needs every weight gradient
         plan.append([_StreamWait(self, "main", ev_wg[0]), []])
         if nl > 1:
@@ -1390,6 +1419,9 @@ class _Workspace(object):
         self.set_inputs(feats, feat_lens)
         self.set_targets(labels, label_lens)
         eng._last_ws = self
+        if eng.peer is not None and eng.step_count % 128 == 127 and eng.peer.timed_out():
+            raise RuntimeError("peer-memory gradient exchange: a rank did not signal within the time-out "
+                               "(OS2S_PEER_TIMEOUT_S); the gradients of the last steps are not rank sums")
         if eng.iter_size > 1:
             return self._accumulating_step()
         if eng.use_cuda_graph and eng._profile is None and (eng.comm is None or eng.graph_with_comm):

@@ -88,3 +88,29 @@ def test_sep_conv_modes_and_frozen_pseudo_variables(cpu_engine):
     assert eng.layers[1].wname == "conv21/pointwise_kernel" and eng.res_wname(eng.layers[2], 0) == "conv22/res/kernel@composed"
     with pytest.raises(AttributeError):
         cpu_engine(MINI_JASPER, opt=dict(max_grad_norm=1.0, larc_eta=0.001))
+
+
+def test_gradient_buckets_tile_the_flat_buffer_and_split_into_aligned_rank_slices(cpu_engine):
+    """Host side of the peer-memory gradient exchange (csrc/peer.cu): the buckets are cut at layer boundaries,
+    last layer first, and cover the flat gradient buffer exactly once; the rank slices of a bucket are 16-byte
+    aligned, disjoint and cover it (empty slices for tiny buckets)."""
+    from openseq2seq_b200.dist import split_bucket
+    for layers in (MINI_JASPER, MINI_QUARTZ):
+        eng = cpu_engine(layers)
+        eng.bucket_bytes = 64 << 10
+        b = eng.grad_buckets()
+        assert len(b) > 1 and b[0][1] == eng._total and b[-1][0] == 0
+        for (s0, e0), (s1, e1) in zip(b[:-1], b[1:]):
+            assert e1 == s0 and s1 < e1
+        assert all(s % 4 == 0 for s, _ in b)
+        firsts = {eng.layer_first_offset(li) for li in range(len(eng.layers))}
+        assert all(s in firsts for s, _ in b)
+    for world in (2, 3, 4, 8, 16):
+        for (s, e) in ((0, 67), (128, 128 + 4 * (4 * world + 3)), (1000, 1000 + 33554432), (64, 64)):
+            sl = split_bucket(s, e, world)
+            assert len(sl) == world and sl[0][0] == s and sl[-1][1] == e
+            for r in range(world):
+                lo, hi = sl[r]
+                assert lo <= hi and (lo == hi or (lo - s) % 4 == 0)
+                if r:
+                    assert lo == sl[r - 1][1]
