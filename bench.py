@@ -80,6 +80,22 @@ class ClockSampler(object):
                 "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
 
 
+def nvlink_counters(index):
+    """(tx_bytes, rx_bytes) moved over all NVLinks of GPU `index` so far (NVML throughput counters, KiB), or
+    None when NVML / the counters are not available."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        v = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        if any(x.nvmlReturn != 0 for x in v):
+            return None
+        return tuple(int(x.value.ullVal) * 1024 for x in v)
+    except Exception:
+        return None
+
+
 def _host_threads():
     """Threads of the CPU arm: every core this process may run on (cgroup / affinity aware), as BASELINE.md
     section 3 asks (`torch.set_num_threads(os.cpu_count())`).  OS2S_CPU_THREADS overrides."""
@@ -328,7 +344,9 @@ def run_own(args):
     for _ in range(3):
         step_resident()
     barrier()
+    nv0 = nvlink_counters(local) if (world > 1 and rank == 0) else None
     ms = timed(step_resident, args.steps)
+    nv1 = nvlink_counters(local) if nv0 is not None else None
     clocks = sampler.stop() if rank == 0 else None
 
     # roofline of the dominant kernel family (tcgen05 implicit-GEMM conv): per-launch CUDA-event
@@ -391,6 +409,12 @@ def run_own(args):
                      "step_frac_of_peak": round(value / world * TRAIN_GFLOP_PER_AUDIO_S / 1000.0 / peak_tf, 4)},
         "loss": last_loss, "skipped_steps": skipped,
     }
+    if world > 1 and nv0 is not None and nv1 is not None:
+        # algorithmic volume of a two-phase sum of the 1.33 GB flat fp32 gradient: 2 (N-1)/N x 1.33 GB each way
+        out["nvlink"] = {"tx_bytes_per_step": (nv1[0] - nv0[0]) // args.steps,
+                         "rx_bytes_per_step": (nv1[1] - nv0[1]) // args.steps,
+                         "algorithmic_bytes_per_step_each_way": int(2 * (world - 1) / world * eng._total * 4),
+                         "how": "NVML NVLink data throughput counters of rank 0's GPU around the timed region"}
     if world > 1:
         out["grad_exchange"] = ("peer memory: copy engines over NVLink + slice-sum kernel (csrc/peer.cu)"
                                 if getattr(eng, "peer", None) is not None else "nccl all_reduce")

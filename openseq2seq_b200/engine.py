@@ -134,6 +134,9 @@ class JasperEngine(object):
         # with a communicator attached (N > 1) the step runs from the eager launch plan unless
         # OS2S_GRAPH_DIST=1 asks for NCCL collectives to be captured into the graph as well
         self.graph_with_comm = os.environ.get("OS2S_GRAPH_DIST", "0") == "1"
+        # the peer-memory exchange is plain kernels + copies with device-resident flag counters: the whole
+        # multi-GPU step replays from a CUDA graph (ranks may capture at different steps; the protocol is the same)
+        self.graph_with_peer = os.environ.get("OS2S_PEER_GRAPH", "1") == "1"
         # weight-gradient kernels run on an auxiliary stream: wgrad(l) (tensor-bound, not on the critical
         # path) overlaps bn_bwd(l-1) (HBM-bound), which co-resides on the SMs (OS2S_OVERLAP_WGRAD=0 disables)
         self.overlap_wgrad = os.environ.get("OS2S_OVERLAP_WGRAD", "1") != "0"
@@ -1424,7 +1427,8 @@ class _Workspace(object):
                                "(OS2S_PEER_TIMEOUT_S); the gradients of the last steps are not rank sums")
         if eng.iter_size > 1:
             return self._accumulating_step()
-        if eng.use_cuda_graph and eng._profile is None and (eng.comm is None or eng.graph_with_comm):
+        if eng.use_cuda_graph and eng._profile is None and (eng.comm is None or eng.graph_with_comm
+                                                            or (eng.peer is not None and eng.graph_with_peer)):
             if self.graph is not None:
                 self.graph.replay()
                 eng.step_count += 1
