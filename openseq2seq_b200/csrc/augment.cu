@@ -82,8 +82,10 @@ augment_signal_phase_kernel(const short* __restrict__ wave, const long long* __r
                             int num_table, const float* __restrict__ noise_amp, unsigned long long seed,
                             float* __restrict__ out, const long long* __restrict__ out_offsets,
                             const int* __restrict__ n_out) {
-  __shared__ float wl[kAugMaxPhases][kAugMaxTaps];
-  __shared__ float wr[kAugMaxPhases][kAugMaxTaps];
+  // odd row stride: the threads of a warp read the SAME tap of DIFFERENT phases (160 floats apart would put all
+  // of them on one bank -- a p-way conflict on every load, measured 0.97 ms per batch in r02_final_kernel_evidence)
+  __shared__ float wl[kAugMaxPhases][kAugMaxTaps + 1];
+  __shared__ float wr[kAugMaxPhases][kAugMaxTaps + 1];
   __shared__ int nl[kAugMaxPhases], nr[kAugMaxPhases];
   const int b = blockIdx.y;
   const int no = n_out[b];

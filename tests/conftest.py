@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the drop-in `open_seq2seq` package: installed once so that every test file can be run on its own
+    import openseq2seq_b200.compat as compat
+    compat.install()
 
 
 @pytest.fixture(scope="session")
