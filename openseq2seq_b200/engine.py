@@ -134,9 +134,11 @@ class JasperEngine(object):
         # with a communicator attached (N > 1) the step runs from the eager launch plan unless
         # OS2S_GRAPH_DIST=1 asks for NCCL collectives to be captured into the graph as well
         self.graph_with_comm = os.environ.get("OS2S_GRAPH_DIST", "0") == "1"
-        # the peer-memory exchange is plain kernels + copies with device-resident flag counters: the whole
-        # multi-GPU step replays from a CUDA graph (ranks may capture at different steps; the protocol is the same)
-        self.graph_with_peer = os.environ.get("OS2S_PEER_GRAPH", "1") == "1"
+        # the peer-memory exchange is plain kernels + copies with device-resident flag counters, so the whole
+        # multi-GPU step can replay from a CUDA graph (ranks may capture at different steps; the protocol is the
+        # same).  Measured at N = 2 only (profiles/r02_peer_graph_n2.jsonl): on by default there, elsewhere with
+        # OS2S_PEER_GRAPH=1 (set_comm decides)
+        self.graph_with_peer = os.environ.get("OS2S_PEER_GRAPH", "") == "1"
         # weight-gradient kernels run on an auxiliary stream: wgrad(l) (tensor-bound, not on the critical
         # path) overlaps bn_bwd(l-1) (HBM-bound), which co-resides on the SMs (OS2S_OVERLAP_WGRAD=0 disables)
         self.overlap_wgrad = os.environ.get("OS2S_OVERLAP_WGRAD", "1") != "0"
@@ -668,6 +670,8 @@ class JasperEngine(object):
         self.peer = None
         if self.comm is not None and hasattr(self.comm, "make_peer_exchange"):
             self.peer = self.comm.make_peer_exchange(self.grad, self.grad_buckets())
+            if os.environ.get("OS2S_PEER_GRAPH", "") == "":
+                self.graph_with_peer = self.comm.size() == 2
         self._ws = collections.OrderedDict()
 
     def grad_buckets(self):
