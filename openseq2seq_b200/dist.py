@@ -7,10 +7,14 @@ uses on this path:
   C2 hvd.broadcast of every global var  -> broadcast of the flat master / momentum / BN buffers
   C3 MPI gather of scalars              -> all_reduce of a scalar
 """
+import ctypes
 import os
+import sys
 
 import torch
 import torch.distributed as dist
+
+from . import _lib as L
 
 
 class TorchDistHvd(object):
@@ -90,7 +94,6 @@ class TorchDistHvd(object):
                               float(os.environ.get("OS2S_PEER_TIMEOUT_S", timeout_s or 120.0)))
         if not px.ok:
             if self._rank == 0:
-                import sys
                 sys.stderr.write("[os2s] peer-memory gradient exchange unavailable (%s); using the NCCL all-reduce\n"
                                  % px.why)
             if mode == "peer":
@@ -116,8 +119,6 @@ class PeerGradExchange(object):
     rendezvous of the 64-byte handles only."""
 
     def __init__(self, hvd, grad, buckets, timeout_s):
-        import ctypes
-        from . import _lib as L
         self.ok, self.why = False, ""
         self.rank, self.world = hvd.rank(), hvd.size()
         self.buckets = [(int(a), int(b)) for a, b in buckets]
@@ -180,16 +181,12 @@ class PeerGradExchange(object):
         self.ok = True
 
     def _export(self, t):
-        import ctypes
-        from . import _lib as L
         h = (ctypes.c_ubyte * 64)()
         off = ctypes.c_longlong(0)
         L.check(self._lib.os2s_ipc_export(ctypes.c_void_p(t.data_ptr()), h, ctypes.byref(off)), "os2s_ipc_export")
         return (bytes(h), int(off.value))
 
     def _open(self, handle):
-        import ctypes
-        from . import _lib as L
         if handle not in self._opened:        # one allocation may hold several exported tensors
             base = ctypes.c_void_p(0)
             buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
@@ -199,20 +196,14 @@ class PeerGradExchange(object):
 
     def exchange_bucket(self, index, stream):
         """Enqueue the two-phase sum of bucket `index` on `stream` (a torch stream)."""
-        import ctypes
-        from . import _lib as L
         L.check(self._lib.os2s_peer_exchange_bucket(self._ctx, int(index), ctypes.c_void_p(stream.cuda_stream)),
                 "os2s_peer_exchange_bucket")
 
     def finish(self, stream):
         """Enqueue the wait for the summed slices of every bucket: afterwards grad holds the sum on this rank."""
-        import ctypes
-        from . import _lib as L
         L.check(self._lib.os2s_peer_finish(self._ctx, ctypes.c_void_p(stream.cuda_stream)), "os2s_peer_finish")
 
     def timed_out(self):
-        import ctypes
-        from . import _lib as L
         f = ctypes.c_int(0)
         L.check(self._lib.os2s_peer_timed_out(self._ctx, ctypes.byref(f)), "os2s_peer_timed_out")
         return bool(f.value)
