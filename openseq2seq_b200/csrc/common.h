@@ -8,7 +8,7 @@
 namespace os2s {
 
 // Status codes returned by every extern "C" entry point (see include/os2s.h).
-enum : int { OK = 0, ERR_INVALID = -1, ERR_CUDA = -2, ERR_UNSUPPORTED = -3, ERR_NCCL = -4 };
+enum : int { OK = 0, ERR_INVALID = -1, ERR_CUDA = -2, ERR_UNSUPPORTED = -3 };
 
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);

@@ -1,9 +1,10 @@
-"""torch.distributed (NCCL over NVLink) stand-in for the three Horovod/MPI collectives the reference
-uses on this path:
+"""Stand-in for the three Horovod/MPI collectives the reference uses on this path;
+torch.distributed (NCCL) provides the rendezvous and the fallbacks:
 
-  C1 hvd.allreduce(grad) per variable   -> ONE all-reduce (sum) over the flat fp32 gradient buffer,
-                                           optionally split into buckets launched on a side stream;
-                                           the 1/N is folded into the optimizer's unscale factor
+  C1 hvd.allreduce(grad) per variable   -> sum of the flat fp32 gradient buffer, bucket by bucket on a side
+                                           stream: over NVLink peer memory (PeerGradExchange / csrc/peer.cu) on
+                                           one node, else NCCL all-reduce; the 1/N is folded into the optimizer's
+                                           unscale factor
   C2 hvd.broadcast of every global var  -> broadcast of the flat master / momentum / BN buffers
   C3 MPI gather of scalars              -> all_reduce of a scalar
 """
@@ -81,7 +82,7 @@ class TorchDistHvd(object):
 
     def make_peer_exchange(self, grad, buckets, timeout_s=None):
         """Gradient sum over NVLink peer memory (csrc/peer.cu) for this process group, or None when it cannot be
-        set up (not NCCL / not one node / CUDA IPC refused / the self-test disagrees with NCCL) -- the decision is
+        set up (not NCCL / not one node / CUDA IPC refused / the self-test does not reproduce the closed-form sums) -- the decision is
         taken jointly so every rank uses the same transport."""
         if self._size < 2 or getattr(self, "_device", "cpu") != "cuda":
             return None

@@ -658,7 +658,7 @@ class JasperEngine(object):
         """Data-parallel gradient exchange (reference: hvd.allreduce per gradient,
         optimizers/optimizers.py:77-104).  Gradients live in one flat fp32 buffer whose tail is
         produced first by the backward pass; contiguous buckets are all-reduced (SUM) on a side stream
-        as soon as the layers that write them have been enqueued, overlapping NCCL with the remaining
+        as soon as the layers that write them have been enqueued, overlapping the exchange with the remaining
         backward kernels; the optimizer waits for the side stream."""
         self.comm = comm if (comm is not None and comm.size() > 1) else None
         if bucket_bytes:
