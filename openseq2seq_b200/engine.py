@@ -773,8 +773,9 @@ class JasperEngine(object):
             name = entry[0].__name__
             n += {"os2s_ctc_loss_fwd_bwd": 3, "os2s_fc_bwd_p": 2, "os2s_bn_bwd_p": 2, "os2s_bn_bwd_apply_p": 1, "zero_slices": 0,
                   "os2s_sepconv_decompose_grad": 2,
-                  "bucket_allreduce": 0, "stream_record": 0, "stream_wait": 0}.get(name, 1)
-        return n + 3 + 3
+                  "bucket_allreduce": 4 if self.peer is not None else 0,   # signal, wait, slice sum, signal
+                  "stream_record": 0, "stream_wait": 0}.get(name, 1)
+        return n + 3 + 3 + (1 if self.peer is not None else 0)              # + os2s_peer_finish's wait
 
     def profile_conv_launches(self, step_fn, steps=2):
         """Time every tensor-core conv launch of `steps` instrumented steps with CUDA events.
