@@ -1,5 +1,4 @@
 """EncoderDecoderModel: encoder -> decoder -> loss glue (open_seq2seq/models/encoder_decoder.py:10-190)."""
-import copy
 
 from open_seq2seq.optimizers.optimizers import optimizer_engine_kwargs
 from .model import Model

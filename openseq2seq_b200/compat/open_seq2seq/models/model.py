@@ -11,7 +11,7 @@ import copy
 import numpy as np
 import tensorflow as tf
 
-from open_seq2seq.utils.utils import check_params, deco_print
+from open_seq2seq.utils.utils import check_params
 
 
 class Model(metaclass=abc.ABCMeta):

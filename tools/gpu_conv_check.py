@@ -1,7 +1,7 @@
 """Bring-up check of the tcgen05 conv kernels against torch (fp32 cuDNN) on a B200.
 Run under gpurun; each case runs in its own subprocess with a timeout so a hung kernel
 cannot eat the whole call.  Usage: python tools/gpu_conv_check.py [case ...]"""
-import ctypes
+
 import json
 import subprocess
 import sys

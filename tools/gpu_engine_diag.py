@@ -35,7 +35,7 @@ R = torch.randn(logits.shape, generator=g)
 R = R * TT.sequence_mask(out_lens.cpu().long(), logits.shape[1], R.dtype)
 (ref_logits * R.double()).sum().backward()
 # step the engine backward manually, layer by layer, dumping dY / dA
-import ctypes
+
 from openseq2seq_b200 import _lib as L
 ws.dlogits.copy_(R.cuda())
 if ws._bwd_plan is None:
