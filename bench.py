@@ -247,16 +247,21 @@ class _CpuPort(object):
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU path (restated port, see _CpuPort) on all host cores, same metric /
-    unit / config as the own arm; each of the K steps is a bounded sample of that workload -- BASELINE.md
-    section 3's batch of 2 utterances, shortened to 4 s each so that K + W steps end within a few minutes."""
+    """`--impl reference`: the reference's CPU path (restated port, see _CpuPort) on the host cores, same metric /
+    unit / config as the own arm; each of the K steps is BASELINE.md section 3's batch -- 2 utterances x 15 s -- and
+    the run stops early after ~200 s of timed steps.  If the single warm-up step shows that one such step takes
+    over a minute, the samples are shortened to 2 x 4 s and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = _host_threads()
-    secs, B = 4.0, 2
+    secs, B = AUDIO_SECONDS, 2
     port = _CpuPort(B, secs, cores)
-    for _ in range(max(1, min(args.warmup, 1))):
+    t0 = time.time()
+    port.step()
+    if time.time() - t0 > 60.0:
+        secs = 4.0
+        port = _CpuPort(B, secs, cores)
         port.step()
     t0 = time.time()
     n = 0
@@ -268,7 +273,7 @@ def run_reference(args):
             break
     dt = time.time() - t0
     val = n * B * secs / dt
-    sample = ("%d training steps of %d utterances x %.0f s each, %d threads (fastest count for an fp32 conv probe among "
+    sample = ("1 warm-up + %d training steps of %d utterances x %.0f s each, %d threads (fastest count for an fp32 conv probe among "
               "the %d usable host CPUs); fp32 torch-CPU port of the reference graph incl. the speed-perturbation "
               "resampler; TF1 not installable offline" % (n, B, secs, cores, _THREADS.get("of", cores)))
     out = {"impl": "reference", "metric": METRIC, "value": round(val, 4),
