@@ -92,7 +92,7 @@ class TorchDistHvd(object):
         if int(os.environ.get("LOCAL_WORLD_SIZE", self._size)) != self._size:
             return None          # more than one node: peer memory does not reach
         px = PeerGradExchange(self, grad, buckets,
-                              float(os.environ.get("OS2S_PEER_TIMEOUT_S", timeout_s or 120.0)))
+                              float(os.environ.get("OS2S_PEER_TIMEOUT_S", timeout_s or 600.0)))
         if not px.ok:
             if self._rank == 0:
                 sys.stderr.write("[os2s] peer-memory gradient exchange unavailable (%s); using the NCCL all-reduce\n"
