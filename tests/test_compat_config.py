@@ -236,3 +236,52 @@ def test_quartznet_config_matches_the_reference_and_sep_conv_topology_builds_on_
     assert p["conv11/depthwise_kernel"].shape == (33, 64, 1) and p["conv11/pointwise_kernel"].shape == (1, 64, 256)
     assert p["conv25/res/depthwise_kernel"].shape == (1, 256, 1) and p["conv25/res/pointwise_kernel"].shape == (1, 256, 256)
     assert "conv25/res_bn/gamma" in p and "conv21/kernel" not in p
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("name,optimizer,policy,larc,aug", [
+    ("jasper10x5_LibriSpeech_nvgrad.py", "NovoGrad", "poly_decay", True, True),
+    ("jasper10x5_LibriSpeech_nvgrad_masks.py", "NovoGrad", "poly_decay", True, True),
+    ("jasper-Mini-for-Jetson.py", "NovoGrad", "poly_decay", True, True),
+    ("quartznet15x5_LibriSpeech.py", "NovoGrad", "cosine_decay", False, True),
+    ("w2l_large_8gpus_mp.py", "Momentum", "poly_decay", True, False),
+    ("w2lplus_large_8gpus.py", "Momentum", "poly_decay", True, False),
+])  # (w2l_large_8gpus.py / w2lplus_large_8gpus_mp.py differ from these two in `dtype` only)
+def test_create_model_dry_run_of_every_tdnn_example_config(monkeypatch, golden_dir, tmp_path, name, optimizer, policy,
+                                                           larc, aug):
+    """run.py's path for `--mode=train_eval` on every TDNNEncoder config under example_configs/speech2text, unchanged
+    except for the dataset paths and the batch size (the reference's toy speech set): get_base_config -> create_model
+    -> Speech2Text(train) + Speech2Text(eval) with their data layers, encoder / decoder / loss plugins, the engine
+    (on the CPU, kernels stubbed) and the optimizer arguments.  Nothing on that path may raise or be dropped."""
+    import copy
+    import openseq2seq_b200.engine as E
+    from open_seq2seq.utils.utils import create_model
+    monkeypatch.setattr(E.JasperEngine, "sync_half_copies", lambda self: None)
+    orig = E.JasperEngine.__init__
+
+    def on_cpu(self, *a, **kw):
+        kw.setdefault("device", "cpu")
+        return orig(self, *a, **kw)
+    monkeypatch.setattr(E.JasperEngine, "__init__", on_cpu)
+    toy = os.path.join(golden_dir, "toy_speech_data")
+    path = os.path.join("/root/reference/example_configs/speech2text", name)
+    args, cfg, model, module = get_base_config(["--config_file=" + path, "--mode=train_eval"])
+    module = dict(module)
+    for k in ("train_params", "eval_params"):
+        module[k] = copy.deepcopy(module[k])
+        module[k]["data_layer_params"]["dataset_files"] = [os.path.join(toy, "toy_data.csv")]
+        if "vocab_file" in module[k]["data_layer_params"]:
+            module[k]["data_layer_params"]["vocab_file"] = os.path.join(toy, "vocab.txt")
+        module[k]["batch_size_per_gpu"] = 2
+    cfg = copy.deepcopy(cfg)
+    cfg.setdefault("data_layer_params", {})["vocab_file"] = os.path.join(toy, "vocab.txt")
+    cfg.update(logdir=str(tmp_path), batch_size_per_gpu=2, use_horovod=False, num_gpus=1)
+    train_model, eval_model = create_model(args, cfg, module, model, None)
+    assert train_model.engine is not None and eval_model.engine is not None
+    opt = train_model.params["optimizer"]
+    assert (opt if isinstance(opt, str) else opt.__name__) == optimizer
+    assert train_model.params["lr_policy"].__name__ == policy
+    assert bool(train_model.params.get("larc_params")) == larc
+    assert bool(train_model.get_data_layer().params.get("augmentation")) == aug
+    assert not eval_model.get_data_layer().params.get("augmentation")
+    assert train_model.engine.hp is not None          # the optimizer arguments reached the engine
