@@ -107,6 +107,14 @@ class Speech2TextDataLayer(DataLayer):
         aug = p.get("augmentation")
         # augmentation is a training-time transform of the librosa backend in every reference config
         # (get_speech_features_psf re-quantises to int16 after it, a path that is not built)
+        if aug and "n_freq_mask" in aug and aug.get("width_freq_mask", 10) > p["num_audio_features"]:
+            raise ValueError("'width_freq_mask'={} should be smaller than 'num_audio_features'={}".format(
+                aug.get("width_freq_mask", 10), p["num_audio_features"]))              # speech2text.py:184-192
+        if aug and "time_stretch_ratio" in aug:                                        # speech2text.py:195-197
+            print("WARNING: Please update time_stretch_ratio to speed_perturbation_ratio")
+            aug = dict(aug)
+            aug["speed_perturbation_ratio"] = aug.pop("time_stretch_ratio")
+            p["augmentation"] = aug
         self._aug = dict(aug) if (aug and p["mode"] == "train") else None
         if self._aug:
             known = {"speed_perturbation_ratio", "noise_level_min", "noise_level_max", "n_freq_mask", "n_time_mask",

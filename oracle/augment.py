@@ -19,9 +19,12 @@ band-limited sinc interpolation after J. O. Smith ("Digital Audio Resampling"):
           by ratio when ratio < 1; y[t] = sum over the left and the right wing of table values linearly
           interpolated between table samples (interp_delta), see `resample` below.
 
-Parity status: UNPINNED by the reference except for the length bounds of speech_utils_test.py:20-43
-(tests/test_oracle.py::test_augmentation_length_bounds_pin); the filter response is additionally checked
-against scipy.signal.resample_poly on a band-limited signal (same test file)."""
+Parity status: the RESAMPLER is unpinned by the reference except for the length bounds of
+speech_utils_test.py:20-43 (tests/test_oracle.py::test_augmentation_length_bounds_pin); its filter response is
+additionally checked against scipy.signal.resample_poly on a band-limited signal (same test file).  The DRAWS
+and the control flow around it (which value is drawn when, with which np.random call, what is added to what) are
+pinned by executing the reference's own augment_audio_signal / get_speech_features_librosa on seeded streams
+(tests/test_reference_executed_cpu.py; fixture tests/golden/reference_augmentation_draws.json)."""
 import numpy as np
 
 

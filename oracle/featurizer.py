@@ -17,8 +17,10 @@ is NOT under /root/reference and is not installed here.  Its published algorithm
   librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax): Slaney mel scale (htk=False), triangular
       filters on np.linspace(0, sr/2, 1+n_fft//2), Slaney area normalisation 2/(f[i+2]-f[i]).
 Parity status: the reference has no golden vectors for this backend ("parity unpinned" by its own
-tests); the restatement is triangulated against torchaudio's independent
-Slaney filterbank and torch.stft in tests/test_oracle_featurizer.py.
+tests).  The librosa / psf PRIMITIVES restated here are triangulated against torchaudio's
+independent Slaney filterbank and torch.stft (tests/test_oracle.py); the COMPOSITION of this module (order of
+the steps and of the random draws, constants, padding, normalisation) is pinned by executing the reference's own
+speech_utils.py on top of these primitives (tests/test_reference_executed_cpu.py, build container only).
 """
 import math
 
@@ -181,27 +183,6 @@ def psf_quantize_and_pad(signal_int16, sample_freq=16000, window_size=20e-3, win
     return signal
 
 
-def psf_logfbank_features(signal_int16, sample_freq=16000, num_features=64, window_size=20e-3,
-                          window_stride=10e-3, pad_to=8, nfft=512, preemph=0.97):
-    """get_speech_features_psf(features_type='logfbank') without augmentation -> ([frames, F] f64, seconds)."""
-    duration = len(signal_int16) * 1.0 / sample_freq
-    signal = psf_quantize_and_pad(signal_int16, sample_freq, window_size, window_stride, pad_to).astype(np.float64)
-    n_win, n_hop = int(sample_freq * window_size), int(sample_freq * window_stride)
-    signal = preemphasis(signal, preemph)
-    slen = len(signal)
-    numframes = 1 if slen <= n_win else 1 + int(math.ceil((1.0 * slen - n_win) / n_hop))
-    padded = np.concatenate([signal, np.zeros((numframes - 1) * n_hop + n_win - slen)])
-    idx = np.arange(n_win)[None, :] + n_hop * np.arange(numframes)[:, None]
-    frames = padded[idx]                                    # rectangular window
-    pspec = (1.0 / nfft) * np.abs(np.fft.rfft(frames, nfft, axis=1)) ** 2
-    fb = psf_mel_filterbank(num_features, nfft, sample_freq, 0.0, sample_freq / 2.0)
-    feat = np.dot(pspec, fb.T)
-    feat = np.where(feat == 0, np.finfo(float).eps, feat)
-    features = np.log(feat)
-    features = (features - np.mean(features)) / np.std(features)   # global normalisation (:531-533)
-    return features, duration
-
-
 def _psf_frames(signal, n_win, n_hop, winfunc):
     """python_speech_features.sigproc.framesig."""
     slen = len(signal)
@@ -211,23 +192,60 @@ def _psf_frames(signal, n_win, n_hop, winfunc):
     return padded[idx] * winfunc(n_win)[None, :]
 
 
+def psf_logpowspec(frames, nfft):
+    """python_speech_features.sigproc.logpowspec(frames, NFFT, norm=1): 10 log10(max(|rfft|^2 / NFFT, 1e-30))
+    minus its maximum."""
+    ps = (1.0 / nfft) * np.abs(np.fft.rfft(frames, nfft, axis=1)) ** 2
+    ps[ps <= 1e-30] = 1e-30
+    lps = 10.0 * np.log10(ps)
+    return lps - np.max(lps)
+
+
+def psf_log_fbank(signal, samplerate, n_win, n_hop, nfilt, nfft, lowfreq, highfreq, preemph):
+    """python_speech_features.base.logfbank = log(fbank(...)[0]): pre-emphasis, RECTANGULAR frames (the
+    reference passes no winfunc), power spectrum / NFFT, HTK-mel triangles, zeros -> float eps, log."""
+    frames = _psf_frames(preemphasis(signal, preemph), n_win, n_hop, np.ones)
+    pspec = (1.0 / nfft) * np.abs(np.fft.rfft(frames, nfft, axis=1)) ** 2
+    fb = psf_mel_filterbank(nfilt, nfft, samplerate, lowfreq, highfreq)
+    feat = np.dot(pspec, fb.T)
+    return np.log(np.where(feat == 0, np.finfo(float).eps, feat))
+
+
+def psf_mfcc(signal, samplerate, n_win, n_hop, numcep, nfilt, nfft, lowfreq, highfreq, preemph, ceplifter):
+    """python_speech_features.base.mfcc(appendEnergy=False): orthonormal DCT-II of the log filterbank energies,
+    first numcep coefficients, sinusoidal lifter 1 + (L/2) sin(pi n / L)."""
+    feat = psf_log_fbank(signal, samplerate, n_win, n_hop, nfilt, nfft, lowfreq, highfreq, preemph)
+    n = np.arange(nfilt)
+    dct = np.cos(np.pi * (n[None, :] + 0.5) * np.arange(nfilt)[:, None] / nfilt)      # DCT-II rows
+    scale = np.full(nfilt, np.sqrt(2.0 / nfilt))
+    scale[0] = np.sqrt(1.0 / nfilt)                                                   # norm='ortho'
+    ceps = np.dot(feat, (dct * scale[:, None]).T)[:, :numcep]
+    L = ceplifter
+    return ceps * (1.0 + (L / 2.0) * np.sin(np.pi * np.arange(numcep) / L))[None, :]
+
+
+def psf_logfbank_features(signal_int16, sample_freq=16000, num_features=64, window_size=20e-3,
+                          window_stride=10e-3, pad_to=8, nfft=512, preemph=0.97):
+    """get_speech_features_psf(features_type='logfbank') without augmentation -> ([frames, F] f64, seconds)."""
+    duration = len(signal_int16) * 1.0 / sample_freq
+    signal = psf_quantize_and_pad(signal_int16, sample_freq, window_size, window_stride, pad_to).astype(np.float64)
+    n_win, n_hop = int(sample_freq * window_size), int(sample_freq * window_stride)
+    features = psf_log_fbank(signal, sample_freq, n_win, n_hop, num_features, nfft, 0.0, sample_freq / 2.0, preemph)
+    features = (features - np.mean(features)) / np.std(features)   # global normalisation (:531-533)
+    return features, duration
+
+
 def psf_spectrogram_features(signal_int16, sample_freq=16000, num_features=161, window_size=20e-3,
                              window_stride=10e-3, pad_to=8):
     """get_speech_features_psf(features_type='spectrogram') (speech_utils.py:490-502): Hann-windowed frames,
-    sigproc.logpowspec(frames, NFFT = window length) = 10*log10(max(|rfft|^2 / NFFT, 1e-30)) minus its
-    maximum (norm=1), the lowest num_features bins, global mean/std normalisation.  NOT built on the GPU
-    (NFFT = 320 is not a power of two); restated for the round that builds it."""
+    sigproc.logpowspec(frames, NFFT = window length), the lowest num_features bins, global mean/std
+    normalisation."""
     duration = len(signal_int16) * 1.0 / sample_freq
     signal = psf_quantize_and_pad(signal_int16, sample_freq, window_size, window_stride, pad_to).astype(np.float64)
     n_win, n_hop = int(sample_freq * window_size), int(sample_freq * window_stride)
     assert num_features <= n_win // 2 + 1, \
         "num_features for spectrogram should be <= (sample_freq * window_size // 2 + 1)"
-    frames = _psf_frames(signal, n_win, n_hop, np.hanning)
-    ps = (1.0 / n_win) * np.abs(np.fft.rfft(frames, n_win, axis=1)) ** 2
-    ps[ps <= 1e-30] = 1e-30
-    lps = 10.0 * np.log10(ps)
-    lps = lps - np.max(lps)
-    features = lps[:, :num_features]
+    features = psf_logpowspec(_psf_frames(signal, n_win, n_hop, np.hanning), n_win)[:, :num_features]
     features = (features - np.mean(features)) / np.std(features)
     return features, duration
 
@@ -235,23 +253,11 @@ def psf_spectrogram_features(signal_int16, sample_freq=16000, num_features=161, 
 def psf_mfcc_features(signal_int16, sample_freq=16000, num_features=13, window_size=20e-3, window_stride=10e-3,
                       pad_to=8, nfft=512, preemph=0.97):
     """get_speech_features_psf(features_type='mfcc') (speech_utils.py:504-512): psf.mfcc(numcep = F,
-    nfilt = 2F, nfft = 512, ceplifter = 2F, appendEnergy = False) = orthonormal DCT-II of the log filterbank
-    energies, first F coefficients, sinusoidal lifter 1 + (L/2) sin(pi n / L); global normalisation."""
+    nfilt = 2F, nfft = 512, ceplifter = 2F, appendEnergy = False); global normalisation."""
     duration = len(signal_int16) * 1.0 / sample_freq
     signal = psf_quantize_and_pad(signal_int16, sample_freq, window_size, window_stride, pad_to).astype(np.float64)
     n_win, n_hop = int(sample_freq * window_size), int(sample_freq * window_stride)
-    frames = _psf_frames(preemphasis(signal, preemph), n_win, n_hop, np.ones)
-    pspec = (1.0 / nfft) * np.abs(np.fft.rfft(frames, nfft, axis=1)) ** 2
-    nfilt = 2 * num_features
-    fb = psf_mel_filterbank(nfilt, nfft, sample_freq, 0.0, sample_freq / 2.0)
-    feat = np.dot(pspec, fb.T)
-    feat = np.log(np.where(feat == 0, np.finfo(float).eps, feat))
-    n = np.arange(nfilt)
-    dct = np.cos(np.pi * (n[None, :] + 0.5) * np.arange(nfilt)[:, None] / nfilt)      # DCT-II rows
-    scale = np.full(nfilt, np.sqrt(2.0 / nfilt))
-    scale[0] = np.sqrt(1.0 / nfilt)                                                   # norm='ortho'
-    ceps = np.dot(feat, (dct * scale[:, None]).T)[:, :num_features]
-    L = 2 * num_features
-    ceps = ceps * (1.0 + (L / 2.0) * np.sin(np.pi * np.arange(num_features) / L))[None, :]
+    ceps = psf_mfcc(signal, sample_freq, n_win, n_hop, num_features, 2 * num_features, nfft, 0.0, sample_freq / 2.0,
+                    preemph, 2 * num_features)
     features = (ceps - np.mean(ceps)) / np.std(ceps)
     return features, duration

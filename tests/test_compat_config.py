@@ -195,10 +195,28 @@ def test_nothing_in_the_headline_config_is_silently_ignored():
     assert set(sr_new.tolist()) == {14400, 16000, 17600}
     assert all(int(n) == int(16000 * (s / 16000.0)) for n, s in zip(n_out, sr_new))
     assert (noise >= 10 ** (-90 / 20.0)).all() and (noise < 10 ** (-46 / 20.0)).all()
+    # the draws of the reference's own augment_audio_signal, executed in the build container (fixture written by
+    # tools/make_golden_reference_draws.py): the data layer's host-side draws reproduce them seed by seed
+    import json
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                     "reference_augmentation_draws.json")))
+    for case in fx["cases"]:
+        dlc = Speech2TextDataLayer(dict(base, augmentation=case["augmentation"]), None, 1, 0)
+        sr_c, noise_c, n_c = dlc._draw_one(fx["n_samples"], np.random.RandomState(case["seed"]))
+        assert n_c == case["n_out"], case
+        want = 0.0 if case["noise_level_db"] is None else 10.0 ** (case["noise_level_db"] / 20.0)
+        assert abs(noise_c - want) <= 1e-7 * max(want, 1.0), case
     eval_dl = Speech2TextDataLayer(dict(base, mode="eval", augmentation=aug, shuffle=False), None, 1, 0)
     assert eval_dl._aug is None                       # training-time transform only
     with pytest.raises(ValueError):
         Speech2TextDataLayer(dict(base, augmentation={"pitch_shift": 2}), None, 1, 0)
+    # speech2text.py:184-197: a frequency mask wider than the feature axis raises; the legacy key is an alias
+    with pytest.raises(ValueError, match="width_freq_mask"):
+        Speech2TextDataLayer(dict(base, augmentation={"n_freq_mask": 1, "width_freq_mask": 65}), None, 1, 0)
+    legacy = Speech2TextDataLayer(dict(base, augmentation={"time_stretch_ratio": 0.05}), None, 1, 0)
+    assert legacy._aug == {"speed_perturbation_ratio": 0.05}
+    s_l, _, n_l = legacy._draw_augmentation([16000] * 200, np.random.RandomState(1))
+    assert s_l.min() >= int(16000 * 0.95) and s_l.max() <= int(16000 * 1.05) and len(set(s_l.tolist())) > 50
     with pytest.raises(NotImplementedError):
         Speech2TextDataLayer(dict(base, backend="psf", augmentation=aug), None, 1, 0)
     with pytest.raises(NotImplementedError):

@@ -309,3 +309,23 @@ def test_separable_conv_restatement():
             if 0 <= s < 37:
                 z[:, t] += D[k, :, 0] * x[:, s]
     assert float((z @ P[0] - TT.sep_conv1d_same(x, D, P, 1, 1)).abs().max()) < 1e-12
+
+
+def test_augmentation_draws_reproduce_the_executed_reference_fixture(golden_dir):
+    """tests/golden/reference_augmentation_draws.json holds what the reference's own augment_audio_signal did for
+    seeded np.random streams (output length, drawn noise level; written by tools/make_golden_reference_draws.py in
+    the build container).  The oracle's draw function and, through it, the GPU data layer's host-side draws have to
+    reproduce them from the same seeds."""
+    import json
+    from oracle import augment as AU
+    fx = json.load(open(os.path.join(golden_dir, "reference_augmentation_draws.json")))
+    n, sr = fx["n_samples"], fx["sample_freq"]
+    assert len(fx["cases"]) >= 32
+    for case in fx["cases"]:
+        sr_new, amp = AU.draw_augmentation(n, sr, case["augmentation"], np.random.RandomState(case["seed"]))
+        n_out = AU.resample_out_len(n, sr, sr_new) if sr_new > 0 else n
+        assert n_out == case["n_out"], case
+        if case["noise_level_db"] is None:
+            assert amp == 0
+        else:
+            assert abs(amp - 10.0 ** (case["noise_level_db"] / 20.0)) < 1e-12, case

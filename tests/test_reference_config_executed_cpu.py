@@ -1,0 +1,226 @@
+"""The reference's OWN config / params code executed here (CPU, build container only) against the drop-in package.
+
+`open_seq2seq/utils/utils.py` is loaded BY PATH from /root/reference (never copied); its only TensorFlow import that
+matters at import time (`tensorflow.python.client.device_lib`) is replaced by an empty stand-in, `tf` itself is the
+repo's minimal stand-in.  What runs is the reference's own get_base_config (argparse + runpy + the nested
+command-line overrides), check_params, flatten_dict / nest_dict / nested_update and the id->text helpers; the
+compat package's versions must return the same objects and raise on the same inputs.  Skipped on the GPU box.
+"""
+import copy
+import importlib.util
+import os
+import sys
+import types
+
+import pytest
+
+import openseq2seq_b200.compat as compat
+
+compat.install()
+from open_seq2seq.utils import utils as OWN  # noqa: E402
+
+REF = "/root/reference/open_seq2seq/utils/utils.py"
+CFG_DIR = "/root/reference/example_configs/speech2text"
+pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="reference checkout not present (GPU box)")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    names = ("tensorflow.python", "tensorflow.python.client", "tensorflow.python.client.device_lib")
+    fake = {n: types.ModuleType(n) for n in names}
+    fake["tensorflow.python.client"].device_lib = fake["tensorflow.python.client.device_lib"]
+    saved = {k: sys.modules.get(k) for k in fake}
+    sys.modules.update(fake)
+    try:
+        spec = importlib.util.spec_from_file_location("_reference_utils", REF)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+def _comparable(x):
+    """Config values -> something == can compare (classes and functions by qualified name)."""
+    if isinstance(x, dict):
+        return {k: _comparable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_comparable(v) for v in x]
+    if isinstance(x, type) or callable(x):
+        return getattr(x, "__module__", "") + "." + getattr(x, "__qualname__", repr(x))
+    return x
+
+
+OVERRIDES = [
+    [],
+    ["--batch_size_per_gpu=4", "--num_epochs=3"],
+    ["--encoder_params/dropout_keep_prob=0.5", "--lr_policy_params/learning_rate=0.1", "--use_horovod=False"],
+    ["--logdir=/tmp/x", "--data_layer_params/num_audio_features=80", "--optimizer_params/epsilon=1e-6",
+     "--larc_params/larc_eta=0.002"],
+]
+
+
+@pytest.mark.parametrize("name", ["jasper10x5_LibriSpeech_nvgrad.py", "quartznet15x5_LibriSpeech.py",
+                                  "w2lplus_large_8gpus_mp.py"])
+@pytest.mark.parametrize("mode", ["train", "train_eval", "eval"])
+def test_get_base_config_equals_the_executed_reference(ref, name, mode):
+    path = os.path.join(CFG_DIR, name)
+    for extra in OVERRIDES:
+        argv = ["--config_file=" + path, "--mode=" + mode] + extra
+        keys = set(ref.flatten_dict(ref.get_base_config(["--config_file=" + path])[1]))
+        usable = [a for a in argv if a.split("=")[0].lstrip("-") in keys or a.startswith(("--config_file", "--mode"))]
+        r_args, r_base, r_model, r_mod = ref.get_base_config(list(usable))
+        o_args, o_base, o_model, o_mod = OWN.get_base_config(list(usable))
+        assert _comparable(r_base) == _comparable(o_base), (name, mode, usable)
+        assert r_model is o_model
+        for k in ("train_params", "eval_params", "infer_params"):
+            assert _comparable(r_mod.get(k)) == _comparable(o_mod.get(k))
+        assert vars(r_args).keys() <= vars(o_args).keys()
+        for k, v in vars(r_args).items():
+            assert getattr(o_args, k) == v, k
+    with pytest.raises(ValueError):
+        ref.get_base_config(["--config_file=" + path, "--mode=nonsense"])
+    with pytest.raises(ValueError):
+        OWN.get_base_config(["--config_file=" + path, "--mode=nonsense"])
+
+
+def test_dict_helpers_equal_the_executed_reference(ref):
+    import random
+    rnd = random.Random(0)
+
+    def rand_dict(depth):
+        d = {}
+        for i in range(rnd.randint(1, 4)):
+            k = "k%d_%d" % (depth, i)
+            t = rnd.random()
+            if t < 0.35 and depth < 3:
+                d[k] = rand_dict(depth + 1)
+            elif t < 0.5:
+                d[k] = rnd.random()
+            elif t < 0.65:
+                d[k] = rnd.randint(-5, 5)
+            elif t < 0.8:
+                d[k] = rnd.choice([True, False])
+            elif t < 0.9:
+                d[k] = "s%d" % rnd.randint(0, 9)
+            else:
+                d[k] = [1, 2, 3]              # lists are dropped by flatten_dict
+        return d
+
+    for _ in range(200):
+        a, b = rand_dict(0), rand_dict(0)
+        assert ref.flatten_dict(a) == OWN.flatten_dict(a)
+        flat = ref.flatten_dict(a)
+        assert ref.nest_dict(flat) == OWN.nest_dict(flat)
+        ra, oa = copy.deepcopy(a), copy.deepcopy(a)
+        r_err = o_err = None
+        try:
+            ref.nested_update(ra, copy.deepcopy(b))
+        except ValueError as e:
+            r_err = str(e)
+        try:
+            OWN.nested_update(oa, copy.deepcopy(b))
+        except ValueError as e:
+            o_err = str(e)
+        assert (r_err is None) == (o_err is None)
+        if r_err is None:
+            assert ra == oa
+
+
+def test_check_params_accepts_and_rejects_like_the_executed_reference(ref):
+    required = {"a": int, "mode": ["train", "eval"], "name": str, "fn": None}
+    optional = {"x": float, "flag": bool, "kind": [None, "p", "q"], "anything": None}
+    base = {"a": 1, "mode": "train", "name": "n", "fn": len}
+    cases = [base, dict(base, x=0.5), dict(base, x=1), dict(base, flag=True), dict(base, flag=1), dict(base, kind="p"),
+             dict(base, kind="z"), dict(base, kind=None), dict(base, anything=object()), dict(base, unknown=1),
+             {k: v for k, v in base.items() if k != "a"}, dict(base, a="1"), dict(base, a=True), dict(base, mode="infer"),
+             dict(base, name=3), dict(base, name=u"unicode")]
+    for cfg in cases:
+        r = o = None
+        try:
+            ref.check_params(cfg, required, optional)
+        except ValueError as e:
+            r = str(e)
+        try:
+            OWN.check_params(cfg, required, optional)
+        except ValueError as e:
+            o = str(e)
+        assert (r is None) == (o is None), (cfg, r, o)
+        if r is not None:
+            assert r.split(" ")[0] == o.split(" ")[0] and r.split()[1:4] == o.split()[1:4], (r, o)
+    assert ref.check_params({"zzz": 1}, None, None) is None and OWN.check_params({"zzz": 1}, None, None) is None
+
+
+def _reference_function(path, name):
+    """Compile ONE top-level function of a reference module that cannot be imported as a whole (TensorFlow at import
+    time) from its source in /root/reference and return it; nothing is copied into the repository."""
+    import ast
+    tree = ast.parse(open(path).read())
+    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+def test_levenshtein_equals_the_executed_reference():
+    """models/speech2text.py:51-71 (the distance behind the reference's WER) on random word and character
+    sequences, next to the known answers of speech2text_test.py:229-256 that tests/test_compat_config.py holds."""
+    import random
+    from open_seq2seq.models.speech2text import levenshtein as own
+    ref_fn = _reference_function("/root/reference/open_seq2seq/models/speech2text.py", "levenshtein")
+    rnd = random.Random(1)
+    words = ["the", "then", "seconds", "a", "cat", "sat", "on", "mat", ""]
+    for _ in range(400):
+        a = [rnd.choice(words) for _ in range(rnd.randint(0, 9))]
+        b = [rnd.choice(words) for _ in range(rnd.randint(0, 9))]
+        assert ref_fn(a, b) == own(a, b)
+        sa, sb = " ".join(a), " ".join(b)
+        assert ref_fn(sa, sb) == own(sa, sb)
+
+
+def test_vocabulary_loader_equals_the_executed_reference(tmp_path, golden_dir):
+    """data/utils.py:28-58 imported by path (it needs nothing beyond `six`): the toy vocabulary of the reference's
+    tests and a word-level file with counts, empty lines and tabs."""
+    from open_seq2seq.data.utils import load_pre_existing_vocabulary as own
+    spec = importlib.util.spec_from_file_location("_reference_data_utils", "/root/reference/open_seq2seq/data/utils.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    toy = os.path.join(golden_dir, "toy_speech_data", "vocab.txt")
+    assert mod.load_pre_existing_vocabulary(toy, read_chars=True) == own(toy, read_chars=True)
+    f = tmp_path / "words.txt"
+    f.write_text(u"the\\t1234\\nof\\t99\\n\\nword with space\\t7\\nlast", encoding="utf-8")
+    for kw in ({}, {"min_idx": 4}, {"read_chars": True}):
+        assert mod.load_pre_existing_vocabulary(str(f), **kw) == own(str(f), **kw), kw
+
+
+@pytest.mark.parametrize("mode", ["train", "eval", "infer"])
+def test_eval_shards_per_worker_equal_the_executed_reference(mode, golden_dir):
+    """Speech2TextDataLayer.split_data (speech2text.py:200-210) compiled from the reference's source and run on a
+    stand-in `self`: evaluation / inference shard the file list contiguously per worker, training does not."""
+    import ast
+    from open_seq2seq.data import Speech2TextDataLayer
+    src = open("/root/reference/open_seq2seq/data/speech2text/speech2text.py").read()
+    cls = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "Speech2TextDataLayer")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "split_data")
+    ns = {}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "speech2text.py", "exec"), ns)
+    toy = os.path.join(golden_dir, "toy_speech_data")
+    for workers in (1, 2, 3, 4):
+        seen = []
+        for wid in range(workers):
+            dl = Speech2TextDataLayer({"mode": mode, "batch_size": 1, "num_audio_features": 64, "input_type": "logfbank",
+                                       "vocab_file": os.path.join(toy, "vocab.txt"), "shuffle": False,
+                                       "dataset_files": [os.path.join(toy, "toy_data.csv")]}, None, workers, wid)
+            all_rows = list(range(dl._all_size))
+            me = types.SimpleNamespace(params={"mode": mode}, _num_workers=workers, _worker_id=wid)
+            want = ns["split_data"](me, all_rows)
+            assert len(dl._files) == len(want), (mode, workers, wid)
+            seen.append(len(want))
+        if mode == "train":
+            assert all(s == dl._all_size for s in seen)
+        else:
+            assert sum(seen) == dl._all_size
