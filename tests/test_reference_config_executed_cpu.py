@@ -224,3 +224,129 @@ def test_eval_shards_per_worker_equal_the_executed_reference(mode, golden_dir):
             assert all(s == dl._all_size for s in seen)
         else:
             assert sum(seen) == dl._all_size
+
+
+def _numpy_tf():
+    """The five TensorFlow symbols optimizers/lr_policies.py touches, with TF 1.x's documented semantics on Python
+    numbers (tf.train.polynomial_decay with cycle=False, exponential_decay, cosine_decay, cond, cast, maximum)."""
+    import math
+    tf = types.ModuleType("tensorflow")
+    tf.float32 = "float32"
+    tf.cast = lambda x, dtype: float(x)
+    tf.cond = lambda pred, true_fn, false_fn, name=None: true_fn() if pred else false_fn()
+    tf.maximum = max
+    tf.train = types.SimpleNamespace()
+
+    def polynomial_decay(learning_rate, global_step, decay_steps, end_learning_rate=0.0001, power=1.0, cycle=False):
+        s = min(global_step, decay_steps)
+        return (learning_rate - end_learning_rate) * (1.0 - s / float(decay_steps)) ** power + end_learning_rate
+
+    def exponential_decay(learning_rate, global_step, decay_steps, decay_rate, staircase=False):
+        p = global_step / float(decay_steps)
+        return learning_rate * decay_rate ** (math.floor(p) if staircase else p)
+
+    def cosine_decay(learning_rate, global_step, decay_steps, alpha=0.0):
+        s = min(global_step, decay_steps)
+        return learning_rate * ((1.0 - alpha) * 0.5 * (1.0 + math.cos(math.pi * s / float(decay_steps))) + alpha)
+    tf.train.polynomial_decay, tf.train.exponential_decay, tf.train.cosine_decay = (
+        polynomial_decay, exponential_decay, cosine_decay)
+    return tf
+
+
+def test_lr_policies_equal_the_executed_reference():
+    """optimizers/lr_policies.py loaded by path over the stand-in above: the reference's own glue (warm-up, the
+    begin_decay_at switch, how min_lr is handed to TF -- as `alpha`, a FRACTION, in cosine_decay) against the
+    oracle's policies, which the device-side schedule of csrc/optim.cu is tested against."""
+    from oracle import optimizer as OO
+    tf = _numpy_tf()
+    fake = {"tensorflow": tf, "tensorflow.python": types.ModuleType("tensorflow.python"),
+            "tensorflow.python.framework": types.ModuleType("tensorflow.python.framework"),
+            "tensorflow.python.framework.ops": types.ModuleType("tensorflow.python.framework.ops")}
+    fake["tensorflow.python.framework"].ops = fake["tensorflow.python.framework.ops"]
+    saved = {k: sys.modules.get(k) for k in fake}
+    sys.modules.update(fake)
+    try:
+        spec = importlib.util.spec_from_file_location("_reference_lr_policies",
+                                                      "/root/reference/open_seq2seq/optimizers/lr_policies.py")
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    steps = list(range(0, 40)) + [99, 100, 101, 499, 500, 501, 999, 1000, 1001, 5000]
+    for kw in (dict(learning_rate=0.02, decay_steps=1000, power=2.0, min_lr=1e-5),                  # Jasper
+               dict(learning_rate=0.05, decay_steps=1000, power=2.0),                               # w2l+
+               dict(learning_rate=0.02, decay_steps=900, power=1.0, begin_decay_at=100, min_lr=1e-4, warmup_steps=30)):
+        for s in steps:
+            assert abs(ref.poly_decay(s, **kw) - OO.poly_decay(s, **kw)) < 1e-12, (kw, s)
+    for kw in (dict(learning_rate=0.01, decay_steps=1000, min_lr=0.0, warmup_steps=10),             # QuartzNet
+               dict(learning_rate=0.01, decay_steps=800, min_lr=0.1, begin_decay_at=200, warmup_steps=20)):
+        for s in steps:
+            assert abs(ref.cosine_decay(s, **kw) - OO.cosine_decay(s, **kw)) < 1e-12, (kw, s)
+    for kw in (dict(learning_rate=0.1, decay_steps=100, decay_rate=0.5, use_staircase_decay=True, begin_decay_at=20,
+                    min_lr=1e-3),
+               dict(learning_rate=0.1, decay_steps=100, decay_rate=0.9, use_staircase_decay=False)):
+        for s in steps:
+            assert abs(ref.exp_decay(s, **kw) - OO.exp_decay(s, **kw)) < 1e-12, (kw, s)
+    assert ref.fixed_lr(7, 0.3) == OO.fixed_lr(7, 0.3)
+
+
+def test_wer_accumulation_equals_the_executed_reference():
+    """Speech2Text.evaluate / finalize_evaluation (models/speech2text.py:244-294) compiled from the reference's
+    source and run on a stand-in `self` with tf.nn.ctc_greedy_decoder's SPARSE output; the drop-in model consumes the
+    dense tokens + lengths that os2s_ctc_greedy writes.  Same per-batch (word errors, word count), same WER."""
+    import ast
+    import collections
+    import random
+    import numpy as np
+    import torch
+    from open_seq2seq.models.speech2text import Speech2Text
+    path = "/root/reference/open_seq2seq/models/speech2text.py"
+    tree = ast.parse(open(path).read())
+    ns = {"deco_print": lambda *a, **k: None}
+    for name in ("levenshtein", "sparse_tensor_to_chars"):
+        ns[name] = _reference_function(path, name)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "Speech2Text")
+    for m in cls.body:
+        if isinstance(m, ast.FunctionDef) and m.name in ("evaluate", "finalize_evaluation"):
+            exec(compile(ast.Module(body=[m], type_ignores=[]), path, "exec"), ns)
+    chars = "abcdefghijklmnopqrstuvwxyz '"
+    idx2char = dict(enumerate(chars))
+    dl = types.SimpleNamespace(params={"idx2char": idx2char})
+    ref_self = types.SimpleNamespace(is_bpe=False, tensor_to_chars=ns["sparse_tensor_to_chars"], tensor_to_char_params={},
+                                     get_data_layer=lambda: dl)
+    own_self = types.SimpleNamespace(get_data_layer=lambda: dl)
+    own_self._decode_batch = types.MethodType(Speech2Text._decode_batch, own_self)
+    Sparse = collections.namedtuple("SparseTensorValue", "indices values dense_shape")
+    rnd = random.Random(3)
+    words = ["the", "then", "seconds", "a", "cat", "sat", "on", "mat"]
+    r_batches, o_batches = [], []
+    for _ in range(12):
+        B = rnd.randint(1, 5)
+        truths = [" ".join(rnd.choice(words) for _ in range(rnd.randint(1, 8))) for _ in range(B)]
+        preds = [" ".join(rnd.choice(words) for _ in range(rnd.randint(0, 8))) for _ in range(B)]
+        enc = lambda s: [chars.index(c) for c in s]
+        L = max(len(t) for t in truths)
+        y = np.zeros((B, L), dtype=np.int32)
+        ylen = np.array([len(t) for t in truths], dtype=np.int32)
+        for b, t in enumerate(truths):
+            y[b, :len(t)] = enc(t)
+        P = max(1, max(len(p) for p in preds))
+        toks = np.zeros((B, P), dtype=np.int32)
+        tl = np.array([len(p) for p in preds], dtype=np.int32)
+        idx, vals = [], []
+        for b, p in enumerate(preds):
+            toks[b, :len(p)] = enc(p)
+            idx += [(b, t) for t in range(len(p))]
+            vals += enc(p)
+        iv = {"source_tensors": [np.zeros((B, 4, 2))], "target_tensors": [y, ylen]}
+        r_batches.append(ns["evaluate"](ref_self, iv, [Sparse(idx, vals, (B, P))]))
+        o_iv = {"target_tensors": (torch.from_numpy(y), torch.from_numpy(ylen))}
+        o_batches.append(Speech2Text.evaluate(own_self, o_iv, (torch.from_numpy(toks), torch.from_numpy(tl))))
+        assert r_batches[-1] == o_batches[-1]
+    want = ns["finalize_evaluation"](ref_self, r_batches)
+    got = Speech2Text.finalize_evaluation(own_self, o_batches)
+    assert want.keys() == got.keys() and abs(want["Eval WER"] - got["Eval WER"]) < 1e-12
