@@ -103,6 +103,17 @@ def larc(grads, weights, lr, larc_eta, larc_mode="clip", min_update=1e-7, eps=1e
     return out
 
 
+def clip_by_global_norm(grads, clip_norm):
+    """optimizers.py:380-480 (_clip_gradients_by_norm / _clip_by_global_norm with the fp32 global norm of
+    _global_norm_with_cast): every gradient times clip_norm * min(1 / global_norm, 1 / clip_norm)."""
+    sq = np.float32(0.0)
+    for g in grads:
+        sq = np.float32(sq + np.sum(np.square(g.astype(np.float32), dtype=np.float32), dtype=np.float32))
+    gnorm = np.float32(np.sqrt(sq))
+    scale = np.float32(clip_norm) * min(np.float32(1.0) / gnorm, np.float32(1.0) / np.float32(clip_norm))
+    return [(g.astype(np.float32) * np.float32(scale)).astype(np.float32) for g in grads], gnorm
+
+
 class NovoGradState(object):
     def __init__(self, n):
         self.ema = [0.0] * n
@@ -176,7 +187,7 @@ def check_grads(grads):
 
 
 def train_step(weights, scaled_grads_per_rank, state, scaler, step, lr_fn, opt_params, larc_params=None,
-               ema_persist=False, algo="novograd", reg_scales=None):
+               ema_persist=False, algo="novograd", reg_scales=None, max_grad_norm=None):
     """One optimize_loss step (optimizers.py:208-281 + mp_wrapper.py:44-122).
 
     scaled_grads_per_rank: list over ranks of lists of gradients of (loss * scaler.scale) wrt the
@@ -192,6 +203,9 @@ def train_step(weights, scaled_grads_per_rank, state, scaler, step, lr_fn, opt_p
         # deferred regulariser gradient on the fp32 copy, added after the un-scaling (mp_wrapper.py:81-95)
         grads = [g + np.float32(r) * w if r else g for g, w, r in zip(grads, weights, reg_scales)]
     lr = lr_fn(step)
+    if max_grad_norm:
+        # post_process_gradients clips before LARC (optimize_loss refuses both at once, optimizers.py:161-164)
+        grads, _ = clip_by_global_norm(grads, max_grad_norm)
     if larc_params is not None:
         grads = larc(grads, weights, lr, **larc_params)
     has_nan, amax = check_grads(grads)

@@ -155,6 +155,11 @@ def test_check_params_accepts_and_rejects_like_the_executed_reference(ref):
     assert ref.check_params({"zzz": 1}, None, None) is None and OWN.check_params({"zzz": 1}, None, None) is None
 
 
+def ast_parse(path):
+    import ast
+    return ast.parse(open(path).read())
+
+
 def _reference_function(path, name):
     """Compile ONE top-level function of a reference module that cannot be imported as a whole (TensorFlow at import
     time) from its source in /root/reference and return it; nothing is copied into the repository."""
@@ -350,3 +355,108 @@ def test_wer_accumulation_equals_the_executed_reference():
     want = ns["finalize_evaluation"](ref_self, r_batches)
     got = Speech2Text.finalize_evaluation(own_self, o_batches)
     assert want.keys() == got.keys() and abs(want["Eval WER"] - got["Eval WER"]) < 1e-12
+
+
+def test_larc_and_global_norm_clipping_equal_the_executed_reference(ref, monkeypatch):
+    """optimizers.py:289-480 (post_process_gradients: tf.clip_by_global_norm on the fp32 global norm, then LARC in
+    'clip' or 'scale' mode) compiled from the reference's source over a NumPy stand-in for the dozen TF symbols it
+    touches, vs oracle.optimizer.larc / clip_by_global_norm -- the functions the device optimizer is tested against."""
+    import collections
+    import collections.abc
+    import contextlib
+    import numpy as np
+    import six
+    from oracle import optimizer as OO
+    monkeypatch.setattr(collections, "Sequence", collections.abc.Sequence, raising=False)   # (Python 2-era alias)
+
+    class Var(np.ndarray):
+        name = "v:0"
+    tf = types.SimpleNamespace(
+        float32=np.float32, int32=np.int32, IndexedSlices=type("IndexedSlices", (), {}),
+        norm=lambda tensor=None, ord=2: np.float32(np.sqrt(np.sum(np.square(tensor, dtype=np.float32), dtype=np.float32))),
+        cast=lambda x, dtype: np.asarray(x).astype(dtype), saturate_cast=lambda x, dtype: np.asarray(x).astype(dtype),
+        maximum=np.maximum, minimum=np.minimum, less=np.less, identity=lambda x, name=None: x,
+        convert_to_tensor=lambda x, name=None: np.asarray(x), ones=lambda shape, dtype=np.float32: np.ones(shape, dtype),
+        global_norm=lambda ts: np.float32(np.sqrt(sum(np.sum(np.square(t, dtype=np.float32), dtype=np.float32)
+                                                      for t in ts))),
+        name_scope=lambda *a, **k: contextlib.nullcontext("clip"), colocate_with=lambda v: contextlib.nullcontext(),
+        summary=types.SimpleNamespace(scalar=lambda *a, **k: None, histogram=lambda *a, **k: None))
+    path = "/root/reference/open_seq2seq/optimizers/optimizers.py"
+    tree = ast_parse(path)
+    ns = {"tf": tf, "check_params": ref.check_params, "mask_nans": None, "collections": collections, "six": six}
+    for name in ("_global_norm_with_cast", "_clip_by_global_norm", "_clip_gradients_by_norm", "post_process_gradients"):
+        node = next(n for n in tree.body if getattr(n, "name", None) == name)
+        exec(compile(__import__("ast").Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    rng = np.random.RandomState(0)
+    shapes = [(11, 8, 16), (16,), (16,), (1, 8, 4), (40, 29), (29,)]
+    for trial in range(6):
+        ws = [(rng.standard_normal(s) * 0.1).astype(np.float32).view(Var) for s in shapes]
+        gs = [(rng.standard_normal(s) * 10.0 ** rng.randint(-4, 2)).astype(np.float32) for s in shapes]
+        lr = float(10.0 ** rng.uniform(-4, -1))
+        for larc_params in ({"larc_eta": 0.001}, {"larc_eta": 0.002, "larc_mode": "scale", "min_update": 1e-6},
+                            {"larc_eta": 0.001, "larc_mode": "clip", "epsilon": 1e-5}):
+            want = ns["post_process_gradients"](list(zip(gs, ws)), [], lr, None, dict(larc_params))
+            kw = dict(larc_params)
+            if "epsilon" in kw:
+                kw["eps"] = kw.pop("epsilon")
+            got = OO.larc(gs, [np.asarray(w) for w in ws], lr, **kw)
+            for (wg, _), g in zip(want, got):
+                assert np.allclose(np.asarray(wg), g, rtol=2e-6, atol=0), (trial, larc_params)
+        for clip in (0.5, 5.0, 1e4):
+            want = ns["post_process_gradients"](list(zip(gs, ws)), [], lr, clip, None)
+            got, gnorm = OO.clip_by_global_norm(gs, clip)
+            for (wg, _), g in zip(want, got):
+                assert np.allclose(np.asarray(wg), g, rtol=2e-6, atol=0), (trial, clip)
+            if clip > gnorm:
+                assert all(np.allclose(g, g0, rtol=1e-6) for g, g0 in zip(got, gs))       # below the threshold: untouched
+
+
+def test_novograd_equals_the_executed_reference_class():
+    """optimizers/novograd.py: the NovoGrad class body compiled from the reference's source on top of a stand-in
+    tf.train.MomentumOptimizer with TensorFlow's documented update (accum <- momentum accum + grad; var <- var - lr
+    accum).  In graph mode apply_gradients runs ONCE and the zero-initialised `nvgrad2_ema` variables are never
+    assigned, so every step sees ema == 0 and normalises by the CURRENT ||g||^2 (the as-written behaviour the oracle
+    and the device optimizer reproduce by default); the stand-in mirrors that by building the "graph" afresh per
+    step.  Several steps, with and without weight decay / gradient averaging."""
+    import ast
+    import numpy as np
+    from oracle import optimizer as OO
+
+    class MomentumOptimizer(object):
+        def __init__(self, learning_rate, momentum, use_locking=False, name="Momentum", use_nesterov=False):
+            assert not use_nesterov
+            self._lr, self._momentum, self.accum = learning_rate, momentum, {}
+
+        def apply_gradients(self, grads_and_vars, global_step=None, name=None):
+            for i, (g, v) in enumerate(grads_and_vars):
+                a = self.accum.get(i)
+                a = g.copy() if a is None else np.float32(self._momentum) * a + g
+                self.accum[i] = a
+                v -= np.float32(self._lr) * a
+
+    tf = types.SimpleNamespace(
+        float32=np.float32, get_variable=lambda name, shape, dtype, initializer, trainable: np.float32(0.0),
+        keras=types.SimpleNamespace(initializers=types.SimpleNamespace(Zeros=lambda: None)),
+        reduce_sum=lambda x: np.sum(x, dtype=np.float32), square=lambda x: np.square(x, dtype=np.float32),
+        cast=lambda x, dtype: np.asarray(x).astype(dtype), equal=lambda a, b: a == b, sqrt=np.sqrt,
+        cond=lambda pred, t, f: t() if pred else f())
+    path = "/root/reference/open_seq2seq/optimizers/novograd.py"
+    cls = next(n for n in ast.parse(open(path).read()).body if isinstance(n, ast.ClassDef) and n.name == "NovoGrad")
+    ns = {"tf": tf, "MomentumOptimizer": MomentumOptimizer}
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), path, "exec"), ns)
+    rng = np.random.RandomState(2)
+    shapes = [(5, 8, 16), (16,), (40, 29)]
+    for kw in (dict(beta1=0.95, beta2=0.98, epsilon=1e-8, weight_decay=0.001),
+               dict(beta1=0.9, beta2=0.5, epsilon=1e-6, weight_decay=0.0, grad_averaging=True)):
+        lr = 0.02
+        w_ref = [(rng.standard_normal(s) * 0.1).astype(np.float32) for s in shapes]
+        w_own = [w.copy() for w in w_ref]
+        opt = ns["NovoGrad"](learning_rate=lr, **kw)
+        state = OO.NovoGradState(len(shapes))
+        for step in range(5):
+            gs = [(rng.standard_normal(s) * 0.05).astype(np.float32) for s in shapes]
+            opt._grads_ema = None                      # the graph is built once: ema reads as 0 on every run
+            opt.apply_gradients([(g.copy(), w) for g, w in zip(gs, w_ref)])
+            OO.novograd_step(w_own, [g.copy() for g in gs], state, lr, **kw)
+            for a, b in zip(w_ref, w_own):
+                assert np.allclose(a, b, rtol=1e-5, atol=1e-7), (kw, step)
