@@ -121,8 +121,7 @@ REF_SPEECH_CONFIGS = "/root/reference/example_configs/speech2text"
 
 @pytest.mark.skipif(not __import__("os").path.isdir(REF_SPEECH_CONFIGS), reason="reference checkout not present")
 @pytest.mark.parametrize("name,layers,params,sep", [
-    ("jasper10x5_LibriSpeech_nvgrad.py", 53, 332632349, False),
-    ("jasper10x5_LibriSpeech_nvgrad_masks.py", 53, 332632349, False),
+    ("jasper10x5_LibriSpeech_nvgrad_masks.py", 53, 332632349, False),   # (same encoder as ..._nvgrad.py)
     ("jasper-Mini-for-Jetson.py", 33, 8192733, True),
     ("quartznet15x5_LibriSpeech.py", 78, 19193949, True),
     ("w2l_large_8gpus.py", 17, 105774877, False),
