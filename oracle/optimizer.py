@@ -20,7 +20,10 @@ a Python list entry to a tf.cond tensor and never assigns the variable, so the p
 moment is v_t = ||g_t||^2 at every step.  `ema_persist=True` is the corrected NovoGrad
 (v_t = beta2*v_{t-1} + (1-beta2)*||g_t||^2 after the first step).
 Parity status: unpinned by the reference's own tests except mp_wrapper_test.py (regulariser grad
-1e-8); see tests/test_oracle_optimizer.py.
+1e-8) and optimizers_test.py (iter_size); see tests/test_oracle.py.  In the build container the reference's OWN
+lr_policies.py, post_process_gradients (global-norm clipping + LARC) and NovoGrad class are executed over stand-ins
+for the TensorFlow symbols they touch and compared with the functions below
+(tests/test_reference_config_executed_cpu.py); the Backoff scaler and the MP wrapper are restated only.
 """
 import numpy as np
 

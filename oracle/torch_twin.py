@@ -9,7 +9,10 @@ Follows the same reference lines as the NumPy oracle:
   open_seq2seq/encoders/tdnn_encoder.py:87-265, open_seq2seq/parts/cnns/conv_blocks.py:61-232,
   open_seq2seq/decoders/fc_decoders.py:105-158, open_seq2seq/losses/ctc_loss.py:44-89,
   open_seq2seq/optimizers/{optimizers.py:289-378,novograd.py:93-126,mp_wrapper.py:44-122}.
-It is validated against the NumPy restatement in tests/test_oracle_encoder.py.
+It is validated against the NumPy restatement in tests/test_oracle.py, and -- in the build container, where
+/root/reference exists -- against the reference's OWN encoder / decoder / loss builders executed over an eager
+stand-in for their TensorFlow symbols (tests/test_reference_encoder_executed_cpu.py: same logits to 1e-10, same
+lengths, same variable set).
 """
 import math
 
