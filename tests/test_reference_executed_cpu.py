@@ -202,3 +202,81 @@ def test_psf_pipeline_matches_the_executed_reference(ref, toy_signal, features_t
         assert np.allclose(want, got, rtol=0, atol=1e-9), (n, np.abs(want - got).max())
         if pad_to:
             assert want.shape[0] % pad_to == 0
+
+
+@pytest.mark.parametrize("config,mode", [("jasper10x5_LibriSpeech_nvgrad.py", "eval"),
+                                         ("jasper10x5_LibriSpeech_nvgrad_masks.py", "train"),
+                                         ("w2lplus_large_8gpus_mp.py", "train")])
+def test_per_utterance_data_path_equals_the_executed_reference(ref, golden_dir, config, mode):
+    """Speech2TextDataLayer._parse_audio_transcript_element (speech2text.py:401-432, the py_func behind the tf.data
+    pipeline) compiled from the reference's source and run with the data-layer params of a REAL example config on the
+    toy wavs: the wav is read and checked, dispatched by `backend` / `input_type` with the config's window, dither,
+    num_fft, norm_per_feature, pad_to and augmentation, the transcript is encoded with the vocabulary.  The drop-in
+    data layer's host side (file list, wav reader, transcript ids) and the oracle's features for those parameters
+    have to agree, from the same np.random stream."""
+    import ast
+    import copy
+    import pandas as pd
+    import six
+    import openseq2seq_b200.compat as compat
+    compat.install()
+    from open_seq2seq.data import Speech2TextDataLayer
+    from open_seq2seq.utils.utils import get_base_config, nested_update
+    path = "/root/reference/open_seq2seq/data/speech2text/speech2text.py"
+    cls = next(n for n in ast.parse(open(path).read()).body if isinstance(n, ast.ClassDef)
+               and n.name == "Speech2TextDataLayer")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "_parse_audio_transcript_element")
+    ns = {"np": np, "six": six, "get_speech_features_from_file": ref.get_speech_features_from_file}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+
+    toy = os.path.join(golden_dir, "toy_speech_data")
+    _, cfg, _, module = get_base_config(["--config_file=/root/reference/example_configs/speech2text/" + config,
+                                         "--mode=" + mode])
+    p = copy.deepcopy(cfg.get("data_layer_params", {}))
+    nested_update(p, copy.deepcopy(module[mode + "_params"]["data_layer_params"]))
+    p.update(dataset_files=[os.path.join(toy, "toy_data.csv")], vocab_file=os.path.join(toy, "vocab.txt"), mode=mode,
+             batch_size=2)
+    dl = Speech2TextDataLayer(copy.deepcopy(p), None, 1, 0)          # the drop-in: file list, vocabulary, defaults
+    rp = dict(dl.params)                                             # what the reference's constructor would hold
+    rp.update(bpe=False, dtype=types.SimpleNamespace(as_numpy_dtype=lambda: np.float32), mel_basis=None)
+    me = types.SimpleNamespace(params=rp, autoregressive=False, end_index=None)
+    rows = pd.read_csv(os.path.join(toy, "toy_data.csv"), encoding="utf-8")
+    librosa_backend = rp.get("backend", "psf") == "librosa"
+    aug = rp.get("augmentation") if mode == "train" else None
+    assert bool(aug) == (config != "w2lplus_large_8gpus_mp.py" and mode == "train")
+    for k in (0, 3, 7):
+        wav = os.path.join(toy, rows["wav_filename"][k]) if not os.path.isabs(rows["wav_filename"][k]) \
+            else rows["wav_filename"][k]
+        if not os.path.exists(wav):
+            wav = os.path.join(toy, "wav_files", os.path.basename(rows["wav_filename"][k]))
+        tr = rows["transcript"][k]
+        np.random.seed(11 + k)
+        src, src_len, tgt, tgt_len, dur = ns["_parse_audio_transcript_element"](
+            me, (wav.encode("utf-8"), tr.encode("utf-8")))
+        # host side of the drop-in
+        sig, ids = dl._load((wav, tr))
+        assert np.array_equal(ids, tgt) and int(tgt_len[0]) == len(ids)
+        # the oracle with this config's parameters, same random stream
+        rng = np.random.RandomState(11 + k)
+        if librosa_backend:
+            x = FZ.normalize_signal(sig.astype(np.float32))
+            if aug:
+                x = AU.augment_audio_signal(x, 16000, aug, rng=rng)
+            if rp.get("dither", 0.0) > 0:
+                x = x + rp["dither"] * rng.randn(*x.shape)
+            S = FZ.stft_power(FZ.preemphasis(x), n_fft=FZ.num_fft_for(rp["window_size"], 16000),
+                              hop=int(16000 * rp["window_stride"]), win_length=int(16000 * rp["window_size"]))
+            f = np.log(np.dot(FZ.mel_filterbank(16000, 512, n_mels=rp["num_audio_features"], fmin=0, fmax=8000), S)
+                       + 1e-20).T
+            axis = 0 if rp.get("norm_per_feature", False) else None
+            f = (f - np.mean(f, axis=axis)) / np.std(f, axis=axis)
+            if aug:
+                f = AU.apply_spec_masks(f, AU.draw_spec_masks(f.shape[0], rp["num_audio_features"], aug, rng))
+            want_dur = len(x) / 16000.0
+        else:
+            assert rp["input_type"] == "logfbank"
+            f, want_dur = FZ.psf_logfbank_features(sig, num_features=rp["num_audio_features"],
+                                                   pad_to=rp.get("pad_to", 8))
+        assert src.shape == f.shape and int(src_len[0]) == f.shape[0]
+        assert np.allclose(src, f, rtol=0, atol=3e-4), (config, k, np.abs(src - f).max())
+        assert abs(float(dur[0]) - want_dur) < 1e-6
