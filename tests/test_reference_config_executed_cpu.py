@@ -460,3 +460,51 @@ def test_novograd_equals_the_executed_reference_class():
             OO.novograd_step(w_own, [g.copy() for g in gs], state, lr, **kw)
             for a, b in zip(w_ref, w_own):
                 assert np.allclose(a, b, rtol=1e-5, atol=1e-7), (kw, step)
+
+
+@pytest.mark.parametrize("dump", [False, True])
+def test_inference_output_files_equal_the_executed_reference(tmp_path, dump):
+    """Speech2Text.finalize_inference (models/speech2text.py:315-354) compiled from the reference's source: the CSV
+    of predicted transcripts and, with `infer_logits_to_pickle`, the {logits, step_size, vocab} pickle that
+    scripts/decode.py reads -- batches arrive in any order and are put back in dataset order."""
+    import ast
+    import pickle
+    import numpy as np
+    import pandas as pd
+    from open_seq2seq.models.speech2text import Speech2Text
+    path = "/root/reference/open_seq2seq/models/speech2text.py"
+    cls = next(n for n in ast.parse(open(path).read()).body if isinstance(n, ast.ClassDef) and n.name == "Speech2Text")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "finalize_inference")
+    ns = {"np": np, "pd": pd, "pickle": pickle}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    files = ["a/%d.wav" % i for i in range(7)]
+    idx2char = dict(enumerate("abcdefghijklmnopqrstuvwxyz '"))
+    layers = [{"stride": [2]}, {"stride": [1]}, {"stride": [1]}]
+    dl_ref = types.SimpleNamespace(all_files=np.array(files), params={"window_stride": 0.01, "idx2char": idx2char})
+    dl_own = types.SimpleNamespace(_files=[(f, None) for f in files], params=dl_ref.params)
+    enc = types.SimpleNamespace(params={"convnet_layers": layers})
+    ref_self = types.SimpleNamespace(dump_outputs=dump, get_data_layer=lambda: dl_ref, encoder=enc)
+    own_self = types.SimpleNamespace(dump_outputs=dump, get_data_layer=lambda: dl_own, encoder=enc)
+    rng = np.random.RandomState(0)
+    order = [np.array([4, 1]), np.array([6, 0, 3]), np.array([5, 2])]
+    if dump:
+        item = {i: rng.standard_normal((5 + i, 29)).astype(np.float32) for i in range(7)}
+    else:
+        item = {i: "text %d" % i for i in range(7)}
+    batches = [([item[int(i)] for i in ids], [ids]) for ids in order]
+    if dump:
+        # (the reference stacks equally long logits into one array; ragged lists need dtype=object in NumPy >= 1.24)
+        orig = np.array
+        ns["np"] = types.SimpleNamespace(array=lambda x: orig(x, dtype=object), hstack=np.hstack, argsort=np.argsort)
+    a, b = str(tmp_path / "ref.out"), str(tmp_path / "own.out")
+    ns["finalize_inference"](ref_self, batches, a)
+    Speech2Text.finalize_inference(own_self, batches, b)
+    if dump:
+        ra, rb = pickle.load(open(a, "rb")), pickle.load(open(b, "rb"))
+        assert ra.keys() == rb.keys() and abs(ra["step_size"] - rb["step_size"]) < 1e-12 and ra["vocab"] == rb["vocab"]
+        assert abs(ra["step_size"] - 0.02) < 1e-12 and list(ra["logits"]) == list(rb["logits"]) == files
+        for f in files:
+            assert np.array_equal(ra["logits"][f], rb["logits"][f])
+    else:
+        assert open(a).read() == open(b).read()
+        assert pd.read_csv(b)["predicted_transcript"].tolist() == ["text %d" % i for i in range(7)]
