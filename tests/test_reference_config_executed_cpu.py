@@ -508,3 +508,147 @@ def test_inference_output_files_equal_the_executed_reference(tmp_path, dump):
     else:
         assert open(a).read() == open(b).read()
         assert pd.read_csv(b)["predicted_transcript"].tolist() == ["text %d" % i for i in range(7)]
+
+
+def _reference_hooks():
+    """RunEvaluationHook / PrintLossAndTimeHook / PrintSamplesHook (utils/hooks.py:57-245) compiled from the
+    reference's source over a stand-in for the tf.train symbols they use; tf.train.SecondOrStepTimer is TensorFlow's
+    (basic_session_run_hooks.py): first call fires, afterwards when step >= last_triggered + every_steps."""
+    import ast
+    import collections
+
+    class SecondOrStepTimer(object):
+        def __init__(self, every_secs=None, every_steps=None):
+            self._every, self._last = every_steps, None
+
+        def should_trigger_for_step(self, step):
+            if self._last is None:
+                return True
+            if self._last == step:
+                return False
+            return step >= self._last + self._every
+
+        def update_last_triggered_step(self, step):
+            self._last = step
+    train = types.SimpleNamespace(SessionRunHook=object, SecondOrStepTimer=SecondOrStepTimer,
+                                  Saver=lambda **kw: types.SimpleNamespace(save=lambda *a, **k: None),
+                                  get_global_step=lambda: "global_step",
+                                  SessionRunArgs=lambda fetches: fetches)
+    path = "/root/reference/open_seq2seq/utils/hooks.py"
+    ns = {"tf": types.SimpleNamespace(train=train), "deco_print": lambda *a, **k: None, "time": __import__("time"),
+          "math": __import__("math"), "os": os, "log_summaries_from_dict": lambda *a, **k: None}
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.ClassDef) and node.name in ("RunEvaluationHook", "PrintLossAndTimeHook",
+                                                             "PrintSamplesHook"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns, collections.namedtuple("RunValues", "results")
+
+
+@pytest.mark.parametrize("every,last_step,first", [(5, 12, 0), (4, 10, 0), (1, 3, 0), (7, 20, 0), (5, 23, 8)])
+def test_hook_cadence_equals_the_executed_reference(every, last_step, first, tmp_path):
+    """When evaluation, loss printing and sample printing fire: the reference's hooks driven the way
+    MonitoredTrainingSession drives them (before_run -> run -> after_run with the global step the run started
+    from) vs the drop-in's training loop on stub models, incl. a resumed run (first global step 8)."""
+    import torch
+    from open_seq2seq.utils import funcs as F
+    ns, RunValues = _reference_hooks()
+    fired = {"eval": [], "loss": [], "samples": []}
+    model = types.SimpleNamespace(
+        params={"num_checkpoints": 2, "save_checkpoint_steps": None, "save_summaries_steps": None, "logdir": str(tmp_path)},
+        on_horovod=False, loss="loss", steps_in_epoch=None, get_output_tensors=lambda i: "out",
+        get_data_layer=lambda i=0: types.SimpleNamespace(input_tensors="in"),
+        finalize_evaluation=lambda results, step: {},
+        maybe_print_logs=lambda i, o, step: fired["samples"].append(int(step)))
+    ns["get_results_for_epoch"] = lambda m, sess, mode, compute_loss: ([], 1.0)
+    hooks = {"eval": ns["RunEvaluationHook"](every, model, last_step=last_step),
+             "loss": ns["PrintLossAndTimeHook"](every, model), "samples": ns["PrintSamplesHook"](every, model)}
+    for h in hooks.values():
+        h.begin()
+    ctx = types.SimpleNamespace(session=None)
+    for k in range(first, last_step):
+        req = {n: h.before_run(ctx) for n, h in hooks.items()}
+        for n, h in hooks.items():
+            wanted = req[n][0]
+            res = [] if not wanted else ([1.0] if n == "loss" else ("in", "out"))
+            before = len(fired["samples"])
+            if n == "eval":
+                calls = []
+                ns["get_results_for_epoch"] = lambda m, sess, mode, compute_loss, c=calls: (c.append(1), ([], 1.0))[1]
+                h.after_run(ctx, RunValues([res, k]))
+                if calls:
+                    fired["eval"].append(k)
+            else:
+                h.after_run(ctx, RunValues([res, k]))
+                if n == "loss" and wanted:
+                    fired["loss"].append(k)
+            assert n != "samples" or len(fired["samples"]) - before == (1 if wanted else 0)
+
+    # the drop-in loop on stub models
+    own = {"eval": [], "loss": [], "samples": []}
+
+    class Eng(object):
+        def __init__(self):
+            self.istate = torch.zeros(8, dtype=torch.int64)
+            self.istate[2] = first
+            self.training = True
+
+        def set_training(self, f):
+            self.training = f
+
+        def greedy_decode(self):
+            return None
+    eng = Eng()
+    n_last = last_step
+
+    class DL(object):
+        def __init__(self, n):
+            self.n, self.iterator = n, None
+            self.build_graph()
+
+        def build_graph(self):
+            self.iterator = iter(range(10 ** 9)) if self.n is None else iter(range(self.n))
+
+    class Train(object):
+        on_horovod, hvd = False, None
+        params = {"print_loss_steps": every, "print_samples_steps": every, "save_checkpoint_steps": None,
+                  "eval_steps": every, "logdir": None, "bench_start": 0}
+        last_step = n_last
+        engine = eng
+        _dl = DL(None)
+
+        def get_data_layer(self):
+            return self._dl
+
+        def train_step(self, batch):
+            self.engine.istate[2] += 1
+            return torch.tensor(1.0), 1.0
+
+        def maybe_print_logs(self, batch, toks, step):
+            own["samples"].append(int(step))
+
+    class Eval(object):
+        on_horovod, hvd = False, None
+        engine = eng
+        _dl = DL(1)
+
+        def get_data_layer(self):
+            return self._dl
+
+        def eval_step(self, batch):
+            return torch.tensor(1.0), {"outputs": [None]}
+
+        def evaluate(self, batch, out):
+            return 0
+
+        def finalize_evaluation(self, results):
+            own["eval"].append(int(eng.istate[2]) - 1)       # the global step the triggering run started from
+            return {}
+    printed = []
+    orig = F.deco_print
+    F.deco_print = lambda line, *a, **k: printed.append(line)
+    try:
+        F.train(Train(), Eval())
+    finally:
+        F.deco_print = orig
+    own["loss"] = [int(l.split()[2].rstrip(":")) for l in printed if l.startswith("Global step")]
+    assert own == fired, (own, fired)

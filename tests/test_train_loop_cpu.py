@@ -109,19 +109,22 @@ def test_train_loop_checkpoints_evaluates_and_keeps_best_models(tmp_path):
               "eval_steps": 5, "num_checkpoints": 2, "logdir": logdir, "bench_start": 2}
     eng = _Engine()
     tm = _Model(params, eng)
-    em = _EvalModel(params, eng, losses=[3.0, 5.0])   # improves at step 5, not at step 10
+    # RunEvaluationHook fires on the first run, then every eval_steps runs, and on the last step (global steps 0, 5
+    # and 9); the losses are 7.0, 3.0 (an improvement, saved as global step + 1 = 6) and 5.0
+    em = _EvalModel(params, eng, losses=[7.0, 3.0, 5.0])
     rate = train(tm, em)
     assert int(eng.istate[2]) == 10 and float(eng.w["a/kernel"][0]) == 10.0
-    assert em.evals == 2                                   # step 5 and the last step
+    assert em.evals == 3
     names = sorted(os.listdir(logdir))
     assert names == ["best_models", "model.ckpt-10.pt", "model.ckpt-8.pt"]   # 4 was rotated out (keep 2)
-    assert os.listdir(os.path.join(logdir, "best_models")) == ["val_loss=3.0000-step-5.pt"]
+    assert sorted(os.listdir(os.path.join(logdir, "best_models"))) == ["val_loss=3.0000-step-6.pt",
+                                                                       "val_loss=7.0000-step-1.pt"]
     assert rate is not None and rate > 0
     # eval / infer pick the latest or, with restore_best_checkpoint, the best checkpoint (utils.py:676-690)
     args = argparse.Namespace(mode="eval", enable_logs=False, continue_learning=False, no_dir_check=False,
                               benchmark=False)
     assert check_logdir(args, {"logdir": logdir}).endswith("model.ckpt-10.pt")
-    assert check_logdir(args, {"logdir": logdir}, True).endswith(os.path.join("best_models", "val_loss=3.0000-step-5.pt"))
+    assert check_logdir(args, {"logdir": logdir}, True).endswith(os.path.join("best_models", "val_loss=3.0000-step-6.pt"))
     # resume: a restored engine continues from its global step instead of starting over
     eng2 = _Engine()
     assert ckpt.restore(eng2, os.path.join(logdir, "model.ckpt-8.pt")) == 8
